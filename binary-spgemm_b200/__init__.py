@@ -1,0 +1,343 @@
+"""binary-spgemm_b200 — Python mirror of the C ABI (include/bspgemm.h, include/bspgemm_host.h).
+
+This package is plumbing, not the product: the product is ``libbspgemm.so`` (hand-written sm_100a CUDA
+behind a C ABI) and ``libbspgemm_host.so`` (the C host surface: readCOO / coo2csc / generators).  The
+functions here only marshal numpy arrays / torch device pointers into those entry points so that the
+parity tests read like the reference's own drivers (final/SpGEMM_mpi_omp.c:294-344).
+
+There is deliberately NO fallback: if the CUDA library is missing, or no GPU is visible, the calls raise.
+Import with ``importlib.import_module("binary-spgemm_b200")`` (the directory name is not an identifier).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libbspgemm.so"
+HOST_LIB_PATH = _HERE / "libbspgemm_host.so"
+
+OK, ERR_CUDA, ERR_NCCL, ERR_OOM, ERR_OVERFLOW32, ERR_BADARG, ERR_NOGPU, ERR_CAPACITY, ERR_STATE = range(9)
+MODE_AUTO, MODE_FUSED, MODE_TWOPHASE = 0, 1, 2
+
+# every symbol include/bspgemm.h declares (tests check the library exports all of them)
+ABI_SYMBOLS = [
+    "bspgemm_strerror", "bspgemm_last_error", "bspgemm_version",
+    "bspgemm_init", "bspgemm_finalize", "bspgemm_num_gpus",
+    "bspgemm_csr", "bspgemm_csr_i64", "bspgemm_csr_into", "bspgemm_csr_slice",
+    "bspgemm_intermediate_products",
+    "bspgemm_SpGEMM_mpi", "bspgemm_SpGEMM_omp", "bspgemm_SpGEMM_bigslice",
+    "bspgemm_dev_create", "bspgemm_dev_destroy", "bspgemm_dev_set_mode",
+    "bspgemm_dev_multiply", "bspgemm_dev_get_stats",
+]
+HOST_SYMBOLS = [
+    "readCOO", "readCOO_status", "coo2csc", "tictoc", "bs_time_stats",
+    "bs_gen_uniform", "bs_gen_rmat", "bs_gen_banded", "bs_gen_blockdiag", "bs_write_mtx",
+    "mm_read_banner", "mm_read_mtx_crd_size", "mm_write_banner", "mm_write_mtx_crd_size",
+    "mm_is_valid", "mm_typecode_to_str",
+]
+
+
+class BSpGEMMError(RuntimeError):
+    def __init__(self, status: int, where: str, detail: str):
+        super().__init__(f"{where}: status {status}: {detail}")
+        self.status = status
+
+
+class Stats(C.Structure):
+    """struct bspgemm_stats (include/bspgemm.h)."""
+    _fields_ = [
+        ("ip", C.c_int64), ("nnz", C.c_int64),
+        ("rows_s", C.c_int64), ("rows_m", C.c_int64), ("rows_l", C.c_int64),
+        ("mode", C.c_int32), ("cap_s", C.c_int32), ("group", C.c_int32), ("launches", C.c_int32),
+        ("ms_total", C.c_float), ("ms_estimate", C.c_float), ("ms_symbolic", C.c_float),
+        ("ms_main", C.c_float), ("ms_numeric", C.c_float),
+        ("algorithmic_bytes", C.c_int64),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+_lib = None
+_host = None
+_libc = C.CDLL(None)
+_libc.free.argtypes = [C.c_void_p]
+
+_I32P = C.POINTER(C.c_int32)
+_I64P = C.POINTER(C.c_int64)
+_U32P = C.POINTER(C.c_uint32)
+
+
+def lib() -> C.CDLL:
+    """libbspgemm.so — raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise FileNotFoundError(f"{LIB_PATH} is missing: build it with `make -C {_HERE}` or __graft_entry__.build(); "
+                                    "there is no CPU fallback")
+        L = C.CDLL(str(LIB_PATH))
+        L.bspgemm_strerror.restype = C.c_char_p
+        L.bspgemm_strerror.argtypes = [C.c_int]
+        L.bspgemm_last_error.restype = C.c_char_p
+        L.bspgemm_version.restype = C.c_char_p
+        L.bspgemm_init.argtypes = [C.c_int]
+        common = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.bspgemm_csr.argtypes = common + [C.POINTER(C.c_void_p), C.c_void_p]
+        L.bspgemm_csr_i64.argtypes = common + [C.POINTER(C.c_void_p), C.c_void_p]
+        L.bspgemm_csr_into.argtypes = common + [C.c_void_p, C.c_int64, C.c_void_p, _I64P]
+        L.bspgemm_csr_slice.argtypes = common + [C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_int]
+        L.bspgemm_intermediate_products.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, _I64P]
+        legacy = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_void_p]
+        L.bspgemm_SpGEMM_mpi.argtypes = legacy + [C.c_int]
+        L.bspgemm_SpGEMM_mpi.restype = None
+        L.bspgemm_SpGEMM_omp.argtypes = legacy + [C.c_int]
+        L.bspgemm_SpGEMM_omp.restype = None
+        L.bspgemm_SpGEMM_bigslice.argtypes = legacy + [_I32P, C.c_int, C.c_int]
+        L.bspgemm_SpGEMM_bigslice.restype = None
+        L.bspgemm_dev_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+        L.bspgemm_dev_destroy.argtypes = [C.c_void_p]
+        L.bspgemm_dev_set_mode.argtypes = [C.c_void_p, C.c_int]
+        L.bspgemm_dev_multiply.argtypes = [C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.c_int, C.c_int64,
+                                           C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64,
+                                           C.c_void_p, C.c_int, C.POINTER(C.c_void_p), _I64P]
+        L.bspgemm_dev_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        _lib = L
+    return _lib
+
+
+def host() -> C.CDLL:
+    """libbspgemm_host.so — the C host surface (reader, converter, generators)."""
+    global _host
+    if _host is None:
+        if not HOST_LIB_PATH.exists():
+            raise FileNotFoundError(f"{HOST_LIB_PATH} is missing: build it with `make -C {_HERE}`")
+        H = C.CDLL(str(HOST_LIB_PATH))
+        H.readCOO_status.argtypes = [C.c_char_p, C.POINTER(_U32P), C.POINTER(_U32P), _U32P, _U32P, _U32P]
+        H.coo2csc.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
+        H.coo2csc.restype = None
+        H.tictoc.restype = C.c_double
+        H.tictoc.argtypes = [C.c_int]
+        H.bs_time_stats.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        H.bs_time_stats.restype = None
+        gen_out = [C.POINTER(_I32P), C.POINTER(_I32P), _I64P]
+        H.bs_gen_uniform.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64] + gen_out
+        H.bs_gen_rmat.argtypes = [C.c_uint32, C.c_uint32, C.c_double, C.c_double, C.c_double, C.c_uint64] + gen_out
+        H.bs_gen_banded.argtypes = [C.c_uint32, C.c_uint32] + gen_out
+        H.bs_gen_blockdiag.argtypes = [C.c_uint32, C.c_uint32] + gen_out
+        H.bs_write_mtx.argtypes = [C.c_char_p, C.c_uint32, C.c_void_p, C.c_void_p]
+        _host = H
+    return _host
+
+
+def _check(status: int, where: str):
+    if status != OK:
+        L = lib()
+        raise BSpGEMMError(status, where, f"{L.bspgemm_strerror(status).decode()}: {L.bspgemm_last_error().decode()}")
+
+
+def _i32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _take(ptr, n: int, dtype) -> np.ndarray:
+    """Copy n elements out of a malloc'ed buffer and free() it (the caller-frees contract of the reference)."""
+    addr = C.cast(ptr, C.c_void_p).value
+    if n > 0:
+        out = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(np.ctypeslib.as_ctypes_type(dtype))), shape=(n,)).copy()
+    else:
+        out = np.zeros(0, dtype=dtype)
+    if addr:
+        _libc.free(addr)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ host surface
+def readCOO(path: str):
+    """readCOO (final/utils.c:47-81): returns (row_pointers, col_indices, M, N, nnz) — transposed on read."""
+    H = host()
+    row, col = _U32P(), _U32P()
+    M, N, nnz = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    rc = H.readCOO_status(os.fsencode(path), C.byref(row), C.byref(col), C.byref(M), C.byref(N), C.byref(nnz))
+    if rc != 0:
+        raise OSError(f"readCOO({path!r}) failed with Matrix Market status {rc}")
+    return _take(row, N.value + 1, np.uint32), _take(col, nnz.value, np.uint32), M.value, N.value, nnz.value
+
+
+def coo2csc(row_coo, col_coo, n: int, is_one_based: int = 0):
+    """coo2csc (final/coo2csc.c:22-64): returns (row_indices[nnz], col_pointers[n+1])."""
+    H = host()
+    r = np.ascontiguousarray(row_coo, dtype=np.uint32)
+    c = np.ascontiguousarray(col_coo, dtype=np.uint32)
+    out_row = np.empty(max(len(r), 1), dtype=np.uint32)
+    out_col = np.empty(n + 1, dtype=np.uint32)
+    H.coo2csc(out_row.ctypes.data, out_col.ctypes.data, r.ctypes.data, c.ctypes.data, len(r), n, is_one_based)
+    return out_row[: len(r)], out_col
+
+
+def _gen(fn, *args):
+    row, col, nnz = _I32P(), _I32P(), C.c_int64()
+    rc = fn(*args, C.byref(row), C.byref(col), C.byref(nnz))
+    if rc != 0:
+        raise MemoryError("generator failed")
+    return row, col, nnz.value
+
+
+def gen_uniform(n: int, d: int, seed: int = 1):
+    row, col, nnz = _gen(host().bs_gen_uniform, n, d, seed)
+    return _take(row, n + 1, np.int32), _take(col, nnz, np.int32)
+
+
+def gen_rmat(scale: int, edge_factor: int = 16, a=0.45, b=0.22, c=0.22, seed: int = 1):
+    row, col, nnz = _gen(host().bs_gen_rmat, scale, edge_factor, a, b, c, seed)
+    return _take(row, (1 << scale) + 1, np.int32), _take(col, nnz, np.int32)
+
+
+def gen_banded(n: int, d: int):
+    row, col, nnz = _gen(host().bs_gen_banded, n, d)
+    return _take(row, n + 1, np.int32), _take(col, nnz, np.int32)
+
+
+def gen_blockdiag(n: int, d: int):
+    row, col, nnz = _gen(host().bs_gen_blockdiag, n, d)
+    return _take(row, n + 1, np.int32), _take(col, nnz, np.int32)
+
+
+def write_mtx(path: str, row, col):
+    row, col = _i32(row), _i32(col)
+    if host().bs_write_mtx(os.fsencode(path), len(row) - 1, row.ctypes.data, col.ctypes.data) != 0:
+        raise OSError(f"cannot write {path}")
+
+
+# ------------------------------------------------------------------------------------------------ host-pointer operators
+def init(ngpus: int = 1):
+    _check(lib().bspgemm_init(ngpus), "bspgemm_init")
+
+
+def finalize():
+    lib().bspgemm_finalize()
+
+
+def num_gpus() -> int:
+    return lib().bspgemm_num_gpus()
+
+
+def spgemm_csr(Acol, Arow, An, Bcol, Brow, Bn, Bm, i64: bool = False):
+    """SpGEMM_mpi replacement (final/SpGEMM_mpi_omp.c:155-225): host CSR in, host CSR out -> (Ccol, Crow)."""
+    L = lib()
+    Acol, Arow, Bcol, Brow = _i32(Acol), _i32(Arow), _i32(Bcol), _i32(Brow)
+    Crow = np.zeros(An + 1, dtype=np.int64 if i64 else np.int32)
+    out = C.c_void_p()
+    fn = L.bspgemm_csr_i64 if i64 else L.bspgemm_csr
+    _check(fn(Acol.ctypes.data, Arow.ctypes.data, An, Bcol.ctypes.data, Brow.ctypes.data, Bn, Bm,
+              C.byref(out), Crow.ctypes.data), "bspgemm_csr")
+    return _take(out, int(Crow[An]), np.int32), Crow
+
+
+def spgemm_csr_into(Acol, Arow, An, Bcol, Brow, Bn, Bm, Ccol_buf: np.ndarray):
+    """SpGEMM_mat replacement (Matlab/inc/BSpGEMM.c:9-47): caller-allocated Ccol -> (nnz, Crow)."""
+    L = lib()
+    Acol, Arow, Bcol, Brow = _i32(Acol), _i32(Arow), _i32(Bcol), _i32(Brow)
+    Crow = np.zeros(An + 1, dtype=np.int32)
+    nnz = C.c_int64()
+    st = L.bspgemm_csr_into(Acol.ctypes.data, Arow.ctypes.data, An, Bcol.ctypes.data, Brow.ctypes.data, Bn, Bm,
+                            Ccol_buf.ctypes.data, Ccol_buf.size, Crow.ctypes.data, C.byref(nnz))
+    if st == ERR_CAPACITY:
+        raise BSpGEMMError(st, "bspgemm_csr_into", f"capacity {Ccol_buf.size} < nnz {nnz.value}")
+    _check(st, "bspgemm_csr_into")
+    return nnz.value, Crow
+
+
+def spgemm_csr_slice(Acol, Arow, An, Bcol, Brow, Bn, Bm, start_row: int, end_row: int):
+    """SpGEMM_bigslice replacement (final/SpGEMM_mpi_omp.c:15-58): slice-relative Crow."""
+    L = lib()
+    Acol, Arow, Bcol, Brow = _i32(Acol), _i32(Arow), _i32(Bcol), _i32(Brow)
+    Crow = np.zeros(end_row - start_row + 1, dtype=np.int32)
+    out = C.c_void_p()
+    _check(L.bspgemm_csr_slice(Acol.ctypes.data, Arow.ctypes.data, An, Bcol.ctypes.data, Brow.ctypes.data, Bn, Bm,
+                               C.byref(out), Crow.ctypes.data, start_row, end_row), "bspgemm_csr_slice")
+    return _take(out, int(Crow[-1]), np.int32), Crow
+
+
+def SpGEMM_mpi(Acol, Arow, An, Bcol, Brow, Bm, tBlock: int = 1):
+    """Legacy-signature drop-in (no Bn argument, exit(1) on failure) — same argument list as the reference."""
+    L = lib()
+    Acol, Arow, Bcol, Brow = _i32(Acol), _i32(Arow), _i32(Bcol), _i32(Brow)
+    Crow = np.zeros(An + 1, dtype=np.int32)
+    out = C.c_void_p()
+    L.bspgemm_SpGEMM_mpi(Acol.ctypes.data, Arow.ctypes.data, An, Bcol.ctypes.data, Brow.ctypes.data, Bm,
+                         C.byref(out), Crow.ctypes.data, tBlock)
+    return _take(out, int(Crow[An]), np.int32), Crow
+
+
+def intermediate_products(Acol, Arow, An, Brow, Bn) -> int:
+    Acol, Arow, Brow = _i32(Acol), _i32(Arow), _i32(Brow)
+    ip = C.c_int64()
+    _check(lib().bspgemm_intermediate_products(Acol.ctypes.data, Arow.ctypes.data, An, Brow.ctypes.data, Bn, C.byref(ip)),
+           "bspgemm_intermediate_products")
+    return ip.value
+
+
+# ------------------------------------------------------------------------------------------------ device-resident operator
+def device_view(ptr: int, n: int, device: int = 0):
+    """View n int32 at a raw device address (e.g. the handle's Ccol arena) as a torch tensor: no copy, not owning."""
+    import torch
+
+    if n <= 0:
+        return torch.empty(0, dtype=torch.int32, device=f"cuda:{device}")
+
+    class _Holder:
+        pass
+
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<i4", "data": (int(ptr), False), "version": 3}
+    return torch.as_tensor(h, device=f"cuda:{device}")
+
+
+class DeviceSpGEMM:
+    """bspgemm_dev_* : one GPU, device pointers in, device pointers out.  Accepts anything with .data_ptr()
+    (torch CUDA tensors) or raw integer device addresses."""
+
+    def __init__(self, device: int = 0, mode: int = MODE_AUTO):
+        self._h = C.c_void_p()
+        _check(lib().bspgemm_dev_create(C.byref(self._h), device), "bspgemm_dev_create")
+        self.device = device
+        if mode != MODE_AUTO:
+            self.set_mode(mode)
+
+    def set_mode(self, mode: int):
+        _check(lib().bspgemm_dev_set_mode(self._h, mode), "bspgemm_dev_set_mode")
+
+    @staticmethod
+    def _p(x):
+        return int(x.data_ptr()) if hasattr(x, "data_ptr") else int(x)
+
+    def multiply(self, dAcol, dArow, An, Annz, dBcol, dBrow, Bn, Bm, Bnnz, dCrow, crow_is_i64=False, stream=None):
+        """Returns (device address of Ccol in the handle's arena, nnz(C))."""
+        out, nnz = C.c_void_p(), C.c_int64()
+        _check(lib().bspgemm_dev_multiply(self._h, C.c_void_p(stream or 0),
+                                          self._p(dAcol), self._p(dArow), An, Annz,
+                                          self._p(dBcol), self._p(dBrow), Bn, Bm, Bnnz,
+                                          self._p(dCrow), 1 if crow_is_i64 else 0, C.byref(out), C.byref(nnz)),
+               "bspgemm_dev_multiply")
+        return out.value or 0, nnz.value
+
+    def stats(self) -> dict:
+        s = Stats()
+        _check(lib().bspgemm_dev_get_stats(self._h, C.byref(s)), "bspgemm_dev_get_stats")
+        return s.as_dict()
+
+    def close(self):
+        if self._h:
+            lib().bspgemm_dev_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,626 @@
+// binary-spgemm_b200/csrc/bspgemm.cu — host side of libbspgemm.so: the C ABI declared in include/bspgemm.h.
+//
+// Layering (replaces final/SpGEMM_mpi_omp.c L1-L3):
+//   DevCtx      one GPU: workspace, output arena, the launch sequence (estimate -> bins -> scan -> fill)
+//   Global ctx  the "communicator": G DevCtx + NCCL comms (dlopen'ed) for the B broadcast
+//   C ABI       host-pointer operators (upload / shard / gather) and the device-resident operator
+// No CPU fallback anywhere: every failure is returned as a status code.
+#include "../../include/bspgemm.h"
+#include "kernels.cuh"
+
+#include <nccl.h>      // types only; the library itself is dlopen'ed so libbspgemm.so loads without it
+#include <dlfcn.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdarg.h>
+#include <algorithm>
+#include <vector>
+#include <mutex>
+
+using namespace bsk;
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
+  return code;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+  return fail(e_ == cudaErrorMemoryAllocation ? BSPGEMM_ERR_OOM : BSPGEMM_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+#define CKS(expr) do { int s_ = (expr); if (s_ != BSPGEMM_OK) return s_; } while (0)
+
+extern "C" const char* bspgemm_strerror(int s) {
+  switch (s) {
+    case BSPGEMM_OK: return "ok";
+    case BSPGEMM_ERR_CUDA: return "CUDA error";
+    case BSPGEMM_ERR_NCCL: return "NCCL error";
+    case BSPGEMM_ERR_OOM: return "out of memory";
+    case BSPGEMM_ERR_OVERFLOW32: return "nnz(C) >= 2^31 on the 32-bit ABI (use the _i64 entry point)";
+    case BSPGEMM_ERR_BADARG: return "bad argument";
+    case BSPGEMM_ERR_NOGPU: return "no CUDA device (no CPU fallback exists)";
+    case BSPGEMM_ERR_CAPACITY: return "output buffer too small";
+    case BSPGEMM_ERR_STATE: return "bspgemm_init not called";
+    default: return "unknown status";
+  }
+}
+extern "C" const char* bspgemm_last_error(void) { return g_err; }
+extern "C" const char* bspgemm_version(void) { return "bspgemm-b200 0.1 (sm_100a)"; }
+
+// ------------------------------------------------------------------------------------------------ per-GPU context
+template <class T> struct DevBuf {
+  T* p = nullptr; size_t cap = 0;
+  int ensure(size_t n, bool keep = false) {           // grow-only; contents dropped unless keep
+    if (n <= cap) return BSPGEMM_OK;
+    size_t want = n + n / 16 + 64;
+    T* q = nullptr;
+    cudaError_t e = cudaMalloc((void**)&q, want * sizeof(T));
+    if (e != cudaSuccess) { want = n; e = cudaMalloc((void**)&q, want * sizeof(T)); }
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(BSPGEMM_ERR_OOM, "cudaMalloc of %zu bytes failed: %s", want * sizeof(T), cudaGetErrorString(e)); }
+    if (keep && p && cap) cudaMemcpy(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice);
+    if (p) cudaFree(p);
+    p = q; cap = want;
+    return BSPGEMM_OK;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct MulArgs {
+  Csr m; int64_t Annz, Bnnz; void* dCrow; int is64;
+};
+
+struct bspgemm_dev {
+  int device = 0, sm_count = 0;
+  size_t smem_optin = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  int mode = BSPGEMM_MODE_AUTO;
+  // workspace
+  DevBuf<u32> ip, cnt, lists, bitmaps;
+  DevBuf<u64> status;
+  DevBuf<int> ccol;                 // output arena
+  DevScalars* d_sc = nullptr;
+  DevScalars* h_sc = nullptr;       // pinned
+  cudaEvent_t ev[8] = {};
+  // per-call state
+  MulArgs a{};
+  int phase = 0;                    // 0 idle, 1 estimate in flight, 2 main in flight, 3 fill in flight, 4 done
+  int used_mode = 0, G = 16, launches = 0;
+  u32 cap_s = 0, cap_m1 = 0, cap_m2 = 0;
+  bool have_m = false, have_m2 = false, have_l = false;
+  u32 bm_words = 0; int l_grid = 0;
+  int* user_ccol = nullptr; int64_t user_cap = 0;   // caller-provided output (device) or null -> arena
+  bspgemm_stats st{};
+  // input staging for the host-pointer API
+  DevBuf<int> in_arow, in_acol, in_brow, in_bcol;
+  DevBuf<char> crow_dev;            // device row pointers for the host API
+  DevBuf<char> crow_tmp;
+};
+
+static int g_cap_s_max() { const char* e = getenv("BSPGEMM_CAP_S"); int v = e ? atoi(e) : 512; if (v < 32) v = 32; if (v > 1024) v = 1024; int p = 32; while (p < v) p <<= 1; return p; }
+static const u32 CAP_M1 = 2048, CAP_M2 = 16384;
+
+template <int MODE> static int launch_rows_warp(bspgemm_dev* d, int grid, size_t smem, u32 ntiles) {
+  const MulArgs& a = d->a;
+  int* ccol = d->user_ccol ? d->user_ccol : d->ccol.p;
+#define LW(Gv) do { \
+    CK(cudaFuncSetAttribute(k_rows_warp<Gv, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_rows_warp<Gv, MODE><<<grid, WARPS_S * 32, smem, d->stream>>>(a.m, d->ip.p, d->cnt.p, d->cap_s, a.dCrow, a.is64, ccol, d->status.p, d->d_sc, ntiles); } while (0)
+  switch (d->G) { case 4: LW(4); break; case 8: LW(8); break; case 16: LW(16); break; default: LW(32); break; }
+#undef LW
+  d->launches++;
+  CK(cudaGetLastError());
+  return BSPGEMM_OK;
+}
+
+template <int MODE> static int occupancy_rows_warp(bspgemm_dev* d, size_t smem, int* blocks_per_sm) {
+#define OW(Gv) do { \
+    CK(cudaFuncSetAttribute(k_rows_warp<Gv, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_rows_warp<Gv, MODE>, WARPS_S * 32, smem)); } while (0)
+  switch (d->G) { case 4: OW(4); break; case 8: OW(8); break; case 16: OW(16); break; default: OW(32); break; }
+#undef OW
+  return BSPGEMM_OK;
+}
+
+template <int MODE> static int launch_bins_ml(bspgemm_dev* d) {
+  const MulArgs& a = d->a;
+  int* ccol = d->user_ccol ? d->user_ccol : d->ccol.p;
+  const size_t An = (size_t)a.m.An;
+  u32* l1 = d->lists.p, *l2 = d->lists.p + An, *l3 = d->lists.p + 2 * An;
+  if (d->have_m) {
+    const size_t smem = 3ull * CAP_M1 * 4;
+    CK(cudaFuncSetAttribute(k_rows_cta<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(3ull * CAP_M2 * 4)));
+    k_rows_cta<MODE><<<d->sm_count * 4, 256, smem, d->stream>>>(a.m, l1, &d->d_sc->n_m1, d->ip.p, d->cnt.p, CAP_M1, d->G, a.dCrow, a.is64, ccol, d->d_sc);
+    d->launches++;
+    CK(cudaGetLastError());
+  }
+  if (d->have_m2) {
+    const size_t smem = 3ull * CAP_M2 * 4;
+    CK(cudaFuncSetAttribute(k_rows_cta<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_rows_cta<MODE><<<d->sm_count, 1024, smem, d->stream>>>(a.m, l2, &d->d_sc->n_m2, d->ip.p, d->cnt.p, CAP_M2, d->G, a.dCrow, a.is64, ccol, d->d_sc);
+    d->launches++;
+    CK(cudaGetLastError());
+  }
+  if (d->have_l) {
+    k_rows_gbitmap<MODE><<<d->l_grid, 1024, 0, d->stream>>>(a.m, l3, &d->d_sc->n_l, d->cnt.p, d->G, d->bitmaps.p, d->bm_words, a.dCrow, a.is64, ccol, d->d_sc);
+    d->launches++;
+    CK(cudaGetLastError());
+  }
+  return BSPGEMM_OK;
+}
+
+static int pick_group(int64_t nnz, int64_t rows) {
+  const int64_t avg = rows > 0 ? (nnz + rows - 1) / rows : 1;
+  return avg <= 4 ? 4 : avg <= 8 ? 8 : avg <= 16 ? 16 : 32;
+}
+
+// phase 1: work estimation (north-star step 1)
+static int mul_launch_estimate(bspgemm_dev* d) {
+  const MulArgs& a = d->a;
+  CK(cudaSetDevice(d->device));
+  const size_t An = (size_t)a.m.An;
+  CKS(d->ip.ensure(An + 1));
+  CKS(d->cnt.ensure(An + 1));
+  d->launches = 0;
+  memset(&d->st, 0, sizeof d->st);
+  CK(cudaEventRecord(d->ev[0], d->stream));
+  CK(cudaMemsetAsync(d->d_sc, 0, sizeof(DevScalars), d->stream));
+  const int ga = pick_group(a.Annz, a.m.An);
+  const long long threads = (long long)An * ga;
+  const int grid = (int)((threads + 255) / 256);
+  switch (ga) {
+    case 4:  k_estimate<4><<<grid, 256, 0, d->stream>>>(a.m, d->ip.p, d->d_sc); break;
+    case 8:  k_estimate<8><<<grid, 256, 0, d->stream>>>(a.m, d->ip.p, d->d_sc); break;
+    case 16: k_estimate<16><<<grid, 256, 0, d->stream>>>(a.m, d->ip.p, d->d_sc); break;
+    default: k_estimate<32><<<grid, 256, 0, d->stream>>>(a.m, d->ip.p, d->d_sc); break;
+  }
+  d->launches++;
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(d->ev[1], d->stream));
+  CK(cudaMemcpyAsync(d->h_sc, d->d_sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, d->stream));
+  d->phase = 1;
+  return BSPGEMM_OK;
+}
+
+// phase 2: bins, symbolic, scan / fused fill
+static int mul_launch_main(bspgemm_dev* d) {
+  const MulArgs& a = d->a;
+  CK(cudaSetDevice(d->device));
+  CK(cudaStreamSynchronize(d->stream));
+  const DevScalars& h = *d->h_sc;
+  if (h.err & 1u) return fail(BSPGEMM_ERR_BADARG, "a column index of A is outside [0,Bn=%d)", a.m.Bn);
+  const size_t An = (size_t)a.m.An;
+  const u64 total_ip = h.total_ip;
+  d->st.ip = (int64_t)total_ip;
+  // bin thresholds
+  u32 cap = 32; const u32 cap_max = (u32)g_cap_s_max();
+  while (cap < h.max_ip && cap < cap_max) cap <<= 1;
+  d->cap_s = cap;
+  d->G = pick_group(a.Bnnz, a.m.Bn);
+  d->have_m = h.max_ip > cap;
+  d->have_m2 = h.max_ip > CAP_M1;
+  d->have_l = h.max_ip > CAP_M2;
+  d->st.cap_s = (int)cap; d->st.group = d->G;
+  if (d->have_m) {
+    CKS(d->lists.ensure(3 * An + 3));
+    k_build_lists<<<(int)((An + 255) / 256), 256, 0, d->stream>>>(d->ip.p, a.m.An, cap, CAP_M1, CAP_M2,
+        d->lists.p, d->lists.p + An, d->lists.p + 2 * An, d->d_sc);
+    d->launches++;
+    CK(cudaGetLastError());
+  }
+  if (d->have_l) {
+    d->bm_words = (u32)(((size_t)a.m.Bm + 31) / 32);
+    d->l_grid = d->sm_count;
+    const size_t need = (size_t)d->l_grid * d->bm_words;
+    if (need > d->bitmaps.cap) { CKS(d->bitmaps.ensure(need)); CK(cudaMemsetAsync(d->bitmaps.p, 0, d->bitmaps.cap * sizeof(u32), d->stream)); }
+  }
+  // mode
+  int mode = d->mode;
+  const size_t smem = (size_t)WARPS_S * 4 * cap * sizeof(u32);
+  if (mode == BSPGEMM_MODE_AUTO) {
+    size_t fr = 0, tot = 0; CK(cudaMemGetInfo(&fr, &tot));
+    const u64 need_bytes = total_ip * 4ull;
+    const u64 have = d->user_ccol ? (u64)d->user_cap * 4ull : (u64)d->ccol.cap * 4ull + (u64)(fr / 2);
+    mode = (need_bytes <= have) ? BSPGEMM_MODE_FUSED : BSPGEMM_MODE_TWOPHASE;
+  }
+  if (mode == BSPGEMM_MODE_FUSED && d->user_ccol && (u64)d->user_cap < total_ip) mode = BSPGEMM_MODE_TWOPHASE;
+  d->used_mode = mode; d->st.mode = mode;
+  CK(cudaEventRecord(d->ev[2], d->stream));
+  if (mode == BSPGEMM_MODE_FUSED) {
+    if (d->have_m) CKS(launch_bins_ml<MODE_COUNT>(d));
+    CK(cudaEventRecord(d->ev[3], d->stream));
+    if (!d->user_ccol) CKS(d->ccol.ensure((size_t)std::max<u64>(total_ip, 1)));
+    const u32 ntiles = (u32)((An + WARPS_S - 1) / WARPS_S);
+    CKS(d->status.ensure(ntiles + 1));
+    CK(cudaMemsetAsync(d->status.p, 0, (size_t)ntiles * sizeof(u64), d->stream));
+    int bps = 1; CKS(occupancy_rows_warp<MODE_FUSED>(d, smem, &bps));
+    if (bps < 1) return fail(BSPGEMM_ERR_CUDA, "fused kernel does not fit on an SM (smem %zu)", smem);
+    const int grid = (int)std::min<long long>((long long)ntiles, (long long)d->sm_count * bps);
+    CKS(launch_rows_warp<MODE_FUSED>(d, grid, smem, ntiles));
+    CK(cudaEventRecord(d->ev[4], d->stream));
+    if (d->have_m) CKS(launch_bins_ml<MODE_FILL>(d));
+    CK(cudaEventRecord(d->ev[5], d->stream));
+  } else {
+    int bps = 1; CKS(occupancy_rows_warp<MODE_COUNT>(d, smem, &bps));
+    const long long want = ((long long)An + WARPS_S - 1) / WARPS_S;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)d->sm_count * std::max(bps, 1) * 4));
+    CKS(launch_rows_warp<MODE_COUNT>(d, grid, smem, 0));
+    if (d->have_m) CKS(launch_bins_ml<MODE_COUNT>(d));
+    CK(cudaEventRecord(d->ev[3], d->stream));
+    const u32 ntiles = (u32)((An + SCAN_THREADS * SCAN_ITEMS - 1) / (SCAN_THREADS * SCAN_ITEMS));
+    CKS(d->status.ensure(ntiles + 1));
+    CK(cudaMemsetAsync(d->status.p, 0, (size_t)ntiles * sizeof(u64), d->stream));
+    k_scan<<<ntiles, SCAN_THREADS, 0, d->stream>>>(d->cnt.p, a.m.An, a.dCrow, a.is64, d->status.p, d->d_sc, ntiles);
+    d->launches++;
+    CK(cudaGetLastError());
+  }
+  CK(cudaMemcpyAsync(d->h_sc, d->d_sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, d->stream));
+  d->phase = 2;
+  return BSPGEMM_OK;
+}
+
+// phase 3 (two-phase mode only): numeric fill at the scanned row pointers
+static int mul_launch_fill(bspgemm_dev* d) {
+  const MulArgs& a = d->a;
+  CK(cudaSetDevice(d->device));
+  CK(cudaStreamSynchronize(d->stream));
+  const DevScalars& h = *d->h_sc;
+  if (h.err & 4u) return fail(BSPGEMM_ERR_BADARG, "a column index of B is outside [0,Bm=%d)", a.m.Bm);
+  if (h.err & 2u) return fail(BSPGEMM_ERR_OVERFLOW32, "nnz(C) = %llu does not fit 32-bit row pointers", (unsigned long long)h.total_nnz);
+  d->st.nnz = (int64_t)h.total_nnz;
+  if (d->used_mode == BSPGEMM_MODE_FUSED) { d->phase = 4; return BSPGEMM_OK; }
+  if (d->user_ccol) { if ((u64)d->user_cap < h.total_nnz) return fail(BSPGEMM_ERR_CAPACITY, "output capacity %lld < nnz(C) %llu", (long long)d->user_cap, (unsigned long long)h.total_nnz); }
+  else CKS(d->ccol.ensure((size_t)std::max<u64>(h.total_nnz, 1)));
+  const size_t An = (size_t)a.m.An;
+  const size_t smem = (size_t)WARPS_S * 4 * d->cap_s * sizeof(u32);
+  int bps = 1; CKS(occupancy_rows_warp<MODE_FILL>(d, smem, &bps));
+  const long long want = ((long long)An + WARPS_S - 1) / WARPS_S;
+  const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)d->sm_count * std::max(bps, 1) * 4));
+  CKS(launch_rows_warp<MODE_FILL>(d, grid, smem, 0));
+  CK(cudaEventRecord(d->ev[4], d->stream));
+  if (d->have_m) CKS(launch_bins_ml<MODE_FILL>(d));
+  CK(cudaEventRecord(d->ev[5], d->stream));
+  d->phase = 3;
+  return BSPGEMM_OK;
+}
+
+static int mul_finish(bspgemm_dev* d) {
+  const MulArgs& a = d->a;
+  CK(cudaSetDevice(d->device));
+  if (d->phase == 3) { CK(cudaStreamSynchronize(d->stream)); d->phase = 4; }
+  CK(cudaGetLastError());
+  const DevScalars& h = *d->h_sc;
+  bspgemm_stats& s = d->st;
+  s.launches = d->launches;
+  for (int b = 0; b < 33; ++b) {
+    const u32 top = b ? ((b >= 32) ? 0xffffffffu : ((1u << b) - 1)) : 0;   // largest IP in the bin
+    if (top <= d->cap_s) s.rows_s += h.hist[b]; else if (top <= CAP_M2) s.rows_m += h.hist[b]; else s.rows_l += h.hist[b];
+  }
+  float ms = 0;
+  cudaEventElapsedTime(&ms, d->ev[0], d->ev[5]); s.ms_total = ms;
+  cudaEventElapsedTime(&ms, d->ev[0], d->ev[1]); s.ms_estimate = ms;
+  cudaEventElapsedTime(&ms, d->ev[2], d->ev[3]); s.ms_symbolic = ms;
+  cudaEventElapsedTime(&ms, d->ev[3], d->ev[4]); s.ms_main = ms;
+  cudaEventElapsedTime(&ms, d->ev[4], d->ev[5]); s.ms_numeric = ms;
+  const int64_t rp = a.is64 ? 8 : 4;
+  s.algorithmic_bytes = 4 * ((int64_t)a.m.An + 1) + 12 * a.Annz + 4 * s.ip + 4 * s.nnz + rp * ((int64_t)a.m.An + 1);
+  return BSPGEMM_OK;
+}
+
+static int mul_run_to_completion(bspgemm_dev* d) {
+  if (d->a.m.An == 0) {   // nothing to do: Crow[0] = 0
+    CK(cudaSetDevice(d->device));
+    CK(cudaMemsetAsync(d->a.dCrow, 0, d->a.is64 ? 8 : 4, d->stream));
+    CK(cudaStreamSynchronize(d->stream));
+    memset(&d->st, 0, sizeof d->st); d->phase = 4;
+    return BSPGEMM_OK;
+  }
+  CKS(mul_launch_estimate(d));
+  CKS(mul_launch_main(d));
+  CKS(mul_launch_fill(d));
+  return mul_finish(d);
+}
+
+static int dev_create(bspgemm_dev** out, int device) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return fail(BSPGEMM_ERR_NOGPU, "no CUDA device visible; this library has no CPU fallback"); }
+  if (device < 0 || device >= n) return fail(BSPGEMM_ERR_BADARG, "device %d out of range (0..%d)", device, n - 1);
+  CK(cudaSetDevice(device));
+  cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, device));
+  if (p.major < 10) return fail(BSPGEMM_ERR_NOGPU, "device %d is sm_%d%d; this library is built for sm_100a only", device, p.major, p.minor);
+  bspgemm_dev* d = new bspgemm_dev();
+  d->device = device; d->sm_count = p.multiProcessorCount; d->smem_optin = p.sharedMemPerBlockOptin;
+  CK(cudaStreamCreateWithFlags(&d->own_stream, cudaStreamNonBlocking));
+  d->stream = d->own_stream;
+  CK(cudaMalloc((void**)&d->d_sc, sizeof(DevScalars)));
+  CK(cudaMallocHost((void**)&d->h_sc, sizeof(DevScalars)));
+  for (auto& e : d->ev) CK(cudaEventCreate(&e));
+  const char* m = getenv("BSPGEMM_MODE");
+  if (m) d->mode = !strcmp(m, "fused") ? BSPGEMM_MODE_FUSED : !strcmp(m, "twophase") ? BSPGEMM_MODE_TWOPHASE : BSPGEMM_MODE_AUTO;
+  *out = d;
+  return BSPGEMM_OK;
+}
+
+static void dev_destroy(bspgemm_dev* d) {
+  if (!d) return;
+  cudaSetDevice(d->device);
+  cudaStreamSynchronize(d->stream);
+  d->ip.release(); d->cnt.release(); d->lists.release(); d->bitmaps.release(); d->status.release(); d->ccol.release();
+  d->in_arow.release(); d->in_acol.release(); d->in_brow.release(); d->in_bcol.release(); d->crow_dev.release(); d->crow_tmp.release();
+  if (d->d_sc) cudaFree(d->d_sc);
+  if (d->h_sc) cudaFreeHost(d->h_sc);
+  for (auto& e : d->ev) if (e) cudaEventDestroy(e);
+  if (d->own_stream) cudaStreamDestroy(d->own_stream);
+  delete d;
+}
+
+// ------------------------------------------------------------------------------------------------ device-resident C ABI
+extern "C" int bspgemm_dev_create(bspgemm_dev** h, int device) { if (!h) return fail(BSPGEMM_ERR_BADARG, "null handle"); return dev_create(h, device); }
+extern "C" int bspgemm_dev_destroy(bspgemm_dev* h) { dev_destroy(h); return BSPGEMM_OK; }
+extern "C" int bspgemm_dev_set_mode(bspgemm_dev* h, int mode) { if (!h || mode < 0 || mode > 2) return fail(BSPGEMM_ERR_BADARG, "bad mode"); h->mode = mode; return BSPGEMM_OK; }
+extern "C" int bspgemm_dev_get_stats(bspgemm_dev* h, bspgemm_stats* out) { if (!h || !out) return fail(BSPGEMM_ERR_BADARG, "null"); *out = h->st; return BSPGEMM_OK; }
+
+extern "C" int bspgemm_dev_multiply(bspgemm_dev* h, void* stream,
+                                    const int* dAcol, const int* dArow, int An, int64_t Annz,
+                                    const int* dBcol, const int* dBrow, int Bn, int Bm, int64_t Bnnz,
+                                    void* dCrow, int crow_is_i64, int** dCcol_out, int64_t* nnz_out) {
+  if (!h || !dArow || !dBrow || !dCrow || An < 0 || Bn < 0 || Bm < 0 || Annz < 0 || Bnnz < 0) return fail(BSPGEMM_ERR_BADARG, "null pointer or negative size");
+  if ((Annz > 0 && !dAcol) || (Bnnz > 0 && !dBcol)) return fail(BSPGEMM_ERR_BADARG, "null column array");
+  h->stream = stream ? (cudaStream_t)stream : h->own_stream;
+  h->a.m = Csr{dArow, dAcol, dBrow, dBcol, An, Bn, Bm};
+  h->a.Annz = Annz; h->a.Bnnz = Bnnz; h->a.dCrow = dCrow; h->a.is64 = crow_is_i64 ? 1 : 0;
+  h->user_ccol = nullptr; h->user_cap = 0;
+  CKS(mul_run_to_completion(h));
+  if (dCcol_out) *dCcol_out = h->ccol.p;
+  if (nnz_out) *nnz_out = h->st.nnz;
+  return BSPGEMM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ global context (the "communicator")
+struct Nccl {
+  void* lib = nullptr;
+  ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+struct Global {
+  std::vector<bspgemm_dev*> devs;
+  std::vector<ncclComm_t> comms;
+  Nccl nccl;
+  bool inited = false;
+};
+static Global g;
+static std::mutex g_mu;
+
+static int nccl_load(Nccl& n) {
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* nm : names) { n.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (n.lib) break; }
+  if (!n.lib) return fail(BSPGEMM_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+#define SYM(field, name) do { *(void**)(&n.field) = dlsym(n.lib, name); if (!n.field) return fail(BSPGEMM_ERR_NCCL, "libnccl lacks %s", name); } while (0)
+  SYM(CommInitAll, "ncclCommInitAll"); SYM(CommDestroy, "ncclCommDestroy"); SYM(Broadcast, "ncclBroadcast");
+  SYM(GroupStart, "ncclGroupStart"); SYM(GroupEnd, "ncclGroupEnd"); SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+  return BSPGEMM_OK;
+}
+#define NK(call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) return fail(BSPGEMM_ERR_NCCL, "%s failed: %s", #call, g.nccl.GetErrorString ? g.nccl.GetErrorString(r_) : "?"); } while (0)
+
+extern "C" int bspgemm_init(int ngpus) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g.inited) return fail(BSPGEMM_ERR_STATE, "bspgemm_init called twice");
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return fail(BSPGEMM_ERR_NOGPU, "no CUDA device visible; this library has no CPU fallback"); }
+  if (ngpus <= 0) ngpus = n;
+  if (ngpus > n) return fail(BSPGEMM_ERR_BADARG, "%d GPUs requested, %d visible", ngpus, n);
+  for (int i = 0; i < ngpus; ++i) {
+    bspgemm_dev* d = nullptr;
+    int s = dev_create(&d, i);
+    if (s != BSPGEMM_OK) { for (auto* x : g.devs) dev_destroy(x); g.devs.clear(); return s; }
+    g.devs.push_back(d);
+  }
+  if (ngpus > 1) {
+    CKS(nccl_load(g.nccl));
+    std::vector<int> ids(ngpus); for (int i = 0; i < ngpus; ++i) ids[i] = i;
+    g.comms.resize(ngpus);
+    NK(g.nccl.CommInitAll(g.comms.data(), ngpus, ids.data()));
+  }
+  g.inited = true;
+  return BSPGEMM_OK;
+}
+
+extern "C" int bspgemm_finalize(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!g.inited) return BSPGEMM_OK;
+  for (auto c : g.comms) if (g.nccl.CommDestroy) g.nccl.CommDestroy(c);
+  g.comms.clear();
+  for (auto* d : g.devs) dev_destroy(d);
+  g.devs.clear();
+  g.inited = false;
+  return BSPGEMM_OK;
+}
+extern "C" int bspgemm_num_gpus(void) { return g.inited ? (int)g.devs.size() : 0; }
+
+static int ensure_init() {
+  if (g.inited) return BSPGEMM_OK;
+  const char* e = getenv("BSPGEMM_GPUS");
+  return bspgemm_init(e ? atoi(e) : 1);
+}
+
+// ------------------------------------------------------------------------------------------------ host-pointer operators
+// Shards rows [0,An) over `ng` GPUs as contiguous blocks (final/SpGEMM_mpi_omp.c:165-171), replicates B
+// (ncclBroadcast from GPU 0), runs all shards concurrently, gathers Ccol/Crow to the host at the
+// displacements (replaces :178-223).
+static int host_multiply(const int* Acol, const int* Arow, int An, const int* Bcol, const int* Brow, int Bn, int Bm,
+                         int** Ccol_malloc, int* Ccol_buf, int64_t capacity, void* Crow, int is64, int64_t* nnz_out, int ng_limit) {
+  if (!Arow || !Brow || !Crow || An < 0 || Bn < 0 || Bm < 0) return fail(BSPGEMM_ERR_BADARG, "null pointer or negative size");
+  CKS(ensure_init());
+  int ng = std::min<int>((int)g.devs.size(), ng_limit);
+  if (An < ng) ng = std::max(1, An);
+  const int64_t a_base = Arow[0], Annz = (int64_t)Arow[An] - a_base;
+  const int64_t b_base = Brow[0], Bnnz = (int64_t)Brow[Bn] - b_base;
+  if (Annz < 0 || Bnnz < 0 || b_base != 0) return fail(BSPGEMM_ERR_BADARG, "row pointers not monotone / Brow[0] != 0");
+  if ((Annz > 0 && !Acol) || (Bnnz > 0 && !Bcol)) return fail(BSPGEMM_ERR_BADARG, "null column array");
+  const size_t rp = is64 ? 8 : 4;
+  std::vector<int> r0(ng + 1);
+  for (int q = 0; q <= ng; ++q) r0[q] = (int)((int64_t)An * q / ng);
+
+  // upload A shards, and B to GPU 0
+  for (int q = 0; q < ng; ++q) {
+    bspgemm_dev* d = g.devs[q];
+    CK(cudaSetDevice(d->device));
+    d->stream = d->own_stream;
+    const int rows = r0[q + 1] - r0[q];
+    const int64_t lo = Arow[r0[q]], hi = Arow[r0[q + 1]];
+    CKS(d->in_arow.ensure((size_t)rows + 1));
+    CKS(d->in_acol.ensure((size_t)std::max<int64_t>(hi - lo, 1)));
+    CKS(d->in_brow.ensure((size_t)Bn + 1));
+    CKS(d->in_bcol.ensure((size_t)std::max<int64_t>(Bnnz, 1)));
+    CKS(d->crow_dev.ensure(((size_t)rows + 1) * rp));
+    CK(cudaMemcpyAsync(d->in_arow.p, Arow + r0[q], ((size_t)rows + 1) * 4, cudaMemcpyHostToDevice, d->stream));
+    if (hi > lo) CK(cudaMemcpyAsync(d->in_acol.p, Acol + lo, (size_t)(hi - lo) * 4, cudaMemcpyHostToDevice, d->stream));
+    if (q == 0) {
+      CK(cudaMemcpyAsync(d->in_brow.p, Brow, ((size_t)Bn + 1) * 4, cudaMemcpyHostToDevice, d->stream));
+      if (Bnnz > 0) CK(cudaMemcpyAsync(d->in_bcol.p, Bcol, (size_t)Bnnz * 4, cudaMemcpyHostToDevice, d->stream));
+    }
+  }
+  if (ng > 1) {   // replicate B over NVLink
+    CK(cudaSetDevice(g.devs[0]->device));
+    CK(cudaStreamSynchronize(g.devs[0]->stream));
+    NK(g.nccl.GroupStart());
+    for (int q = 0; q < ng; ++q) NK(g.nccl.Broadcast(g.devs[0]->in_brow.p, g.devs[q]->in_brow.p, (size_t)Bn + 1, ncclInt32, 0, g.comms[q], g.devs[q]->stream));
+    NK(g.nccl.GroupEnd());
+    if (Bnnz > 0) {
+      NK(g.nccl.GroupStart());
+      for (int q = 0; q < ng; ++q) NK(g.nccl.Broadcast(g.devs[0]->in_bcol.p, g.devs[q]->in_bcol.p, (size_t)Bnnz, ncclInt32, 0, g.comms[q], g.devs[q]->stream));
+      NK(g.nccl.GroupEnd());
+    }
+  }
+  // run the shards concurrently: launch phase k on every GPU, then wait
+  for (int q = 0; q < ng; ++q) {
+    bspgemm_dev* d = g.devs[q];
+    const int rows = r0[q + 1] - r0[q];
+    const int64_t lo = Arow[r0[q]], hi = Arow[r0[q + 1]];
+    // Arow holds absolute offsets; shift the base pointer so that Acol_dev[Arow[i]] addresses the shard copy
+    const int* acol_dev = (const int*)((uintptr_t)d->in_acol.p - (uintptr_t)lo * 4u);
+    d->a.m = Csr{d->in_arow.p, acol_dev, d->in_brow.p, d->in_bcol.p, rows, Bn, Bm};
+    d->a.Annz = hi - lo; d->a.Bnnz = Bnnz; d->a.dCrow = d->crow_dev.p; d->a.is64 = is64;
+    d->user_ccol = nullptr; d->user_cap = 0;
+    d->phase = 0;
+  }
+  auto for_all = [&](int (*fn)(bspgemm_dev*)) -> int {
+    for (int q = 0; q < ng; ++q) { bspgemm_dev* d = g.devs[q]; if (d->a.m.An == 0) continue; CKS(fn(d)); }
+    return BSPGEMM_OK;
+  };
+  CKS(for_all(mul_launch_estimate));
+  CKS(for_all(mul_launch_main));
+  CKS(for_all(mul_launch_fill));
+  CKS(for_all(mul_finish));
+
+  // displacements (host exclusive scan, replaces :189-196), allocation (:200), gather (:203-204) with the
+  // row-pointer offset applied on the device (replaces :211-223)
+  std::vector<int64_t> disp(ng + 1, 0);
+  for (int q = 0; q < ng; ++q) disp[q + 1] = disp[q] + (g.devs[q]->a.m.An ? g.devs[q]->st.nnz : 0);
+  const int64_t nnz = disp[ng];
+  if (nnz_out) *nnz_out = nnz;
+  if (!is64 && nnz > 0x7fffffffLL) return fail(BSPGEMM_ERR_OVERFLOW32, "nnz(C) = %lld does not fit 32-bit row pointers", (long long)nnz);
+  int* out = Ccol_buf;
+  if (Ccol_malloc) {
+    out = (int*)malloc((size_t)std::max<int64_t>(nnz, 1) * sizeof(int));
+    if (!out) return fail(BSPGEMM_ERR_OOM, "malloc of %lld ints failed", (long long)nnz);
+  } else if (capacity < nnz) return fail(BSPGEMM_ERR_CAPACITY, "output capacity %lld < nnz(C) %lld", (long long)capacity, (long long)nnz);
+  if (is64) ((int64_t*)Crow)[0] = 0; else ((int*)Crow)[0] = 0;
+  for (int q = 0; q < ng; ++q) {
+    bspgemm_dev* d = g.devs[q];
+    const int rows = r0[q + 1] - r0[q];
+    if (rows == 0) continue;
+    CK(cudaSetDevice(d->device));
+    const char* src = (const char*)d->crow_dev.p;
+    if (disp[q] != 0) {
+      CKS(d->crow_tmp.ensure(((size_t)rows + 1) * rp));
+      k_offset_rowptr<<<(rows + 1 + 255) / 256, 256, 0, d->stream>>>(d->crow_dev.p, d->crow_tmp.p, is64, (long long)rows + 1, (long long)disp[q]);
+      CK(cudaGetLastError());
+      src = (const char*)d->crow_tmp.p;
+    }
+    CK(cudaMemcpyAsync((char*)Crow + ((size_t)r0[q] + 1) * rp, src + rp, (size_t)rows * rp, cudaMemcpyDeviceToHost, d->stream));
+    if (d->st.nnz > 0) CK(cudaMemcpyAsync(out + disp[q], d->ccol.p, (size_t)d->st.nnz * 4, cudaMemcpyDeviceToHost, d->stream));
+  }
+  for (int q = 0; q < ng; ++q) { CK(cudaSetDevice(g.devs[q]->device)); CK(cudaStreamSynchronize(g.devs[q]->stream)); }
+  if (Ccol_malloc) *Ccol_malloc = out;
+  return BSPGEMM_OK;
+}
+
+extern "C" int bspgemm_csr(const int* Acol, const int* Arow, int An, const int* Bcol, const int* Brow, int Bn, int Bm, int** Ccol, int* Crow) {
+  if (!Ccol) return fail(BSPGEMM_ERR_BADARG, "null Ccol");
+  int64_t nnz = 0;
+  return host_multiply(Acol, Arow, An, Bcol, Brow, Bn, Bm, Ccol, nullptr, 0, Crow, 0, &nnz, 1 << 30);
+}
+extern "C" int bspgemm_csr_i64(const int* Acol, const int* Arow, int An, const int* Bcol, const int* Brow, int Bn, int Bm, int** Ccol, int64_t* Crow) {
+  if (!Ccol) return fail(BSPGEMM_ERR_BADARG, "null Ccol");
+  int64_t nnz = 0;
+  return host_multiply(Acol, Arow, An, Bcol, Brow, Bn, Bm, Ccol, nullptr, 0, Crow, 1, &nnz, 1 << 30);
+}
+extern "C" int bspgemm_csr_into(const int* Acol, const int* Arow, int An, const int* Bcol, const int* Brow, int Bn, int Bm,
+                                int* Ccol_buf, int64_t capacity, int* Crow, int64_t* nnz_out) {
+  if (!Ccol_buf && capacity > 0) return fail(BSPGEMM_ERR_BADARG, "null Ccol_buf");
+  return host_multiply(Acol, Arow, An, Bcol, Brow, Bn, Bm, nullptr, Ccol_buf, capacity, Crow, 0, nnz_out, 1 << 30);
+}
+extern "C" int bspgemm_csr_slice(const int* Acol, const int* Arow, int An, const int* Bcol, const int* Brow, int Bn, int Bm,
+                                 int** Ccol, int* Crow, int start_row, int end_row) {
+  if (!Ccol || start_row < 0 || end_row < start_row || end_row > An) return fail(BSPGEMM_ERR_BADARG, "bad slice [%d,%d) of %d rows", start_row, end_row, An);
+  int64_t nnz = 0;
+  return host_multiply(Acol, Arow + start_row, end_row - start_row, Bcol, Brow, Bn, Bm, Ccol, nullptr, 0, Crow, 0, &nnz, 1);
+}
+
+extern "C" int bspgemm_intermediate_products(const int* Acol, const int* Arow, int An, const int* Brow, int Bn, int64_t* ip_out) {
+  if (!Arow || !Brow || !ip_out || An < 0 || Bn < 0) return fail(BSPGEMM_ERR_BADARG, "null pointer or negative size");
+  CKS(ensure_init());
+  bspgemm_dev* d = g.devs[0];
+  CK(cudaSetDevice(d->device));
+  d->stream = d->own_stream;
+  const int64_t lo = Arow[0], hi = Arow[An];
+  *ip_out = 0;
+  if (An == 0) return BSPGEMM_OK;
+  CKS(d->in_arow.ensure((size_t)An + 1)); CKS(d->in_acol.ensure((size_t)std::max<int64_t>(hi - lo, 1))); CKS(d->in_brow.ensure((size_t)Bn + 1));
+  CK(cudaMemcpyAsync(d->in_arow.p, Arow, ((size_t)An + 1) * 4, cudaMemcpyHostToDevice, d->stream));
+  if (hi > lo) CK(cudaMemcpyAsync(d->in_acol.p, Acol + lo, (size_t)(hi - lo) * 4, cudaMemcpyHostToDevice, d->stream));
+  CK(cudaMemcpyAsync(d->in_brow.p, Brow, ((size_t)Bn + 1) * 4, cudaMemcpyHostToDevice, d->stream));
+  const int* acol_dev = (const int*)((uintptr_t)d->in_acol.p - (uintptr_t)lo * 4u);
+  d->a.m = Csr{d->in_arow.p, acol_dev, d->in_brow.p, nullptr, An, Bn, 0};
+  d->a.Annz = hi - lo; d->a.Bnnz = 0; d->a.dCrow = nullptr; d->a.is64 = 0;
+  CKS(mul_launch_estimate(d));
+  CK(cudaStreamSynchronize(d->stream));
+  d->phase = 0;
+  if (d->h_sc->err & 1u) return fail(BSPGEMM_ERR_BADARG, "a column index of A is outside [0,Bn=%d)", Bn);
+  *ip_out = (int64_t)d->h_sc->total_ip;
+  return BSPGEMM_OK;
+}
+
+// ---- legacy-signature drop-ins (void, exit(1) on failure like final/utils.c:54-61) ----
+static int derive_bn(const int* Acol, const int* Arow, int An) {
+  int mx = -1;
+  for (int64_t p = Arow[0]; p < Arow[An]; ++p) mx = std::max(mx, Acol[p]);
+  return mx + 1;
+}
+static void die_on(int s, const char* who) {
+  if (s == BSPGEMM_OK) return;
+  fprintf(stderr, "%s: %s: %s\n", who, bspgemm_strerror(s), bspgemm_last_error());
+  exit(1);
+}
+extern "C" void bspgemm_SpGEMM_mpi(int* Acol, int* Arow, int An, int* Bcol, int* Brow, int Bm, int** Ccol, int* Crow, int tBlock) {
+  (void)tBlock;
+  die_on(bspgemm_csr(Acol, Arow, An, Bcol, Brow, derive_bn(Acol, Arow, An), Bm, Ccol, Crow), "SpGEMM_mpi");
+}
+extern "C" void bspgemm_SpGEMM_omp(int* Acol, int* Arow, int An, int* Bcol, int* Brow, int Bm, int** Ccol, int* Crow, int tBlock) {
+  (void)tBlock;
+  die_on(bspgemm_csr_slice(Acol, Arow, An, Bcol, Brow, derive_bn(Acol, Arow, An), Bm, Ccol, Crow, 0, An), "SpGEMM_omp");
+}
+extern "C" void bspgemm_SpGEMM_bigslice(int* Acol, int* Arow, int An, int* Bcol, int* Brow, int Bm, int** Ccol, int* Crow, int* Csize,
+                                        int start_row, int end_row) {
+  // The reference appends into a caller-owned growable *Ccol (:28-31); here the old buffer is released
+  // and replaced by an exact-size one, and *Csize is updated to its capacity.
+  int* fresh = nullptr;
+  die_on(bspgemm_csr_slice(Acol, Arow, An, Bcol, Brow, derive_bn(Acol, Arow + start_row, end_row - start_row), Bm, &fresh, Crow, start_row, end_row), "SpGEMM_bigslice");
+  if (Ccol) { free(*Ccol); *Ccol = fresh; } else free(fresh);
+  if (Csize) *Csize = Crow[end_row - start_row];
+}

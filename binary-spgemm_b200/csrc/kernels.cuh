@@ -1,0 +1,602 @@
+// binary-spgemm_b200/csrc/kernels.cuh — sm_100a kernels for the boolean CSR product C = A·B.
+//
+// Replaces the reference's CPU hot loop SpGEMM_bigslice (final/SpGEMM_mpi_omp.c:15-58: Gustavson row
+// product + `xb` flag de-duplication + per-row quickSort) and the concatenation / row-pointer fix-up of
+// SpGEMM_omp (:111-141).  Result contract: Crow[0]=0, Crow[i+1]-Crow[i] = number of
+// distinct k with A(i,j) and B(j,k), Ccol ascending inside each row.
+//
+// Design: rows are binned by their intermediate-product count IP_i (k_estimate):
+//   S  (IP <= cap_s)  one warp per row, table in shared memory              k_rows_warp<G,MODE>
+//   M  (IP <= cap_m)  one CTA per row, table in shared memory               k_rows_cta<MODE>
+//   L  (larger)       one CTA per row, bitmap over [0,Bm) in global memory  k_rows_gbitmap<MODE>
+// De-duplication AND sorting are one step: an *ordered* open-addressing table.  Keys are placed by a
+// monotone map slot = floor((k-lo)*T/(hi-lo+1)) and collisions are resolved with atomicMin + "the larger
+// key moves one slot right" (no wrap-around).  The final table, read left to right, is the sorted set of
+// distinct keys — no comparison sort anywhere (the reference spends 2/3 of its time in quickSort).
+// Rows whose column span is narrow use a bitmap over [lo,hi] in the same memory instead.
+// MODE_FUSED additionally carries a decoupled-look-back scan over row tiles so that B is gathered once
+// and C is written once, directly at its final position (one pass; north-star steps 2+3+4 in one launch).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bsk {
+
+typedef unsigned long long u64;
+typedef uint32_t u32;
+
+constexpr u32 EMPTY = 0xFFFFFFFFu;
+constexpr int MODE_COUNT = 0;   // symbolic: cnt[row] = nnz(C_row)
+constexpr int MODE_FILL  = 1;   // numeric : Ccol[Crow[row]..] = sorted distinct columns
+constexpr int MODE_FUSED = 2;   // symbolic + scan + numeric in one pass (tiles of consecutive rows)
+
+constexpr int WARPS_S = 8;      // warps per CTA in the warp-per-row kernel (= rows per tile in MODE_FUSED)
+
+// status word of the decoupled look-back chain: [63:62] flag, [61:0] value
+constexpr u64 ST_AGG = 1ull << 62;
+constexpr u64 ST_INC = 2ull << 62;
+constexpr u64 ST_VAL = (1ull << 62) - 1;
+
+struct Csr {            // A and B as the reference passes them (final/SpGEMM_mpi_omp.c:155-157)
+  const int* __restrict__ Arow;   // An+1 ABSOLUTE offsets into Acol (Arow[0] need not be 0, cf. :171)
+  const int* __restrict__ Acol;
+  const int* __restrict__ Brow;   // Bn+1
+  const int* __restrict__ Bcol;
+  int An, Bn, Bm;
+};
+
+struct DevScalars {     // one per context, in device memory; copied to the host between phases
+  u64 total_ip;         // Σ IP_i
+  u64 total_nnz;        // nnz(C) (written by the scan / fused kernel)
+  u32 hist[33];         // hist[b] = #rows with IP in [2^(b-1), 2^b), hist[0] = #rows with IP==0
+  u32 max_ip;
+  u32 err;              // bit0: column index of A out of [0,Bn); bit1: 32-bit row pointer overflow; bit2: column of B out of [0,Bm)
+  u32 n_m1, n_m2, n_l;  // list lengths (k_build_lists)
+  u32 tile_counter;     // dynamic tile ids (fused kernel / scan kernel)
+  u32 pad;
+};
+
+// ------------------------------------------------------------------------------------------------ helpers
+__device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31; }
+
+__device__ __forceinline__ u32 warp_incl_scan(u32 v) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, v, d); if ((int)lane_id() >= d) v += t; }
+  return v;
+}
+
+__device__ __forceinline__ u64 ld_status(const u64* p) {
+  u64 v; asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_status(u64* p, u64 v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
+// Store / load a row pointer in the caller's width (32-bit ABI of the reference, or the _i64 variant).
+__device__ __forceinline__ void st_rowptr(void* Crow, int is64, size_t i, u64 v, u32* err) {
+  if (is64) ((long long*)Crow)[i] = (long long)v;
+  else { if (v > 0x7fffffffull) atomicOr(err, 2u); ((int*)Crow)[i] = (int)v; }
+}
+__device__ __forceinline__ u64 ld_rowptr(const void* Crow, int is64, size_t i) {
+  return is64 ? (u64)((const long long*)Crow)[i] : (u64)(u32)((const int*)Crow)[i];
+}
+
+// Exclusive prefix of this tile in the chain (decoupled look-back, executed by one full warp).
+// status[] must be zero before the launch; tiles are handed out by an atomic counter, so every
+// predecessor of a running tile has already started: the spin cannot deadlock.
+__device__ __forceinline__ u64 lookback_exclusive(u64* status, u32 tile, u64 aggregate) {
+  const u32 lane = lane_id();
+  if (tile == 0) { if (lane == 0) st_status(&status[0], ST_INC | aggregate); return 0; }
+  if (lane == 0) st_status(&status[tile], ST_AGG | aggregate);
+  u64 excl = 0;
+  long long idx = (long long)tile - 1;
+  while (true) {
+    long long my = idx - lane;
+    u64 s;
+    do {
+      s = (my >= 0) ? ld_status(&status[my]) : ST_INC;          // before tile 0: inclusive prefix 0
+    } while (__any_sync(0xffffffffu, (s >> 62) == 0));
+    u32 inc_mask = __ballot_sync(0xffffffffu, (s >> 62) == 2);
+    u32 first = inc_mask ? (u32)(__ffs(inc_mask) - 1) : 32u;     // nearest predecessor with a full prefix
+    u64 v = (lane <= first) ? (s & ST_VAL) : 0;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    excl += v;
+    if (inc_mask) break;
+    idx -= 32;
+  }
+  if (lane == 0) st_status(&status[tile], ST_INC | (excl + aggregate));
+  return excl;
+}
+
+// ------------------------------------------------------------------------------------------------ (1) work estimation
+// ip[i] = Σ_{jj in A.row(i)} len(B.row(Acol[jj]))  — the trip count of final/SpGEMM_mpi_omp.c:33-37.
+// G lanes per row (G chosen from the mean A row length); Acol is read coalesced, Brow is a gather
+// (Brow is small and L2-resident).  Also builds the log2 histogram used to pick the bin thresholds.
+template <int G>
+__global__ void __launch_bounds__(256) k_estimate(Csr m, u32* __restrict__ ip, DevScalars* sc) {
+  __shared__ u32 s_hist[33];
+  __shared__ u64 s_sum;
+  __shared__ u32 s_max;
+  if (threadIdx.x < 33) s_hist[threadIdx.x] = 0;
+  if (threadIdx.x == 0) { s_sum = 0; s_max = 0; }
+  __syncthreads();
+  const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long row = gtid / G;
+  const int l = (int)(gtid % G);
+  u64 sum = 0;
+  u32 bad = 0;
+  if (row < m.An) {
+    const int a0 = m.Arow[row], a1 = m.Arow[row + 1];
+    for (int jj = a0 + l; jj < a1; jj += G) {
+      const int j = m.Acol[jj];
+      if ((u32)j < (u32)m.Bn) sum += (u32)(m.Brow[j + 1] - m.Brow[j]); else bad = 1;
+    }
+  }
+#pragma unroll
+  for (int d = G / 2; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+  if (bad) atomicOr(&sc->err, 1u);
+  if (row < m.An && l == 0) {
+    const u32 v = sum > 0xfffffffeull ? 0xfffffffeu : (u32)sum;
+    ip[row] = v;
+    atomicAdd(&s_hist[v ? 32 - __clz(v) : 0], 1u);
+    atomicAdd(&s_sum, sum);
+    atomicMax(&s_max, v);
+  }
+  __syncthreads();
+  if (threadIdx.x < 33 && s_hist[threadIdx.x]) atomicAdd(&sc->hist[threadIdx.x], s_hist[threadIdx.x]);
+  if (threadIdx.x == 0) { if (s_sum) atomicAdd(&sc->total_ip, s_sum); atomicMax(&sc->max_ip, s_max); }
+}
+
+// Row lists for the CTA-per-row bins (order inside a list is irrelevant).
+__global__ void __launch_bounds__(256) k_build_lists(const u32* __restrict__ ip, int An, u32 cap_s, u32 cap_m1, u32 cap_m2,
+                                                     u32* __restrict__ list_m1, u32* __restrict__ list_m2,
+                                                     u32* __restrict__ list_l, DevScalars* sc) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= An) return;
+  const u32 v = ip[i];
+  if (v <= cap_s) return;
+  if (v <= cap_m1)      list_m1[atomicAdd(&sc->n_m1, 1u)] = (u32)i;
+  else if (v <= cap_m2) list_m2[atomicAdd(&sc->n_m2, 1u)] = (u32)i;
+  else                  list_l[atomicAdd(&sc->n_l, 1u)] = (u32)i;
+}
+
+// ------------------------------------------------------------------------------------------------ ordered table primitives
+// Monotone slot map: slot = floor((k-lo) * T / range) computed as umulhi(k-lo, floor(T*2^32/range)).
+__device__ __forceinline__ u32 slot_scale(u32 T, u32 range) { return (u32)((((u64)T) << 32) / range); }
+
+// Insert key x at/after slot s.  atomicMin keeps the smaller key in the slot; the larger one (the
+// newcomer or the evicted resident) moves right.  Returns 1 if a new distinct key was added.
+// Invariant on exit of all inserts: non-empty slots read left-to-right are strictly ascending.
+__device__ __forceinline__ u32 ordered_insert(u32* tab, u32 s, u32 x, u32& max_slot) {
+  while (true) {
+    const u32 old = atomicMin(&tab[s], x);
+    if (old == EMPTY) { max_slot = max(max_slot, s); return 1u; }
+    if (old == x) return 0u;
+    x = max(old, x);
+    ++s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ (2a) S bin: one warp per row
+// Shared memory per warp: tab[3*cap] | stage[cap]   (cap = power of two >= largest IP in the bin).
+//   1. gather the IP_i candidate columns into stage[] (G lanes walk one B row; positions from a warp scan)
+//   2. lo/hi by warp reduction; narrow span -> bitmap over [lo,hi], otherwise ordered table with
+//      T = 2*IP home slots + IP overflow slots (a key can be pushed right by at most IP-1 slots)
+//   3. COUNT: number of successful insertions.  FILL/FUSED: compact the table into stage[] (sorted).
+// Returns nnz(C_row); in FILL/FUSED the sorted columns are in stage[0..cnt).
+template <int G, int MODE>
+__device__ __forceinline__ u32 warp_row(const Csr& m, int row, u32 ipr, u32 cap, u32* tab, u32* stage, u32* err) {
+  const u32 lane = lane_id();
+  constexpr int SPW = 32 / G;                 // B rows (segments) walked per warp step
+  const u32 sub = lane / G, off0 = lane % G;
+  const int a0 = m.Arow[row], a1 = m.Arow[row + 1];
+
+  // ---- 1. gather
+  u32 vmin = EMPTY, vmax = 0, pos_base = 0;
+  for (int b0 = a0; b0 < a1; b0 += 32) {
+    const int jj = b0 + (int)lane;
+    u32 bs = 0, len = 0;
+    if (jj < a1) {
+      const int j = m.Acol[jj];
+      if ((u32)j < (u32)m.Bn) { bs = (u32)m.Brow[j]; len = (u32)m.Brow[j + 1] - bs; }
+    }
+    const u32 incl = warp_incl_scan(len);
+    const u32 excl = incl - len;
+    const u32 tot = __shfl_sync(0xffffffffu, incl, 31);
+    const int nseg = min(32, a1 - b0);
+    for (int s = 0; s < nseg; s += 4 * SPW) {
+      u32 sbs[4], slen[4], spos[4], v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int src = s + u * SPW + (int)sub;          // lanes >= nseg carry len 0
+        sbs[u]  = __shfl_sync(0xffffffffu, bs,   src & 31);
+        slen[u] = __shfl_sync(0xffffffffu, len,  src & 31);
+        spos[u] = __shfl_sync(0xffffffffu, excl, src & 31);
+        if (src >= 32) slen[u] = 0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = (off0 < slen[u]) ? (u32)__ldg(&m.Bcol[sbs[u] + off0]) : 0u;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (off0 < slen[u]) { stage[pos_base + spos[u] + off0] = v[u]; vmin = min(vmin, v[u]); vmax = max(vmax, v[u]); }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        for (u32 o = off0 + G; o < slen[u]; o += G) {    // B rows longer than G
+          const u32 w = (u32)__ldg(&m.Bcol[sbs[u] + o]);
+          stage[pos_base + spos[u] + o] = w; vmin = min(vmin, w); vmax = max(vmax, w);
+        }
+    }
+    pos_base += tot;
+  }
+  const u32 lo = __reduce_min_sync(0xffffffffu, vmin);
+  const u32 hi = __reduce_max_sync(0xffffffffu, vmax);
+  if (hi >= (u32)m.Bm) { if (lane == 0) atomicOr(err, 4u); return 0; }   // B column outside [0,Bm): refuse
+  __syncwarp();
+
+  const u32 range = hi - lo + 1;
+  const u32 nwords = 3 * cap;
+  u32 cnt = 0;
+  if (range <= 32 * nwords) {
+    // ---- 2a. bitmap over [lo,hi]
+    const u32 nW = (range + 31) >> 5;
+    for (u32 w = lane; w < nW; w += 32) tab[w] = 0;
+    __syncwarp();
+    u32 added = 0;
+    for (u32 p = lane; p < ipr; p += 32) {
+      const u32 v = stage[p] - lo, bit = 1u << (v & 31);
+      const u32 old = atomicOr(&tab[v >> 5], bit);
+      added += (old & bit) ? 0u : 1u;
+    }
+    __syncwarp();
+    if (MODE == MODE_COUNT) return __reduce_add_sync(0xffffffffu, added);
+    for (u32 w0 = 0; w0 < nW; w0 += 32) {
+      const u32 w = w0 + lane;
+      u32 word = (w < nW) ? tab[w] : 0u;
+      const u32 c = __popc(word);
+      const u32 inc = warp_incl_scan(c);
+      u32 o = cnt + inc - c;
+      const u32 base = lo + (w << 5);
+      while (word) { const u32 b = __ffs(word) - 1; word &= word - 1; stage[o++] = base + b; }
+      cnt += __shfl_sync(0xffffffffu, inc, 31);
+    }
+  } else {
+    // ---- 2b. ordered table
+    const u32 T = 2 * ipr;                       // ipr <= cap  =>  T + ipr <= 3*cap
+    const u32 limit = T + ipr;
+    const u32 scale = slot_scale(T, range);      // range > 96*cap > T  =>  scale < 2^32
+    {
+      uint4* t4 = reinterpret_cast<uint4*>(tab);
+      const uint4 e = make_uint4(EMPTY, EMPTY, EMPTY, EMPTY);
+      for (u32 q = lane; q < (limit + 3) / 4; q += 32) t4[q] = e;
+    }
+    __syncwarp();
+    u32 added = 0, max_slot = 0;
+    for (u32 p = lane; p < ipr; p += 32) {
+      const u32 x = stage[p];
+      added += ordered_insert(tab, __umulhi(x - lo, scale), x, max_slot);
+    }
+    __syncwarp();
+    if (MODE == MODE_COUNT) return __reduce_add_sync(0xffffffffu, added);
+    max_slot = __reduce_max_sync(0xffffffffu, max_slot);
+    for (u32 s0 = 0; s0 <= max_slot; s0 += 32) {
+      const u32 s = s0 + lane;
+      const u32 v = (s <= max_slot) ? tab[s] : EMPTY;
+      const u32 mk = __ballot_sync(0xffffffffu, v != EMPTY);
+      if (v != EMPTY) stage[cnt + __popc(mk & ((1u << lane) - 1))] = v;
+      cnt += __popc(mk);
+    }
+  }
+  __syncwarp();
+  return cnt;
+}
+
+// Kernel for the S bin.
+//   MODE_COUNT: grid-stride over rows, cnt[row] written for rows with IP <= cap (others untouched).
+//   MODE_FILL : grid-stride over rows, writes Ccol[Crow[row] ...] for rows with IP <= cap.
+//   MODE_FUSED: dynamic tiles of WARPS_S consecutive rows; rows with IP > cap take their count from
+//               cnt[] (written earlier by the M/L symbolic kernels) and are filled later by the M/L
+//               numeric kernels; all row pointers and the S rows' columns are written here.
+template <int G, int MODE>
+__global__ void __launch_bounds__(WARPS_S * 32) k_rows_warp(Csr m, const u32* __restrict__ ip, u32* __restrict__ cnt, u32 cap,
+                                                           void* __restrict__ Crow, int is64, int* __restrict__ Ccol,
+                                                           u64* __restrict__ status, DevScalars* sc, u32 ntiles) {
+  extern __shared__ __align__(16) u32 smem[];
+  const u32 warp = threadIdx.x >> 5, lane = lane_id();
+  u32* tab = smem + (size_t)warp * (4 * cap);
+  u32* stage = tab + 3 * cap;
+
+  if (MODE != MODE_FUSED) {
+    const long long nw = (long long)gridDim.x * WARPS_S;
+    for (long long row = (long long)blockIdx.x * WARPS_S + warp; row < m.An; row += nw) {
+      const u32 ipr = ip[row];
+      if (ipr > cap) continue;
+      u32 c = 0;
+      if (ipr) c = warp_row<G, MODE>(m, (int)row, ipr, cap, tab, stage, &sc->err);
+      if (MODE == MODE_COUNT) { if (lane == 0) cnt[row] = c; }
+      else {
+        const u64 base = ld_rowptr(Crow, is64, (size_t)row);
+        for (u32 p = lane; p < c; p += 32) Ccol[base + p] = (int)stage[p];
+      }
+      __syncwarp();
+    }
+    return;
+  }
+
+  __shared__ u32 s_tile;
+  __shared__ u32 s_cnt[WARPS_S];
+  __shared__ u64 s_off[WARPS_S];
+  while (true) {
+    if (threadIdx.x == 0) s_tile = atomicAdd(&sc->tile_counter, 1u);
+    __syncthreads();
+    const u32 tile = s_tile;
+    if (tile >= ntiles) break;
+    const long long row = (long long)tile * WARPS_S + warp;
+    u32 c = 0;
+    bool mine = false;
+    if (row < m.An) {
+      const u32 ipr = ip[row];
+      if (ipr > cap) c = cnt[row];
+      else if (ipr) { c = warp_row<G, MODE_FUSED>(m, (int)row, ipr, cap, tab, stage, &sc->err); mine = true; }
+    }
+    if (lane == 0) s_cnt[warp] = c;
+    __syncthreads();
+    if (warp == 0) {
+      const u32 v = (lane < WARPS_S) ? s_cnt[lane] : 0u;
+      const u32 inc = warp_incl_scan(v);
+      const u64 agg = __shfl_sync(0xffffffffu, inc, 31);
+      const u64 excl = lookback_exclusive(status, tile, agg);
+      if (lane < WARPS_S) {
+        s_off[lane] = excl + inc - v;
+        const long long r = (long long)tile * WARPS_S + lane;
+        if (r < m.An) st_rowptr(Crow, is64, (size_t)r + 1, excl + inc, &sc->err);
+      }
+      if (tile == 0 && lane == 0) st_rowptr(Crow, is64, 0, 0, &sc->err);
+      if (tile == ntiles - 1 && lane == 0) sc->total_nnz = excl + agg;
+    }
+    __syncthreads();
+    if (mine) {
+      const u64 base = s_off[warp];
+      for (u32 p = lane; p < c; p += 32) Ccol[base + p] = (int)stage[p];
+    }
+    // the next iteration's first __syncthreads orders these reads of s_off/stage before they are rewritten
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ (2b) M bin: one CTA per row
+// Walk all candidate columns of a row with the whole CTA: groups of G lanes take one A nonzero each.
+template <class F>
+__device__ __forceinline__ void cta_for_each_product(const Csr& m, int a0, int a1, int G, F f) {
+  const int ngroups = (int)blockDim.x / G, g = (int)threadIdx.x / G, l = (int)threadIdx.x % G;
+  for (int jj = a0 + g; jj < a1; jj += ngroups) {
+    const int j = m.Acol[jj];
+    if ((u32)j >= (u32)m.Bn) continue;
+    const int bs = m.Brow[j], be = m.Brow[j + 1];
+    for (int o = bs + l; o < be; o += G) f((u32)__ldg(&m.Bcol[o]));
+  }
+}
+
+__device__ __forceinline__ u32 block_reduce_add(u32 v, u32* s_red) {   // s_red: 33 words
+  v = __reduce_add_sync(0xffffffffu, v);
+  if (lane_id() == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    u32 w = (threadIdx.x < (blockDim.x >> 5)) ? s_red[threadIdx.x] : 0u;
+    w = __reduce_add_sync(0xffffffffu, w);
+    if (threadIdx.x == 0) s_red[32] = w;
+  }
+  __syncthreads();
+  const u32 r = s_red[32];
+  __syncthreads();
+  return r;
+}
+
+// Block-wide exclusive scan of one value per thread; returns the exclusive prefix, total in *total.
+__device__ __forceinline__ u32 block_excl_scan(u32 v, u32* s_red, u32* total) {
+  const u32 inc = warp_incl_scan(v);
+  const u32 w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (lane_id() == 31) s_red[w] = inc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const u32 x = (threadIdx.x < nw) ? s_red[threadIdx.x] : 0u;
+    const u32 xi = warp_incl_scan(x);
+    s_red[threadIdx.x] = xi - x;
+    if (threadIdx.x == 31) s_red[32] = xi;
+  }
+  __syncthreads();
+  const u32 r = s_red[w] + inc - v;
+  *total = s_red[32];
+  __syncthreads();
+  return r;
+}
+
+// Shared memory: tab[3*cap] words.  The B rows are walked twice (lo/hi pass, insert pass); the second
+// walk hits L1/L2.  COUNT writes cnt[row]; FILL compacts the table straight into Ccol at Crow[row].
+template <int MODE>
+__global__ void __launch_bounds__(1024) k_rows_cta(Csr m, const u32* __restrict__ list, const u32* __restrict__ nlist,
+                                                   const u32* __restrict__ ip, u32* __restrict__ cnt, u32 cap, int G,
+                                                   const void* __restrict__ Crow, int is64, int* __restrict__ Ccol,
+                                                   DevScalars* sc) {
+  extern __shared__ __align__(16) u32 tab[];
+  __shared__ u32 s_red[33];
+  __shared__ u32 s_lo, s_hi, s_maxslot;
+  const u32 n = *nlist;
+  for (u32 idx = blockIdx.x; idx < n; idx += gridDim.x) {
+    const int row = (int)list[idx];
+    const u32 ipr = ip[row];
+    const int a0 = m.Arow[row], a1 = m.Arow[row + 1];
+    if (threadIdx.x == 0) { s_lo = EMPTY; s_hi = 0; s_maxslot = 0; }
+    __syncthreads();
+    u32 vmin = EMPTY, vmax = 0;
+    cta_for_each_product(m, a0, a1, G, [&](u32 v) { vmin = min(vmin, v); vmax = max(vmax, v); });
+    vmin = __reduce_min_sync(0xffffffffu, vmin);
+    vmax = __reduce_max_sync(0xffffffffu, vmax);
+    if (lane_id() == 0) { atomicMin(&s_lo, vmin); atomicMax(&s_hi, vmax); }
+    __syncthreads();
+    const u32 lo = s_lo, hi = s_hi;
+    if (hi >= (u32)m.Bm) { if (threadIdx.x == 0) { atomicOr(&sc->err, 4u); if (MODE == MODE_COUNT) cnt[row] = 0; } __syncthreads(); continue; }
+    const u32 range = hi - lo + 1;
+    const u64 base = (MODE == MODE_FILL) ? ld_rowptr(Crow, is64, (size_t)row) : 0;
+    if (range <= 32u * 3u * cap) {
+      const u32 nW = (range + 31) >> 5;
+      for (u32 w = threadIdx.x; w < nW; w += blockDim.x) tab[w] = 0;
+      __syncthreads();
+      u32 added = 0;
+      cta_for_each_product(m, a0, a1, G, [&](u32 v) {
+        v -= lo; const u32 bit = 1u << (v & 31);
+        const u32 old = atomicOr(&tab[v >> 5], bit);
+        added += (old & bit) ? 0u : 1u;
+      });
+      __syncthreads();
+      if (MODE == MODE_COUNT) {
+        const u32 c = block_reduce_add(added, s_red);
+        if (threadIdx.x == 0) cnt[row] = c;
+      } else {
+        u32 done = 0;
+        for (u32 w0 = 0; w0 < nW; w0 += blockDim.x) {
+          const u32 w = w0 + threadIdx.x;
+          u32 word = (w < nW) ? tab[w] : 0u, tot;
+          u32 o = done + block_excl_scan(__popc(word), s_red, &tot);
+          const u32 b0 = lo + (w << 5);
+          while (word) { const u32 b = __ffs(word) - 1; word &= word - 1; Ccol[base + o++] = (int)(b0 + b); }
+          done += tot;
+        }
+      }
+    } else {
+      const u32 T = 2 * ipr, limit = T + ipr;
+      const u32 scale = slot_scale(T, range);
+      for (u32 q = threadIdx.x; q < limit; q += blockDim.x) tab[q] = EMPTY;
+      __syncthreads();
+      u32 added = 0, max_slot = 0;
+      cta_for_each_product(m, a0, a1, G, [&](u32 x) { added += ordered_insert(tab, __umulhi(x - lo, scale), x, max_slot); });
+      if (MODE == MODE_COUNT) {
+        const u32 c = block_reduce_add(added, s_red);
+        if (threadIdx.x == 0) cnt[row] = c;
+      } else {
+        max_slot = __reduce_max_sync(0xffffffffu, max_slot);
+        if (lane_id() == 0) atomicMax(&s_maxslot, max_slot);
+        __syncthreads();
+        const u32 ms = s_maxslot;
+        u32 done = 0;
+        for (u32 s0 = 0; s0 <= ms; s0 += blockDim.x) {
+          const u32 s = s0 + threadIdx.x;
+          const u32 v = (s <= ms) ? tab[s] : EMPTY;
+          u32 tot;
+          const u32 o = done + block_excl_scan(v != EMPTY ? 1u : 0u, s_red, &tot);
+          if (v != EMPTY) Ccol[base + o] = (int)v;
+          done += tot;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ (2c) L bin: global bitmap
+// One CTA per row; bitmap over [0,Bm) in global memory (one per resident CTA, zero between rows).
+template <int MODE>
+__global__ void __launch_bounds__(1024) k_rows_gbitmap(Csr m, const u32* __restrict__ list, const u32* __restrict__ nlist,
+                                                       u32* __restrict__ cnt, int G, u32* __restrict__ bitmaps, u32 words_per_cta,
+                                                       const void* __restrict__ Crow, int is64, int* __restrict__ Ccol,
+                                                       DevScalars* sc) {
+  __shared__ u32 s_red[33];
+  __shared__ u32 s_wlo, s_whi, s_bad;
+  u32* bm = bitmaps + (size_t)blockIdx.x * words_per_cta;
+  const u32 n = *nlist;
+  for (u32 idx = blockIdx.x; idx < n; idx += gridDim.x) {
+    const int row = (int)list[idx];
+    const int a0 = m.Arow[row], a1 = m.Arow[row + 1];
+    if (threadIdx.x == 0) { s_wlo = EMPTY; s_whi = 0; s_bad = 0; }
+    __syncthreads();
+    u32 added = 0, wlo = EMPTY, whi = 0, bad = 0;
+    cta_for_each_product(m, a0, a1, G, [&](u32 v) {
+      if (v >= (u32)m.Bm) { bad = 1; return; }
+      const u32 w = v >> 5, bit = 1u << (v & 31);
+      const u32 old = atomicOr(&bm[w], bit);
+      added += (old & bit) ? 0u : 1u;
+      wlo = min(wlo, w); whi = max(whi, w);
+    });
+    wlo = __reduce_min_sync(0xffffffffu, wlo);
+    whi = __reduce_max_sync(0xffffffffu, whi);
+    if (lane_id() == 0) { atomicMin(&s_wlo, wlo); atomicMax(&s_whi, whi); if (bad) s_bad = 1; }
+    if (__any_sync(0xffffffffu, bad) && lane_id() == 0) s_bad = 1;
+    __syncthreads();
+    if (s_bad && threadIdx.x == 0) atomicOr(&sc->err, 4u);
+    const u32 w_lo = s_wlo, w_hi = s_whi;
+    if (MODE == MODE_COUNT) {
+      const u32 c = block_reduce_add(added, s_red);
+      if (threadIdx.x == 0) cnt[row] = c;
+    } else if (w_lo != EMPTY) {
+      const u64 base = ld_rowptr(Crow, is64, (size_t)row);
+      u64 done = 0;
+      for (u32 w0 = w_lo; w0 <= w_hi; w0 += blockDim.x) {
+        const u32 w = w0 + threadIdx.x;
+        u32 word = (w <= w_hi) ? __ldcg(&bm[w]) : 0u, tot;
+        u64 o = done + block_excl_scan(__popc(word), s_red, &tot);
+        const u32 b0 = w << 5;
+        while (word) { const u32 b = __ffs(word) - 1; word &= word - 1; Ccol[base + o++] = (int)(b0 + b); }
+        done += tot;
+        if (w0 + blockDim.x < w0) break;   // overflow guard
+      }
+    }
+    __syncthreads();
+    if (w_lo != EMPTY) for (u32 w = w_lo + threadIdx.x; w <= w_hi; w += blockDim.x) bm[w] = 0;
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ (3) device prefix scan
+// Crow[i+1] = Σ_{r<=i} cnt[r], Crow[0] = 0 — single pass, decoupled look-back over tiles of
+// SCAN_THREADS*SCAN_ITEMS counts.  Replaces the serial fix-up loops (final/SpGEMM_mpi_omp.c:135-141, :215-221).
+constexpr int SCAN_THREADS = 256, SCAN_ITEMS = 8;
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan(const u32* __restrict__ cnt, int An, void* __restrict__ Crow, int is64,
+                                                       u64* __restrict__ status, DevScalars* sc, u32 ntiles) {
+  __shared__ u32 s_tile;
+  __shared__ u64 s_wsum[SCAN_THREADS / 32];
+  __shared__ u64 s_excl;
+  if (threadIdx.x == 0) s_tile = atomicAdd(&sc->tile_counter, 1u);
+  __syncthreads();
+  const u32 tile = s_tile;
+  if (tile >= ntiles) return;
+  const long long base = (long long)tile * (SCAN_THREADS * SCAN_ITEMS) + (long long)threadIdx.x * SCAN_ITEMS;
+  u32 v[SCAN_ITEMS];
+  u64 tsum = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) { v[k] = (base + k < An) ? cnt[base + k] : 0u; tsum += v[k]; }
+  // warp scan of thread sums (64-bit)
+  u64 inc = tsum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { u64 t = __shfl_up_sync(0xffffffffu, inc, d); if ((int)lane_id() >= d) inc += t; }
+  const u32 w = threadIdx.x >> 5;
+  if (lane_id() == 31) s_wsum[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    u64 x = (lane_id() < SCAN_THREADS / 32) ? s_wsum[lane_id()] : 0;
+    u64 xi = x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { u64 t = __shfl_up_sync(0xffffffffu, xi, d); if ((int)lane_id() >= d) xi += t; }
+    const u64 agg = __shfl_sync(0xffffffffu, xi, 31);
+    if (lane_id() < SCAN_THREADS / 32) s_wsum[lane_id()] = xi - x;
+    const u64 excl = lookback_exclusive(status, tile, agg);
+    if (lane_id() == 0) { s_excl = excl; if (tile == ntiles - 1) sc->total_nnz = excl + agg; if (tile == 0) st_rowptr(Crow, is64, 0, 0, &sc->err); }
+  }
+  __syncthreads();
+  u64 run = s_excl + s_wsum[w] + inc - tsum;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    run += v[k];
+    if (base + k < An) st_rowptr(Crow, is64, (size_t)(base + k) + 1, run, &sc->err);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ multi-GPU helper
+// Adds a shard's displacement to its slice-relative row pointers while copying them into the gathered
+// array (replaces the root's fix-up loop final/SpGEMM_mpi_omp.c:211-223).
+__global__ void k_offset_rowptr(const void* __restrict__ src, void* __restrict__ dst, int is64, long long n, long long disp) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (is64) ((long long*)dst)[i] = ((const long long*)src)[i] + disp;
+  else ((int*)dst)[i] = (int)(((const int*)src)[i] + disp);
+}
+
+}  // namespace bsk

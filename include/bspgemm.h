@@ -1,0 +1,131 @@
+/*
+ * include/bspgemm.h — C ABI of libbspgemm.so: boolean (pattern-only) CSR SpGEMM  C = A·B  on B200 (sm_100a).
+ *
+ * This is the drop-in boundary for the reference's hot path (pavlidic/Binary-SpGEMM, final/):
+ * plain C, plain pointers and sizes, no torch / C++ types.  Every entry point names the reference
+ * interface it replaces (file:line under /root/reference).  There is NO CPU fallback behind any of
+ * them: without a usable GPU they return BSPGEMM_ERR_NOGPU.
+ *
+ * Conventions kept from the reference:
+ *   - argument order "col before row" (final/SpGEMM_mpi_omp.c:155-158);
+ *   - A.row pointers are ABSOLUTE offsets into Acol, so a row block can be passed as a shifted Arow
+ *     pointer with the unshifted Acol, exactly like `&Arow[rank*tasksize]` (:171);
+ *   - *Ccol is allocated by the callee with malloc() and released by the caller with free() (:115/:200, :327);
+ *   - Crow is caller-allocated, An+1 entries (:311);
+ *   - result contract: Crow[0]=0; Ccol strictly ascending inside each row; empty rows allowed.
+ * Additions the reference lacks: explicit Bn (rows of B — the reference never needs it on the CPU),
+ * int status codes instead of void/exit(1), a 64-bit row-pointer variant (nnz(C) >= 2^31), any An and any
+ * number of GPUs (the reference silently drops rows unless An % (tasks*tBlock) == 0, :77,:165).
+ */
+#ifndef BSPGEMM_H
+#define BSPGEMM_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes (the reference returns void and exit(1)s, final/utils.c:54-61) ---- */
+#define BSPGEMM_OK             0
+#define BSPGEMM_ERR_CUDA       1   /* a CUDA runtime call failed (message in bspgemm_last_error) */
+#define BSPGEMM_ERR_NCCL       2   /* NCCL could not be loaded / a collective failed */
+#define BSPGEMM_ERR_OOM        3   /* host or device allocation failed */
+#define BSPGEMM_ERR_OVERFLOW32 4   /* nnz(C) >= 2^31 on the 32-bit row-pointer ABI: use the _i64 entry */
+#define BSPGEMM_ERR_BADARG     5   /* NULL / negative sizes / column index outside [0,Bn) or [0,Bm) */
+#define BSPGEMM_ERR_NOGPU      6   /* no CUDA device (there is no CPU fallback) */
+#define BSPGEMM_ERR_CAPACITY   7   /* caller-provided Ccol buffer too small (needed nnz is reported) */
+#define BSPGEMM_ERR_STATE      8   /* bspgemm_init not called / called twice */
+
+const char *bspgemm_strerror(int status);
+const char *bspgemm_last_error(void);          /* detail of the last failure on this thread */
+const char *bspgemm_version(void);
+
+/* ---- process-wide context: stands in for MPI_Init_thread / MPI_Comm_size / MPI_Finalize
+ *      (final/SpGEMM_mpi_omp.c:352-355,:364).  ngpus = number of "tasks"; 0 = all visible GPUs.
+ *      With ngpus > 1 an NCCL communicator over the GPUs is created (ncclCommInitAll). ---- */
+int bspgemm_init(int ngpus);
+int bspgemm_finalize(void);
+int bspgemm_num_gpus(void);                    /* 0 before init */
+
+/* ---- host-pointer operators (inputs and outputs in host memory; H2D/D2H inside) ----
+ * Replaces SpGEMM_mpi (final/SpGEMM_mpi_omp.c:155-225): A is split into contiguous row blocks, one per
+ * GPU (the rank split :165-171); B is uploaded once to GPU 0 and replicated with ncclBroadcast (the
+ * reference replicates B by having every rank read the file, :309); shards are gathered to the host at
+ * their displacements with the row-pointer offset applied on the device (replaces :178-223). */
+int bspgemm_csr(const int *Acol, const int *Arow, int An,
+                const int *Bcol, const int *Brow, int Bn, int Bm,
+                int **Ccol, int *Crow);
+/* same, 64-bit row pointers for C (A and B stay 32-bit) */
+int bspgemm_csr_i64(const int *Acol, const int *Arow, int An,
+                    const int *Bcol, const int *Brow, int Bn, int Bm,
+                    int **Ccol, int64_t *Crow);
+/* Caller-allocated output, replaces SpGEMM_mat (Matlab/inc/BSpGEMM.h:2-4; Matlab/inc/BSpGEMM.c:9-47).
+ * Ccol_buf may be pinned memory.  *nnz_out is always set; BSPGEMM_ERR_CAPACITY if capacity < nnz(C). */
+int bspgemm_csr_into(const int *Acol, const int *Arow, int An,
+                     const int *Bcol, const int *Brow, int Bn, int Bm,
+                     int *Ccol_buf, int64_t capacity, int *Crow, int64_t *nnz_out);
+/* Rows [start_row,end_row) only, slice-relative Crow (Crow[0]=0, end_row-start_row+1 entries):
+ * replaces SpGEMM_bigslice (final/SpGEMM_mpi_omp.c:15-58).  Runs on GPU 0. */
+int bspgemm_csr_slice(const int *Acol, const int *Arow, int An,
+                      const int *Bcol, const int *Brow, int Bn, int Bm,
+                      int **Ccol, int *Crow, int start_row, int end_row);
+/* Σ_{(i,j) in A} len(B_j): the intermediate-product count the throughput metric is quoted in
+ * (trip count of final/SpGEMM_mpi_omp.c:33-37), computed by the work-estimation kernel on GPU 0. */
+int bspgemm_intermediate_products(const int *Acol, const int *Arow, int An,
+                                  const int *Brow, int Bn, int64_t *ip_out);
+
+/* Legacy-signature drop-ins: same names' worth of arguments as the reference, void return, print to
+ * stderr and exit(1) on failure like the reference's I/O paths.  Bn is derived as max(Acol)+1 bounded by
+ * nothing else, so Brow must have at least that many + 1 entries (true for any valid CSR pair).
+ * tBlock is accepted and ignored (it only sizes the CPU thread slices, :77). */
+void bspgemm_SpGEMM_mpi(int *Acol, int *Arow, int An, int *Bcol, int *Brow, int Bm,
+                        int **Ccol, int *Crow, int tBlock);                       /* :155-158 */
+void bspgemm_SpGEMM_omp(int *Acol, int *Arow, int An, int *Bcol, int *Brow, int Bm,
+                        int **Ccol, int *Crow, int tBlock);                       /* :71-74  (GPU 0 only) */
+void bspgemm_SpGEMM_bigslice(int *Acol, int *Arow, int An, int *Bcol, int *Brow, int Bm,
+                             int **Ccol, int *Crow, int *Csize,
+                             int start_row, int end_row);                         /* :15-18 */
+
+/* ---- device-resident operator (one GPU; what each torch.distributed rank / each shard calls) ----
+ * All pointers are device pointers on `device`.  Work is enqueued on `stream` (a cudaStream_t, NULL =
+ * the handle's own stream) and the call returns after the result size is known (it synchronises the
+ * stream twice: after work estimation and at the end).  dCrow: An+1 entries of 32- or 64-bit.
+ * *dCcol_out points into an arena owned by the handle, valid until the next multiply / destroy. */
+typedef struct bspgemm_dev bspgemm_dev;
+
+#define BSPGEMM_MODE_AUTO     0   /* fused one-pass when the IP bound fits in memory, else two-phase */
+#define BSPGEMM_MODE_FUSED    1   /* estimate -> [M/L symbolic] -> fused symbolic+scan+fill -> [M/L numeric] */
+#define BSPGEMM_MODE_TWOPHASE 2   /* estimate -> symbolic -> scan -> numeric (north-star steps 1-4 as 4 launches) */
+
+typedef struct bspgemm_stats {
+  int64_t ip;                 /* intermediate products of the last multiply */
+  int64_t nnz;                /* nnz(C) */
+  int64_t rows_s, rows_m, rows_l;   /* rows per bin (warp / CTA shared-memory / CTA global bitmap) */
+  int32_t mode;               /* BSPGEMM_MODE_FUSED or _TWOPHASE actually used */
+  int32_t cap_s;              /* S-bin capacity (max IP handled by one warp) */
+  int32_t group;              /* lanes cooperating on one B row (G) */
+  int32_t launches;           /* kernels launched by the last multiply */
+  float   ms_total;           /* CUDA-event time, first launch .. last launch */
+  float   ms_estimate;        /* work-estimation kernel */
+  float   ms_symbolic;        /* symbolic kernels (two-phase: all bins; fused: M/L bins only) */
+  float   ms_main;            /* fused kernel (fused mode) or scan + S numeric kernel (two-phase) */
+  float   ms_numeric;         /* M/L numeric kernels */
+  int64_t algorithmic_bytes;  /* 4(An+1)+12nnzA+4IP+4nnzC+4(An+1) (8-byte terms for _i64 Crow) */
+} bspgemm_stats;
+
+int bspgemm_dev_create(bspgemm_dev **h, int device);
+int bspgemm_dev_destroy(bspgemm_dev *h);
+int bspgemm_dev_set_mode(bspgemm_dev *h, int mode);
+int bspgemm_dev_multiply(bspgemm_dev *h, void *stream,
+                         const int *dAcol, const int *dArow, int An, int64_t Annz,
+                         const int *dBcol, const int *dBrow, int Bn, int Bm, int64_t Bnnz,
+                         void *dCrow, int crow_is_i64,
+                         int **dCcol_out, int64_t *nnz_out);
+int bspgemm_dev_get_stats(bspgemm_dev *h, bspgemm_stats *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BSPGEMM_H */

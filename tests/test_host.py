@@ -1,0 +1,145 @@
+"""Host C surface (libbspgemm_host.so): readCOO / coo2csc / mmio-compatible reader / generators / stats.
+Mirrors how the reference's drivers use them (final/SpGEMM_mpi_omp.c:307-309, :330-333).  CPU only."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import crc
+
+
+def _write_fixture_mtx(path, f):
+    with open(path, "w") as fh:
+        fh.write("%%MatrixMarket matrix coordinate pattern general\n% Generated 15-Oct-2021\n")
+        fh.write(f"{int(f['M'])} {int(f['N'])} {len(f['I'])}\n")
+        for i, j in zip(f["I"].tolist(), f["J"].tolist()):
+            fh.write(f"{i + 1} {j + 1}\n")
+
+
+def test_readCOO_fixture_golden(bs, fixture_npz, tmp_path):
+    p = tmp_path / "validity_test.mtx"
+    _write_fixture_mtx(p, fixture_npz)
+    row, col, M, N, nnz = bs.readCOO(str(p))
+    assert (M, N, nnz) == (50000, 50000, 25000)
+    assert crc(row) == "0327ec62" and crc(col) == "3d773ff2"          # SURVEY.md §4 golden values
+    assert (row == fixture_npz["Arow"]).all() and (col == fixture_npz["Acol"]).all()
+
+
+def test_readCOO_transposes_on_read(bs, tmp_path):
+    p = tmp_path / "t.mtx"
+    # file matrix entries (row, col): (1,2) (3,2) (2,3) (1,1)  -> pointers by file column, indices = file rows, stable
+    p.write_text("%%MatrixMarket matrix coordinate pattern general\n%c\n\n3 3 4\n1 2\n3 2\n2 3\n1 1\n")
+    row, col, M, N, nnz = bs.readCOO(str(p))
+    assert row.tolist() == [0, 1, 3, 4] and col.tolist() == [0, 0, 2, 1]
+
+
+def test_readCOO_value_columns_are_skipped(bs, tmp_path):
+    p = tmp_path / "r.mtx"
+    p.write_text("%%MatrixMarket matrix coordinate real general\n2 2 2\n1 1 3.5\n2 1 -1e3\n")
+    row, col, *_ = bs.readCOO(str(p))
+    assert row.tolist() == [0, 2, 2] and col.tolist() == [0, 1]
+    p.write_text("%%MatrixMarket matrix coordinate complex general\n2 2 1\n2 2 1.0 2.0\n")
+    row, col, *_ = bs.readCOO(str(p))
+    assert row.tolist() == [0, 0, 1] and col.tolist() == [1]
+
+
+@pytest.mark.parametrize("text,why", [
+    ("%%NotMatrixMarket matrix coordinate pattern general\n1 1 0\n", "banner"),
+    ("%%MatrixMarket matrix coordinate pattern\n1 1 0\n", "short banner"),
+    ("%%MatrixMarket matrix array real general\n1 1\n", "dense"),
+    ("%%MatrixMarket matrix coordinate pattern general\n2 2 2\n1 1\n", "premature eof"),
+    ("%%MatrixMarket matrix coordinate pattern general\n2 2 1\n3 1\n", "index out of range"),
+])
+def test_readCOO_errors(bs, tmp_path, text, why):
+    p = tmp_path / "bad.mtx"
+    p.write_text(text)
+    with pytest.raises(OSError):
+        bs.readCOO(str(p))
+    with pytest.raises(OSError):
+        bs.readCOO(str(tmp_path / "missing.mtx"))
+
+
+def test_readCOO_exit1_like_reference(bs, tmp_path):
+    """The void readCOO exits with status 1 on failure (final/utils.c:54-61)."""
+    code = ("import importlib,sys,ctypes;sys.path.insert(0,%r);b=importlib.import_module('binary-spgemm_b200');"
+            "h=b.host();h.readCOO(b'/nonexistent.mtx',None,None,None,None,None)") % str(os.path.dirname(os.path.dirname(__file__)))
+    r = subprocess.run(["python", "-c", code], capture_output=True)
+    assert r.returncode == 1
+
+
+def test_coo2csc_matches_oracle_and_is_stable(bs, oracle):
+    rng = np.random.default_rng(3)
+    for n in (1, 7, 100, 5000):
+        nnz = int(rng.integers(0, 6 * n))
+        r = rng.integers(0, n, nnz).astype(np.uint32)
+        c = rng.integers(0, n, nnz).astype(np.uint32)
+        a = bs.coo2csc(r, c, n)
+        b = oracle.coo2csc(r, c, n)
+        assert (a[0] == b[0]).all() and (a[1] == b[1]).all()
+        # stability: inside each bucket the entries keep input order
+        order = np.argsort(c, kind="stable")
+        assert (a[0] == r[order]).all()
+    a = bs.coo2csc(np.array([1, 2], np.uint32), np.array([2, 1], np.uint32), 2, 1)     # 1-based flag
+    assert a[1].tolist() == [0, 1, 2] and a[0].tolist() == [1, 0]
+
+
+def test_mm_banner_surface(bs, tmp_path):
+    H = bs.host()
+    libc = C.CDLL(None)
+    libc.fopen.restype = C.c_void_p
+    libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+    libc.fclose.argtypes = [C.c_void_p]
+    H.mm_read_banner.argtypes = [C.c_void_p, C.c_char_p]
+    H.mm_read_mtx_crd_size.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    p = tmp_path / "b.mtx"
+    p.write_text("%%MatrixMarket MATRIX Coordinate Integer Symmetric\n% c1\n% c2\n\n 5 6 7\n")
+    f = libc.fopen(str(p).encode(), b"r")
+    code = C.create_string_buffer(4)
+    assert H.mm_read_banner(f, code) == 0 and code.raw == b"MCIS"
+    M, N, nz = C.c_int(), C.c_int(), C.c_int()
+    assert H.mm_read_mtx_crd_size(f, C.byref(M), C.byref(N), C.byref(nz)) == 0
+    assert (M.value, N.value, nz.value) == (5, 6, 7)
+    libc.fclose(f)
+    for text, err in [("%%MatrixMarket vector coordinate real general\n", 15), ("%%Foo matrix coordinate real general\n", 14),
+                      ("%%MatrixMarket matrix coordinate real\n", 12), ("%%MatrixMarket matrix coordinate quaternion general\n", 15)]:
+        p.write_text(text)
+        f = libc.fopen(str(p).encode(), b"r")
+        assert H.mm_read_banner(f, code) == err          # MM_UNSUPPORTED_TYPE / MM_NO_HEADER / MM_PREMATURE_EOF
+        libc.fclose(f)
+
+
+def test_time_stats_like_reference(bs):
+    """mean, lower median = sorted[(times-1)/2], fastest (final/SpGEMM_mpi_omp.c:330-333)."""
+    H = bs.host()
+    for vals in ([3.0, 1.0, 2.0, 4.0], [5.0], [2.0, 9.0, 4.0, 1.0, 7.0]):
+        t = np.array(vals)
+        mean, med, fast = C.c_double(), C.c_double(), C.c_double()
+        H.bs_time_stats(t.ctypes.data, len(t), C.byref(mean), C.byref(med), C.byref(fast))
+        s = sorted(vals)
+        assert abs(mean.value - sum(vals) / len(vals)) < 1e-12 and med.value == s[(len(s) - 1) // 2] and fast.value == s[0]
+
+
+def test_generators(bs, tmp_path):
+    row, col = bs.gen_uniform(5000, 16, 1)
+    assert row[0] == 0 and len(col) == row[-1] and col.max() < 5000
+    lens = np.diff(row)
+    assert lens.max() <= 16 and lens.min() >= 1
+    for i in range(0, 5000, 500):
+        assert (np.diff(col[row[i]:row[i + 1]]) > 0).all()
+    r2, c2 = bs.gen_uniform(5000, 16, 1)
+    assert (r2 == row).all() and (c2 == col).all()
+    r3, c3 = bs.gen_uniform(5000, 16, 2)
+    assert not (len(c3) == len(col) and (c3 == col).all())
+    row, col = bs.gen_banded(100, 32)
+    assert col[row[50]:row[51]].tolist() == list(range(34, 66))
+    row, col = bs.gen_blockdiag(100, 32)
+    assert col[row[40]:row[41]].tolist() == list(range(32, 64)) and col[row[99]:row[100]].tolist() == [96, 97, 98, 99]
+    row, col = bs.gen_rmat(10, 8)
+    assert len(row) == 1025 and col.max() < 1024
+    # .mtx round trip through the transposing reader
+    p = tmp_path / "g.mtx"
+    bs.write_mtx(str(p), row, col)
+    rr, cc, M, N, nnz = bs.readCOO(str(p))
+    assert (rr == row).all() and (cc == col).all()
