@@ -26,7 +26,7 @@ MODE_AUTO, MODE_FUSED, MODE_TWOPHASE = 0, 1, 2
 # every symbol include/bspgemm.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
     "bspgemm_strerror", "bspgemm_last_error", "bspgemm_version",
-    "bspgemm_init", "bspgemm_finalize", "bspgemm_num_gpus",
+    "bspgemm_init", "bspgemm_init_devices", "bspgemm_finalize", "bspgemm_num_gpus",
     "bspgemm_csr", "bspgemm_csr_i64", "bspgemm_csr_into", "bspgemm_csr_slice",
     "bspgemm_intermediate_products",
     "bspgemm_SpGEMM_mpi", "bspgemm_SpGEMM_omp", "bspgemm_SpGEMM_bigslice",
@@ -214,8 +214,12 @@ def write_mtx(path: str, row, col):
 
 
 # ------------------------------------------------------------------------------------------------ host-pointer operators
-def init(ngpus: int = 1):
-    _check(lib().bspgemm_init(ngpus), "bspgemm_init")
+def init(ngpus: int = 1, devices=None):
+    if devices is not None:
+        arr = (C.c_int * len(devices))(*devices)
+        _check(lib().bspgemm_init_devices(arr, len(devices)), "bspgemm_init_devices")
+    else:
+        _check(lib().bspgemm_init(ngpus), "bspgemm_init")
 
 
 def finalize():

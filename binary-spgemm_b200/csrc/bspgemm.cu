@@ -406,27 +406,32 @@ static int nccl_load(Nccl& n) {
 }
 #define NK(call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) return fail(BSPGEMM_ERR_NCCL, "%s failed: %s", #call, g.nccl.GetErrorString ? g.nccl.GetErrorString(r_) : "?"); } while (0)
 
-extern "C" int bspgemm_init(int ngpus) {
-  std::lock_guard<std::mutex> lk(g_mu);
+static int init_devices_locked(const int* devices, int ngpus) {
   if (g.inited) return fail(BSPGEMM_ERR_STATE, "bspgemm_init called twice");
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return fail(BSPGEMM_ERR_NOGPU, "no CUDA device visible; this library has no CPU fallback"); }
   if (ngpus <= 0) ngpus = n;
   if (ngpus > n) return fail(BSPGEMM_ERR_BADARG, "%d GPUs requested, %d visible", ngpus, n);
+  std::vector<int> ids(ngpus);
+  for (int i = 0; i < ngpus; ++i) ids[i] = devices ? devices[i] : i;
   for (int i = 0; i < ngpus; ++i) {
     bspgemm_dev* d = nullptr;
-    int s = dev_create(&d, i);
+    int s = dev_create(&d, ids[i]);
     if (s != BSPGEMM_OK) { for (auto* x : g.devs) dev_destroy(x); g.devs.clear(); return s; }
     g.devs.push_back(d);
   }
   if (ngpus > 1) {
     CKS(nccl_load(g.nccl));
-    std::vector<int> ids(ngpus); for (int i = 0; i < ngpus; ++i) ids[i] = i;
     g.comms.resize(ngpus);
     NK(g.nccl.CommInitAll(g.comms.data(), ngpus, ids.data()));
   }
   g.inited = true;
   return BSPGEMM_OK;
+}
+extern "C" int bspgemm_init(int ngpus) { std::lock_guard<std::mutex> lk(g_mu); return init_devices_locked(nullptr, ngpus); }
+extern "C" int bspgemm_init_devices(const int* devices, int ngpus) {
+  if (!devices || ngpus <= 0) return fail(BSPGEMM_ERR_BADARG, "null device list");
+  std::lock_guard<std::mutex> lk(g_mu); return init_devices_locked(devices, ngpus);
 }
 
 extern "C" int bspgemm_finalize(void) {

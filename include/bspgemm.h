@@ -46,6 +46,8 @@ const char *bspgemm_version(void);
  *      (final/SpGEMM_mpi_omp.c:352-355,:364).  ngpus = number of "tasks"; 0 = all visible GPUs.
  *      With ngpus > 1 an NCCL communicator over the GPUs is created (ncclCommInitAll). ---- */
 int bspgemm_init(int ngpus);
+/* Same with an explicit device list (e.g. one process per GPU under torchrun: {LOCAL_RANK}). */
+int bspgemm_init_devices(const int *devices, int ngpus);
 int bspgemm_finalize(void);
 int bspgemm_num_gpus(void);                    /* 0 before init */
 

@@ -1,0 +1,279 @@
+"""Parity of the CUDA path against the oracle — every call goes through the C ABI (include/bspgemm.h).
+Bit-exact bar: identical Crow, identical ascending Ccol (integer/index work, no tolerance)."""
+import numpy as np
+import pytest
+
+from helpers import assert_csr_contract, crc, gen_case, random_csr
+
+pytestmark = pytest.mark.gpu
+
+
+def _explain(got_col, got_row, want_col, want_row):
+    want_row = np.asarray(want_row, np.int64)
+    got_row = np.asarray(got_row, np.int64)
+    if len(got_row) != len(want_row):
+        return f"Crow length {len(got_row)} != {len(want_row)}"
+    bad = np.nonzero(got_row != want_row)[0]
+    if len(bad):
+        i = int(bad[0])
+        return f"Crow differs first at [{i}]: got {got_row[i]} want {want_row[i]} ({len(bad)} entries differ; nnz got {got_row[-1]} want {want_row[-1]})"
+    bad = np.nonzero(got_col != want_col)[0]
+    if len(bad):
+        p = int(bad[0])
+        r = int(np.searchsorted(want_row, p, side="right") - 1)
+        s, e = int(want_row[r]), int(want_row[r + 1])
+        return (f"Ccol differs first at [{p}] (row {r}, len {e - s}): got {got_col[s:e][:40].tolist()} "
+                f"want {want_col[s:e][:40].tolist()} ({len(bad)} entries differ)")
+    return ""
+
+
+def check(bs, oracle, Acol, Arow, An, Bcol, Brow, Bn, Bm, mode=None):
+    want_col, want_row = oracle.spgemm(Acol, Arow, An, Bcol, Brow, Bm)
+    got_col, got_row = bs.spgemm_csr(Acol, Arow, An, Bcol, Brow, Bn, Bm)
+    msg = _explain(got_col, got_row, want_col, want_row)
+    assert not msg, msg
+    return got_col, got_row
+
+
+def dev_multiply(bs, mode, Acol, Arow, An, Bcol, Brow, Bn, Bm, i64=False):
+    import torch
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(dev)
+    dAc, dAr, dBc, dBr = t(Acol), t(Arow), t(Bcol), t(Brow)
+    dCr = torch.full((An + 1,), -7, dtype=torch.int64 if i64 else torch.int32, device=dev)
+    h = bs.DeviceSpGEMM(0, mode)
+    ptr, nnz = h.multiply(dAc, dAr, An, len(Acol), dBc, dBr, Bn, Bm, len(Bcol), dCr, crow_is_i64=i64)
+    torch.cuda.synchronize()
+    col = bs.device_view(ptr, nnz, 0).cpu().numpy().copy()
+    st = h.stats()
+    h.close()
+    return col, dCr.cpu().numpy(), st
+
+
+def test_fixture_golden(gpu_ctx, fixture_npz):
+    """Config 1: the reference's validity_test.mtx, C = A·A; absolute crc32s from SURVEY.md §4."""
+    f = fixture_npz
+    M = int(f["M"])
+    Ccol, Crow = gpu_ctx.spgemm_csr(f["Acol"], f["Arow"], M, f["Acol"], f["Arow"], M, M)
+    assert crc(Crow) == "62b292d7" and crc(Ccol) == "77f3757b"
+    assert (Crow == f["Crow"]).all() and (Ccol == f["Ccol"]).all()
+    assert gpu_ctx.intermediate_products(f["Acol"], f["Arow"], M, f["Arow"], M) == 12502
+
+
+def test_kats(gpu_ctx, kats):
+    for k in kats:
+        An, Bn = len(k["Arow"]) - 1, len(k["Brow"]) - 1
+        Ccol, Crow = gpu_ctx.spgemm_csr(k["Acol"], k["Arow"], An, k["Bcol"], k["Brow"], Bn, k["Bm"])
+        assert Crow.tolist() == k["Crow"] and Ccol.tolist() == k["Ccol"], k["name"]
+
+
+def test_seeded_cases_golden(gpu_ctx, seeded_cases):
+    """Committed checksums produced by the compiled reference (tests/golden/make_golden.py)."""
+    for c in seeded_cases:
+        row, col = gen_case(gpu_ctx, c)
+        n = c["n"]
+        Ccol, Crow = gpu_ctx.spgemm_csr(col, row, n, col, row, n, n)
+        assert int(Crow[-1]) == c["nnzC"], c["name"]
+        assert crc(Crow) == c["Crow_crc"] and crc(Ccol) == c["Ccol_crc"], c["name"]
+        assert_csr_contract(Ccol, Crow, n)
+
+
+@pytest.mark.parametrize("mode", ["fused", "twophase"])
+def test_device_operator_modes(bs, oracle, seeded_cases, mode):
+    m = bs.MODE_FUSED if mode == "fused" else bs.MODE_TWOPHASE
+    for c in seeded_cases:
+        row, col = gen_case(bs, c)
+        n = c["n"]
+        want_col, want_row = oracle.spgemm(col, row, n, col, row, n)
+        got_col, got_row, st = dev_multiply(bs, m, col, row, n, col, row, n, n)
+        msg = _explain(got_col, got_row, want_col, want_row)
+        assert not msg, f"{c['name']} [{mode}] {msg}"
+        assert st["mode"] == m and st["nnz"] == len(want_col)
+        assert st["ip"] == oracle.intermediate_products(col, row, n, row)
+
+
+def test_random_rectangular_unsorted_duplicates(gpu_ctx, oracle):
+    """A(n x k) · B(k x m), unsorted rows and repeated columns on input (legal for the reference)."""
+    rng = np.random.default_rng(17)
+    for trial in range(40):
+        n, k, m = (int(x) for x in rng.integers(1, 700, 3))
+        Arow, Acol = random_csr(rng, n, k, rng.uniform(0, 8), sort=trial % 2 == 0, dups=trial % 3 == 0)
+        Brow, Bcol = random_csr(rng, k, m, rng.uniform(0, 8), sort=trial % 2 == 1, dups=trial % 3 == 1)
+        check(gpu_ctx, oracle, Acol, Arow, n, Bcol, Brow, k, m)
+
+
+def test_edge_cases(gpu_ctx, oracle):
+    z = np.zeros(0, np.int32)
+    # no rows at all
+    Ccol, Crow = gpu_ctx.spgemm_csr(z, [0], 0, z, [0], 0, 0)
+    assert Crow.tolist() == [0] and len(Ccol) == 0
+    # rows but no entries
+    Ccol, Crow = gpu_ctx.spgemm_csr(z, [0] * 6, 5, z, [0] * 4, 3, 9)
+    assert Crow.tolist() == [0] * 6 and len(Ccol) == 0
+    # A nonzeros that only select empty B rows
+    check(gpu_ctx, oracle, [0, 1, 2, 1], [0, 2, 4], 2, [5], [0, 0, 0, 0, 1], 4, 8)
+    # one dense row (IP = n*n/…): every column present
+    n = 300
+    Arow = np.array([0, n], np.int32)
+    Acol = np.arange(n, dtype=np.int32)
+    Brow = (np.arange(n + 1) * n).astype(np.int32)
+    Bcol = np.tile(np.arange(n, dtype=np.int32), n)
+    Ccol, Crow = check(gpu_ctx, oracle, Acol, Arow, 1, Bcol, Brow, n, n)
+    assert Ccol.tolist() == list(range(n))
+    # single-entry matrices, last column
+    check(gpu_ctx, oracle, [0], [0, 1], 1, [6], [0, 1], 1, 7)
+    # ragged: very long A row pointing at mostly empty B rows
+    k = 5000
+    Arow = np.array([0, k, k, k + 3], np.int32)
+    Acol = np.concatenate([np.arange(k), [1, 2, 3]]).astype(np.int32)
+    blen = np.zeros(k, np.int64); blen[::97] = 3
+    Brow = np.concatenate([[0], np.cumsum(blen)]).astype(np.int32)
+    Bcol = (np.arange(Brow[-1]) * 7 % 1000).astype(np.int32)
+    check(gpu_ctx, oracle, Acol, Arow, 3, Bcol, Brow, k, 1000)
+
+
+def test_every_bin_is_exercised(bs, oracle):
+    """Rows for the warp bin (hash + bitmap), both CTA bins and the global-bitmap bin in one matrix."""
+    rng = np.random.default_rng(23)
+    Bm = 1 << 20
+    k = 4096
+    blen = rng.integers(0, 40, k)
+    blen[:64] = 3000                                # long B rows -> huge IP for rows that select them
+    Brow = np.concatenate([[0], np.cumsum(blen)]).astype(np.int32)
+    Bcol = np.concatenate([np.sort(rng.choice(Bm, l, replace=False)) for l in blen]).astype(np.int32)
+    rows = []
+    rows.append(rng.choice(np.arange(64, k), 10, replace=False))          # S bin, wide span -> ordered table
+    rows.append(np.arange(64, 64 + 300))                                   # IP ~ 6000 -> CTA bin (M2)
+    rows.append(np.arange(64, 64 + 60))                                    # IP ~ 1200 -> CTA bin (M1)
+    rows.append(np.arange(0, 20))                                          # IP = 60000 -> global bitmap
+    rows.append(np.arange(0, 64))                                          # IP = 192000 -> global bitmap
+    rows.append(np.zeros(0, np.int64))
+    for _ in range(200):
+        rows.append(rng.choice(np.arange(64, k), int(rng.integers(0, 12)), replace=False))
+    Arow = np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.int32)
+    Acol = np.concatenate(rows).astype(np.int32)
+    An = len(rows)
+    want_col, want_row = oracle.spgemm(Acol, Arow, An, Bcol, Brow, Bm)
+    for mode in (bs.MODE_FUSED, bs.MODE_TWOPHASE):
+        got_col, got_row, st = dev_multiply(bs, mode, Acol, Arow, An, Bcol, Brow, k, Bm)
+        msg = _explain(got_col, got_row, want_col, want_row)
+        assert not msg, f"mode {mode}: {msg}"
+        assert st["rows_m"] > 0 and st["rows_l"] > 0 and st["rows_s"] > 0
+
+
+def test_narrow_span_rows_use_bitmap_and_match(gpu_ctx, oracle):
+    """Clustered columns (banded / block-diagonal): the [lo,hi] bitmap path inside the warp and CTA bins."""
+    for gen, args in ((gpu_ctx.gen_banded, (3000, 32)), (gpu_ctx.gen_blockdiag, (3000, 32)), (gpu_ctx.gen_banded, (500, 8))):
+        row, col = gen(*args)
+        n = len(row) - 1
+        check(gpu_ctx, oracle, col, row, n, col, row, n, n)
+
+
+def test_i64_row_pointers_and_slices(gpu_ctx, oracle, bs):
+    row, col = bs.gen_uniform(20000, 8, 9)
+    n = 20000
+    want_col, want_row = oracle.spgemm(col, row, n, col, row, n)
+    Ccol, Crow = bs.spgemm_csr(col, row, n, col, row, n, n, i64=True)
+    assert Crow.dtype == np.int64 and (Crow == want_row).all() and (Ccol == want_col).all()
+    # SpGEMM_bigslice replacement: slice-relative row pointers (final/SpGEMM_mpi_omp.c:20,26,54)
+    s, e = 3333, 17001
+    Scol, Srow = bs.spgemm_csr_slice(col, row, n, col, row, n, n, s, e)
+    assert (Srow == want_row[s:e + 1] - want_row[s]).all()
+    assert (Scol == want_col[want_row[s]:want_row[e]]).all()
+    # shifted Arow pointer with absolute offsets, like &Arow[rank*tasksize] (:171)
+    Pcol, Prow = bs.spgemm_csr(col, row[s:], e - s, col, row, n, n)
+    assert (Prow == Srow).all() and (Pcol == Scol).all()
+
+
+def test_caller_allocated_output_and_legacy_signature(gpu_ctx, oracle, bs):
+    row, col = bs.gen_uniform(3000, 8, 4)
+    n = 3000
+    want_col, want_row = oracle.spgemm(col, row, n, col, row, n)
+    buf = np.empty(len(want_col) + 10, np.int32)
+    nnz, Crow = bs.spgemm_csr_into(col, row, n, col, row, n, n, buf)
+    assert nnz == len(want_col) and (buf[:nnz] == want_col).all() and (Crow == want_row).all()
+    with pytest.raises(bs.BSpGEMMError) as ei:
+        bs.spgemm_csr_into(col, row, n, col, row, n, n, np.empty(5, np.int32))
+    assert ei.value.status == bs.ERR_CAPACITY
+    Lcol, Lrow = bs.SpGEMM_mpi(col, row, n, col, row, n, 375)      # reference argument list, no Bn
+    assert (Lrow == want_row).all() and (Lcol == want_col).all()
+
+
+def test_bad_arguments_are_reported_not_computed(gpu_ctx, bs):
+    with pytest.raises(bs.BSpGEMMError) as ei:
+        bs.spgemm_csr([0, 5], [0, 2], 1, [0], [0, 1, 1], 2, 4)      # A column 5 outside Bn=2
+    assert ei.value.status == bs.ERR_BADARG
+    with pytest.raises(bs.BSpGEMMError) as ei:
+        bs.spgemm_csr([0], [0, 1], 1, [9], [0, 1], 1, 4)            # B column 9 outside Bm=4
+    assert ei.value.status == bs.ERR_BADARG
+    # the context stays usable afterwards
+    Ccol, Crow = bs.spgemm_csr([0], [0, 1], 1, [3], [0, 1], 1, 4)
+    assert Ccol.tolist() == [3] and Crow.tolist() == [0, 1]
+
+
+def test_repeated_calls_reuse_the_context(gpu_ctx, oracle, bs):
+    """The driver calls the operator `times` times (final/SpGEMM_mpi_omp.c:318-328)."""
+    row, col = bs.gen_uniform(10000, 8, 2)
+    want_col, want_row = oracle.spgemm(col, row, 10000, col, row, 10000)
+    for _ in range(5):
+        Ccol, Crow = bs.spgemm_csr(col, row, 10000, col, row, 10000, 10000)
+        assert (Crow == want_row).all() and (Ccol == want_col).all()
+    row2, col2 = bs.gen_banded(777, 16)
+    Ccol, Crow = bs.spgemm_csr(col2, row2, 777, col2, row2, 777, 777)
+    w2c, w2r = oracle.spgemm(col2, row2, 777, col2, row2, 777)
+    assert (Crow == w2r).all() and (Ccol == w2c).all()
+
+
+def test_config2_full_size_bit_exact(bs, oracle):
+    """BASELINE config 2: uniform random n=2^20, d=8, C = A·A — full bit-exact compare with the oracle."""
+    n = 1 << 20
+    row, col = bs.gen_uniform(n, 8, 1)
+    want_col, want_row = oracle.spgemm(col, row, n, col, row, n)
+    for mode in (bs.MODE_FUSED, bs.MODE_TWOPHASE):
+        got_col, got_row, st = dev_multiply(bs, mode, col, row, n, col, row, n, n)
+        assert st["ip"] == oracle.intermediate_products(col, row, n, row)
+        msg = _explain(got_col, got_row, want_col, want_row)
+        assert not msg, msg
+
+
+def test_config3_full_size_properties(bs, oracle):
+    """BASELINE config 3 (the bench workload): n=2^22, d=16.  Size-independent properties on the full output
+    (row-pointer monotonicity, strict ascent inside rows, nnz <= IP, fused == two-phase checksums) plus a
+    bit-exact compare of a contiguous row block and of scattered rows against the oracle."""
+    import torch
+    n = 1 << 22
+    row, col = bs.gen_uniform(n, 16, 1)
+    dev = torch.device("cuda:0")
+    dAr, dAc = torch.from_numpy(row).to(dev), torch.from_numpy(col).to(dev)
+    sums = []
+    for mode in (bs.MODE_FUSED, bs.MODE_TWOPHASE):
+        h = bs.DeviceSpGEMM(0, mode)
+        dCr = torch.zeros(n + 1, dtype=torch.int32, device=dev)
+        ptr, nnz = h.multiply(dAc, dAr, n, len(col), dAc, dAr, n, n, len(col), dCr)
+        torch.cuda.synchronize()
+        st = h.stats()
+        C = bs.device_view(ptr, nnz, 0)
+        Cr = dCr.to(torch.int64)
+        assert int(Cr[0]) == 0 and int(Cr[-1]) == nnz and bool((Cr[1:] >= Cr[:-1]).all())
+        assert nnz <= st["ip"] and st["ip"] == int((torch.from_numpy(np.diff(row).astype(np.int64))[torch.from_numpy(col).long()]).sum())
+        # strictly ascending except across row boundaries
+        d = C[1:] > C[:-1]
+        starts = Cr[1:-1]
+        starts = starts[(starts > 0) & (starts < nnz)]
+        d[starts - 1] = True
+        assert bool(d.all())
+        assert int(C.min()) >= 0 and int(C.max()) < n
+        sums.append((nnz, int(C.to(torch.int64).sum()), int((C.to(torch.int64) * (torch.arange(nnz, device=dev) % 1000003)).sum()), int(Cr.sum())))
+        if mode == bs.MODE_FUSED:
+            # bit-exact block + scattered rows vs the oracle
+            r0, r1 = 1234567, 1234567 + 50000
+            wc, wr = oracle.spgemm(col, row[r0:], r1 - r0, col, row, n)
+            gr = Cr[r0:r1 + 1].cpu().numpy()
+            assert (gr - gr[0] == wr).all()
+            assert (C[gr[0]:gr[-1]].cpu().numpy() == wc).all()
+            for r in (0, 1, n // 2, n - 1):
+                wc, wr = oracle.spgemm(col, row[r:], 1, col, row, n)
+                assert (C[int(Cr[r]):int(Cr[r + 1])].cpu().numpy() == wc).all()
+        del C
+        h.close()
+    assert sums[0] == sums[1]
