@@ -88,6 +88,9 @@ struct bspgemm_dev {
   u32 cap_s = 0, cap_m1 = 0, cap_m2 = 0;
   bool have_m = false, have_m2 = false, have_l = false;
   u32 bm_words = 0; int l_grid = 0;
+  bool skip_estimate = false; u32 row_ip_bound = 0, max_len_b = 0;
+  u32 hist_rows[34] = {};
+  int fused_bps[4][16] = {};        // cached occupancy of k_fused<G> per log2(cap)
   int* user_ccol = nullptr; int64_t user_cap = 0;   // caller-provided output (device) or null -> arena
   bspgemm_stats st{};
   // input staging for the host-pointer API
@@ -99,12 +102,31 @@ struct bspgemm_dev {
 static int g_cap_s_max() { const char* e = getenv("BSPGEMM_CAP_S"); int v = e ? atoi(e) : 512; if (v < 32) v = 32; if (v > 1024) v = 1024; int p = 32; while (p < v) p <<= 1; return p; }
 static const u32 CAP_M1 = 2048, CAP_M2 = 16384;
 
-template <int MODE> static int launch_rows_warp(bspgemm_dev* d, int grid, size_t smem, u32 ntiles) {
+// Every kernel that uses dynamic shared memory gets the opt-in maximum once, at context creation.
+static int set_kernel_attributes(int smem_optin) {
+  // dynamic + static shared memory must stay within the opt-in limit
+#define ATTR(k) do { cudaFuncAttributes fa_; CK(cudaFuncGetAttributes(&fa_, k)); \
+    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - (int)fa_.sharedSizeBytes)); } while (0)
+#define ATTR_G(Gv) ATTR((k_rows_warp<Gv, MODE_COUNT>)); ATTR((k_rows_warp<Gv, MODE_FILL>)); ATTR((k_fused<Gv>))
+  ATTR_G(4); ATTR_G(8); ATTR_G(16); ATTR_G(32);
+  ATTR(k_rows_cta<MODE_COUNT>); ATTR(k_rows_cta<MODE_FILL>);
+#undef ATTR_G
+#undef ATTR
+  return BSPGEMM_OK;
+}
+
+static int gidx(int G) { return G == 4 ? 0 : G == 8 ? 1 : G == 16 ? 2 : 3; }
+
+template <int MODE> static int launch_rows_warp(bspgemm_dev* d) {
   const MulArgs& a = d->a;
   int* ccol = d->user_ccol ? d->user_ccol : d->ccol.p;
+  const size_t smem = (size_t)WARPS_S * (tab_words(d->cap_s) + d->cap_s) * sizeof(u32);
+  int bps = 0;
 #define LW(Gv) do { \
-    CK(cudaFuncSetAttribute(k_rows_warp<Gv, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    k_rows_warp<Gv, MODE><<<grid, WARPS_S * 32, smem, d->stream>>>(a.m, d->ip.p, d->cnt.p, d->cap_s, a.dCrow, a.is64, ccol, d->status.p, d->d_sc, ntiles); } while (0)
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_rows_warp<Gv, MODE>, WARPS_S * 32, smem)); \
+    const long long want = ((long long)a.m.An + WARPS_S - 1) / WARPS_S; \
+    const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)d->sm_count * std::max(bps, 1) * 2)); \
+    k_rows_warp<Gv, MODE><<<grid, WARPS_S * 32, smem, d->stream>>>(a.m, d->ip.p, d->cnt.p, d->cap_s, a.dCrow, a.is64, ccol, d->d_sc); } while (0)
   switch (d->G) { case 4: LW(4); break; case 8: LW(8); break; case 16: LW(16); break; default: LW(32); break; }
 #undef LW
   d->launches++;
@@ -112,12 +134,20 @@ template <int MODE> static int launch_rows_warp(bspgemm_dev* d, int grid, size_t
   return BSPGEMM_OK;
 }
 
-template <int MODE> static int occupancy_rows_warp(bspgemm_dev* d, size_t smem, int* blocks_per_sm) {
-#define OW(Gv) do { \
-    CK(cudaFuncSetAttribute(k_rows_warp<Gv, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_rows_warp<Gv, MODE>, WARPS_S * 32, smem)); } while (0)
-  switch (d->G) { case 4: OW(4); break; case 8: OW(8); break; case 16: OW(16); break; default: OW(32); break; }
-#undef OW
+static int launch_fused(bspgemm_dev* d, u32 ntiles, int acc_ip) {
+  const MulArgs& a = d->a;
+  int* ccol = d->user_ccol ? d->user_ccol : d->ccol.p;
+  const size_t smem = (size_t)WARPS_S * fused_warp_words(d->cap_s) * sizeof(u32);
+  int& bps = d->fused_bps[gidx(d->G)][31 - __builtin_clz(d->cap_s)];
+#define LF(Gv) do { \
+    if (bps == 0) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_fused<Gv>, WARPS_S * 32, smem)); \
+    if (bps < 1) return fail(BSPGEMM_ERR_CUDA, "fused kernel does not fit on an SM (smem %zu)", smem); \
+    const int grid = (int)std::min<long long>((long long)ntiles, (long long)d->sm_count * bps); \
+    k_fused<Gv><<<grid, WARPS_S * 32, smem, d->stream>>>(a.m, d->cnt.p, d->cap_s, a.dCrow, a.is64, ccol, d->status.p, d->d_sc, ntiles, acc_ip); } while (0)
+  switch (d->G) { case 4: LF(4); break; case 8: LF(8); break; case 16: LF(16); break; default: LF(32); break; }
+#undef LF
+  d->launches++;
+  CK(cudaGetLastError());
   return BSPGEMM_OK;
 }
 
@@ -127,16 +157,12 @@ template <int MODE> static int launch_bins_ml(bspgemm_dev* d) {
   const size_t An = (size_t)a.m.An;
   u32* l1 = d->lists.p, *l2 = d->lists.p + An, *l3 = d->lists.p + 2 * An;
   if (d->have_m) {
-    const size_t smem = 3ull * CAP_M1 * 4;
-    CK(cudaFuncSetAttribute(k_rows_cta<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(3ull * CAP_M2 * 4)));
-    k_rows_cta<MODE><<<d->sm_count * 4, 256, smem, d->stream>>>(a.m, l1, &d->d_sc->n_m1, d->ip.p, d->cnt.p, CAP_M1, d->G, a.dCrow, a.is64, ccol, d->d_sc);
+    k_rows_cta<MODE><<<d->sm_count * 4, 256, 3ull * CAP_M1 * 4, d->stream>>>(a.m, l1, &d->d_sc->n_m1, d->ip.p, d->cnt.p, CAP_M1, d->G, a.dCrow, a.is64, ccol, d->d_sc);
     d->launches++;
     CK(cudaGetLastError());
   }
   if (d->have_m2) {
-    const size_t smem = 3ull * CAP_M2 * 4;
-    CK(cudaFuncSetAttribute(k_rows_cta<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_rows_cta<MODE><<<d->sm_count, 1024, smem, d->stream>>>(a.m, l2, &d->d_sc->n_m2, d->ip.p, d->cnt.p, CAP_M2, d->G, a.dCrow, a.is64, ccol, d->d_sc);
+    k_rows_cta<MODE><<<d->sm_count, 1024, 3ull * CAP_M2 * 4, d->stream>>>(a.m, l2, &d->d_sc->n_m2, d->ip.p, d->cnt.p, CAP_M2, d->G, a.dCrow, a.is64, ccol, d->d_sc);
     d->launches++;
     CK(cudaGetLastError());
   }
@@ -153,17 +179,10 @@ static int pick_group(int64_t nnz, int64_t rows) {
   return avg <= 4 ? 4 : avg <= 8 ? 8 : avg <= 16 ? 16 : 32;
 }
 
-// phase 1: work estimation (north-star step 1)
-static int mul_launch_estimate(bspgemm_dev* d) {
+static int launch_estimate_kernel(bspgemm_dev* d) {
   const MulArgs& a = d->a;
-  CK(cudaSetDevice(d->device));
   const size_t An = (size_t)a.m.An;
   CKS(d->ip.ensure(An + 1));
-  CKS(d->cnt.ensure(An + 1));
-  d->launches = 0;
-  memset(&d->st, 0, sizeof d->st);
-  CK(cudaEventRecord(d->ev[0], d->stream));
-  CK(cudaMemsetAsync(d->d_sc, 0, sizeof(DevScalars), d->stream));
   const int ga = pick_group(a.Annz, a.m.An);
   const long long threads = (long long)An * ga;
   const int grid = (int)((threads + 255) / 256);
@@ -175,9 +194,44 @@ static int mul_launch_estimate(bspgemm_dev* d) {
   }
   d->launches++;
   CK(cudaGetLastError());
-  CK(cudaEventRecord(d->ev[1], d->stream));
+  return BSPGEMM_OK;
+}
+
+// phase 0: longest rows of A and B (decides whether the work-estimation pass can be skipped)
+static int mul_launch_probe(bspgemm_dev* d) {
+  const MulArgs& a = d->a;
+  CK(cudaSetDevice(d->device));
+  d->launches = 0;
+  memset(&d->st, 0, sizeof d->st);
+  CK(cudaEventRecord(d->ev[0], d->stream));
+  CK(cudaMemsetAsync(d->d_sc, 0, sizeof(DevScalars), d->stream));
+  const int nmax = std::max(a.m.An, a.m.Bn);
+  k_maxlen<<<(nmax + 255) / 256, 256, 0, d->stream>>>(a.m.Arow, a.m.An, a.m.Brow, a.m.Bn, d->d_sc);
+  d->launches++;
+  CK(cudaGetLastError());
   CK(cudaMemcpyAsync(d->h_sc, d->d_sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, d->stream));
   d->phase = 1;
+  return BSPGEMM_OK;
+}
+
+// phase 1: work estimation (north-star step 1) — skipped when maxlen(A)*maxlen(B) bounds every row's IP
+// by the S-bin capacity (then no row can leave the S bin and Σip <= nnzA*maxlen(B)).
+static int mul_launch_estimate(bspgemm_dev* d) {
+  const MulArgs& a = d->a;
+  CK(cudaSetDevice(d->device));
+  CK(cudaStreamSynchronize(d->stream));
+  const DevScalars& h = *d->h_sc;
+  const u64 bound = (u64)h.max_len_a * (u64)h.max_len_b;
+  d->max_len_b = h.max_len_b;
+  d->skip_estimate = d->mode != BSPGEMM_MODE_TWOPHASE && bound <= (u64)g_cap_s_max() && !getenv("BSPGEMM_FORCE_ESTIMATE");
+  d->row_ip_bound = (u32)std::min<u64>(bound, 0xfffffffeull);
+  CK(cudaEventRecord(d->ev[6], d->stream));
+  if (!d->skip_estimate) {
+    CKS(launch_estimate_kernel(d));
+    CK(cudaMemcpyAsync(d->h_sc, d->d_sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, d->stream));
+  }
+  CK(cudaEventRecord(d->ev[1], d->stream));
+  d->phase = 2;
   return BSPGEMM_OK;
 }
 
@@ -185,21 +239,35 @@ static int mul_launch_estimate(bspgemm_dev* d) {
 static int mul_launch_main(bspgemm_dev* d) {
   const MulArgs& a = d->a;
   CK(cudaSetDevice(d->device));
-  CK(cudaStreamSynchronize(d->stream));
-  const DevScalars& h = *d->h_sc;
-  if (h.err & 1u) return fail(BSPGEMM_ERR_BADARG, "a column index of A is outside [0,Bn=%d)", a.m.Bn);
   const size_t An = (size_t)a.m.An;
-  const u64 total_ip = h.total_ip;
-  d->st.ip = (int64_t)total_ip;
+  u64 ip_bound;                      // upper bound of nnz(C) used to size the fused output arena
+  u32 max_ip;
+  if (d->skip_estimate) {
+    max_ip = d->row_ip_bound;
+    ip_bound = (u64)a.Annz * (u64)d->max_len_b;
+  } else {
+    CK(cudaStreamSynchronize(d->stream));
+    const DevScalars& h = *d->h_sc;
+    if (h.err & 1u) return fail(BSPGEMM_ERR_BADARG, "a column index of A is outside [0,Bn=%d)", a.m.Bn);
+    max_ip = h.max_ip;
+    ip_bound = h.total_ip;
+    d->st.ip = (int64_t)h.total_ip;
+    for (int b = 0; b < 34; ++b) {
+      const u64 top = b ? (1ull << (b - 1)) : 0;                       // largest IP in the bin
+      d->hist_rows[b] = h.hist[b];
+      (void)top;
+    }
+  }
   // bin thresholds
   u32 cap = 32; const u32 cap_max = (u32)g_cap_s_max();
-  while (cap < h.max_ip && cap < cap_max) cap <<= 1;
+  while (cap < max_ip && cap < cap_max) cap <<= 1;
   d->cap_s = cap;
   d->G = pick_group(a.Bnnz, a.m.Bn);
-  d->have_m = h.max_ip > cap;
-  d->have_m2 = h.max_ip > CAP_M1;
-  d->have_l = h.max_ip > CAP_M2;
+  d->have_m = max_ip > cap;
+  d->have_m2 = max_ip > CAP_M1;
+  d->have_l = max_ip > CAP_M2;
   d->st.cap_s = (int)cap; d->st.group = d->G;
+  CKS(d->cnt.ensure(An + 1));
   if (d->have_m) {
     CKS(d->lists.ensure(3 * An + 3));
     k_build_lists<<<(int)((An + 255) / 256), 256, 0, d->stream>>>(d->ip.p, a.m.An, cap, CAP_M1, CAP_M2,
@@ -215,35 +283,39 @@ static int mul_launch_main(bspgemm_dev* d) {
   }
   // mode
   int mode = d->mode;
-  const size_t smem = (size_t)WARPS_S * 4 * cap * sizeof(u32);
   if (mode == BSPGEMM_MODE_AUTO) {
-    size_t fr = 0, tot = 0; CK(cudaMemGetInfo(&fr, &tot));
-    const u64 need_bytes = total_ip * 4ull;
-    const u64 have = d->user_ccol ? (u64)d->user_cap * 4ull : (u64)d->ccol.cap * 4ull + (u64)(fr / 2);
-    mode = (need_bytes <= have) ? BSPGEMM_MODE_FUSED : BSPGEMM_MODE_TWOPHASE;
+    const u64 have_now = d->user_ccol ? (u64)d->user_cap : (u64)d->ccol.cap;
+    if (ip_bound <= have_now) mode = BSPGEMM_MODE_FUSED;
+    else if (d->user_ccol) mode = BSPGEMM_MODE_TWOPHASE;
+    else {
+      size_t fr = 0, tot = 0; CK(cudaMemGetInfo(&fr, &tot));
+      mode = (ip_bound * 4ull <= (u64)d->ccol.cap * 4ull + (u64)(fr / 2)) ? BSPGEMM_MODE_FUSED : BSPGEMM_MODE_TWOPHASE;
+    }
   }
-  if (mode == BSPGEMM_MODE_FUSED && d->user_ccol && (u64)d->user_cap < total_ip) mode = BSPGEMM_MODE_TWOPHASE;
+  if (mode == BSPGEMM_MODE_FUSED && d->user_ccol && (u64)d->user_cap < ip_bound) mode = BSPGEMM_MODE_TWOPHASE;
+  if (mode == BSPGEMM_MODE_TWOPHASE && d->skip_estimate) {            // two-phase needs ip[]: run the estimate after all
+    d->skip_estimate = false;
+    CKS(launch_estimate_kernel(d));
+    CK(cudaMemcpyAsync(d->h_sc, d->d_sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, d->stream));
+    CK(cudaEventRecord(d->ev[1], d->stream));
+    return mul_launch_main(d);
+  }
   d->used_mode = mode; d->st.mode = mode;
   CK(cudaEventRecord(d->ev[2], d->stream));
   if (mode == BSPGEMM_MODE_FUSED) {
     if (d->have_m) CKS(launch_bins_ml<MODE_COUNT>(d));
     CK(cudaEventRecord(d->ev[3], d->stream));
-    if (!d->user_ccol) CKS(d->ccol.ensure((size_t)std::max<u64>(total_ip, 1)));
-    const u32 ntiles = (u32)((An + WARPS_S - 1) / WARPS_S);
+    if (!d->user_ccol) CKS(d->ccol.ensure((size_t)std::max<u64>(ip_bound, 1)));
+    const u32 rows_per_tile = WARPS_S * FUSED_R;
+    const u32 ntiles = (u32)((An + rows_per_tile - 1) / rows_per_tile);
     CKS(d->status.ensure(ntiles + 1));
     CK(cudaMemsetAsync(d->status.p, 0, (size_t)ntiles * sizeof(u64), d->stream));
-    int bps = 1; CKS(occupancy_rows_warp<MODE_FUSED>(d, smem, &bps));
-    if (bps < 1) return fail(BSPGEMM_ERR_CUDA, "fused kernel does not fit on an SM (smem %zu)", smem);
-    const int grid = (int)std::min<long long>((long long)ntiles, (long long)d->sm_count * bps);
-    CKS(launch_rows_warp<MODE_FUSED>(d, grid, smem, ntiles));
+    CKS(launch_fused(d, ntiles, d->skip_estimate ? 1 : 0));
     CK(cudaEventRecord(d->ev[4], d->stream));
     if (d->have_m) CKS(launch_bins_ml<MODE_FILL>(d));
     CK(cudaEventRecord(d->ev[5], d->stream));
   } else {
-    int bps = 1; CKS(occupancy_rows_warp<MODE_COUNT>(d, smem, &bps));
-    const long long want = ((long long)An + WARPS_S - 1) / WARPS_S;
-    const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)d->sm_count * std::max(bps, 1) * 4));
-    CKS(launch_rows_warp<MODE_COUNT>(d, grid, smem, 0));
+    CKS(launch_rows_warp<MODE_COUNT>(d));
     if (d->have_m) CKS(launch_bins_ml<MODE_COUNT>(d));
     CK(cudaEventRecord(d->ev[3], d->stream));
     const u32 ntiles = (u32)((An + SCAN_THREADS * SCAN_ITEMS - 1) / (SCAN_THREADS * SCAN_ITEMS));
@@ -254,7 +326,7 @@ static int mul_launch_main(bspgemm_dev* d) {
     CK(cudaGetLastError());
   }
   CK(cudaMemcpyAsync(d->h_sc, d->d_sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, d->stream));
-  d->phase = 2;
+  d->phase = 3;
   return BSPGEMM_OK;
 }
 
@@ -264,40 +336,37 @@ static int mul_launch_fill(bspgemm_dev* d) {
   CK(cudaSetDevice(d->device));
   CK(cudaStreamSynchronize(d->stream));
   const DevScalars& h = *d->h_sc;
+  if (h.err & 1u) return fail(BSPGEMM_ERR_BADARG, "a column index of A is outside [0,Bn=%d)", a.m.Bn);
   if (h.err & 4u) return fail(BSPGEMM_ERR_BADARG, "a column index of B is outside [0,Bm=%d)", a.m.Bm);
   if (h.err & 2u) return fail(BSPGEMM_ERR_OVERFLOW32, "nnz(C) = %llu does not fit 32-bit row pointers", (unsigned long long)h.total_nnz);
   d->st.nnz = (int64_t)h.total_nnz;
-  if (d->used_mode == BSPGEMM_MODE_FUSED) { d->phase = 4; return BSPGEMM_OK; }
+  d->st.ip = (int64_t)h.total_ip;
+  if (d->used_mode == BSPGEMM_MODE_FUSED) { d->phase = 5; return BSPGEMM_OK; }
   if (d->user_ccol) { if ((u64)d->user_cap < h.total_nnz) return fail(BSPGEMM_ERR_CAPACITY, "output capacity %lld < nnz(C) %llu", (long long)d->user_cap, (unsigned long long)h.total_nnz); }
   else CKS(d->ccol.ensure((size_t)std::max<u64>(h.total_nnz, 1)));
-  const size_t An = (size_t)a.m.An;
-  const size_t smem = (size_t)WARPS_S * 4 * d->cap_s * sizeof(u32);
-  int bps = 1; CKS(occupancy_rows_warp<MODE_FILL>(d, smem, &bps));
-  const long long want = ((long long)An + WARPS_S - 1) / WARPS_S;
-  const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)d->sm_count * std::max(bps, 1) * 4));
-  CKS(launch_rows_warp<MODE_FILL>(d, grid, smem, 0));
+  CKS(launch_rows_warp<MODE_FILL>(d));
   CK(cudaEventRecord(d->ev[4], d->stream));
   if (d->have_m) CKS(launch_bins_ml<MODE_FILL>(d));
   CK(cudaEventRecord(d->ev[5], d->stream));
-  d->phase = 3;
+  d->phase = 4;
   return BSPGEMM_OK;
 }
 
 static int mul_finish(bspgemm_dev* d) {
   const MulArgs& a = d->a;
   CK(cudaSetDevice(d->device));
-  if (d->phase == 3) { CK(cudaStreamSynchronize(d->stream)); d->phase = 4; }
+  if (d->phase == 4) { CK(cudaStreamSynchronize(d->stream)); d->phase = 5; }
   CK(cudaGetLastError());
-  const DevScalars& h = *d->h_sc;
   bspgemm_stats& s = d->st;
   s.launches = d->launches;
-  for (int b = 0; b < 33; ++b) {
-    const u32 top = b ? ((b >= 32) ? 0xffffffffu : ((1u << b) - 1)) : 0;   // largest IP in the bin
-    if (top <= d->cap_s) s.rows_s += h.hist[b]; else if (top <= CAP_M2) s.rows_m += h.hist[b]; else s.rows_l += h.hist[b];
+  if (d->skip_estimate) s.rows_s = a.m.An;
+  else for (int b = 0; b < 34; ++b) {
+    const u64 top = b ? (1ull << (b - 1)) : 0;                         // largest IP in the bin
+    if (top <= d->cap_s) s.rows_s += d->hist_rows[b]; else if (top <= CAP_M2) s.rows_m += d->hist_rows[b]; else s.rows_l += d->hist_rows[b];
   }
   float ms = 0;
   cudaEventElapsedTime(&ms, d->ev[0], d->ev[5]); s.ms_total = ms;
-  cudaEventElapsedTime(&ms, d->ev[0], d->ev[1]); s.ms_estimate = ms;
+  cudaEventElapsedTime(&ms, d->ev[6], d->ev[1]); s.ms_estimate = ms;
   cudaEventElapsedTime(&ms, d->ev[2], d->ev[3]); s.ms_symbolic = ms;
   cudaEventElapsedTime(&ms, d->ev[3], d->ev[4]); s.ms_main = ms;
   cudaEventElapsedTime(&ms, d->ev[4], d->ev[5]); s.ms_numeric = ms;
@@ -311,9 +380,10 @@ static int mul_run_to_completion(bspgemm_dev* d) {
     CK(cudaSetDevice(d->device));
     CK(cudaMemsetAsync(d->a.dCrow, 0, d->a.is64 ? 8 : 4, d->stream));
     CK(cudaStreamSynchronize(d->stream));
-    memset(&d->st, 0, sizeof d->st); d->phase = 4;
+    memset(&d->st, 0, sizeof d->st); d->phase = 5;
     return BSPGEMM_OK;
   }
+  CKS(mul_launch_probe(d));
   CKS(mul_launch_estimate(d));
   CKS(mul_launch_main(d));
   CKS(mul_launch_fill(d));
@@ -334,6 +404,7 @@ static int dev_create(bspgemm_dev** out, int device) {
   CK(cudaMalloc((void**)&d->d_sc, sizeof(DevScalars)));
   CK(cudaMallocHost((void**)&d->h_sc, sizeof(DevScalars)));
   for (auto& e : d->ev) CK(cudaEventCreate(&e));
+  CKS(set_kernel_attributes((int)d->smem_optin));
   const char* m = getenv("BSPGEMM_MODE");
   if (m) d->mode = !strcmp(m, "fused") ? BSPGEMM_MODE_FUSED : !strcmp(m, "twophase") ? BSPGEMM_MODE_TWOPHASE : BSPGEMM_MODE_AUTO;
   *out = d;
@@ -517,6 +588,7 @@ static int host_multiply(const int* Acol, const int* Arow, int An, const int* Bc
     for (int q = 0; q < ng; ++q) { bspgemm_dev* d = g.devs[q]; if (d->a.m.An == 0) continue; CKS(fn(d)); }
     return BSPGEMM_OK;
   };
+  CKS(for_all(mul_launch_probe));
   CKS(for_all(mul_launch_estimate));
   CKS(for_all(mul_launch_main));
   CKS(for_all(mul_launch_fill));
@@ -593,7 +665,10 @@ extern "C" int bspgemm_intermediate_products(const int* Acol, const int* Arow, i
   const int* acol_dev = (const int*)((uintptr_t)d->in_acol.p - (uintptr_t)lo * 4u);
   d->a.m = Csr{d->in_arow.p, acol_dev, d->in_brow.p, nullptr, An, Bn, 0};
   d->a.Annz = hi - lo; d->a.Bnnz = 0; d->a.dCrow = nullptr; d->a.is64 = 0;
-  CKS(mul_launch_estimate(d));
+  CK(cudaMemsetAsync(d->d_sc, 0, sizeof(DevScalars), d->stream));
+  d->launches = 0;
+  CKS(launch_estimate_kernel(d));
+  CK(cudaMemcpyAsync(d->h_sc, d->d_sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, d->stream));
   CK(cudaStreamSynchronize(d->stream));
   d->phase = 0;
   if (d->h_sc->err & 1u) return fail(BSPGEMM_ERR_BADARG, "a column index of A is outside [0,Bn=%d)", Bn);

@@ -48,11 +48,12 @@ struct Csr {            // A and B as the reference passes them (final/SpGEMM_mp
 struct DevScalars {     // one per context, in device memory; copied to the host between phases
   u64 total_ip;         // Σ IP_i
   u64 total_nnz;        // nnz(C) (written by the scan / fused kernel)
-  u32 hist[33];         // hist[b] = #rows with IP in [2^(b-1), 2^b), hist[0] = #rows with IP==0
+  u32 hist[34];         // hist[0] = #rows with IP==0, hist[1]: IP==1, hist[b]: IP in (2^(b-2), 2^(b-1)]
   u32 max_ip;
   u32 err;              // bit0: column index of A out of [0,Bn); bit1: 32-bit row pointer overflow; bit2: column of B out of [0,Bm)
   u32 n_m1, n_m2, n_l;  // list lengths (k_build_lists)
   u32 tile_counter;     // dynamic tile ids (fused kernel / scan kernel)
+  u32 max_len_a, max_len_b;   // longest row of A / of B (k_maxlen)
   u32 pad;
 };
 
@@ -115,10 +116,10 @@ __device__ __forceinline__ u64 lookback_exclusive(u64* status, u32 tile, u64 agg
 // (Brow is small and L2-resident).  Also builds the log2 histogram used to pick the bin thresholds.
 template <int G>
 __global__ void __launch_bounds__(256) k_estimate(Csr m, u32* __restrict__ ip, DevScalars* sc) {
-  __shared__ u32 s_hist[33];
+  __shared__ u32 s_hist[34];
   __shared__ u64 s_sum;
   __shared__ u32 s_max;
-  if (threadIdx.x < 33) s_hist[threadIdx.x] = 0;
+  if (threadIdx.x < 34) s_hist[threadIdx.x] = 0;
   if (threadIdx.x == 0) { s_sum = 0; s_max = 0; }
   __syncthreads();
   const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -139,12 +140,12 @@ __global__ void __launch_bounds__(256) k_estimate(Csr m, u32* __restrict__ ip, D
   if (row < m.An && l == 0) {
     const u32 v = sum > 0xfffffffeull ? 0xfffffffeu : (u32)sum;
     ip[row] = v;
-    atomicAdd(&s_hist[v ? 32 - __clz(v) : 0], 1u);
+    atomicAdd(&s_hist[v == 0 ? 0 : (v == 1 ? 1 : 33 - __clz(v - 1))], 1u);
     atomicAdd(&s_sum, sum);
     atomicMax(&s_max, v);
   }
   __syncthreads();
-  if (threadIdx.x < 33 && s_hist[threadIdx.x]) atomicAdd(&sc->hist[threadIdx.x], s_hist[threadIdx.x]);
+  if (threadIdx.x < 34 && s_hist[threadIdx.x]) atomicAdd(&sc->hist[threadIdx.x], s_hist[threadIdx.x]);
   if (threadIdx.x == 0) { if (s_sum) atomicAdd(&sc->total_ip, s_sum); atomicMax(&sc->max_ip, s_max); }
 }
 
@@ -179,21 +180,140 @@ __device__ __forceinline__ u32 ordered_insert(u32* tab, u32 s, u32 x, u32& max_s
 }
 
 // ------------------------------------------------------------------------------------------------ (2a) S bin: one warp per row
-// Shared memory per warp: tab[3*cap] | stage[cap]   (cap = power of two >= largest IP in the bin).
-//   1. gather the IP_i candidate columns into stage[] (G lanes walk one B row; positions from a warp scan)
-//   2. lo/hi by warp reduction; narrow span -> bitmap over [lo,hi], otherwise ordered table with
-//      T = 2*IP home slots + IP overflow slots (a key can be pushed right by at most IP-1 slots)
-//   3. COUNT: number of successful insertions.  FILL/FUSED: compact the table into stage[] (sorted).
-// Returns nnz(C_row); in FILL/FUSED the sorted columns are in stage[0..cnt).
-template <int G, int MODE>
-__device__ __forceinline__ u32 warp_row(const Csr& m, int row, u32 ipr, u32 cap, u32* tab, u32* stage, u32* err) {
+// Shared memory per warp: tab[TABW(cap)] | stage[R*cap]   (cap = power of two >= largest IP in the bin).
+// Table words per warp: the first attempt of the ordered table needs 2*cap+32 slots rounded up to the
+// compaction geometry (128 * odd number of uint4 per lane).  cap=256 -> 640 words.
+__host__ __device__ constexpr u32 tab_words(u32 cap) { return cap < 128u ? 384u : 128u * ((((2u * cap + 32u) + 127u) >> 7) | 1u); }
+
+// Sorted distinct keys of stage[0..ipr) -> stage[0..cnt), executed by one warp.  `tab` is the warp's table.
+//   narrow span (hi-lo < 32*3cap): bitmap over [lo,hi], emitted with popc/ffs (ascending by construction)
+//   wide span: ordered table, T = 2*IP home slots.  First attempt initialises only T+32 slots (+ padding to
+//   the compaction geometry) and treats a probe that runs past them as overflow; the retry uses the full
+//   T+IP slots, which cannot overflow (a key is pushed right past at most IP-1 smaller distinct keys).
+//   Inserts are issued 8 per lane back to back (independent ATOMS.MIN), collisions resolved afterwards.
+//   Compaction: lane l owns 4*S consecutive slots (S odd -> conflict-free LDS.128), one warp scan.
+template <int MODE>
+__device__ __forceinline__ u32 process_row(u32* stage, const u32 ipr, u32* tab, const u32 tabw, const u32 Bm, u32* err) {
   const u32 lane = lane_id();
-  constexpr int SPW = 32 / G;                 // B rows (segments) walked per warp step
+  u32 vmin = EMPTY, vmax = 0;
+#pragma unroll 8
+  for (u32 p = lane; p < ipr; p += 32) { const u32 v = stage[p]; vmin = min(vmin, v); vmax = max(vmax, v); }
+  const u32 lo = __reduce_min_sync(0xffffffffu, vmin);
+  const u32 hi = __reduce_max_sync(0xffffffffu, vmax);
+  if (hi >= Bm) { if (lane == 0) atomicOr(err, 4u); return 0; }     // B column outside [0,Bm): refuse
+  const u32 range = hi - lo + 1;
+  u32 cnt = 0;
+  if (range <= 32u * tabw) {
+    const u32 nW = (range + 31) >> 5;
+    for (u32 w = lane; w < nW; w += 32) tab[w] = 0;
+    __syncwarp();
+    u32 added = 0;
+#pragma unroll 4
+    for (u32 p = lane; p < ipr; p += 32) {
+      const u32 v = stage[p] - lo, bit = 1u << (v & 31);
+      const u32 old = atomicOr(&tab[v >> 5], bit);
+      added += (old & bit) ? 0u : 1u;
+    }
+    __syncwarp();
+    if (MODE == MODE_COUNT) return __reduce_add_sync(0xffffffffu, added);
+    for (u32 w0 = 0; w0 < nW; w0 += 32) {
+      const u32 w = w0 + lane;
+      u32 word = (w < nW) ? tab[w] : 0u;
+      const u32 c = __popc(word);
+      const u32 inc = warp_incl_scan(c);
+      u32 o = cnt + inc - c;
+      const u32 base = lo + (w << 5);
+      while (word) { const u32 b = __ffs(word) - 1; word &= word - 1; stage[o++] = base + b; }
+      cnt += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    __syncwarp();
+    return cnt;
+  }
+
+  uint4* const t4 = reinterpret_cast<uint4*>(tab);
+  u32 added = 0, max_slot = 0;
+  for (int attempt = 0;; ++attempt) {
+    // attempt 0: T = 2*IP home slots + 32 spill slots (overflow detected); attempt 1: T = tabw - IP home
+    // slots + IP spill slots, which cannot overflow.  range > 32*tabw > T  =>  scale < 2^32.
+    const u32 T = attempt ? tabw - ipr : 2 * ipr;
+    const u32 limit = attempt ? tabw : T + 32;      // slots a key may occupy in this attempt
+    const u32 scale = slot_scale(T, range);
+    u32 S = (limit + 127) >> 7; S |= 1u;            // uint4 per lane, odd
+    {
+      const uint4 e = make_uint4(EMPTY, EMPTY, EMPTY, EMPTY);
+      for (u32 q = lane; q < 32 * S; q += 32) t4[q] = e;
+    }
+    __syncwarp();
+    added = 0; max_slot = 0;
+    u32 ovf = 0;
+    for (u32 base = 0; base < ipr; base += 256) {
+      u32 x[8], s[8], old[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const u32 p = base + 32 * u + lane;
+        x[u] = (p < ipr) ? stage[p] : EMPTY;
+        s[u] = __umulhi(x[u] - lo, scale);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) old[u] = (x[u] != EMPTY) ? atomicMin(&tab[s[u]], x[u]) : x[u];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (x[u] == EMPTY) continue;
+        if (old[u] == EMPTY) { ++added; max_slot = max(max_slot, s[u]); continue; }
+        if (old[u] == x[u]) continue;
+        u32 k = max(old[u], x[u]), sl = s[u] + 1;
+        while (true) {                               // the larger key moves right
+          if (sl >= limit) { ovf = 1; break; }
+          const u32 o2 = atomicMin(&tab[sl], k);
+          if (o2 == EMPTY) { ++added; max_slot = max(max_slot, sl); break; }
+          if (o2 == k) break;
+          k = max(o2, k); ++sl;
+        }
+      }
+    }
+    __syncwarp();
+    if (!__any_sync(0xffffffffu, ovf)) break;
+  }
+  if (MODE == MODE_COUNT) return __reduce_add_sync(0xffffffffu, added);
+  max_slot = __reduce_max_sync(0xffffffffu, max_slot);
+  {
+    u32 S = (max_slot + 128) >> 7; S |= 1u;         // covers slots [0, max_slot], within the initialised region
+    const uint4* mine = t4 + lane * S;
+    u32 c = 0;
+    for (u32 q = 0; q < S; ++q) { const uint4 v = mine[q]; c += (v.x != EMPTY) + (v.y != EMPTY) + (v.z != EMPTY) + (v.w != EMPTY); }
+    const u32 inc = warp_incl_scan(c);
+    u32 o = inc - c;
+    cnt = __shfl_sync(0xffffffffu, inc, 31);
+    for (u32 q = 0; q < S; ++q) {
+      const uint4 v = mine[q];
+      if (v.x != EMPTY) stage[o++] = v.x;
+      if (v.y != EMPTY) stage[o++] = v.y;
+      if (v.z != EMPTY) stage[o++] = v.z;
+      if (v.w != EMPTY) stage[o++] = v.w;
+    }
+  }
+  __syncwarp();
+  return cnt;
+}
+
+// Gather the candidate columns of one row into stage[] with the whole warp (any row length, any B row
+// length): batches of 32 A nonzeros, G lanes walk one B row, positions from a warp scan.  Returns the
+// number gathered (= IP of the row); gathers nothing and returns the IP if it exceeds `cap`.
+template <int G>
+__device__ __forceinline__ u32 gather_row(const Csr& m, int row, u32 cap, u32* stage) {
+  const u32 lane = lane_id();
+  constexpr int SPW = 32 / G;
   const u32 sub = lane / G, off0 = lane % G;
   const int a0 = m.Arow[row], a1 = m.Arow[row + 1];
-
-  // ---- 1. gather
-  u32 vmin = EMPTY, vmax = 0, pos_base = 0;
+  u64 total = 0;
+  for (int b0 = a0; b0 < a1; b0 += 32) {            // pass 1: IP of the row
+    const int jj = b0 + (int)lane;
+    u32 len = 0;
+    if (jj < a1) { const int j = m.Acol[jj]; if ((u32)j < (u32)m.Bn) len = (u32)(m.Brow[j + 1] - m.Brow[j]); }
+    total += __reduce_add_sync(0xffffffffu, len);
+  }
+  if (total > cap) return total > 0xfffffffeull ? 0xfffffffeu : (u32)total;
+  u32 pos_base = 0;
   for (int b0 = a0; b0 < a1; b0 += 32) {
     const int jj = b0 + (int)lane;
     u32 bs = 0, len = 0;
@@ -218,149 +338,217 @@ __device__ __forceinline__ u32 warp_row(const Csr& m, int row, u32 ipr, u32 cap,
 #pragma unroll
       for (int u = 0; u < 4; ++u) v[u] = (off0 < slen[u]) ? (u32)__ldg(&m.Bcol[sbs[u] + off0]) : 0u;
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (off0 < slen[u]) { stage[pos_base + spos[u] + off0] = v[u]; vmin = min(vmin, v[u]); vmax = max(vmax, v[u]); }
+      for (int u = 0; u < 4; ++u) if (off0 < slen[u]) stage[pos_base + spos[u] + off0] = v[u];
 #pragma unroll
       for (int u = 0; u < 4; ++u)
-        for (u32 o = off0 + G; o < slen[u]; o += G) {    // B rows longer than G
-          const u32 w = (u32)__ldg(&m.Bcol[sbs[u] + o]);
-          stage[pos_base + spos[u] + o] = w; vmin = min(vmin, w); vmax = max(vmax, w);
-        }
+        for (u32 o = off0 + G; o < slen[u]; o += G) stage[pos_base + spos[u] + o] = (u32)__ldg(&m.Bcol[sbs[u] + o]);   // B rows longer than G
     }
     pos_base += tot;
   }
-  const u32 lo = __reduce_min_sync(0xffffffffu, vmin);
-  const u32 hi = __reduce_max_sync(0xffffffffu, vmax);
-  if (hi >= (u32)m.Bm) { if (lane == 0) atomicOr(err, 4u); return 0; }   // B column outside [0,Bm): refuse
   __syncwarp();
-
-  const u32 range = hi - lo + 1;
-  const u32 nwords = 3 * cap;
-  u32 cnt = 0;
-  if (range <= 32 * nwords) {
-    // ---- 2a. bitmap over [lo,hi]
-    const u32 nW = (range + 31) >> 5;
-    for (u32 w = lane; w < nW; w += 32) tab[w] = 0;
-    __syncwarp();
-    u32 added = 0;
-    for (u32 p = lane; p < ipr; p += 32) {
-      const u32 v = stage[p] - lo, bit = 1u << (v & 31);
-      const u32 old = atomicOr(&tab[v >> 5], bit);
-      added += (old & bit) ? 0u : 1u;
-    }
-    __syncwarp();
-    if (MODE == MODE_COUNT) return __reduce_add_sync(0xffffffffu, added);
-    for (u32 w0 = 0; w0 < nW; w0 += 32) {
-      const u32 w = w0 + lane;
-      u32 word = (w < nW) ? tab[w] : 0u;
-      const u32 c = __popc(word);
-      const u32 inc = warp_incl_scan(c);
-      u32 o = cnt + inc - c;
-      const u32 base = lo + (w << 5);
-      while (word) { const u32 b = __ffs(word) - 1; word &= word - 1; stage[o++] = base + b; }
-      cnt += __shfl_sync(0xffffffffu, inc, 31);
-    }
-  } else {
-    // ---- 2b. ordered table
-    const u32 T = 2 * ipr;                       // ipr <= cap  =>  T + ipr <= 3*cap
-    const u32 limit = T + ipr;
-    const u32 scale = slot_scale(T, range);      // range > 96*cap > T  =>  scale < 2^32
-    {
-      uint4* t4 = reinterpret_cast<uint4*>(tab);
-      const uint4 e = make_uint4(EMPTY, EMPTY, EMPTY, EMPTY);
-      for (u32 q = lane; q < (limit + 3) / 4; q += 32) t4[q] = e;
-    }
-    __syncwarp();
-    u32 added = 0, max_slot = 0;
-    for (u32 p = lane; p < ipr; p += 32) {
-      const u32 x = stage[p];
-      added += ordered_insert(tab, __umulhi(x - lo, scale), x, max_slot);
-    }
-    __syncwarp();
-    if (MODE == MODE_COUNT) return __reduce_add_sync(0xffffffffu, added);
-    max_slot = __reduce_max_sync(0xffffffffu, max_slot);
-    for (u32 s0 = 0; s0 <= max_slot; s0 += 32) {
-      const u32 s = s0 + lane;
-      const u32 v = (s <= max_slot) ? tab[s] : EMPTY;
-      const u32 mk = __ballot_sync(0xffffffffu, v != EMPTY);
-      if (v != EMPTY) stage[cnt + __popc(mk & ((1u << lane) - 1))] = v;
-      cnt += __popc(mk);
-    }
-  }
-  __syncwarp();
-  return cnt;
+  return pos_base;
 }
 
-// Kernel for the S bin.
-//   MODE_COUNT: grid-stride over rows, cnt[row] written for rows with IP <= cap (others untouched).
-//   MODE_FILL : grid-stride over rows, writes Ccol[Crow[row] ...] for rows with IP <= cap.
-//   MODE_FUSED: dynamic tiles of WARPS_S consecutive rows; rows with IP > cap take their count from
-//               cnt[] (written earlier by the M/L symbolic kernels) and are filled later by the M/L
-//               numeric kernels; all row pointers and the S rows' columns are written here.
+// Two-phase kernels of the S bin (grid-stride, one warp per row; rows with IP > cap belong to other bins).
+//   MODE_COUNT: cnt[row] = nnz(C_row).   MODE_FILL: Ccol[Crow[row] ...] = sorted distinct columns.
 template <int G, int MODE>
 __global__ void __launch_bounds__(WARPS_S * 32) k_rows_warp(Csr m, const u32* __restrict__ ip, u32* __restrict__ cnt, u32 cap,
-                                                           void* __restrict__ Crow, int is64, int* __restrict__ Ccol,
-                                                           u64* __restrict__ status, DevScalars* sc, u32 ntiles) {
+                                                           const void* __restrict__ Crow, int is64, int* __restrict__ Ccol,
+                                                           DevScalars* sc) {
   extern __shared__ __align__(16) u32 smem[];
   const u32 warp = threadIdx.x >> 5, lane = lane_id();
-  u32* tab = smem + (size_t)warp * (4 * cap);
-  u32* stage = tab + 3 * cap;
-
-  if (MODE != MODE_FUSED) {
-    const long long nw = (long long)gridDim.x * WARPS_S;
-    for (long long row = (long long)blockIdx.x * WARPS_S + warp; row < m.An; row += nw) {
-      const u32 ipr = ip[row];
-      if (ipr > cap) continue;
-      u32 c = 0;
-      if (ipr) c = warp_row<G, MODE>(m, (int)row, ipr, cap, tab, stage, &sc->err);
-      if (MODE == MODE_COUNT) { if (lane == 0) cnt[row] = c; }
-      else {
-        const u64 base = ld_rowptr(Crow, is64, (size_t)row);
-        for (u32 p = lane; p < c; p += 32) Ccol[base + p] = (int)stage[p];
-      }
-      __syncwarp();
+  u32* tab = smem + (size_t)warp * (tab_words(cap) + cap);
+  u32* stage = tab + tab_words(cap);
+  const long long nw = (long long)gridDim.x * WARPS_S;
+  for (long long row = (long long)blockIdx.x * WARPS_S + warp; row < m.An; row += nw) {
+    const u32 ipr = ip[row];
+    if (ipr > cap) continue;
+    u32 c = 0;
+    if (ipr) { gather_row<G>(m, (int)row, cap, stage); c = process_row<MODE>(stage, ipr, tab, tab_words(cap), (u32)m.Bm, &sc->err); }
+    if (MODE == MODE_COUNT) { if (lane == 0) cnt[row] = c; }
+    else {
+      const u64 base = ld_rowptr(Crow, is64, (size_t)row);
+      for (u32 p = lane; p < c; p += 32) Ccol[base + p] = (int)stage[p];
     }
-    return;
+    __syncwarp();
   }
+}
 
+// ------------------------------------------------------------------------------------------------ fused one-pass kernel
+// Tiles of 32 consecutive rows (8 warps x R=4 rows), handed out by an atomic counter.  Per warp:
+//   1. one coalesced load of the R+1 row pointers, one of the warp's contiguous Acol range (<= EMAX entries),
+//      one gather of the Brow pairs -> (start,len) descriptors in registers: 3 dependent round trips per R rows;
+//   2. positions by a warp scan (row IP falls out of it; rows with IP > cap are "big": their count comes
+//      from cnt_big[], written beforehand by the M/L symbolic kernels, and they are filled afterwards);
+//   3. all R rows' B rows gathered into shared memory in one burst (G lanes per B row, 4 loads in flight per lane);
+//   4. process_row per row; 5. tile counts -> look-back scan -> Crow; 6. sorted rows streamed to their final
+//      position in Ccol.  B is gathered once, C written once, IP is never materialised.
+// Warps whose R rows hold more than EMAX A nonzeros take the generic per-row path (gather_row).
+constexpr int FUSED_R = 4, FUSED_EPL = 4, FUSED_EMAX = 32 * FUSED_EPL;
+__host__ __device__ constexpr u32 fused_warp_words(u32 cap) { return tab_words(cap) + FUSED_R * cap; }
+
+template <int G>
+__global__ void __launch_bounds__(WARPS_S * 32, 4) k_fused(Csr m, const u32* __restrict__ cnt_big, u32 cap,
+                                                       void* __restrict__ Crow, int is64, int* __restrict__ Ccol,
+                                                       u64* __restrict__ status, DevScalars* sc, u32 ntiles, int acc_ip) {
+  constexpr int R = FUSED_R, EPL = FUSED_EPL, EMAX = FUSED_EMAX, SPW = 32 / G;
+  extern __shared__ __align__(16) u32 smem[];
   __shared__ u32 s_tile;
-  __shared__ u32 s_cnt[WARPS_S];
-  __shared__ u64 s_off[WARPS_S];
+  __shared__ u32 s_cnt[WARPS_S * R];
+  __shared__ u64 s_off[WARPS_S * R];
+  const u32 warp = threadIdx.x >> 5, lane = lane_id();
+  const u32 sub = lane / G, off0 = lane % G;
+  u32* tab = smem + (size_t)warp * fused_warp_words(cap);
+  u32* stage = tab + tab_words(cap);
+  u32* pfx = tab;                                   // EMAX+1 exclusive prefix of B-row lengths (dead before the table is used)
+  u64 ip_sum = 0;
+  u32 ip_max = 0;
+
   while (true) {
     if (threadIdx.x == 0) s_tile = atomicAdd(&sc->tile_counter, 1u);
     __syncthreads();
     const u32 tile = s_tile;
     if (tile >= ntiles) break;
-    const long long row = (long long)tile * WARPS_S + warp;
-    u32 c = 0;
-    bool mine = false;
-    if (row < m.An) {
-      const u32 ipr = ip[row];
-      if (ipr > cap) c = cnt[row];
-      else if (ipr) { c = warp_row<G, MODE_FUSED>(m, (int)row, ipr, cap, tab, stage, &sc->err); mine = true; }
+    const long long row0 = (long long)tile * (WARPS_S * R) + (long long)warp * R;
+    const int nrows = (int)max(0ll, min((long long)R, (long long)m.An - row0));
+    u32 c_r[R];
+    bool mine[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) { c_r[r] = 0; mine[r] = false; }
+
+    if (nrows > 0) {
+      const int ar = m.Arow[row0 + min((int)lane, nrows)];
+      int a[R + 1];
+#pragma unroll
+      for (int r = 0; r <= R; ++r) a[r] = __shfl_sync(0xffffffffu, ar, r);
+      const int E = a[R] - a[0];
+      if (E <= EMAX) {
+        // ---- descriptors of all A nonzeros of the warp's rows: entry e -> lane e%32, register e/32
+        u32 bs[EPL], len[EPL], pos[EPL];
+        int j[EPL];
+#pragma unroll
+        for (int k = 0; k < EPL; ++k) { const int e = k * 32 + (int)lane; j[k] = (e < E) ? m.Acol[a[0] + e] : -1; }
+        u32 bad = 0;
+#pragma unroll
+        for (int k = 0; k < EPL; ++k) {
+          bs[k] = 0; len[k] = 0;
+          if (j[k] >= 0) { if ((u32)j[k] < (u32)m.Bn) { bs[k] = (u32)m.Brow[j[k]]; len[k] = (u32)m.Brow[j[k] + 1] - bs[k]; } else bad = 1; }
+        }
+        if (bad) atomicOr(&sc->err, 1u);
+        u32 run = 0;
+#pragma unroll
+        for (int k = 0; k < EPL; ++k) {
+          const u32 inc = warp_incl_scan(len[k]);
+          pos[k] = run + inc - len[k];
+          pfx[k * 32 + lane] = pos[k];
+          run += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) pfx[EMAX] = run;
+        __syncwarp();
+        u32 S[R + 1], ipr[R];
+#pragma unroll
+        for (int r = 0; r <= R; ++r) { const int e = a[r] - a[0]; S[r] = (e >= E) ? run : pfx[e]; }
+        bool big[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) { ipr[r] = S[r + 1] - S[r]; big[r] = ipr[r] > cap; ip_sum += ipr[r]; ip_max = max(ip_max, ipr[r]); }
+        // ---- staging position of every entry: row_local*cap + offset inside the row; big rows are skipped
+#pragma unroll
+        for (int k = 0; k < EPL; ++k) {
+          const int e = k * 32 + (int)lane;
+          int r = 0;
+#pragma unroll
+          for (int q = 1; q < R; ++q) r += (e >= a[q] - a[0]) ? 1 : 0;
+          u32 Sr = S[0]; bool bg = big[0];
+#pragma unroll
+          for (int q = 1; q < R; ++q) if (r == q) { Sr = S[q]; bg = big[q]; }
+          pos[k] = (u32)r * cap + (pos[k] - Sr);
+          if (bg) len[k] = 0;
+        }
+        // ---- one burst: G lanes per B row, 4 independent loads in flight per lane
+#pragma unroll
+        for (int k = 0; k < EPL; ++k) {
+          if (k * 32 >= E) break;
+          const int nseg = min(32, E - k * 32);
+          for (int s = 0; s < nseg; s += 4 * SPW) {
+            u32 sbs[4], slen[4], spos[4], v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int src = s + u * SPW + (int)sub;
+              sbs[u]  = __shfl_sync(0xffffffffu, bs[k],  src & 31);
+              slen[u] = __shfl_sync(0xffffffffu, len[k], src & 31);
+              spos[u] = __shfl_sync(0xffffffffu, pos[k], src & 31);
+              if (src >= 32) slen[u] = 0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = (off0 < slen[u]) ? (u32)__ldg(&m.Bcol[sbs[u] + off0]) : 0u;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (off0 < slen[u]) stage[spos[u] + off0] = v[u];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              for (u32 o = off0 + G; o < slen[u]; o += G) stage[spos[u] + o] = (u32)__ldg(&m.Bcol[sbs[u] + o]);
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          if (r >= nrows) break;
+          if (big[r]) c_r[r] = cnt_big[row0 + r];
+          else if (ipr[r]) { c_r[r] = process_row<MODE_FUSED>(stage + r * cap, ipr[r], tab, tab_words(cap), (u32)m.Bm, &sc->err); mine[r] = true; }
+        }
+      } else {
+        // ---- generic path: row by row
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          if (r >= nrows) break;
+          const u32 ipr = gather_row<G>(m, (int)(row0 + r), cap, stage + r * cap);
+          ip_sum += ipr; ip_max = max(ip_max, ipr);
+          if (ipr > cap) c_r[r] = cnt_big[row0 + r];
+          else if (ipr) { c_r[r] = process_row<MODE_FUSED>(stage + r * cap, ipr, tab, tab_words(cap), (u32)m.Bm, &sc->err); mine[r] = true; }
+        }
+      }
     }
-    if (lane == 0) s_cnt[warp] = c;
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) s_cnt[warp * R + r] = c_r[r];
+    }
     __syncthreads();
-    if (warp == 0) {
-      const u32 v = (lane < WARPS_S) ? s_cnt[lane] : 0u;
+    if (warp == 0) {                                // 32 rows per tile: one per lane
+      const u32 v = s_cnt[lane];
       const u32 inc = warp_incl_scan(v);
       const u64 agg = __shfl_sync(0xffffffffu, inc, 31);
       const u64 excl = lookback_exclusive(status, tile, agg);
-      if (lane < WARPS_S) {
-        s_off[lane] = excl + inc - v;
-        const long long r = (long long)tile * WARPS_S + lane;
-        if (r < m.An) st_rowptr(Crow, is64, (size_t)r + 1, excl + inc, &sc->err);
-      }
+      s_off[lane] = excl + inc - v;
+      const long long rr = (long long)tile * (WARPS_S * R) + lane;
+      if (rr < m.An) st_rowptr(Crow, is64, (size_t)rr + 1, excl + inc, &sc->err);
       if (tile == 0 && lane == 0) st_rowptr(Crow, is64, 0, 0, &sc->err);
       if (tile == ntiles - 1 && lane == 0) sc->total_nnz = excl + agg;
     }
     __syncthreads();
-    if (mine) {
-      const u64 base = s_off[warp];
-      for (u32 p = lane; p < c; p += 32) Ccol[base + p] = (int)stage[p];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (!mine[r]) continue;
+      const u64 base = s_off[warp * R + r];
+      const u32* src = stage + r * cap;
+      for (u32 p = lane; p < c_r[r]; p += 32) Ccol[base + p] = (int)src[p];
     }
     // the next iteration's first __syncthreads orders these reads of s_off/stage before they are rewritten
   }
+  if (acc_ip && lane == 0) {   // per-lane copies are identical: lane 0 publishes
+    if (ip_sum) atomicAdd(&sc->total_ip, ip_sum);
+    atomicMax(&sc->max_ip, ip_max);
+  }
+}
+
+// Longest row of A and of B (two streaming passes over the row pointers).  If maxA*maxB <= the S-bin capacity
+// no row can leave the S bin and Σip <= nnzA*maxB, so the work-estimation pass can be skipped entirely.
+__global__ void __launch_bounds__(256) k_maxlen(const int* __restrict__ Arow, int An, const int* __restrict__ Brow, int Bn, DevScalars* sc) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  u32 la = 0, lb = 0;
+  if (i < An) la = (u32)(Arow[i + 1] - Arow[i]);
+  if (i < Bn) lb = (u32)(Brow[i + 1] - Brow[i]);
+  la = __reduce_max_sync(0xffffffffu, la);
+  lb = __reduce_max_sync(0xffffffffu, lb);
+  if (lane_id() == 0) { if (la) atomicMax(&sc->max_len_a, la); if (lb) atomicMax(&sc->max_len_b, lb); }
 }
 
 // ------------------------------------------------------------------------------------------------ (2b) M bin: one CTA per row

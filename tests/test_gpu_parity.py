@@ -92,6 +92,33 @@ def test_device_operator_modes(bs, oracle, seeded_cases, mode):
         assert st["ip"] == oracle.intermediate_products(col, row, n, row)
 
 
+def test_forced_estimate_path_matches(bs, oracle, seeded_cases, monkeypatch):
+    """Small-degree inputs normally skip the work-estimation pass (maxlen(A)*maxlen(B) bounds every row);
+    force it so that estimate -> fused is covered on the same inputs."""
+    monkeypatch.setenv("BSPGEMM_FORCE_ESTIMATE", "1")
+    for c in seeded_cases[:4]:
+        row, col = gen_case(bs, c)
+        n = c["n"]
+        want_col, want_row = oracle.spgemm(col, row, n, col, row, n)
+        got_col, got_row, st = dev_multiply(bs, bs.MODE_FUSED, col, row, n, col, row, n, n)
+        msg = _explain(got_col, got_row, want_col, want_row)
+        assert not msg, f"{c['name']} {msg}"
+        assert st["ip"] == oracle.intermediate_products(col, row, n, row)
+
+
+def test_small_capacity_forces_cta_bins(bs, oracle, monkeypatch):
+    """BSPGEMM_CAP_S=32: most rows of a d=8 matrix (IP ~ 64) leave the warp bin -> M symbolic + fused + M numeric."""
+    monkeypatch.setenv("BSPGEMM_CAP_S", "32")
+    row, col = bs.gen_uniform(20000, 8, 11)
+    n = 20000
+    want_col, want_row = oracle.spgemm(col, row, n, col, row, n)
+    for mode in (bs.MODE_FUSED, bs.MODE_TWOPHASE):
+        got_col, got_row, st = dev_multiply(bs, mode, col, row, n, col, row, n, n)
+        msg = _explain(got_col, got_row, want_col, want_row)
+        assert not msg, f"mode {mode}: {msg}"
+        assert st["cap_s"] == 32 and st["rows_m"] > 0
+
+
 def test_random_rectangular_unsorted_duplicates(gpu_ctx, oracle):
     """A(n x k) · B(k x m), unsorted rows and repeated columns on input (legal for the reference)."""
     rng = np.random.default_rng(17)
