@@ -107,7 +107,7 @@ static int set_kernel_attributes(int smem_optin) {
   // dynamic + static shared memory must stay within the opt-in limit
 #define ATTR(k) do { cudaFuncAttributes fa_; CK(cudaFuncGetAttributes(&fa_, k)); \
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - (int)fa_.sharedSizeBytes)); } while (0)
-#define ATTR_G(Gv) ATTR((k_rows_warp<Gv, MODE_COUNT>)); ATTR((k_rows_warp<Gv, MODE_FILL>)); ATTR((k_fused<Gv>))
+#define ATTR_G(Gv) ATTR((k_rows_warp<Gv, MODE_COUNT>)); ATTR((k_rows_warp<Gv, MODE_FILL>)); ATTR((k_fused<Gv, true>)); ATTR((k_fused<Gv, false>))
   ATTR_G(4); ATTR_G(8); ATTR_G(16); ATTR_G(32);
   ATTR(k_rows_cta<MODE_COUNT>); ATTR(k_rows_cta<MODE_FILL>);
 #undef ATTR_G
@@ -137,13 +137,18 @@ template <int MODE> static int launch_rows_warp(bspgemm_dev* d) {
 static int launch_fused(bspgemm_dev* d, u32 ntiles, int acc_ip) {
   const MulArgs& a = d->a;
   int* ccol = d->user_ccol ? d->user_ccol : d->ccol.p;
-  const size_t smem = (size_t)WARPS_S * fused_warp_words(d->cap_s) * sizeof(u32);
-  int& bps = d->fused_bps[gidx(d->G)][31 - __builtin_clz(d->cap_s)];
+  // one persistent CTA per SM; every warp is an independent worker with its own shared-memory region
+  const size_t per_warp = (size_t)fused_warp_words(d->cap_s) * sizeof(u32);
+  const size_t avail = d->smem_optin - 64;
+  int warps = (int)std::min<size_t>(32, avail / per_warp);
+  if (warps < 1) return fail(BSPGEMM_ERR_CUDA, "fused kernel does not fit on an SM (%zu bytes per warp)", per_warp);
+  const size_t smem = per_warp * warps;
+  const long long want = ((long long)ntiles + warps - 1) / warps;
+  const int grid = (int)std::max<long long>(1, std::min<long long>(want, d->sm_count));
+  const bool notail = d->max_len_b <= (u32)d->G;
 #define LF(Gv) do { \
-    if (bps == 0) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_fused<Gv>, WARPS_S * 32, smem)); \
-    if (bps < 1) return fail(BSPGEMM_ERR_CUDA, "fused kernel does not fit on an SM (smem %zu)", smem); \
-    const int grid = (int)std::min<long long>((long long)ntiles, (long long)d->sm_count * bps); \
-    k_fused<Gv><<<grid, WARPS_S * 32, smem, d->stream>>>(a.m, d->cnt.p, d->cap_s, a.dCrow, a.is64, ccol, d->status.p, d->d_sc, ntiles, acc_ip); } while (0)
+    if (notail) k_fused<Gv, true><<<grid, warps * 32, smem, d->stream>>>(a.m, d->cnt.p, d->cap_s, a.dCrow, a.is64, ccol, d->status.p, d->d_sc, ntiles, acc_ip); \
+    else        k_fused<Gv, false><<<grid, warps * 32, smem, d->stream>>>(a.m, d->cnt.p, d->cap_s, a.dCrow, a.is64, ccol, d->status.p, d->d_sc, ntiles, acc_ip); } while (0)
   switch (d->G) { case 4: LF(4); break; case 8: LF(8); break; case 16: LF(16); break; default: LF(32); break; }
 #undef LF
   d->launches++;
@@ -306,7 +311,7 @@ static int mul_launch_main(bspgemm_dev* d) {
     if (d->have_m) CKS(launch_bins_ml<MODE_COUNT>(d));
     CK(cudaEventRecord(d->ev[3], d->stream));
     if (!d->user_ccol) CKS(d->ccol.ensure((size_t)std::max<u64>(ip_bound, 1)));
-    const u32 rows_per_tile = WARPS_S * FUSED_R;
+    const u32 rows_per_tile = FUSED_R;
     const u32 ntiles = (u32)((An + rows_per_tile - 1) / rows_per_tile);
     CKS(d->status.ensure(ntiles + 1));
     CK(cudaMemsetAsync(d->status.p, 0, (size_t)ntiles * sizeof(u64), d->stream));

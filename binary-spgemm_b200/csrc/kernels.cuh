@@ -94,9 +94,11 @@ __device__ __forceinline__ u64 lookback_exclusive(u64* status, u32 tile, u64 agg
   while (true) {
     long long my = idx - lane;
     u64 s;
-    do {
+    while (true) {
       s = (my >= 0) ? ld_status(&status[my]) : ST_INC;          // before tile 0: inclusive prefix 0
-    } while (__any_sync(0xffffffffu, (s >> 62) == 0));
+      if (!__any_sync(0xffffffffu, (s >> 62) == 0)) break;
+      __nanosleep(64);
+    }
     u32 inc_mask = __ballot_sync(0xffffffffu, (s >> 62) == 2);
     u32 first = inc_mask ? (u32)(__ffs(inc_mask) - 1) : 32u;     // nearest predecessor with a full prefix
     u64 v = (lane <= first) ? (s & ST_VAL) : 0;
@@ -180,29 +182,41 @@ __device__ __forceinline__ u32 ordered_insert(u32* tab, u32 s, u32 x, u32& max_s
 }
 
 // ------------------------------------------------------------------------------------------------ (2a) S bin: one warp per row
-// Shared memory per warp: tab[TABW(cap)] | stage[R*cap]   (cap = power of two >= largest IP in the bin).
 // Table words per warp: the first attempt of the ordered table needs 2*cap+32 slots rounded up to the
 // compaction geometry (128 * odd number of uint4 per lane).  cap=256 -> 640 words.
 __host__ __device__ constexpr u32 tab_words(u32 cap) { return cap < 128u ? 384u : 128u * ((((2u * cap + 32u) + 127u) >> 7) | 1u); }
 
-// Sorted distinct keys of stage[0..ipr) -> stage[0..cnt), executed by one warp.  `tab` is the warp's table.
-//   narrow span (hi-lo < 32*3cap): bitmap over [lo,hi], emitted with popc/ffs (ascending by construction)
-//   wide span: ordered table, T = 2*IP home slots.  First attempt initialises only T+32 slots (+ padding to
-//   the compaction geometry) and treats a probe that runs past them as overflow; the retry uses the full
-//   T+IP slots, which cannot overflow (a key is pushed right past at most IP-1 smaller distinct keys).
-//   Inserts are issued 8 per lane back to back (independent ATOMS.MIN), collisions resolved afterwards.
-//   Compaction: lane l owns 4*S consecutive slots (S odd -> conflict-free LDS.128), one warp scan.
-template <int MODE>
-__device__ __forceinline__ u32 process_row(u32* stage, const u32 ipr, u32* tab, const u32 tabw, const u32 Bm, u32* err) {
+// What a built table looks like to the emitter.
+struct RowTable {
+  u32 lo;        // smallest candidate column (bitmap origin / slot map origin)
+  u32 span;      // bitmap: number of words; ordered table: largest occupied slot
+  u32 count;     // distinct columns
+  u32 bitmap;    // 1 = bitmap over [lo,hi], 0 = ordered table
+  u32 ok;        // 0 = the optimistic build failed (bad lo/hi hint or spill overflow): rebuild exactly
+};
+
+__device__ __forceinline__ void table_init_empty(u32* tab, u32 words) {      // words: multiple of 128
+  uint4* t4 = reinterpret_cast<uint4*>(tab);
+  const uint4 e = make_uint4(EMPTY, EMPTY, EMPTY, EMPTY);
+  for (u32 q = lane_id(); q < words / 4; q += 32) t4[q] = e;
+}
+
+// Exact build from staged candidates stage[0..ipr): lo/hi by reduction, then
+//   narrow span (hi-lo < 32*tabw): bitmap over [lo,hi];
+//   wide span: ordered table.  Attempt 0: T = 2*IP home slots + 32 spill slots (overflow detected);
+//   attempt 1: T = tabw-IP home slots + IP spill slots, which cannot overflow (a key is pushed right past
+//   at most IP-1 smaller distinct keys).  range > 32*tabw > T  =>  the slot scale fits 32 bits.
+__device__ __noinline__ RowTable build_staged(const u32* stage, const u32 ipr, u32* tab, const u32 tabw, const u32 Bm, u32* err) {
   const u32 lane = lane_id();
+  RowTable t; t.ok = 1; t.count = 0; t.span = 0; t.bitmap = 0;
   u32 vmin = EMPTY, vmax = 0;
-#pragma unroll 8
+#pragma unroll 4
   for (u32 p = lane; p < ipr; p += 32) { const u32 v = stage[p]; vmin = min(vmin, v); vmax = max(vmax, v); }
   const u32 lo = __reduce_min_sync(0xffffffffu, vmin);
   const u32 hi = __reduce_max_sync(0xffffffffu, vmax);
-  if (hi >= Bm) { if (lane == 0) atomicOr(err, 4u); return 0; }     // B column outside [0,Bm): refuse
+  t.lo = lo;
+  if (hi >= Bm) { if (lane == 0) atomicOr(err, 4u); return t; }      // B column outside [0,Bm): refuse (count 0)
   const u32 range = hi - lo + 1;
-  u32 cnt = 0;
   if (range <= 32u * tabw) {
     const u32 nW = (range + 31) >> 5;
     for (u32 w = lane; w < nW; w += 32) tab[w] = 0;
@@ -215,92 +229,75 @@ __device__ __forceinline__ u32 process_row(u32* stage, const u32 ipr, u32* tab, 
       added += (old & bit) ? 0u : 1u;
     }
     __syncwarp();
-    if (MODE == MODE_COUNT) return __reduce_add_sync(0xffffffffu, added);
-    for (u32 w0 = 0; w0 < nW; w0 += 32) {
-      const u32 w = w0 + lane;
-      u32 word = (w < nW) ? tab[w] : 0u;
-      const u32 c = __popc(word);
-      const u32 inc = warp_incl_scan(c);
-      u32 o = cnt + inc - c;
-      const u32 base = lo + (w << 5);
-      while (word) { const u32 b = __ffs(word) - 1; word &= word - 1; stage[o++] = base + b; }
-      cnt += __shfl_sync(0xffffffffu, inc, 31);
-    }
-    __syncwarp();
-    return cnt;
+    t.bitmap = 1; t.span = nW; t.count = __reduce_add_sync(0xffffffffu, added);
+    return t;
   }
-
-  uint4* const t4 = reinterpret_cast<uint4*>(tab);
   u32 added = 0, max_slot = 0;
   for (int attempt = 0;; ++attempt) {
-    // attempt 0: T = 2*IP home slots + 32 spill slots (overflow detected); attempt 1: T = tabw - IP home
-    // slots + IP spill slots, which cannot overflow.  range > 32*tabw > T  =>  scale < 2^32.
     const u32 T = attempt ? tabw - ipr : 2 * ipr;
-    const u32 limit = attempt ? tabw : T + 32;      // slots a key may occupy in this attempt
+    const u32 limit = attempt ? tabw : T + 32;
     const u32 scale = slot_scale(T, range);
-    u32 S = (limit + 127) >> 7; S |= 1u;            // uint4 per lane, odd
-    {
-      const uint4 e = make_uint4(EMPTY, EMPTY, EMPTY, EMPTY);
-      for (u32 q = lane; q < 32 * S; q += 32) t4[q] = e;
-    }
+    table_init_empty(tab, 128u * (((limit + 127) >> 7) | 1u));
     __syncwarp();
     added = 0; max_slot = 0;
     u32 ovf = 0;
-    for (u32 base = 0; base < ipr; base += 256) {
-      u32 x[8], s[8], old[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const u32 p = base + 32 * u + lane;
-        x[u] = (p < ipr) ? stage[p] : EMPTY;
-        s[u] = __umulhi(x[u] - lo, scale);
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) old[u] = (x[u] != EMPTY) ? atomicMin(&tab[s[u]], x[u]) : x[u];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        if (x[u] == EMPTY) continue;
-        if (old[u] == EMPTY) { ++added; max_slot = max(max_slot, s[u]); continue; }
-        if (old[u] == x[u]) continue;
-        u32 k = max(old[u], x[u]), sl = s[u] + 1;
-        while (true) {                               // the larger key moves right
-          if (sl >= limit) { ovf = 1; break; }
-          const u32 o2 = atomicMin(&tab[sl], k);
-          if (o2 == EMPTY) { ++added; max_slot = max(max_slot, sl); break; }
-          if (o2 == k) break;
-          k = max(o2, k); ++sl;
-        }
+    for (u32 p = lane; p < ipr; p += 32) {
+      u32 x = stage[p], s = __umulhi(x - lo, scale);
+      while (true) {
+        if (s >= limit) { ovf = 1; break; }
+        const u32 old = atomicMin(&tab[s], x);
+        if (old == EMPTY) { ++added; max_slot = max(max_slot, s); break; }
+        if (old == x) break;
+        x = max(old, x); ++s;
       }
     }
     __syncwarp();
     if (!__any_sync(0xffffffffu, ovf)) break;
   }
-  if (MODE == MODE_COUNT) return __reduce_add_sync(0xffffffffu, added);
-  max_slot = __reduce_max_sync(0xffffffffu, max_slot);
-  {
-    u32 S = (max_slot + 128) >> 7; S |= 1u;         // covers slots [0, max_slot], within the initialised region
-    const uint4* mine = t4 + lane * S;
+  t.span = __reduce_max_sync(0xffffffffu, max_slot);
+  t.count = __reduce_add_sync(0xffffffffu, added);
+  return t;
+}
+
+// Sorted distinct columns of a built table -> out[0..count).  Bitmap: popc/ffs per word.  Ordered table:
+// lane l owns 4*S consecutive slots (S odd -> conflict-free LDS.128), one warp scan gives its offset.
+__device__ __noinline__ void emit_sorted(const u32* tab, const RowTable t, u32* out) {
+  const u32 lane = lane_id();
+  if (t.bitmap) {
+    u32 cnt = 0;
+    for (u32 w0 = 0; w0 < t.span; w0 += 32) {
+      const u32 w = w0 + lane;
+      u32 word = (w < t.span) ? tab[w] : 0u;
+      const u32 c = __popc(word);
+      const u32 inc = warp_incl_scan(c);
+      u32 o = cnt + inc - c;
+      const u32 base = t.lo + (w << 5);
+      while (word) { const u32 b = __ffs(word) - 1; word &= word - 1; out[o++] = base + b; }
+      cnt += __shfl_sync(0xffffffffu, inc, 31);
+    }
+  } else {
+    const u32 S = ((t.span + 128) >> 7) | 1u;       // covers slots [0, span], inside the initialised region
+    const uint4* mine = reinterpret_cast<const uint4*>(tab) + lane * S;
     u32 c = 0;
     for (u32 q = 0; q < S; ++q) { const uint4 v = mine[q]; c += (v.x != EMPTY) + (v.y != EMPTY) + (v.z != EMPTY) + (v.w != EMPTY); }
     const u32 inc = warp_incl_scan(c);
     u32 o = inc - c;
-    cnt = __shfl_sync(0xffffffffu, inc, 31);
     for (u32 q = 0; q < S; ++q) {
       const uint4 v = mine[q];
-      if (v.x != EMPTY) stage[o++] = v.x;
-      if (v.y != EMPTY) stage[o++] = v.y;
-      if (v.z != EMPTY) stage[o++] = v.z;
-      if (v.w != EMPTY) stage[o++] = v.w;
+      if (v.x != EMPTY) out[o++] = v.x;
+      if (v.y != EMPTY) out[o++] = v.y;
+      if (v.z != EMPTY) out[o++] = v.z;
+      if (v.w != EMPTY) out[o++] = v.w;
     }
   }
   __syncwarp();
-  return cnt;
 }
 
 // Gather the candidate columns of one row into stage[] with the whole warp (any row length, any B row
 // length): batches of 32 A nonzeros, G lanes walk one B row, positions from a warp scan.  Returns the
 // number gathered (= IP of the row); gathers nothing and returns the IP if it exceeds `cap`.
 template <int G>
-__device__ __forceinline__ u32 gather_row(const Csr& m, int row, u32 cap, u32* stage) {
+__device__ __noinline__ u32 gather_row(const Csr& m, int row, u32 cap, u32* stage) {
   const u32 lane = lane_id();
   constexpr int SPW = 32 / G;
   const u32 sub = lane / G, off0 = lane % G;
@@ -325,23 +322,12 @@ __device__ __forceinline__ u32 gather_row(const Csr& m, int row, u32 cap, u32* s
     const u32 excl = incl - len;
     const u32 tot = __shfl_sync(0xffffffffu, incl, 31);
     const int nseg = min(32, a1 - b0);
-    for (int s = 0; s < nseg; s += 4 * SPW) {
-      u32 sbs[4], slen[4], spos[4], v[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int src = s + u * SPW + (int)sub;          // lanes >= nseg carry len 0
-        sbs[u]  = __shfl_sync(0xffffffffu, bs,   src & 31);
-        slen[u] = __shfl_sync(0xffffffffu, len,  src & 31);
-        spos[u] = __shfl_sync(0xffffffffu, excl, src & 31);
-        if (src >= 32) slen[u] = 0;
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = (off0 < slen[u]) ? (u32)__ldg(&m.Bcol[sbs[u] + off0]) : 0u;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) if (off0 < slen[u]) stage[pos_base + spos[u] + off0] = v[u];
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        for (u32 o = off0 + G; o < slen[u]; o += G) stage[pos_base + spos[u] + o] = (u32)__ldg(&m.Bcol[sbs[u] + o]);   // B rows longer than G
+    for (int s = 0; s < nseg; s += SPW) {
+      const int src = s + (int)sub;                     // lanes >= nseg carry len 0
+      const u32 sbs = __shfl_sync(0xffffffffu, bs, src & 31);
+      const u32 slen = __shfl_sync(0xffffffffu, len, src & 31);
+      const u32 spos = __shfl_sync(0xffffffffu, excl, src & 31);
+      for (u32 o = off0; o < slen; o += G) stage[pos_base + spos + o] = (u32)__ldg(&m.Bcol[sbs + o]);
     }
     pos_base += tot;
   }
@@ -364,174 +350,246 @@ __global__ void __launch_bounds__(WARPS_S * 32) k_rows_warp(Csr m, const u32* __
     const u32 ipr = ip[row];
     if (ipr > cap) continue;
     u32 c = 0;
-    if (ipr) { gather_row<G>(m, (int)row, cap, stage); c = process_row<MODE>(stage, ipr, tab, tab_words(cap), (u32)m.Bm, &sc->err); }
-    if (MODE == MODE_COUNT) { if (lane == 0) cnt[row] = c; }
-    else {
-      const u64 base = ld_rowptr(Crow, is64, (size_t)row);
-      for (u32 p = lane; p < c; p += 32) Ccol[base + p] = (int)stage[p];
+    if (ipr) {
+      gather_row<G>(m, (int)row, cap, stage);
+      const RowTable t = build_staged(stage, ipr, tab, tab_words(cap), (u32)m.Bm, &sc->err);
+      c = t.count;
+      if (MODE == MODE_FILL && c) {
+        emit_sorted(tab, t, stage);
+        const u64 base = ld_rowptr(Crow, is64, (size_t)row);
+        for (u32 p = lane; p < c; p += 32) Ccol[base + p] = (int)stage[p];
+      }
     }
+    if (MODE == MODE_COUNT && lane == 0) cnt[row] = c;
     __syncwarp();
   }
 }
 
 // ------------------------------------------------------------------------------------------------ fused one-pass kernel
-// Tiles of 32 consecutive rows (8 warps x R=4 rows), handed out by an atomic counter.  Per warp:
-//   1. one coalesced load of the R+1 row pointers, one of the warp's contiguous Acol range (<= EMAX entries),
-//      one gather of the Brow pairs -> (start,len) descriptors in registers: 3 dependent round trips per R rows;
-//   2. positions by a warp scan (row IP falls out of it; rows with IP > cap are "big": their count comes
-//      from cnt_big[], written beforehand by the M/L symbolic kernels, and they are filled afterwards);
-//   3. all R rows' B rows gathered into shared memory in one burst (G lanes per B row, 4 loads in flight per lane);
-//   4. process_row per row; 5. tile counts -> look-back scan -> Crow; 6. sorted rows streamed to their final
-//      position in Ccol.  B is gathered once, C written once, IP is never materialised.
-// Warps whose R rows hold more than EMAX A nonzeros take the generic per-row path (gather_row).
-constexpr int FUSED_R = 4, FUSED_EPL = 4, FUSED_EMAX = 32 * FUSED_EPL;
-__host__ __device__ constexpr u32 fused_warp_words(u32 cap) { return tab_words(cap) + FUSED_R * cap; }
+// Every WARP is an independent worker: it takes tiles of R=4 consecutive rows from an atomic counter (the
+// next tile id is fetched one tile ahead), and there is no __syncthreads anywhere.  Per tile:
+//   1. one coalesced load of the R+1 row pointers, one of the tile's contiguous Acol range (<= EMAX entries),
+//      one gather of the Brow pairs -> (start,len) descriptors in shared memory, plus the first and last
+//      column of every selected B row: 3 dependent round trips per R rows;
+//   2. a warp scan of the lengths gives every row's IP; rows with IP > cap are "big": their count comes from
+//      cnt_big[] (written beforehand by the M/L symbolic kernels) and they are filled afterwards;
+//   3. per row, OPTIMISTIC build straight from the gather registers: [lo,hi] is taken from the B rows' first
+//      and last entries (exact when B rows are sorted, which nothing guarantees), every gathered column is
+//      validated against it, first probes are issued 4 at a time (independent ATOMS.MIN), colliding keys go
+//      to a shared-memory queue that is drained with all lanes busy.  A failed validation or a spill past
+//      the 32 spare slots falls back to the exact staged build (gather_row + build_staged);
+//   4. emit_sorted into the row's staging area; 5. the tile's 4 counts enter the look-back chain (one status
+//      word per tile, the warp's 32 lanes inspect 32 predecessors at once), Crow is written;
+//   6. the sorted rows are streamed to their final position in Ccol.
+// B is gathered once, C is written once, IP is never materialised.
+constexpr int FUSED_R = 4, FUSED_EPL = 2, FUSED_EMAX = 32 * FUSED_EPL;
+__host__ __device__ constexpr u32 fused_warp_words(u32 cap) { return tab_words(cap) + FUSED_R * cap + 2 * FUSED_EMAX + 4; }
 
-template <int G>
-__global__ void __launch_bounds__(WARPS_S * 32, 4) k_fused(Csr m, const u32* __restrict__ cnt_big, u32 cap,
-                                                       void* __restrict__ Crow, int is64, int* __restrict__ Ccol,
-                                                       u64* __restrict__ status, DevScalars* sc, u32 ntiles, int acc_ip) {
-  constexpr int R = FUSED_R, EPL = FUSED_EPL, EMAX = FUSED_EMAX, SPW = 32 / G;
+template <int G, bool NOTAIL, bool BITMAP>
+__device__ __forceinline__ void direct_insert_loop(const Csr& m, const uint2* desc, int e0, int e1, u32* tab, u32* queue,
+                                                   u32 lo, u32 range, u32 scale, u32& added, u32& max_slot, u32& bad, u32* qn) {
+  constexpr int SPW = 32 / G;
+  const u32 lane = lane_id(), sub = lane / G, off0 = lane % G;
+  for (int q = e0; q < e1; q += 4 * SPW) {
+    u32 bs[4], len[4], v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int seg = q + u * SPW + (int)sub;
+      const uint2 d = (seg < e1) ? desc[seg] : make_uint2(0u, 0u);
+      bs[u] = d.x; len[u] = d.y;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = (off0 < len[u]) ? (u32)__ldg(&m.Bcol[bs[u] + off0]) : EMPTY;
+    if (BITMAP) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const u32 d = v[u] - lo;
+        if (v[u] != EMPTY) { if (d < range) { const u32 bit = 1u << (d & 31); const u32 old = atomicOr(&tab[d >> 5], bit); added += (old & bit) ? 0u : 1u; } else bad = 1; }
+      }
+    } else {
+      u32 s[4], old[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const u32 d = v[u] - lo; if (v[u] != EMPTY && d >= range) { bad = 1; v[u] = EMPTY; } s[u] = __umulhi(d, scale); }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) old[u] = (v[u] != EMPTY) ? atomicMin(&tab[s[u]], v[u]) : v[u];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (v[u] == EMPTY) continue;
+        if (old[u] == EMPTY) { ++added; max_slot = max(max_slot, s[u]); }
+        else if (old[u] != v[u]) queue[atomicAdd(qn, 1u)] = max(old[u], v[u]);   // the larger key re-enters from its home slot
+      }
+    }
+    if (!NOTAIL) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        for (u32 o = off0 + G; o < len[u]; o += G) {      // B rows longer than G
+          const u32 x = (u32)__ldg(&m.Bcol[bs[u] + o]);
+          const u32 d = x - lo;
+          if (d >= range) { bad = 1; continue; }
+          if (BITMAP) { const u32 bit = 1u << (d & 31); const u32 old = atomicOr(&tab[d >> 5], bit); added += (old & bit) ? 0u : 1u; }
+          else queue[atomicAdd(qn, 1u)] = x;
+        }
+    }
+  }
+}
+
+template <int G, bool NOTAIL>
+__global__ void __launch_bounds__(1024, 1) k_fused(Csr m, const u32* __restrict__ cnt_big, u32 cap,
+                                                  void* __restrict__ Crow, int is64, int* __restrict__ Ccol,
+                                                  u64* __restrict__ status, DevScalars* sc, u32 ntiles, int acc_ip) {
+  constexpr int R = FUSED_R, EPL = FUSED_EPL, EMAX = FUSED_EMAX;
   extern __shared__ __align__(16) u32 smem[];
-  __shared__ u32 s_tile;
-  __shared__ u32 s_cnt[WARPS_S * R];
-  __shared__ u64 s_off[WARPS_S * R];
   const u32 warp = threadIdx.x >> 5, lane = lane_id();
-  const u32 sub = lane / G, off0 = lane % G;
+  const u32 tabw = tab_words(cap);
   u32* tab = smem + (size_t)warp * fused_warp_words(cap);
-  u32* stage = tab + tab_words(cap);
-  u32* pfx = tab;                                   // EMAX+1 exclusive prefix of B-row lengths (dead before the table is used)
+  u32* stage = tab + tabw;
+  uint2* desc = reinterpret_cast<uint2*>(stage + R * cap);   // (start, length) of the B row each A nonzero selects
+  u32* pfx = tab;                                             // EMAX+1 prefix of the lengths; dead before the table is used
+  u32* qn = reinterpret_cast<u32*>(desc + EMAX);              // collision-queue length
   u64 ip_sum = 0;
   u32 ip_max = 0;
 
-  while (true) {
-    if (threadIdx.x == 0) s_tile = atomicAdd(&sc->tile_counter, 1u);
-    __syncthreads();
-    const u32 tile = s_tile;
-    if (tile >= ntiles) break;
-    const long long row0 = (long long)tile * (WARPS_S * R) + (long long)warp * R;
-    const int nrows = (int)max(0ll, min((long long)R, (long long)m.An - row0));
-    u32 c_r[R];
-    bool mine[R];
+  u32 tile = 0;
+  if (lane == 0) tile = atomicAdd(&sc->tile_counter, 1u);
+  tile = __shfl_sync(0xffffffffu, tile, 0);
+  while (tile < ntiles) {
+    u32 next = 0;
+    if (lane == 0) next = atomicAdd(&sc->tile_counter, 1u);   // consumed at the end of this tile
+    const long long row0 = (long long)tile * R;
+    const int nrows = (int)min((long long)R, (long long)m.An - row0);
+    const int ar = m.Arow[row0 + min((int)lane, nrows)];
+    int a[R + 1];
 #pragma unroll
-    for (int r = 0; r < R; ++r) { c_r[r] = 0; mine[r] = false; }
-
-    if (nrows > 0) {
-      const int ar = m.Arow[row0 + min((int)lane, nrows)];
-      int a[R + 1];
+    for (int r = 0; r <= R; ++r) a[r] = __shfl_sync(0xffffffffu, ar, r);
+    const int E = a[R] - a[0];
+    u32 S[R + 1], lo_r[R], hi_r[R];
+    const bool fast = E <= EMAX;
+    if (fast) {
+      u32 run = 0;
+      u32 first[EPL], last[EPL], len[EPL];
 #pragma unroll
-      for (int r = 0; r <= R; ++r) a[r] = __shfl_sync(0xffffffffu, ar, r);
-      const int E = a[R] - a[0];
-      if (E <= EMAX) {
-        // ---- descriptors of all A nonzeros of the warp's rows: entry e -> lane e%32, register e/32
-        u32 bs[EPL], len[EPL], pos[EPL];
-        int j[EPL];
-#pragma unroll
-        for (int k = 0; k < EPL; ++k) { const int e = k * 32 + (int)lane; j[k] = (e < E) ? m.Acol[a[0] + e] : -1; }
-        u32 bad = 0;
-#pragma unroll
-        for (int k = 0; k < EPL; ++k) {
-          bs[k] = 0; len[k] = 0;
-          if (j[k] >= 0) { if ((u32)j[k] < (u32)m.Bn) { bs[k] = (u32)m.Brow[j[k]]; len[k] = (u32)m.Brow[j[k] + 1] - bs[k]; } else bad = 1; }
+      for (int k = 0; k < EPL; ++k) {
+        const int e = k * 32 + (int)lane;
+        u32 bs = 0; len[k] = 0;
+        if (e < E) {
+          const int j = m.Acol[a[0] + e];
+          if ((u32)j < (u32)m.Bn) { bs = (u32)m.Brow[j]; len[k] = (u32)m.Brow[j + 1] - bs; } else atomicOr(&sc->err, 1u);
         }
-        if (bad) atomicOr(&sc->err, 1u);
-        u32 run = 0;
+        desc[e] = make_uint2(bs, len[k]);
+        first[k] = len[k] ? (u32)__ldg(&m.Bcol[bs]) : EMPTY;
+        last[k]  = len[k] ? (u32)__ldg(&m.Bcol[bs + len[k] - 1]) : 0u;
+      }
 #pragma unroll
-        for (int k = 0; k < EPL; ++k) {
-          const u32 inc = warp_incl_scan(len[k]);
-          pos[k] = run + inc - len[k];
-          pfx[k * 32 + lane] = pos[k];
-          run += __shfl_sync(0xffffffffu, inc, 31);
-        }
-        if (lane == 0) pfx[EMAX] = run;
-        __syncwarp();
-        u32 S[R + 1], ipr[R];
+      for (int k = 0; k < EPL; ++k) {
+        const u32 inc = warp_incl_scan(len[k]);
+        pfx[k * 32 + lane] = run + inc - len[k];
+        run += __shfl_sync(0xffffffffu, inc, 31);
+      }
+      __syncwarp();
 #pragma unroll
-        for (int r = 0; r <= R; ++r) { const int e = a[r] - a[0]; S[r] = (e >= E) ? run : pfx[e]; }
-        bool big[R];
+      for (int r = 0; r <= R; ++r) { const int e = a[r] - a[0]; S[r] = (e >= E) ? run : pfx[e]; }
 #pragma unroll
-        for (int r = 0; r < R; ++r) { ipr[r] = S[r + 1] - S[r]; big[r] = ipr[r] > cap; ip_sum += ipr[r]; ip_max = max(ip_max, ipr[r]); }
-        // ---- staging position of every entry: row_local*cap + offset inside the row; big rows are skipped
+      for (int r = 0; r < R; ++r) {          // [lo,hi] hint of every row from its B rows' end points
+        u32 mn = EMPTY, mx = 0;
 #pragma unroll
         for (int k = 0; k < EPL; ++k) {
           const int e = k * 32 + (int)lane;
-          int r = 0;
-#pragma unroll
-          for (int q = 1; q < R; ++q) r += (e >= a[q] - a[0]) ? 1 : 0;
-          u32 Sr = S[0]; bool bg = big[0];
-#pragma unroll
-          for (int q = 1; q < R; ++q) if (r == q) { Sr = S[q]; bg = big[q]; }
-          pos[k] = (u32)r * cap + (pos[k] - Sr);
-          if (bg) len[k] = 0;
+          if (len[k] && e >= a[r] - a[0] && e < a[r + 1] - a[0]) { mn = min(mn, min(first[k], last[k])); mx = max(mx, max(first[k], last[k])); }
         }
-        // ---- one burst: G lanes per B row, 4 independent loads in flight per lane
+        lo_r[r] = __reduce_min_sync(0xffffffffu, mn);
+        hi_r[r] = __reduce_max_sync(0xffffffffu, mx);
+      }
+      __syncwarp();
+    }
+    u32 c_mine = 0;                               // lane r keeps the count of row r
+    u32 mine_mask = 0;
+#pragma unroll 1
+    for (int r = 0; r < nrows; ++r) {
+      u32 c = 0;
+      u32* out = stage + r * cap;
+      bool need_exact = !fast;
+      u32 ipr = 0;
+      RowTable t; t.ok = 0; t.count = 0; t.bitmap = 0; t.lo = 0; t.span = 0;
+      if (fast) {
+        u32 Sa = S[0], Sb = S[1], lo = lo_r[0], hi = hi_r[0]; int e0 = a[0], e1 = a[1];
 #pragma unroll
-        for (int k = 0; k < EPL; ++k) {
-          if (k * 32 >= E) break;
-          const int nseg = min(32, E - k * 32);
-          for (int s = 0; s < nseg; s += 4 * SPW) {
-            u32 sbs[4], slen[4], spos[4], v[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int src = s + u * SPW + (int)sub;
-              sbs[u]  = __shfl_sync(0xffffffffu, bs[k],  src & 31);
-              slen[u] = __shfl_sync(0xffffffffu, len[k], src & 31);
-              spos[u] = __shfl_sync(0xffffffffu, pos[k], src & 31);
-              if (src >= 32) slen[u] = 0;
+        for (int q = 1; q < R; ++q) if (r == q) { Sa = S[q]; Sb = S[q + 1]; lo = lo_r[q]; hi = hi_r[q]; e0 = a[q]; e1 = a[q + 1]; }
+        e0 -= a[0]; e1 -= a[0];
+        ipr = Sb - Sa;
+        if (ipr > cap || ipr == 0) need_exact = false;
+        else if (hi >= (u32)m.Bm || hi < lo) need_exact = true;
+        else {
+          const u32 range = hi - lo + 1;
+          u32 added = 0, max_slot = 0, bad = 0;
+          t.lo = lo;
+          if (range <= 32u * tabw) {
+            const u32 nW = (range + 31) >> 5;
+            for (u32 w = lane; w < nW; w += 32) tab[w] = 0;
+            __syncwarp();
+            direct_insert_loop<G, NOTAIL, true>(m, desc, e0, e1, tab, out, lo, range, 0u, added, max_slot, bad, qn);
+            __syncwarp();
+            t.bitmap = 1; t.span = nW;
+          } else {
+            const u32 T = 2 * ipr, limit = T + 32;
+            const u32 scale = slot_scale(T, range);
+            table_init_empty(tab, 128u * (((limit + 127) >> 7) | 1u));
+            __syncwarp();
+            if (lane == 0) *qn = 0;
+            __syncwarp();
+            direct_insert_loop<G, NOTAIL, false>(m, desc, e0, e1, tab, out, lo, range, scale, added, max_slot, bad, qn);
+            __syncwarp();
+            const u32 nq = *qn;
+            for (u32 i = lane; i < nq; i += 32) {                   // drain the collision queue, all lanes busy
+              u32 x = out[i], s = __umulhi(x - lo, scale);
+              while (true) {
+                if (s >= limit) { bad = 1; break; }
+                const u32 old = atomicMin(&tab[s], x);
+                if (old == EMPTY) { ++added; max_slot = max(max_slot, s); break; }
+                if (old == x) break;
+                x = max(old, x); ++s;
+              }
             }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = (off0 < slen[u]) ? (u32)__ldg(&m.Bcol[sbs[u] + off0]) : 0u;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) if (off0 < slen[u]) stage[spos[u] + off0] = v[u];
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              for (u32 o = off0 + G; o < slen[u]; o += G) stage[spos[u] + o] = (u32)__ldg(&m.Bcol[sbs[u] + o]);
+            __syncwarp();
+            t.span = __reduce_max_sync(0xffffffffu, max_slot);
           }
-        }
-        __syncwarp();
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          if (r >= nrows) break;
-          if (big[r]) c_r[r] = cnt_big[row0 + r];
-          else if (ipr[r]) { c_r[r] = process_row<MODE_FUSED>(stage + r * cap, ipr[r], tab, tab_words(cap), (u32)m.Bm, &sc->err); mine[r] = true; }
-        }
-      } else {
-        // ---- generic path: row by row
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          if (r >= nrows) break;
-          const u32 ipr = gather_row<G>(m, (int)(row0 + r), cap, stage + r * cap);
-          ip_sum += ipr; ip_max = max(ip_max, ipr);
-          if (ipr > cap) c_r[r] = cnt_big[row0 + r];
-          else if (ipr) { c_r[r] = process_row<MODE_FUSED>(stage + r * cap, ipr, tab, tab_words(cap), (u32)m.Bm, &sc->err); mine[r] = true; }
+          t.count = __reduce_add_sync(0xffffffffu, added);
+          t.ok = __any_sync(0xffffffffu, bad) ? 0u : 1u;
+          need_exact = !t.ok;
         }
       }
+      if (need_exact) {
+        ipr = gather_row<G>(m, (int)(row0 + r), cap, out);
+        t.ok = 0;
+        if (ipr <= cap && ipr > 0) { t = build_staged(out, ipr, tab, tabw, (u32)m.Bm, &sc->err); }
+      }
+      if (!fast) { ip_sum += ipr; ip_max = max(ip_max, ipr); }
+      if (ipr > cap) c = cnt_big[row0 + r];
+      else if (ipr > 0 && t.ok && t.count) { emit_sorted(tab, t, out); c = t.count; mine_mask |= 1u << r; }
+      if ((int)lane == r) c_mine = c;
     }
-    if (lane == 0) {
+    if (fast) { ip_sum += S[R] - S[0]; 
 #pragma unroll
-      for (int r = 0; r < R; ++r) s_cnt[warp * R + r] = c_r[r];
-    }
-    __syncthreads();
-    if (warp == 0) {                                // 32 rows per tile: one per lane
-      const u32 v = s_cnt[lane];
-      const u32 inc = warp_incl_scan(v);
-      const u64 agg = __shfl_sync(0xffffffffu, inc, 31);
-      const u64 excl = lookback_exclusive(status, tile, agg);
-      s_off[lane] = excl + inc - v;
-      const long long rr = (long long)tile * (WARPS_S * R) + lane;
-      if (rr < m.An) st_rowptr(Crow, is64, (size_t)rr + 1, excl + inc, &sc->err);
-      if (tile == 0 && lane == 0) st_rowptr(Crow, is64, 0, 0, &sc->err);
-      if (tile == ntiles - 1 && lane == 0) sc->total_nnz = excl + agg;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      if (!mine[r]) continue;
-      const u64 base = s_off[warp * R + r];
+      for (int r = 0; r < R; ++r) ip_max = max(ip_max, S[r + 1] - S[r]); }
+
+    // ---- chain the tile into the scan, write row pointers, stream the rows out
+    const u32 v = ((int)lane < nrows) ? c_mine : 0u;
+    const u32 inc = warp_incl_scan(v);
+    const u64 agg = __shfl_sync(0xffffffffu, inc, 31);
+    const u64 excl = lookback_exclusive(status, tile, agg);
+    if ((int)lane < nrows) st_rowptr(Crow, is64, (size_t)(row0 + lane) + 1, excl + inc, &sc->err);
+    if (tile == 0 && lane == 0) st_rowptr(Crow, is64, 0, 0, &sc->err);
+    if (tile == ntiles - 1 && lane == 0) sc->total_nnz = excl + agg;
+#pragma unroll 1
+    for (int r = 0; r < nrows; ++r) {
+      const u32 cr = __shfl_sync(0xffffffffu, v, r);
+      const u32 off = __shfl_sync(0xffffffffu, inc - v, r);
+      if (!((mine_mask >> r) & 1u)) continue;
       const u32* src = stage + r * cap;
-      for (u32 p = lane; p < c_r[r]; p += 32) Ccol[base + p] = (int)src[p];
+      int* dst = Ccol + (excl + off);
+      for (u32 p = lane; p < cr; p += 32) dst[p] = (int)src[p];
     }
-    // the next iteration's first __syncthreads orders these reads of s_off/stage before they are rewritten
+    __syncwarp();
+    tile = __shfl_sync(0xffffffffu, next, 0);
   }
   if (acc_ip && lane == 0) {   // per-lane copies are identical: lane 0 publishes
     if (ip_sum) atomicAdd(&sc->total_ip, ip_sum);
