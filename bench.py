@@ -335,8 +335,15 @@ def main():
         traffic = json.loads((ROOT / "profiles" / "traffic.json").read_text()).get(args.workload)
     except Exception:
         pass
+    last = stats[-1]
+    if last["mode"] != bs.MODE_FUSED:
+        kernel_name = "scan + k_rows_warp<G,MODE_FILL>"
+    elif last.get("variant", 0) == 1:
+        kernel_name = "k_fused_ell<W=%d,R=%d>" % (last["group"], last["rows_per_tile"])
+    else:
+        kernel_name = "k_fused<G=%d>" % last["group"]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
-                "traffic": traffic, "kernel": "k_rows_warp<G,MODE_FUSED>" if stats[-1]["mode"] == bs.MODE_FUSED else "scan + k_rows_warp<G,MODE_FILL>",
+                "traffic": traffic, "kernel": kernel_name,
                 "kernel_ms": main_ms, "algorithmic_bytes_per_launch": alg_bytes_launch, "peak_source": peak_src,
                 "frac_of_8TBs": achieved / 8000.0, "step_frac": (alg_bytes_launch / (ms_per_step * 1e-3) / 1e9) / peak_gbs}
 
@@ -403,7 +410,8 @@ def main():
             "config": config, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(launches_total), "clocks": clocks,
             "out_nnz_per_s": nnz_total / (t_max / args.steps), "ip": int(ip_total), "nnz_c": int(nnz_total), "nnz_a": nnzA,
-            "pipeline": {"mode": "fused" if stats[-1]["mode"] == bs.MODE_FUSED else "twophase", "cap_s": stats[-1]["cap_s"],
+            "pipeline": {"mode": "fused" if stats[-1]["mode"] == bs.MODE_FUSED else "twophase", "variant": "ell" if stats[-1].get("variant", 0) == 1 else "csr",
+                         "rows_per_tile": stats[-1].get("rows_per_tile", 0), "cap_s": stats[-1]["cap_s"],
                          "group": stats[-1]["group"], "rows_s": stats[-1]["rows_s"], "rows_m": stats[-1]["rows_m"], "rows_l": stats[-1]["rows_l"],
                          "ms_estimate": est_ms, "ms_main": main_ms,
                          "ms_symbolic": float(np.mean([s["ms_symbolic"] for s in stats])),

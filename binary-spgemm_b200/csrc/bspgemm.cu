@@ -7,6 +7,7 @@
 // No CPU fallback anywhere: every failure is returned as a status code.
 #include "../../include/bspgemm.h"
 #include "kernels.cuh"
+#include "fused_ell.cuh"
 
 #include <nccl.h>      // types only; the library itself is dlopen'ed so libbspgemm.so loads without it
 #include <dlfcn.h>
@@ -75,7 +76,7 @@ struct bspgemm_dev {
   cudaStream_t own_stream = nullptr, stream = nullptr;
   int mode = BSPGEMM_MODE_AUTO;
   // workspace
-  DevBuf<u32> ip, cnt, lists, bitmaps;
+  DevBuf<u32> ip, cnt, lists, bitmaps, bell;
   DevBuf<u64> status;
   DevBuf<int> ccol;                 // output arena
   DevScalars* d_sc = nullptr;
@@ -89,6 +90,7 @@ struct bspgemm_dev {
   bool have_m = false, have_m2 = false, have_l = false;
   u32 bm_words = 0; int l_grid = 0;
   bool skip_estimate = false; u32 row_ip_bound = 0, max_len_b = 0;
+  bool use_ell = false; int ell_W = 0, ell_R = 0, ell_warps = 0; u32 ell_TW = 0;   // ELL fast path plan (fused_ell.cuh)
   u32 hist_rows[34] = {};
   int fused_bps[4][16] = {};        // cached occupancy of k_fused<G> per log2(cap)
   int* user_ccol = nullptr; int64_t user_cap = 0;   // caller-provided output (device) or null -> arena
@@ -110,6 +112,9 @@ static int set_kernel_attributes(int smem_optin) {
 #define ATTR_G(Gv) ATTR((k_rows_warp<Gv, MODE_COUNT>)); ATTR((k_rows_warp<Gv, MODE_FILL>)); ATTR((k_fused<Gv, true>)); ATTR((k_fused<Gv, false>))
   ATTR_G(4); ATTR_G(8); ATTR_G(16); ATTR_G(32);
   ATTR(k_rows_cta<MODE_COUNT>); ATTR(k_rows_cta<MODE_FILL>);
+#define ATTR_E(Wv) ATTR((k_fused_ell<Wv, 1>)); ATTR((k_fused_ell<Wv, 2>)); ATTR((k_fused_ell<Wv, 4>)); ATTR((k_fused_ell<Wv, 8>))
+  ATTR_E(4); ATTR_E(8); ATTR_E(16); ATTR_E(32);
+#undef ATTR_E
 #undef ATTR_G
 #undef ATTR
   return BSPGEMM_OK;
@@ -179,6 +184,69 @@ template <int MODE> static int launch_bins_ml(bspgemm_dev* d) {
   return BSPGEMM_OK;
 }
 
+// ---- ELL fast path (fused_ell.cuh): usable when every B row has <= 32 columns and padding B to W columns
+// per row at most doubles it; every output row then has IP <= max_len(A)*W and fits one warp's table.
+static bool ell_plan(bspgemm_dev* d) {
+  const MulArgs& a = d->a;
+  const DevScalars& h = *d->h_sc;
+  d->use_ell = false;
+  // explicit bin / estimate overrides select the CSR-gather kernels
+  if (d->mode == BSPGEMM_MODE_TWOPHASE || getenv("BSPGEMM_NO_ELL") || getenv("BSPGEMM_CAP_S") || getenv("BSPGEMM_FORCE_ESTIMATE")) return false;
+  if (h.max_len_a == 0 || h.max_len_b == 0 || h.max_len_b > 32) return false;
+  int W = 4; while (W < (int)h.max_len_b) W <<= 1;
+  if ((u64)a.m.Bn * (u64)W > 2ull * (u64)a.Bnnz + 4096ull) return false;        // padding waste
+  const u32 TW = ell_table_limit(h.max_len_a, (u32)W);
+  if (TW > 8192u || (u64)a.m.Bm < 4ull * TW) return false;
+  const size_t avail = d->smem_optin - 64;
+  const int64_t avgA = std::max<int64_t>(1, (a.Annz + a.m.An - 1) / std::max(a.m.An, 1));
+  int R = 8;
+  while (R > 1 && ((int64_t)R * avgA > 64 || (size_t)ell_warp_words(R, TW) * 4 * 8 > avail)) R >>= 1;
+  const size_t per_warp = (size_t)ell_warp_words(R, TW) * 4;
+  const int warps = (int)std::min<size_t>(ELL_MAX_WARPS, avail / per_warp);
+  if (warps < 4) return false;
+  d->use_ell = true; d->ell_W = W; d->ell_R = R; d->ell_TW = TW; d->ell_warps = warps;
+  return true;
+}
+
+static int launch_ell(bspgemm_dev* d) {
+  const MulArgs& a = d->a;
+  int* ccol = d->user_ccol ? d->user_ccol : d->ccol.p;
+  const int W = d->ell_W, R = d->ell_R;
+  CKS(d->bell.ensure((size_t)a.m.Bn * W + 4));
+  {
+    const long long threads = (long long)a.m.Bn * (W / 4);
+    const int grid = (int)((threads + 255) / 256);
+    switch (W) {
+      case 4:  k_build_ell<4><<<grid, 256, 0, d->stream>>>(a.m.Brow, a.m.Bcol, a.m.Bn, (u32)a.m.Bm, d->bell.p, d->d_sc); break;
+      case 8:  k_build_ell<8><<<grid, 256, 0, d->stream>>>(a.m.Brow, a.m.Bcol, a.m.Bn, (u32)a.m.Bm, d->bell.p, d->d_sc); break;
+      case 16: k_build_ell<16><<<grid, 256, 0, d->stream>>>(a.m.Brow, a.m.Bcol, a.m.Bn, (u32)a.m.Bm, d->bell.p, d->d_sc); break;
+      default: k_build_ell<32><<<grid, 256, 0, d->stream>>>(a.m.Brow, a.m.Bcol, a.m.Bn, (u32)a.m.Bm, d->bell.p, d->d_sc); break;
+    }
+    d->launches++;
+    CK(cudaGetLastError());
+  }
+  const u32 ntiles = (u32)(((size_t)a.m.An + R - 1) / R);
+  CKS(d->status.ensure(ntiles + 1));
+  CK(cudaMemsetAsync(d->status.p, 0, (size_t)ntiles * sizeof(u64), d->stream));
+  CK(cudaEventRecord(d->ev[3], d->stream));
+  EllArgs p;
+  p.Arow = a.m.Arow; p.Acol = a.m.Acol; p.Bell = d->bell.p; p.An = a.m.An; p.Bn = a.m.Bn;
+  p.unit = (u32)(((u64)(2 * W) << 32) / (u64)a.m.Bm);
+  p.TW = d->ell_TW; p.Bm = (u32)a.m.Bm; p.Crow = a.dCrow; p.is64 = a.is64; p.Ccol = ccol; p.status = d->status.p; p.sc = d->d_sc; p.ntiles = ntiles;
+  const int warps = d->ell_warps;
+  const size_t smem = (size_t)ell_warp_words(R, d->ell_TW) * 4 * warps;
+  const long long want = ((long long)ntiles + warps - 1) / warps;
+  const int grid = (int)std::max<long long>(1, std::min<long long>(want, d->sm_count));
+#define LE(Wv, Rv) k_fused_ell<Wv, Rv><<<grid, warps * 32, smem, d->stream>>>(p)
+#define LER(Wv) do { switch (R) { case 1: LE(Wv, 1); break; case 2: LE(Wv, 2); break; case 4: LE(Wv, 4); break; default: LE(Wv, 8); break; } } while (0)
+  switch (W) { case 4: LER(4); break; case 8: LER(8); break; case 16: LER(16); break; default: LER(32); break; }
+#undef LER
+#undef LE
+  d->launches++;
+  CK(cudaGetLastError());
+  return BSPGEMM_OK;
+}
+
 static int pick_group(int64_t nnz, int64_t rows) {
   const int64_t avg = rows > 0 ? (nnz + rows - 1) / rows : 1;
   return avg <= 4 ? 4 : avg <= 8 ? 8 : avg <= 16 ? 16 : 32;
@@ -229,6 +297,7 @@ static int mul_launch_estimate(bspgemm_dev* d) {
   const u64 bound = (u64)h.max_len_a * (u64)h.max_len_b;
   d->max_len_b = h.max_len_b;
   d->skip_estimate = d->mode != BSPGEMM_MODE_TWOPHASE && bound <= (u64)g_cap_s_max() && !getenv("BSPGEMM_FORCE_ESTIMATE");
+  if (ell_plan(d)) d->skip_estimate = true;
   d->row_ip_bound = (u32)std::min<u64>(bound, 0xfffffffeull);
   CK(cudaEventRecord(d->ev[6], d->stream));
   if (!d->skip_estimate) {
@@ -247,6 +316,33 @@ static int mul_launch_main(bspgemm_dev* d) {
   const size_t An = (size_t)a.m.An;
   u64 ip_bound;                      // upper bound of nnz(C) used to size the fused output arena
   u32 max_ip;
+  if (d->use_ell) {
+    // ELL fast path: every row fits one warp's table by construction; needs the Σip bound to fit the output arena
+    ip_bound = (u64)a.Annz * (u64)d->max_len_b;
+    bool fits;
+    if (d->user_ccol) fits = (u64)d->user_cap >= ip_bound;
+    else if (ip_bound <= (u64)d->ccol.cap) fits = true;
+    else { size_t fr = 0, tot = 0; CK(cudaMemGetInfo(&fr, &tot)); fits = ip_bound * 4ull + (u64)a.m.Bn * d->ell_W * 4ull <= (u64)d->ccol.cap * 4ull + (u64)(fr / 2); }
+    if (fits) {
+      d->cap_s = d->ell_TW; d->G = d->ell_W; d->have_m = d->have_m2 = d->have_l = false;
+      d->st.cap_s = (int)d->ell_TW; d->st.group = d->ell_W; d->st.variant = 1; d->st.rows_per_tile = d->ell_R;
+      d->used_mode = BSPGEMM_MODE_FUSED; d->st.mode = BSPGEMM_MODE_FUSED;
+      CK(cudaEventRecord(d->ev[2], d->stream));
+      if (!d->user_ccol) CKS(d->ccol.ensure((size_t)std::max<u64>(ip_bound, 1)));
+      CKS(launch_ell(d));                               // records ev[3] between the ELL build and the fused kernel
+      CK(cudaEventRecord(d->ev[4], d->stream));
+      CK(cudaEventRecord(d->ev[5], d->stream));
+      CK(cudaMemcpyAsync(d->h_sc, d->d_sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, d->stream));
+      d->phase = 3;
+      return BSPGEMM_OK;
+    }
+    d->use_ell = false;
+    d->skip_estimate = false;
+    CKS(launch_estimate_kernel(d));
+    CK(cudaMemcpyAsync(d->h_sc, d->d_sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, d->stream));
+    CK(cudaEventRecord(d->ev[1], d->stream));
+    return mul_launch_main(d);
+  }
   if (d->skip_estimate) {
     max_ip = d->row_ip_bound;
     ip_bound = (u64)a.Annz * (u64)d->max_len_b;

@@ -304,3 +304,63 @@ def test_config3_full_size_properties(bs, oracle):
         del C
         h.close()
     assert sums[0] == sums[1]
+
+
+def test_ell_fast_path_variants(bs, oracle):
+    """The ELL fast path (fused_ell.cuh): every ELL width W and tile height R, ragged / empty / long A rows,
+    unsorted B rows, repeated A columns (every key duplicated), 64-bit row pointers."""
+    rng = np.random.default_rng(31)
+    cases = []
+    for d in (3, 6, 12, 24):                       # W = 4, 8, 16, 32
+        row, col = bs.gen_uniform(30000, d, 5 + d)
+        cases.append((f"uniform d={d}", col, row, 30000, col, row, 30000, 30000))
+    # A: ragged row lengths 0..40 (tiles with E > 64, empty rows), B: d<=16 unsorted
+    n, m = 20000, 1 << 18
+    Arow, Acol = random_csr(rng, n, n, 14.0, sort=False, dups=True)
+    Brow, Bcol = random_csr(rng, n, m, 10.0, sort=True, dups=False)
+    Bcol = Bcol.copy()
+    for i in range(n):                               # shuffle inside every B row: nothing guarantees sorted input rows
+        rng.shuffle(Bcol[Brow[i]:Brow[i + 1]])
+    cases.append(("ragged A, unsorted B", Acol, Arow, n, Bcol, Brow, n, m))
+    # short A rows (R = 8), tiny B rows
+    Arow, Acol = random_csr(rng, n, n, 2.0, sort=True, dups=False)
+    Brow, Bcol = random_csr(rng, n, m, 2.5, sort=True, dups=False)
+    cases.append(("short rows", Acol, Arow, n, Bcol, Brow, n, m))
+    seen = set()
+    for name, Acol, Arow, An, Bcol, Brow, Bn, Bm in cases:
+        want_col, want_row = oracle.spgemm(Acol, Arow, An, Bcol, Brow, Bm)
+        for i64 in (False, True):
+            got_col, got_row, st = dev_multiply(bs, bs.MODE_AUTO, Acol, Arow, An, Bcol, Brow, Bn, Bm, i64=i64)
+            msg = _explain(got_col, got_row, want_col, want_row)
+            assert not msg, f"{name} i64={i64}: {msg}"
+            assert st["ip"] == oracle.intermediate_products(Acol, Arow, An, Brow), name
+            if np.diff(Brow).max() <= 32:
+                assert st["variant"] == 1, f"{name}: expected the ELL fast path, stats {st}"
+                seen.add((st["group"], st["rows_per_tile"]))
+    assert {w for w, _ in seen} == {4, 8, 16, 32}, seen
+    assert len({r for _, r in seen}) >= 3, seen
+
+
+def test_ell_clustered_columns_spill_and_rebuild(bs, oracle):
+    """Columns of B concentrated in a sliver of a wide [0,Bm): the global monotone slot map sends every key of a
+    row to a handful of slots, chains run past the 32 spare slots, the row is rebuilt by the exact path."""
+    rng = np.random.default_rng(37)
+    n, Bm = 6000, 1 << 22
+    Arow, Acol = random_csr(rng, n, n, 12.0, sort=True, dups=False)
+    blen = rng.integers(8, 17, n)
+    Brow = np.concatenate([[0], np.cumsum(blen)]).astype(np.int32)
+    base = 3_000_000
+    Bcol = np.concatenate([np.sort(rng.choice(300, l, replace=False)) + base for l in blen]).astype(np.int32)
+    want_col, want_row = oracle.spgemm(Acol, Arow, n, Bcol, Brow, Bm)
+    got_col, got_row, st = dev_multiply(bs, bs.MODE_AUTO, Acol, Arow, n, Bcol, Brow, n, Bm)
+    msg = _explain(got_col, got_row, want_col, want_row)
+    assert not msg, msg
+    assert st["variant"] == 1
+    # two clusters far apart + a few uniform columns: partial spills
+    Bcol2 = Bcol.copy()
+    sel = rng.random(len(Bcol2)) < 0.3
+    Bcol2[sel] = rng.integers(0, Bm, int(sel.sum()))
+    want_col, want_row = oracle.spgemm(Acol, Arow, n, Bcol2, Brow, Bm)
+    got_col, got_row, st = dev_multiply(bs, bs.MODE_AUTO, Acol, Arow, n, Bcol2, Brow, n, Bm)
+    msg = _explain(got_col, got_row, want_col, want_row)
+    assert not msg, msg
