@@ -194,7 +194,7 @@ static bool ell_plan(bspgemm_dev* d) {
   if (d->mode == BSPGEMM_MODE_TWOPHASE || getenv("BSPGEMM_NO_ELL") || getenv("BSPGEMM_CAP_S") || getenv("BSPGEMM_FORCE_ESTIMATE")) return false;
   if (h.max_len_a == 0 || h.max_len_b == 0 || h.max_len_b > 32) return false;
   int W = 4; while (W < (int)h.max_len_b) W <<= 1;
-  if ((u64)a.m.Bn * (u64)W > 2ull * (u64)a.Bnnz + 4096ull) return false;        // padding waste
+  if ((u64)a.m.Bn * (u64)W > 4ull * (u64)a.Bnnz + 4096ull && !getenv("BSPGEMM_FORCE_ELL")) return false;   // padding waste
   const u32 TW = ell_table_limit(h.max_len_a, (u32)W);
   if (TW > 8192u || (u64)a.m.Bm < 4ull * TW) return false;
   const size_t avail = d->smem_optin - 64;
@@ -226,13 +226,17 @@ static int launch_ell(bspgemm_dev* d) {
     CK(cudaGetLastError());
   }
   const u32 ntiles = (u32)(((size_t)a.m.An + R - 1) / R);
-  CKS(d->status.ensure(ntiles + 1));
-  CK(cudaMemsetAsync(d->status.p, 0, (size_t)ntiles * sizeof(u64), d->stream));
+  const size_t chain_words = tile_chain_words64(ntiles), ngroups = ((size_t)ntiles + 31) / 32;
+  CKS(d->status.ensure(chain_words));
+  CK(cudaMemsetAsync(d->status.p, 0, chain_words * sizeof(u64), d->stream));
   CK(cudaEventRecord(d->ev[3], d->stream));
-  EllArgs p;
+  EllArgs p{};
+  p.chain.gsum = d->status.p; p.chain.ginc = d->status.p + ngroups; p.chain.s0 = reinterpret_cast<u32*>(d->status.p + 2 * ngroups);
   p.Arow = a.m.Arow; p.Acol = a.m.Acol; p.Bell = d->bell.p; p.An = a.m.An; p.Bn = a.m.Bn;
   p.unit = (u32)(((u64)(2 * W) << 32) / (u64)a.m.Bm);
-  p.TW = d->ell_TW; p.Bm = (u32)a.m.Bm; p.Crow = a.dCrow; p.is64 = a.is64; p.Ccol = ccol; p.status = d->status.p; p.sc = d->d_sc; p.ntiles = ntiles;
+  p.TW = d->ell_TW; p.Bm = (u32)a.m.Bm; p.Crow = a.dCrow; p.is64 = a.is64; p.Ccol = ccol; p.sc = d->d_sc;
+  p.ntiles = ntiles;
+  p.debug_nochain = getenv("BSPGEMM_DEBUG_NOCHAIN") ? (u32)(R * d->h_sc->max_len_a * W) : 0u;   // WRONG RESULTS: timing experiments only
   const int warps = d->ell_warps;
   const size_t smem = (size_t)ell_warp_words(R, d->ell_TW) * 4 * warps;
   const long long want = ((long long)ntiles + warps - 1) / warps;
