@@ -197,7 +197,7 @@ static bool ell_plan(bspgemm_dev* d) {
   if ((u64)a.m.Bn * (u64)W > 4ull * (u64)a.Bnnz + 4096ull && !getenv("BSPGEMM_FORCE_ELL")) return false;   // padding waste
   const u32 TW = ell_table_limit(h.max_len_a, (u32)W);
   if (TW > 8192u || (u64)a.m.Bm < 4ull * TW) return false;
-  const size_t avail = d->smem_optin - 64;
+  const size_t avail = d->smem_optin - 64 - ELL_CTA_WORDS * 4;
   const int64_t avgA = std::max<int64_t>(1, (a.Annz + a.m.An - 1) / std::max(a.m.An, 1));
   int R = 8;
   while (R > 1 && ((int64_t)R * avgA > 64 || (size_t)ell_warp_words(R, TW) * 4 * 8 > avail)) R >>= 1;
@@ -226,21 +226,22 @@ static int launch_ell(bspgemm_dev* d) {
     CK(cudaGetLastError());
   }
   const u32 ntiles = (u32)(((size_t)a.m.An + R - 1) / R);
-  const size_t chain_words = tile_chain_words64(ntiles), ngroups = ((size_t)ntiles + 31) / 32;
-  CKS(d->status.ensure(chain_words));
-  CK(cudaMemsetAsync(d->status.p, 0, chain_words * sizeof(u64), d->stream));
+  const int warps = d->ell_warps;
+  const size_t smem = ((size_t)ell_warp_words(R, d->ell_TW) * warps + ELL_CTA_WORDS) * 4;
+  const long long want = ((long long)ntiles + warps - 1) / warps;
+  const int grid = (int)std::max<long long>(1, std::min<long long>(want, d->sm_count));
+  const size_t niter = ((size_t)ntiles + (size_t)grid * warps - 1) / ((size_t)grid * warps);
+  const size_t nblocks = niter * grid + 1;
+  CKS(d->status.ensure(nblocks));
+  CK(cudaMemsetAsync(d->status.p, 0, nblocks * sizeof(u64), d->stream));
   CK(cudaEventRecord(d->ev[3], d->stream));
   EllArgs p{};
-  p.chain.gsum = d->status.p; p.chain.ginc = d->status.p + ngroups; p.chain.s0 = reinterpret_cast<u32*>(d->status.p + 2 * ngroups);
+  p.blk_status = d->status.p;
   p.Arow = a.m.Arow; p.Acol = a.m.Acol; p.Bell = d->bell.p; p.An = a.m.An; p.Bn = a.m.Bn;
   p.unit = (u32)(((u64)(2 * W) << 32) / (u64)a.m.Bm);
   p.TW = d->ell_TW; p.Bm = (u32)a.m.Bm; p.Crow = a.dCrow; p.is64 = a.is64; p.Ccol = ccol; p.sc = d->d_sc;
   p.ntiles = ntiles;
   p.debug_nochain = getenv("BSPGEMM_DEBUG_NOCHAIN") ? (u32)(R * d->h_sc->max_len_a * W) : 0u;   // WRONG RESULTS: timing experiments only
-  const int warps = d->ell_warps;
-  const size_t smem = (size_t)ell_warp_words(R, d->ell_TW) * 4 * warps;
-  const long long want = ((long long)ntiles + warps - 1) / warps;
-  const int grid = (int)std::max<long long>(1, std::min<long long>(want, d->sm_count));
 #define LE(Wv, Rv) k_fused_ell<Wv, Rv><<<grid, warps * 32, smem, d->stream>>>(p)
 #define LER(Wv) do { switch (R) { case 1: LE(Wv, 1); break; case 2: LE(Wv, 2); break; case 4: LE(Wv, 4); break; default: LE(Wv, 8); break; } } while (0)
   switch (W) { case 4: LER(4); break; case 8: LER(8); break; case 16: LER(16); break; default: LER(32); break; }

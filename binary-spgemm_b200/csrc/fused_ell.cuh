@@ -20,15 +20,13 @@
 // by ballot/popc (conflict-free LDS/STS) and copied to its final position in Ccol with coalesced stores.
 // B is gathered once, C is written once.
 //
-// The scan that gives every tile its output offset is a TWO-LEVEL decoupled look-back (TileChain): with one
-// warp per tile ~350 tiles finish per microsecond at the target rate, far more than a flat 32-wide look-back
-// window can retire per L2 round trip (profiles/r01_v4_ell_flat_lookback.txt: 76 % of all issued instructions
-// were the spin).  Tiles post their aggregate (a) as a flagged word and (b) into a packed per-group counter
-// (32 tiles per group, one 64-bit atomicAdd: count<<40 | sum); a tile's offset = exclusive prefix of its group
-// (walked 32 groups = 1024 tiles per round trip, published once per group) + the flagged words before it in
-// its own group.  The aggregate is known right after the inserts (it is the number of atomicMin that found an
-// EMPTY slot) and is posted BEFORE the compaction, so predecessors have normally published by the time a
-// warp needs its offset.
+// The scan that gives every tile its output offset must not stall the row work: with the rows written in order,
+// any warp-granular look-back makes every warp wait for the slowest earlier tile (profiles/r01_v4_ell_*: 25 ms with
+// the chain, 6.4 ms without).  So (a) the aggregate of a tile is posted right after its inserts (it is the number
+// of atomicMin that found an EMPTY slot), (b) the tile is compacted into a staging buffer and COMMITTED ONE TILE
+// LATER, after the next tile's inserts — by then its offset is known without waiting — and (c) the chain is
+// hierarchical (CtaChain below): shared memory inside a CTA, a flat decoupled look-back over CTA blocks in global
+// memory.
 #pragma once
 #include "kernels.cuh"
 
@@ -37,12 +35,6 @@ namespace bsk {
 constexpr int ELL_MAX_WARPS = 24;        // warps per CTA (one persistent CTA per SM)
 constexpr int ELL_QCAP = 192;            // loser-queue entries per warp (a batch adds at most 128)
 
-struct TileChain {        // all zero before the launch
-  u32* s0;                // [ntiles]  bit31 = posted, low bits = aggregate of the tile
-  u64* gsum;              // [ngroups] (tiles posted << 40) | sum of their aggregates
-  u64* ginc;              // [ngroups] bit63 = known, low bits = exclusive prefix of the group
-};
-__host__ __device__ inline size_t tile_chain_words64(size_t ntiles) { const size_t ng = (ntiles + 31) / 32; return 2 * ng + (ntiles + 1) / 2 + 2; }
 
 struct EllArgs {
   const int* __restrict__ Arow;   // An+1 absolute offsets
@@ -54,14 +46,16 @@ struct EllArgs {
   u32 Bm;
   void* Crow; int is64;
   int* Ccol;
-  TileChain chain;
+  u64* blk_status;                // [iterations * gridDim.x] block-level look-back words, zero before the launch
   DevScalars* sc;
   u32 ntiles;
   u32 debug_nochain;              // timing experiments only (BSPGEMM_DEBUG_NOCHAIN): skip the scan, rows land at upper-bound offsets
 };
 
 __host__ __device__ constexpr u32 ell_table_limit(u32 lenA, u32 W) { return ((2u * W * lenA + 31u) & ~31u) + 32u; }
-__host__ __device__ constexpr u32 ell_warp_words(u32 R, u32 TW) { return R * TW + 2u * ELL_QCAP + 2u * 8u; }
+__host__ __device__ constexpr u32 ell_stage_words(u32 R, u32 TW) { return R * ((TW - 32u) / 2u); }      // a tile's compacted rows (R * maxlenA * W)
+__host__ __device__ constexpr u32 ell_warp_words(u32 R, u32 TW) { return R * TW + ell_stage_words(R, TW) + 2u * ELL_QCAP + 2u * 8u; }
+constexpr u32 ELL_CTA_WORDS = 160;       // CtaChain, after the warp regions
 
 // ---- B (CSR) -> ELL.  LPR = W/4 lanes write one row as uint4 each; also validates B's columns.
 template <int W>
@@ -87,57 +81,93 @@ __global__ void __launch_bounds__(256) k_build_ell(const int* __restrict__ Brow,
   if (bad) atomicOr(&sc->err, 4u);
 }
 
-// ------------------------------------------------------------------------------------------------ two-level tile chain
-__device__ __forceinline__ u32 ld_relaxed_u32(const u32* p) {
-  u32 v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
-}
-constexpr u64 CH_KNOWN = 1ull << 63;
-constexpr u64 CH_SUM = (1ull << 40) - 1;
+// ------------------------------------------------------------------------------------------------ hierarchical tile chain
+// Level 1 (shared memory): the warps of a CTA work on NW consecutive tiles per iteration ("block" b = iteration *
+// gridDim.x + blockIdx.x); they post their aggregates into a 4-deep ring of slots.  The last poster of a slot (the
+// agent) publishes the block total in global memory.  Level 2 (global): a flat decoupled look-back over blocks —
+// ~16 blocks per microsecond at the target rate instead of ~350 tiles, and one poller per CTA instead of one per warp
+// (3256 warps polling the same few status lines starved the L2 slices that also had to take the posts).
+// The offset of a tile is needed only one whole tile later (deferred commit), when all earlier blocks have long been
+// posted: the first warp of the CTA that needs it resolves it (CtaChain::lock), the others spin on shared memory.
+struct CtaChain {
+  u32 cnt[4];             // warps that have posted in the slot (reset two iterations ahead by the agent)
+  u32 lock[4];            // iteration+1 of the newest resolve claimed on the slot (monotone, atomicMax)
+  u64 base[4];            // (tag << 48) | exclusive prefix of the block, tag = (iteration & 0xfff) + 1
+  u32 agg[4][32];         // (tag << 20) | aggregate of warp w's tile
+};
+constexpr u32 CH_AGG_MASK = (1u << 20) - 1;
+constexpr u64 CH_BASE_MASK = (1ull << 48) - 1;
 
-// lane 0 publishes the tile's aggregate
-__device__ __forceinline__ void chain_post(const TileChain& c, u32 tile, u32 agg) {
-  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(c.s0 + tile), "r"(0x80000000u | agg) : "memory");
-  asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" :: "l"(c.gsum + (tile >> 5)), "l"((1ull << 40) + (u64)agg) : "memory");
-}
-
-// Exclusive prefix of `tile` (whole warp).  Every tile a running tile waits for belongs to a resident warp (see the
-// tile assignment in k_fused_ell), and aggregates are posted before anybody waits, so the spins terminate.
-__device__ __noinline__ u64 chain_exclusive(const TileChain c, u32 tile, u32 ntiles) {
+// Publish this warp's tile aggregate for `iter`.  expected = warps of this CTA that own a tile in `iter`.
+__device__ __forceinline__ void chain_post(CtaChain* cc, u64* blk_status, u32 iter, u32 warp, u32 agg, u32 expected, u32 blk) {
   const u32 lane = lane_id();
-  const u32 g = tile >> 5, k = tile & 31;
-  u32 w = (lane < k) ? ld_relaxed_u32(c.s0 + (g << 5) + lane) : 0x80000000u;
-  u64 e = (g == 0) ? CH_KNOWN : ld_status(c.ginc + g);
-  while (__any_sync(0xffffffffu, !(w >> 31))) {
-    __nanosleep(40);
-    if (!(w >> 31)) w = ld_relaxed_u32(c.s0 + (g << 5) + lane);
+  const u32 s = iter & 3u, tag = (iter & 0xfffu) + 1u;
+  u32 old = 0;
+  if (lane == 0) {
+    *reinterpret_cast<volatile u32*>(&cc->agg[s][warp]) = (tag << 20) | agg;
+    __threadfence_block();
+    old = atomicAdd(&cc->cnt[s], 1u);
   }
-  u64 intra = __reduce_add_sync(0xffffffffu, w & 0x7fffffffu);
-  if (e & CH_KNOWN) return (e & ~CH_KNOWN) + intra;
-  u64 acc = 0;
-  long long idx = (long long)g - 1;
-  while (true) {
-    const long long my = idx - lane;
-    const u64 need = (my >= 0) ? (u64)min(32ll, (long long)ntiles - 32 * my) : 0ull;
-    u64 gi = CH_KNOWN, gs = 0;
-    u32 first;
-    while (true) {
-      if (my >= 0) { gi = ld_status(c.ginc + my); gs = ld_status(c.gsum + my); }
-      const u32 known = __ballot_sync(0xffffffffu, (gi & CH_KNOWN) != 0);
-      first = known ? (u32)(__ffs(known) - 1) : 32u;
-      const bool pending = (lane <= first) && ((gs >> 40) != need);
-      if (!__any_sync(0xffffffffu, pending)) break;
-      __nanosleep(40);
+  old = __shfl_sync(0xffffffffu, old, 0);
+  if (old + 1u == expected) {                                     // the agent: every warp of the block has posted
+    const u32 w = (lane < expected) ? (*reinterpret_cast<volatile u32*>(&cc->agg[s][lane]) & CH_AGG_MASK) : 0u;
+    const u32 total = __reduce_add_sync(0xffffffffu, w);
+    if (lane == 0) {
+      const u32 s2 = (iter + 2u) & 3u;                             // everybody has committed iteration iter-2: recycle its slot
+      cc->cnt[s2] = 0;
+      __threadfence();
+      st_status(&blk_status[blk], ST_AGG | (u64)total);
     }
-    u64 v = (lane <= first) ? (gs & CH_SUM) : 0ull;
-    if (lane == first) v += gi & ~CH_KNOWN;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-    acc += v;
-    if (first < 32u) break;
-    idx -= 32;
   }
-  if (lane == 0) st_status(c.ginc + g, CH_KNOWN | acc);
-  return acc + intra;
+}
+
+// Exclusive prefix of this warp's tile of iteration `iter` (whole warp).  Called one tile after chain_post(iter).
+__device__ __noinline__ u64 chain_resolve(CtaChain* cc, u64* blk_status, u32 iter, u32 warp, u32 blk) {
+  const u32 lane = lane_id();
+  const u32 s = iter & 3u, tag = (iter & 0xfffu) + 1u;
+  volatile u64* basep = &cc->base[s];
+  u64 bw = *basep;
+  if ((u32)(bw >> 48) != tag) {
+    u32 claimed = 0;
+    if (lane == 0) claimed = atomicMax(&cc->lock[s], iter + 1u) < iter + 1u ? 1u : 0u;
+    claimed = __shfl_sync(0xffffffffu, claimed, 0);
+    if (claimed) {                                                // flat decoupled look-back over blocks; our AGG is (being) published by the agent
+      u64 own;
+      while (((own = ld_status(&blk_status[blk])) >> 62) == 0) __nanosleep(100);
+      u64 excl = 0;
+      if (blk > 0) {
+        long long idx = (long long)blk - 1;
+        while (true) {
+          const long long my = idx - lane;
+          u64 st;
+          while (true) {
+            st = (my >= 0) ? ld_status(&blk_status[my]) : ST_INC;
+            if (!__any_sync(0xffffffffu, (st >> 62) == 0)) break;
+            __nanosleep(100);
+          }
+          const u32 inc_mask = __ballot_sync(0xffffffffu, (st >> 62) == 2);
+          const u32 first = inc_mask ? (u32)(__ffs(inc_mask) - 1) : 32u;
+          u64 v = (lane <= first) ? (st & ST_VAL) : 0;
+#pragma unroll
+          for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+          excl += v;
+          if (inc_mask) break;
+          idx -= 32;
+        }
+      }
+      if (lane == 0) {
+        st_status(&blk_status[blk], ST_INC | (excl + (own & ST_VAL)));
+        *basep = ((u64)tag << 48) | excl;
+        __threadfence_block();
+      }
+      __syncwarp();
+      bw = ((u64)tag << 48) | excl;
+    } else {
+      while ((u32)((bw = *basep) >> 48) != tag) __nanosleep(100);
+    }
+  }
+  const u32 w = (lane < warp) ? (*reinterpret_cast<volatile u32*>(&cc->agg[s][lane]) & CH_AGG_MASK) : 0u;
+  return (bw & CH_BASE_MASK) + __reduce_add_sync(0xffffffffu, w);
 }
 
 // ------------------------------------------------------------------------------------------------ slow paths (out of line)
@@ -195,7 +225,12 @@ __device__ __noinline__ u32 ell_count_table(const u32* tabr, u32 lim) {     // o
 }
 
 // ------------------------------------------------------------------------------------------------ the fused kernel
-// Every warp is an independent worker on tiles of R consecutive rows.
+// Every warp is an independent worker on tiles of R consecutive rows.  Per iteration (tile t):
+//   1. init the R tables; insert the B rows of tile t (loaded one iteration ago); drain the losers;
+//   2. post the tile's aggregate (CtaChain);
+//   3. COMMIT tile t-1 (its offset is known by now): row pointers + staging buffer -> Ccol, coalesced;
+//   4. start the Acol loads of tile t+1; compact the tables of tile t into the staging buffer;
+//   5. start the B-row loads of tile t+1.
 template <int W, int R>
 __global__ void __launch_bounds__(ELL_MAX_WARPS * 32, 1) k_fused_ell(const EllArgs p) {
   constexpr int LPR = W / 4;               // lanes per B row
@@ -203,21 +238,27 @@ __global__ void __launch_bounds__(ELL_MAX_WARPS * 32, 1) k_fused_ell(const EllAr
   constexpr int NBS = 64 / NSEG;           // batches per chunk of 64 A nonzeros
   constexpr int NBG = NBS < 8 ? NBS : 8;   // batches in flight (a "group")
   extern __shared__ __align__(16) u32 smem[];
-  const u32 warp = threadIdx.x >> 5, lane = lane_id();
+  const u32 warp = threadIdx.x >> 5, lane = lane_id(), nwarps = blockDim.x >> 5;
   const u32 TW = p.TW;
   u32* tab = smem + (size_t)warp * ell_warp_words(R, TW);
-  uint2* queue = reinterpret_cast<uint2*>(tab + R * TW);
+  u32* stage = tab + R * TW;               // compacted rows of the tile awaiting its commit, packed back to back
+  uint2* queue = reinterpret_cast<uint2*>(stage + ell_stage_words(R, TW));
   uint2* par = queue + ELL_QCAP;            // per row: (slot scale, spill limit as word index into tab)
+  CtaChain* cc = reinterpret_cast<CtaChain*>(smem + (size_t)nwarps * ell_warp_words(R, TW));
+  for (u32 i = threadIdx.x; i < sizeof(CtaChain) / 4; i += blockDim.x) reinterpret_cast<u32*>(cc)[i] = 0;
+  __syncthreads();                          // the only CTA-wide barrier
   const u32 sub = lane / LPR, part = lane % LPR;
   const u32 ltmask = (1u << lane) - 1u;
   const uint4* __restrict__ Bell4 = reinterpret_cast<const uint4*>(p.Bell);
   u32 ipc = 0;                              // intermediate products seen by this lane
 
-  // Tiles are dealt round-robin: in iteration i, warp gw works on tile i*stride + gw.  Consecutive tiles are then
-  // processed at the same time by neighbouring warps, so a tile's predecessors publish their aggregates when it
-  // does (handing out ids from an atomic counter one tile ahead delayed every look-back by a whole tile time).
-  // Every warp of the grid is resident (one CTA per SM), so the chain cannot wait on a tile that never runs.
-  const u32 stride = gridDim.x * (blockDim.x >> 5);
+  // Tiles are dealt round-robin: in iteration i, warp w of CTA c works on tile i*stride + c*nwarps + w.  Consecutive
+  // tiles are processed at the same time by neighbouring warps (ids from an atomic counter, taken a tile ahead,
+  // delayed every commit by a tile time).  Every warp of the grid is resident (one CTA per SM), so the chain
+  // cannot wait on a tile that never runs.
+  const u32 stride = gridDim.x * nwarps;
+  const u32 cta_first = blockIdx.x * nwarps;
+
   auto load_rowptr = [&](u32 t) -> int {     // lane r (r <= R) gets Arow[t*R + r], clamped to the matrix
     if (t >= p.ntiles) return 0;
     const long long r0 = (long long)t * R;
@@ -245,9 +286,22 @@ __global__ void __launch_bounds__(ELL_MAX_WARPS * 32, 1) k_fused_ell(const EllAr
       if (j >= 0) v[u] = __ldg(&Bell4[(size_t)j * LPR + part]);
     }
   };
+  // commit of a finished tile: its rows are in stage[0..total), lane r holds the inclusive count of row r
+  auto commit = [&](u32 t, u32 iter, u32 incl_mine, u32 total) {
+    const u32 blk = iter * gridDim.x + blockIdx.x;
+    const u64 excl = p.debug_nochain ? (u64)t * (u64)p.debug_nochain : chain_resolve(cc, p.blk_status, iter, warp, blk);
+    const long long row0 = (long long)t * R;
+    const int nrows = (int)min((long long)R, (long long)p.An - row0);
+    if ((int)lane < nrows) st_rowptr(p.Crow, p.is64, (size_t)(row0 + lane) + 1, excl + incl_mine, &p.sc->err);
+    if (t == 0 && lane == 0) st_rowptr(p.Crow, p.is64, 0, 0, &p.sc->err);
+    if (t == p.ntiles - 1 && lane == 0) p.sc->total_nnz = excl + total;
+    int* dst = p.Ccol + excl;
+    for (u32 q = lane; q < total; q += 32) dst[q] = (int)stage[q];
+    __syncwarp();
+  };
 
   // ---- pipeline prologue
-  u32 tile = blockIdx.x * (blockDim.x >> 5) + warp;
+  u32 tile = cta_first + warp, iter = 0;
   int a[R + 1];
   {
     const int ar = load_rowptr(tile);
@@ -259,12 +313,11 @@ __global__ void __launch_bounds__(ELL_MAX_WARPS * 32, 1) k_fused_ell(const EllAr
   load_acol(a[0], 0, a[R] - a[0], j0, j1);
   check_acol(j0, j1);
   load_group(0, j0, j1, v);
+  u32 prev_tile = 0xffffffffu, prev_incl = 0, prev_total = 0;      // the tile awaiting its commit
 
   while (tile < p.ntiles) {
     const u32 next = (tile + stride < tile) ? 0xffffffffu : tile + stride;
     const int ar_n = load_rowptr(next);                            // in flight during the inserts
-    const long long row0 = (long long)tile * R;
-    const int nrows = (int)min((long long)R, (long long)p.An - row0);
     const int E = a[R] - a[0];
     int b[R];                                                      // first A nonzero of every row, relative to the tile
 #pragma unroll
@@ -284,7 +337,7 @@ __global__ void __launch_bounds__(ELL_MAX_WARPS * 32, 1) k_fused_ell(const EllAr
         for (u32 q = lane * 4; q < lim[r]; q += 128) *reinterpret_cast<uint4*>(tab + r * TW + q) = make_uint4(EMPTY, EMPTY, EMPTY, EMPTY);
     __syncwarp();
 
-    // ---- insert: chunk 0 / group 0 is already in v[] (loaded one tile ago)
+    // ---- 1. insert: chunk 0 / group 0 is already in v[] (loaded one tile ago)
     u32 ovf = 0, qn = 0, added = 0;
     for (int e0 = 0; e0 < E; e0 += 64) {
       if (e0 > 0) { load_acol(a[0], e0, E, j0, j1); check_acol(j0, j1); }
@@ -335,63 +388,53 @@ __global__ void __launch_bounds__(ELL_MAX_WARPS * 32, 1) k_fused_ell(const EllAr
 #pragma unroll
       for (int r = 0; r < R; ++r) if (a[r + 1] > a[r]) agg += ell_count_table(tab + r * TW, lim[r]);
     }
-    if (lane == 0) chain_post(p.chain, tile, agg);                 // published before the compaction
+    // ---- 2. publish the aggregate
+    if (!p.debug_nochain) {
+      const u32 blk_first = iter * stride + cta_first;             // first tile of this CTA's block
+      const u32 expected = min(nwarps, p.ntiles - blk_first);
+      chain_post(cc, p.blk_status, iter, warp, agg, expected, iter * gridDim.x + blockIdx.x);
+    }
+    // ---- 3. commit the previous tile (frees the staging buffer)
+    if (prev_tile != 0xffffffffu) commit(prev_tile, iter - 1u, prev_incl, prev_total);
 
-    // ---- next tile: row pointers have arrived, start its Acol loads
+    // ---- 4. next tile: row pointers have arrived, start its Acol loads; compact this tile into the staging buffer
     int an[R + 1];
 #pragma unroll
     for (int r = 0; r <= R; ++r) an[r] = __shfl_sync(0xffffffffu, ar_n, r);
     int j0n, j1n;
     load_acol(an[0], 0, an[R] - an[0], j0n, j1n);
 
-    // ---- compact every table in place (ascending, duplicate-free), count
-    u32 c[R];
+    u32 run = 0, incl_mine = 0;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      u32 base = 0;
       if (a[r + 1] > a[r]) {
-        u32* t = tab + r * TW;
+        const u32* t = tab + r * TW;
         for (u32 q = 0; q < lim[r]; q += 64) {
           const u32 v0 = t[q + lane];
           const u32 v1 = (q + 32 < lim[r]) ? t[q + 32 + lane] : EMPTY;
           const u32 m0 = __ballot_sync(0xffffffffu, v0 != EMPTY);
           const u32 m1 = __ballot_sync(0xffffffffu, v1 != EMPTY);
           const u32 n0 = __popc(m0);
-          if (v0 != EMPTY) t[base + __popc(m0 & ltmask)] = v0;
-          if (v1 != EMPTY) t[base + n0 + __popc(m1 & ltmask)] = v1;
-          base += n0 + __popc(m1);
+          if (v0 != EMPTY) stage[run + __popc(m0 & ltmask)] = v0;
+          if (v1 != EMPTY) stage[run + n0 + __popc(m1 & ltmask)] = v1;
+          run += n0 + __popc(m1);
         }
       }
-      c[r] = base;
+      if ((int)lane == r) incl_mine = run;
     }
     __syncwarp();
 
-    // ---- next tile: Acol has arrived, start its B-row loads (v[] is free again)
+    // ---- 5. next tile: Acol has arrived, start its B-row loads (v[] is free again)
     check_acol(j0n, j1n);
     load_group(0, j0n, j1n, v);
 
-    // ---- the tile's offset, row pointers, rows to their final position
-    u32 incl_mine = 0, run = 0;
-#pragma unroll
-    for (int r = 0; r < R; ++r) { run += c[r]; if ((int)lane == r) incl_mine = run; }
-    const u64 excl = p.debug_nochain ? (u64)tile * (u64)(p.debug_nochain) : chain_exclusive(p.chain, tile, p.ntiles);
-    if ((int)lane < nrows) st_rowptr(p.Crow, p.is64, (size_t)(row0 + lane) + 1, excl + incl_mine, &p.sc->err);
-    if (tile == 0 && lane == 0) st_rowptr(p.Crow, p.is64, 0, 0, &p.sc->err);
-    if (tile == p.ntiles - 1 && lane == 0) p.sc->total_nnz = excl + run;
-    u32 off = 0;
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const u32* src = tab + r * TW;
-      int* dst = p.Ccol + (excl + off);
-      for (u32 q = lane; q < c[r]; q += 32) dst[q] = (int)src[q];
-      off += c[r];
-    }
-    __syncwarp();
-    tile = next;
+    prev_tile = tile; prev_incl = incl_mine; prev_total = run;
+    tile = next; ++iter;
 #pragma unroll
     for (int r = 0; r <= R; ++r) a[r] = an[r];
     j0 = j0n; j1 = j1n;
   }
+  if (prev_tile != 0xffffffffu) commit(prev_tile, iter - 1u, prev_incl, prev_total);
   u64 ips = ipc;
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) ips += __shfl_xor_sync(0xffffffffu, ips, d);
