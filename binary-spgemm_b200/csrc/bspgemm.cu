@@ -201,6 +201,7 @@ static bool ell_plan(bspgemm_dev* d) {
   const int64_t avgA = std::max<int64_t>(1, (a.Annz + a.m.An - 1) / std::max(a.m.An, 1));
   int R = 8;
   while (R > 1 && ((int64_t)R * avgA > 64 || (size_t)ell_warp_words(R, TW) * 4 * 8 > avail)) R >>= 1;
+  if (const char* e = getenv("BSPGEMM_ELL_R")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) R = std::min(R, v); }   // tuning knob
   const size_t per_warp = (size_t)ell_warp_words(R, TW) * 4;
   const int warps = (int)std::min<size_t>(ELL_MAX_WARPS, avail / per_warp);
   if (warps < 4) return false;

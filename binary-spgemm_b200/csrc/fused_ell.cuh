@@ -132,29 +132,33 @@ __device__ __noinline__ u64 chain_resolve(CtaChain* cc, u64* blk_status, u32 ite
     if (lane == 0) claimed = atomicMax(&cc->lock[s], iter + 1u) < iter + 1u ? 1u : 0u;
     claimed = __shfl_sync(0xffffffffu, claimed, 0);
     if (claimed) {                                                // flat decoupled look-back over blocks; our AGG is (being) published by the agent
-      u64 own;
-      while (((own = ld_status(&blk_status[blk])) >> 62) == 0) __nanosleep(100);
+      // All earlier blocks posted their totals about a tile time ago, so nothing here normally spins; the K windows
+      // (32 blocks each) are loaded together: one L2 round trip instead of one per window.
+      constexpr int K = 5;
+      u64 own = ld_status(&blk_status[blk]);
       u64 excl = 0;
-      if (blk > 0) {
-        long long idx = (long long)blk - 1;
-        while (true) {
-          const long long my = idx - lane;
-          u64 st;
-          while (true) {
-            st = (my >= 0) ? ld_status(&blk_status[my]) : ST_INC;
-            if (!__any_sync(0xffffffffu, (st >> 62) == 0)) break;
-            __nanosleep(100);
-          }
-          const u32 inc_mask = __ballot_sync(0xffffffffu, (st >> 62) == 2);
+      long long idx = (long long)blk - 1;
+      bool done = (blk == 0);
+      while (!done) {
+        u64 st[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) { const long long my = idx - 32 * k - lane; st[k] = (my >= 0) ? ld_status(&blk_status[my]) : ST_INC; }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          if (done) break;
+          const long long my = idx - 32 * k - lane;
+          while (__any_sync(0xffffffffu, (st[k] >> 62) == 0)) { __nanosleep(100); if ((st[k] >> 62) == 0) st[k] = ld_status(&blk_status[my]); }
+          const u32 inc_mask = __ballot_sync(0xffffffffu, (st[k] >> 62) == 2);
           const u32 first = inc_mask ? (u32)(__ffs(inc_mask) - 1) : 32u;
-          u64 v = (lane <= first) ? (st & ST_VAL) : 0;
+          u64 v = (lane <= first) ? (st[k] & ST_VAL) : 0;
 #pragma unroll
           for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
           excl += v;
-          if (inc_mask) break;
-          idx -= 32;
+          if (inc_mask) done = true;
         }
+        idx -= 32 * K;
       }
+      while ((own >> 62) == 0) { __nanosleep(100); own = ld_status(&blk_status[blk]); }
       if (lane == 0) {
         st_status(&blk_status[blk], ST_INC | (excl + (own & ST_VAL)));
         *basep = ((u64)tag << 48) | excl;
@@ -163,7 +167,7 @@ __device__ __noinline__ u64 chain_resolve(CtaChain* cc, u64* blk_status, u32 ite
       __syncwarp();
       bw = ((u64)tag << 48) | excl;
     } else {
-      while ((u32)((bw = *basep) >> 48) != tag) __nanosleep(100);
+      while ((u32)((bw = *basep) >> 48) != tag) __nanosleep(400);
     }
   }
   const u32 w = (lane < warp) ? (*reinterpret_cast<volatile u32*>(&cc->agg[s][lane]) & CH_AGG_MASK) : 0u;
