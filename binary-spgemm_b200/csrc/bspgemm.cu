@@ -15,6 +15,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <stdarg.h>
+#include <math.h>
 #include <algorithm>
 #include <vector>
 #include <mutex>
@@ -90,7 +91,7 @@ struct bspgemm_dev {
   bool have_m = false, have_m2 = false, have_l = false;
   u32 bm_words = 0; int l_grid = 0;
   bool skip_estimate = false; u32 row_ip_bound = 0, max_len_b = 0;
-  bool use_ell = false; int ell_W = 0, ell_R = 0, ell_warps = 0; u32 ell_TW = 0;   // ELL fast path plan (fused_ell.cuh)
+  bool use_ell = false; int ell_W = 0, ell_R = 0, ell_warps = 0; u32 ell_TW = 0, ell_maxA = 0;   // ELL fast path plan (fused_ell.cuh)
   u32 hist_rows[34] = {};
   int fused_bps[4][16] = {};        // cached occupancy of k_fused<G> per log2(cap)
   int* user_ccol = nullptr; int64_t user_cap = 0;   // caller-provided output (device) or null -> arena
@@ -199,13 +200,15 @@ static bool ell_plan(bspgemm_dev* d) {
   if (TW > 8192u || (u64)a.m.Bm < 4ull * TW) return false;
   const size_t avail = d->smem_optin - 64 - ELL_CTA_WORDS * 4;
   const int64_t avgA = std::max<int64_t>(1, (a.Annz + a.m.An - 1) / std::max(a.m.An, 1));
+  // R rows per tile: as many as keep (a) the tile's A nonzeros within one 64-entry chunk on average and (b) the CTA at
+  // ELL_MAX_WARPS warps (shared memory per warp grows with R; occupancy matters more than amortising the tile overhead)
+  auto warps_for = [&](int r) { return (int)std::min<size_t>(ELL_MAX_WARPS, avail / ((size_t)ell_warp_words(r, TW, r * h.max_len_a * W) * 4)); };
   int R = 8;
-  while (R > 1 && ((int64_t)R * avgA > 64 || (size_t)ell_warp_words(R, TW) * 4 * 8 > avail)) R >>= 1;
-  if (const char* e = getenv("BSPGEMM_ELL_R")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) R = std::min(R, v); }   // tuning knob
-  const size_t per_warp = (size_t)ell_warp_words(R, TW) * 4;
-  const int warps = (int)std::min<size_t>(ELL_MAX_WARPS, avail / per_warp);
+  while (R > 1 && ((int64_t)R * avgA > 64 || warps_for(R) < ELL_MAX_WARPS)) R >>= 1;
+  if (const char* e = getenv("BSPGEMM_ELL_R")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) R = v; }   // tuning knob
+  const int warps = warps_for(R);
   if (warps < 4) return false;
-  d->use_ell = true; d->ell_W = W; d->ell_R = R; d->ell_TW = TW; d->ell_warps = warps;
+  d->use_ell = true; d->ell_W = W; d->ell_R = R; d->ell_TW = TW; d->ell_warps = warps; d->ell_maxA = h.max_len_a;
   return true;
 }
 
@@ -228,7 +231,8 @@ static int launch_ell(bspgemm_dev* d) {
   }
   const u32 ntiles = (u32)(((size_t)a.m.An + R - 1) / R);
   const int warps = d->ell_warps;
-  const size_t smem = ((size_t)ell_warp_words(R, d->ell_TW) * warps + ELL_CTA_WORDS) * 4;
+  const u32 SW = (u32)R * d->ell_maxA * (u32)W;
+  const size_t smem = ((size_t)ell_warp_words(R, d->ell_TW, SW) * warps + ELL_CTA_WORDS) * 4;
   const long long want = ((long long)ntiles + warps - 1) / warps;
   const int grid = (int)std::max<long long>(1, std::min<long long>(want, d->sm_count));
   const size_t niter = ((size_t)ntiles + (size_t)grid * warps - 1) / ((size_t)grid * warps);
@@ -239,10 +243,11 @@ static int launch_ell(bspgemm_dev* d) {
   EllArgs p{};
   p.blk_status = d->status.p;
   p.Arow = a.m.Arow; p.Acol = a.m.Acol; p.Bell = d->bell.p; p.An = a.m.An; p.Bn = a.m.Bn;
-  p.unit = (u32)(((u64)(2 * W) << 32) / (u64)a.m.Bm);
+  { const double inv = 4294967296.0 / (double)a.m.Bm * (1.0 - 1.0 / 1048576.0); float f = (float)inv; if ((double)f > inv) f = nextafterf(f, 0.0f); p.inv_bm = f; }
+  p.SW = SW;
   p.TW = d->ell_TW; p.Bm = (u32)a.m.Bm; p.Crow = a.dCrow; p.is64 = a.is64; p.Ccol = ccol; p.sc = d->d_sc;
   p.ntiles = ntiles;
-  p.debug_nochain = getenv("BSPGEMM_DEBUG_NOCHAIN") ? (u32)(R * d->h_sc->max_len_a * W) : 0u;   // WRONG RESULTS: timing experiments only
+  p.debug_nochain = getenv("BSPGEMM_DEBUG_NOCHAIN") ? (u32)(R * d->ell_maxA * W) : 0u;   // WRONG RESULTS: timing experiments only
 #define LE(Wv, Rv) k_fused_ell<Wv, Rv><<<grid, warps * 32, smem, d->stream>>>(p)
 #define LER(Wv) do { switch (R) { case 1: LE(Wv, 1); break; case 2: LE(Wv, 2); break; case 4: LE(Wv, 4); break; default: LE(Wv, 8); break; } } while (0)
   switch (W) { case 4: LER(4); break; case 8: LER(8); break; case 16: LER(16); break; default: LER(32); break; }

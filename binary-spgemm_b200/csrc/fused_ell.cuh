@@ -41,8 +41,9 @@ struct EllArgs {
   const int* __restrict__ Acol;
   const u32* __restrict__ Bell;   // Bn rows of W columns, EMPTY-padded
   int An, Bn;
-  u32 unit;                       // floor(2*W*2^32 / Bm): slot scale of a row with one A nonzero
-  u32 TW;                         // table words per output row (multiple of 32)
+  float inv_bm;                   // slightly less than 2^32 / Bm: slot = umulhi(key, floor(T_home * inv_bm)) < T_home
+  u32 TW;                         // table words per output row (multiple of 128)
+  u32 SW;                         // staging words per tile = R * max_len(A) * W
   u32 Bm;
   void* Crow; int is64;
   int* Ccol;
@@ -52,9 +53,17 @@ struct EllArgs {
   u32 debug_nochain;              // timing experiments only (BSPGEMM_DEBUG_NOCHAIN): skip the scan, rows land at upper-bound offsets
 };
 
-__host__ __device__ constexpr u32 ell_table_limit(u32 lenA, u32 W) { return ((2u * W * lenA + 31u) & ~31u) + 32u; }
-__host__ __device__ constexpr u32 ell_stage_words(u32 R, u32 TW) { return R * ((TW - 32u) / 2u); }      // a tile's compacted rows (R * maxlenA * W)
-__host__ __device__ constexpr u32 ell_warp_words(u32 R, u32 TW) { return R * TW + ell_stage_words(R, TW) + 2u * ELL_QCAP + 2u * 8u; }
+// Table geometry of a row with lenA nonzeros in A (cap = lenA*W >= its IP): `lim` slots, a multiple of 128 (the
+// compaction reads 128 slots per warp instruction); keys are mapped to the first lim-32 "home" slots, the last 32 only
+// take keys pushed right by collisions.  Load factor of the home slots <= 4/7.
+__host__ __device__ constexpr u32 ell_table_limit(u32 lenA, u32 W) {
+  const u32 cap = lenA * W;
+  u32 lim = (2u * cap + 127u) & ~127u;
+  if (lim < 128u) lim = 128u;
+  if ((lim - 32u) * 4u < cap * 7u) lim += 128u;
+  return lim;
+}
+__host__ __device__ constexpr u32 ell_warp_words(u32 R, u32 TW, u32 SW) { return R * TW + SW + 2u * ELL_QCAP + 4u * 8u; }
 constexpr u32 ELL_CTA_WORDS = 160;       // CtaChain, after the warp regions
 
 // ---- B (CSR) -> ELL.  LPR = W/4 lanes write one row as uint4 each; also validates B's columns.
@@ -99,7 +108,8 @@ constexpr u32 CH_AGG_MASK = (1u << 20) - 1;
 constexpr u64 CH_BASE_MASK = (1ull << 48) - 1;
 
 // Publish this warp's tile aggregate for `iter`.  expected = warps of this CTA that own a tile in `iter`.
-__device__ __forceinline__ void chain_post(CtaChain* cc, u64* blk_status, u32 iter, u32 warp, u32 agg, u32 expected, u32 blk) {
+// Returns 0, or in the block's agent (the last poster) 1 + the block total.
+__device__ __forceinline__ u32 chain_post(CtaChain* cc, u64* blk_status, u32 iter, u32 warp, u32 agg, u32 expected, u32 blk) {
   const u32 lane = lane_id();
   const u32 s = iter & 3u, tag = (iter & 0xfffu) + 1u;
   u32 old = 0;
@@ -109,20 +119,76 @@ __device__ __forceinline__ void chain_post(CtaChain* cc, u64* blk_status, u32 it
     old = atomicAdd(&cc->cnt[s], 1u);
   }
   old = __shfl_sync(0xffffffffu, old, 0);
-  if (old + 1u == expected) {                                     // the agent: every warp of the block has posted
-    const u32 w = (lane < expected) ? (*reinterpret_cast<volatile u32*>(&cc->agg[s][lane]) & CH_AGG_MASK) : 0u;
-    const u32 total = __reduce_add_sync(0xffffffffu, w);
-    if (lane == 0) {
-      const u32 s2 = (iter + 2u) & 3u;                             // everybody has committed iteration iter-2: recycle its slot
-      cc->cnt[s2] = 0;
-      __threadfence();
-      st_status(&blk_status[blk], ST_AGG | (u64)total);
-    }
+  if (old + 1u != expected) return 0u;
+  // the agent: every warp of the block has posted
+  const u32 w = (lane < expected) ? (*reinterpret_cast<volatile u32*>(&cc->agg[s][lane]) & CH_AGG_MASK) : 0u;
+  const u32 total = __reduce_add_sync(0xffffffffu, w);
+  if (lane == 0) {
+    const u32 s2 = (iter + 2u) & 3u;                               // everybody has committed iteration iter-2: recycle its slot
+    cc->cnt[s2] = 0;
+    __threadfence();
+    st_status(&blk_status[blk], ST_AGG | (u64)total);
   }
+  return total + 1u;
+}
+
+// Flat decoupled look-back over blocks: exclusive prefix of block `blk` (whole warp).  K windows of 32 blocks are
+// loaded together (one L2 round trip).  Non-blocking mode gives up (returns false) on a block that has not posted.
+__device__ __noinline__ bool chain_walk(const u64* blk_status, u32 blk, bool blocking, u64* out) {
+  constexpr int K = 5;
+  const u32 lane = lane_id();
+  u64 excl = 0;
+  long long idx = (long long)blk - 1;
+  bool done = (blk == 0);
+  while (!done) {
+    u64 st[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) { const long long my = idx - 32 * k - lane; st[k] = (my >= 0) ? ld_status(&blk_status[my]) : ST_INC; }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      if (done) break;
+      const long long my = idx - 32 * k - lane;
+      const u32 inc0 = __ballot_sync(0xffffffffu, (st[k] >> 62) == 2);
+      const u32 first0 = inc0 ? (u32)(__ffs(inc0) - 1) : 32u;
+      while (__any_sync(0xffffffffu, lane <= first0 && (st[k] >> 62) == 0)) {   // only blocks nearer than the first INC matter
+        if (!blocking) return false;
+        __nanosleep(200);
+        if ((st[k] >> 62) == 0) st[k] = ld_status(&blk_status[my]);
+      }
+      const u32 inc_mask = __ballot_sync(0xffffffffu, lane <= first0 && (st[k] >> 62) == 2);
+      const u32 first = inc_mask ? (u32)(__ffs(inc_mask) - 1) : 32u;
+      u64 v = (lane <= first) ? (st[k] & ST_VAL) : 0;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+      excl += v;
+      if (inc_mask) done = true;
+    }
+    idx -= 32 * K;
+  }
+  *out = excl;
+  return true;
+}
+
+__device__ __forceinline__ void chain_publish(CtaChain* cc, u64* blk_status, u32 iter, u32 blk, u64 excl, u64 total) {   // lane 0
+  st_status(&blk_status[blk], ST_INC | (excl + total));
+  *reinterpret_cast<volatile u64*>(&cc->base[iter & 3u]) = ((u64)((iter & 0xfffu) + 1u) << 48) | excl;
+  __threadfence_block();
+}
+
+// The agent, some time after posting (after its compaction): resolve the block's offset if every earlier block has
+// posted by now, so that nobody waits for it at commit time.  Racing with a lazy resolver is benign: both derive the
+// same values from the same inputs (the block total always comes from the CTA's own shared-memory slots).
+__device__ __noinline__ void chain_try_resolve(CtaChain* cc, u64* blk_status, u32 iter, u32 blk, u32 total) {
+  const u32 tag = (iter & 0xfffu) + 1u;
+  if ((u32)(*reinterpret_cast<volatile u64*>(&cc->base[iter & 3u]) >> 48) == tag) return;
+  u64 excl;
+  if (!chain_walk(blk_status, blk, false, &excl)) return;
+  if (lane_id() == 0) chain_publish(cc, blk_status, iter, blk, excl, total);
+  __syncwarp();
 }
 
 // Exclusive prefix of this warp's tile of iteration `iter` (whole warp).  Called one tile after chain_post(iter).
-__device__ __noinline__ u64 chain_resolve(CtaChain* cc, u64* blk_status, u32 iter, u32 warp, u32 blk) {
+__device__ __noinline__ u64 chain_resolve(CtaChain* cc, u64* blk_status, u32 iter, u32 warp, u32 blk, u32 expected) {
   const u32 lane = lane_id();
   const u32 s = iter & 3u, tag = (iter & 0xfffu) + 1u;
   volatile u64* basep = &cc->base[s];
@@ -131,43 +197,21 @@ __device__ __noinline__ u64 chain_resolve(CtaChain* cc, u64* blk_status, u32 ite
     u32 claimed = 0;
     if (lane == 0) claimed = atomicMax(&cc->lock[s], iter + 1u) < iter + 1u ? 1u : 0u;
     claimed = __shfl_sync(0xffffffffu, claimed, 0);
-    if (claimed) {                                                // flat decoupled look-back over blocks; our AGG is (being) published by the agent
-      // All earlier blocks posted their totals about a tile time ago, so nothing here normally spins; the K windows
-      // (32 blocks each) are loaded together: one L2 round trip instead of one per window.
-      constexpr int K = 5;
-      u64 own = ld_status(&blk_status[blk]);
-      u64 excl = 0;
-      long long idx = (long long)blk - 1;
-      bool done = (blk == 0);
-      while (!done) {
-        u64 st[K];
-#pragma unroll
-        for (int k = 0; k < K; ++k) { const long long my = idx - 32 * k - lane; st[k] = (my >= 0) ? ld_status(&blk_status[my]) : ST_INC; }
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-          if (done) break;
-          const long long my = idx - 32 * k - lane;
-          while (__any_sync(0xffffffffu, (st[k] >> 62) == 0)) { __nanosleep(100); if ((st[k] >> 62) == 0) st[k] = ld_status(&blk_status[my]); }
-          const u32 inc_mask = __ballot_sync(0xffffffffu, (st[k] >> 62) == 2);
-          const u32 first = inc_mask ? (u32)(__ffs(inc_mask) - 1) : 32u;
-          u64 v = (lane <= first) ? (st[k] & ST_VAL) : 0;
-#pragma unroll
-          for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-          excl += v;
-          if (inc_mask) done = true;
-        }
-        idx -= 32 * K;
+    if (claimed) {
+      u32 w;                                                      // the block total: every warp's slot must carry this iteration's tag
+      while (true) {
+        w = (lane < expected) ? *reinterpret_cast<volatile u32*>(&cc->agg[s][lane]) : (tag << 20);
+        if (!__any_sync(0xffffffffu, (w >> 20) != tag)) break;
+        __nanosleep(200);
       }
-      while ((own >> 62) == 0) { __nanosleep(100); own = ld_status(&blk_status[blk]); }
-      if (lane == 0) {
-        st_status(&blk_status[blk], ST_INC | (excl + (own & ST_VAL)));
-        *basep = ((u64)tag << 48) | excl;
-        __threadfence_block();
-      }
+      const u32 total = __reduce_add_sync(0xffffffffu, w & CH_AGG_MASK);
+      u64 excl;
+      chain_walk(blk_status, blk, true, &excl);
+      if (lane == 0) chain_publish(cc, blk_status, iter, blk, excl, total);
       __syncwarp();
       bw = ((u64)tag << 48) | excl;
     } else {
-      while ((u32)((bw = *basep) >> 48) != tag) __nanosleep(400);
+      while ((u32)((bw = *basep) >> 48) != tag) __nanosleep(500);
     }
   }
   const u32 w = (lane < warp) ? (*reinterpret_cast<volatile u32*>(&cc->agg[s][lane]) & CH_AGG_MASK) : 0u;
@@ -175,21 +219,43 @@ __device__ __noinline__ u64 chain_resolve(CtaChain* cc, u64* blk_status, u32 ite
 }
 
 // ------------------------------------------------------------------------------------------------ slow paths (out of line)
-// Re-insert the queued losers (key, next slot | spill limit << 16; both are word indices into the warp's region,
-// < 2^16), all lanes busy.  Returns (rows whose table spilled past its limit) << 16 | (#keys that found an EMPTY slot).
-__device__ __noinline__ u32 ell_drain(u32* tab, const uint2* queue, u32 qn, u32 TW) {
+// Shared memory is addressed with 32-bit shared-window addresses in the hot path: through generic pointers the compiler
+// re-derives the window base (S2R SR_CgaCtaId, LEA) next to every predicated store.
+__device__ __forceinline__ u32 atoms_min(u32 saddr, u32 x) {
+  u32 old; asm volatile("atom.shared.min.u32 %0, [%1], %2;" : "=r"(old) : "r"(saddr), "r"(x)); return old;
+}
+__device__ __forceinline__ uint4 lds128(u32 saddr) {
+  uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr)); return v;
+}
+__device__ __forceinline__ uint2 lds64(u32 saddr) {
+  uint2 v; asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr)); return v;
+}
+__device__ __forceinline__ u32 lds32(u32 saddr) {
+  u32 v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr)); return v;
+}
+__device__ __forceinline__ void sts32(u32 saddr, u32 v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(saddr), "r"(v)); }
+__device__ __forceinline__ void sts64(u32 saddr, u32 a, u32 b) { asm volatile("st.shared.v2.u32 [%0], {%1,%2};" :: "r"(saddr), "r"(a), "r"(b)); }
+__device__ __forceinline__ void sts128(u32 saddr, u32 a, u32 b, u32 c, u32 d) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d));
+}
+
+// Queue entry: (key, y) with y = next slot (shared byte address, 18 bits) | (lim/128) << 18 | row << 24.
+// Re-insert the queued losers [lo,hi) in rounds of 32 (one entry per lane, every lane walks its collision chain).
+// Returns (rows whose table spilled past its limit) << 16 | (#keys that found an EMPTY slot).
+__device__ __noinline__ u32 ell_drain(u32 tab_s, u32 queue_s, u32 lo, u32 hi, u32 TW) {
   u32 ovf = 0, added = 0;
   __syncwarp();
-  for (u32 i = lane_id(); i < qn; i += 32) {
-    const uint2 ent = queue[i];
-    u32 x = ent.x, s = ent.y & 0xffffu;
-    const u32 l = ent.y >> 16;
+  for (u32 i = lo + lane_id(); i < hi; i += 32) {
+    const uint2 ent = lds64(queue_s + 8u * i);
+    u32 x = ent.x, addr = ent.y & 0x3ffffu;
+    const u32 r = ent.y >> 24;
+    const u32 lim = tab_s + 4u * (r * TW + (((ent.y >> 18) & 63u) << 7));
     while (true) {
-      if (s >= l) { ovf |= 0x10000u << ((l - 1u) / TW); break; }      // limit of row r = r*TW + lim_r, lim_r <= TW
-      const u32 old = atomicMin(&tab[s], x);
+      if (addr >= lim) { ovf |= 0x10000u << r; break; }
+      const u32 old = atoms_min(addr, x);
       if (old == EMPTY) { ++added; break; }
       if (old == x) break;
-      x = max(old, x); ++s;
+      x = max(old, x); addr += 4u;
     }
   }
   __syncwarp();
@@ -203,7 +269,7 @@ __device__ __noinline__ void ell_rebuild_row(const int* __restrict__ Acol, const
                                               u32* tabr, int a0, int a1) {
   const u32 lane = lane_id();
   const u32 cap = (u32)(a1 - a0) * W;
-  const u32 T = TW - cap;                                         // >= cap + 32 by construction of TW
+  const u32 T = TW - cap;                                         // >= cap by construction of TW
   const u32 scale = (u32)min((u64)0xffffffffull, (((u64)T) << 32) / Bm);
   for (u32 q = lane * 4; q < TW; q += 128) *reinterpret_cast<uint4*>(tabr + q) = make_uint4(EMPTY, EMPTY, EMPTY, EMPTY);
   __syncwarp();
@@ -244,11 +310,13 @@ __global__ void __launch_bounds__(ELL_MAX_WARPS * 32, 1) k_fused_ell(const EllAr
   extern __shared__ __align__(16) u32 smem[];
   const u32 warp = threadIdx.x >> 5, lane = lane_id(), nwarps = blockDim.x >> 5;
   const u32 TW = p.TW;
-  u32* tab = smem + (size_t)warp * ell_warp_words(R, TW);
-  u32* stage = tab + R * TW;               // compacted rows of the tile awaiting its commit, packed back to back
-  uint2* queue = reinterpret_cast<uint2*>(stage + ell_stage_words(R, TW));
-  uint2* par = queue + ELL_QCAP;            // per row: (slot scale, spill limit as word index into tab)
-  CtaChain* cc = reinterpret_cast<CtaChain*>(smem + (size_t)nwarps * ell_warp_words(R, TW));
+  const u32 wwords = ell_warp_words(R, TW, p.SW);
+  u32* tab = smem + (size_t)warp * wwords;
+  // warp region: R tables | staging (compacted rows of the tile awaiting its commit, back to back) | loser queue |
+  // per-row parameters (slot scale, table byte address, queue tag, -)
+  const u32 tab_s = (u32)__cvta_generic_to_shared(tab);
+  const u32 stage_s = tab_s + R * TW * 4u, queue_s = stage_s + p.SW * 4u, par_s = queue_s + ELL_QCAP * 8u;
+  CtaChain* cc = reinterpret_cast<CtaChain*>(smem + (size_t)nwarps * wwords);
   for (u32 i = threadIdx.x; i < sizeof(CtaChain) / 4; i += blockDim.x) reinterpret_cast<u32*>(cc)[i] = 0;
   __syncthreads();                          // the only CTA-wide barrier
   const u32 sub = lane / LPR, part = lane % LPR;
@@ -293,14 +361,15 @@ __global__ void __launch_bounds__(ELL_MAX_WARPS * 32, 1) k_fused_ell(const EllAr
   // commit of a finished tile: its rows are in stage[0..total), lane r holds the inclusive count of row r
   auto commit = [&](u32 t, u32 iter, u32 incl_mine, u32 total) {
     const u32 blk = iter * gridDim.x + blockIdx.x;
-    const u64 excl = p.debug_nochain ? (u64)t * (u64)p.debug_nochain : chain_resolve(cc, p.blk_status, iter, warp, blk);
+    const u32 expected = min(nwarps, p.ntiles - (iter * stride + cta_first));
+    const u64 excl = p.debug_nochain ? (u64)t * (u64)p.debug_nochain : chain_resolve(cc, p.blk_status, iter, warp, blk, expected);
     const long long row0 = (long long)t * R;
     const int nrows = (int)min((long long)R, (long long)p.An - row0);
     if ((int)lane < nrows) st_rowptr(p.Crow, p.is64, (size_t)(row0 + lane) + 1, excl + incl_mine, &p.sc->err);
     if (t == 0 && lane == 0) st_rowptr(p.Crow, p.is64, 0, 0, &p.sc->err);
     if (t == p.ntiles - 1 && lane == 0) p.sc->total_nnz = excl + total;
     int* dst = p.Ccol + excl;
-    for (u32 q = lane; q < total; q += 32) dst[q] = (int)stage[q];
+    for (u32 q = lane; q < total; q += 32) dst[q] = (int)lds32(stage_s + 4u * q);
     __syncwarp();
   };
 
@@ -330,15 +399,16 @@ __global__ void __launch_bounds__(ELL_MAX_WARPS * 32, 1) k_fused_ell(const EllAr
 #pragma unroll
     for (int r = 0; r < R; ++r) lim[r] = ell_table_limit((u32)(a[r + 1] - a[r]), W);
     if (lane < R) {
-      u32 len = 0, l = 0;
+      u32 l = 128;
 #pragma unroll
-      for (int r = 0; r < R; ++r) if ((int)lane == r) { len = (u32)(a[r + 1] - a[r]); l = lim[r]; }
-      par[lane] = make_uint2(len * p.unit, lane * TW + l);
+      for (int r = 0; r < R; ++r) if ((int)lane == r) l = lim[r];
+      const u32 scale = __float2uint_rd(__fmul_rd((float)(l - 32u), p.inv_bm));
+      sts128(par_s + 16u * lane, scale, tab_s + lane * TW * 4u, (lane << 24) | ((l >> 7) << 18) | 4u, 0u);
     }
 #pragma unroll
     for (int r = 0; r < R; ++r)
       if (a[r + 1] > a[r])
-        for (u32 q = lane * 4; q < lim[r]; q += 128) *reinterpret_cast<uint4*>(tab + r * TW + q) = make_uint4(EMPTY, EMPTY, EMPTY, EMPTY);
+        for (u32 q = lane * 4; q < lim[r]; q += 128) sts128(tab_s + (r * TW + q) * 4u, EMPTY, EMPTY, EMPTY, EMPTY);
     __syncwarp();
 
     // ---- 1. insert: chunk 0 / group 0 is already in v[] (loaded one tile ago)
@@ -356,16 +426,14 @@ __global__ void __launch_bounds__(ELL_MAX_WARPS * 32, 1) k_fused_ell(const EllAr
           u32 r = 0;
 #pragma unroll
           for (int q = 1; q < R; ++q) r += (e >= b[q]) ? 1u : 0u;
-          const uint2 pr = par[r];
-          const u32 tabr = r * TW;
+          const uint4 pr = lds128(par_s + 16u * r);
           const u32 x[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-          u32 s[4], old[4];
+          u32 sa[4], old[4];
           // padding (EMPTY) takes a harmless atomicMin(.., EMPTY) on a private bank: no branch around the atomics
 #pragma unroll
-          for (int k = 0; k < 4; ++k) s[k] = tabr + ((x[k] != EMPTY) ? __umulhi(x[k], pr.x) : lane);
+          for (int k = 0; k < 4; ++k) sa[k] = pr.y + 4u * ((x[k] != EMPTY) ? __umulhi(x[k], pr.x) : lane);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) old[k] = atomicMin(&tab[s[k]], x[k]);
-          const u32 hi = (pr.y << 16) + 1u;                  // queue entry: (key, next slot | spill limit << 16)
+          for (int k = 0; k < 4; ++k) old[k] = atoms_min(sa[k], x[k]);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const bool valid = x[k] != EMPTY;
@@ -374,14 +442,16 @@ __global__ void __launch_bounds__(ELL_MAX_WARPS * 32, 1) k_fused_ell(const EllAr
             ipc += valid ? 1u : 0u;
             added += fresh ? 1u : 0u;
             const u32 m = __ballot_sync(0xffffffffu, lose);
-            if (lose) queue[qn + __popc(m & ltmask)] = make_uint2(max(old[k], x[k]), s[k] + hi);
+            if (lose) sts64(queue_s + 8u * (qn + __popc(m & ltmask)), max(old[k], x[k]), sa[k] + pr.z);
             qn += __popc(m);
           }
-          if (qn > ELL_QCAP - 128) { const u32 d = ell_drain(tab, queue, qn, TW); ovf |= d >> 16; added += d & 0xffffu; qn = 0; }
+          if (qn > ELL_QCAP - 128) {                              // full rounds only; the remainder waits for company
+            const u32 d = ell_drain(tab_s, queue_s, qn & 31u, qn, TW); ovf |= d >> 16; added += d & 0xffffu; qn &= 31u;
+          }
         }
       }
     }
-    if (qn) { const u32 d = ell_drain(tab, queue, qn, TW); ovf |= d >> 16; added += d & 0xffffu; }
+    if (qn) { const u32 d = ell_drain(tab_s, queue_s, 0u, qn, TW); ovf |= d >> 16; added += d & 0xffffu; }
     ovf = __reduce_or_sync(0xffffffffu, ovf);
     u32 agg = __reduce_add_sync(0xffffffffu, added);
     if (ovf) {                                                     // rare: exact rebuild of the spilled rows, recount
@@ -393,10 +463,11 @@ __global__ void __launch_bounds__(ELL_MAX_WARPS * 32, 1) k_fused_ell(const EllAr
       for (int r = 0; r < R; ++r) if (a[r + 1] > a[r]) agg += ell_count_table(tab + r * TW, lim[r]);
     }
     // ---- 2. publish the aggregate
+    u32 agent = 0;
     if (!p.debug_nochain) {
       const u32 blk_first = iter * stride + cta_first;             // first tile of this CTA's block
       const u32 expected = min(nwarps, p.ntiles - blk_first);
-      chain_post(cc, p.blk_status, iter, warp, agg, expected, iter * gridDim.x + blockIdx.x);
+      agent = chain_post(cc, p.blk_status, iter, warp, agg, expected, iter * gridDim.x + blockIdx.x);
     }
     // ---- 3. commit the previous tile (frees the staging buffer)
     if (prev_tile != 0xffffffffu) commit(prev_tile, iter - 1u, prev_incl, prev_total);
@@ -412,16 +483,18 @@ __global__ void __launch_bounds__(ELL_MAX_WARPS * 32, 1) k_fused_ell(const EllAr
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       if (a[r + 1] > a[r]) {
-        const u32* t = tab + r * TW;
-        for (u32 q = 0; q < lim[r]; q += 64) {
-          const u32 v0 = t[q + lane];
-          const u32 v1 = (q + 32 < lim[r]) ? t[q + 32 + lane] : EMPTY;
-          const u32 m0 = __ballot_sync(0xffffffffu, v0 != EMPTY);
-          const u32 m1 = __ballot_sync(0xffffffffu, v1 != EMPTY);
-          const u32 n0 = __popc(m0);
-          if (v0 != EMPTY) stage[run + __popc(m0 & ltmask)] = v0;
-          if (v1 != EMPTY) stage[run + n0 + __popc(m1 & ltmask)] = v1;
-          run += n0 + __popc(m1);
+        const u32 tb = tab_s + (r * TW + lane * 4u) * 4u;          // lane l owns slots q+4l .. q+4l+3 of every 128-slot chunk
+        for (u32 q = 0; q < lim[r]; q += 128) {
+          const uint4 t4 = lds128(tb + q * 4u);
+          const bool p0 = t4.x != EMPTY, p1 = t4.y != EMPTY, p2 = t4.z != EMPTY, p3 = t4.w != EMPTY;
+          const u32 m0 = __ballot_sync(0xffffffffu, p0), m1 = __ballot_sync(0xffffffffu, p1);
+          const u32 m2 = __ballot_sync(0xffffffffu, p2), m3 = __ballot_sync(0xffffffffu, p3);
+          u32 o = stage_s + 4u * (run + __popc(m0 & ltmask) + __popc(m1 & ltmask) + __popc(m2 & ltmask) + __popc(m3 & ltmask));
+          if (p0) { sts32(o, t4.x); o += 4u; }
+          if (p1) { sts32(o, t4.y); o += 4u; }
+          if (p2) { sts32(o, t4.z); o += 4u; }
+          if (p3) sts32(o, t4.w);
+          run += __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
         }
       }
       if ((int)lane == r) incl_mine = run;
@@ -431,6 +504,7 @@ __global__ void __launch_bounds__(ELL_MAX_WARPS * 32, 1) k_fused_ell(const EllAr
     // ---- 5. next tile: Acol has arrived, start its B-row loads (v[] is free again)
     check_acol(j0n, j1n);
     load_group(0, j0n, j1n, v);
+    if (agent) chain_try_resolve(cc, p.blk_status, iter, iter * gridDim.x + blockIdx.x, agent - 1u);
 
     prev_tile = tile; prev_incl = incl_mine; prev_total = run;
     tile = next; ++iter;
