@@ -338,6 +338,8 @@ def main():
     last = stats[-1]
     if last["mode"] != bs.MODE_FUSED:
         kernel_name = "scan + k_rows_warp<G,MODE_FILL>"
+    elif last.get("variant", 0) == 2:
+        kernel_name = "k_fused_sort<W=%d> (%d rows per tile)" % (last["group"], last["rows_per_tile"])
     elif last.get("variant", 0) == 1:
         kernel_name = "k_fused_ell<W=%d,R=%d>" % (last["group"], last["rows_per_tile"])
     else:
@@ -410,7 +412,7 @@ def main():
             "config": config, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(launches_total), "clocks": clocks,
             "out_nnz_per_s": nnz_total / (t_max / args.steps), "ip": int(ip_total), "nnz_c": int(nnz_total), "nnz_a": nnzA,
-            "pipeline": {"mode": "fused" if stats[-1]["mode"] == bs.MODE_FUSED else "twophase", "variant": "ell" if stats[-1].get("variant", 0) == 1 else "csr",
+            "pipeline": {"mode": "fused" if stats[-1]["mode"] == bs.MODE_FUSED else "twophase", "variant": {0: "csr", 1: "ell-hash", 2: "ell-sort"}.get(stats[-1].get("variant", 0)),
                          "rows_per_tile": stats[-1].get("rows_per_tile", 0), "cap_s": stats[-1]["cap_s"],
                          "group": stats[-1]["group"], "rows_s": stats[-1]["rows_s"], "rows_m": stats[-1]["rows_m"], "rows_l": stats[-1]["rows_l"],
                          "ms_estimate": est_ms, "ms_main": main_ms,

@@ -8,6 +8,7 @@
 #include "../../include/bspgemm.h"
 #include "kernels.cuh"
 #include "fused_ell.cuh"
+#include "fused_sort.cuh"
 
 #include <nccl.h>      // types only; the library itself is dlopen'ed so libbspgemm.so loads without it
 #include <dlfcn.h>
@@ -91,7 +92,8 @@ struct bspgemm_dev {
   bool have_m = false, have_m2 = false, have_l = false;
   u32 bm_words = 0; int l_grid = 0;
   bool skip_estimate = false; u32 row_ip_bound = 0, max_len_b = 0;
-  bool use_ell = false; int ell_W = 0, ell_R = 0, ell_warps = 0; u32 ell_TW = 0, ell_maxA = 0;   // ELL fast path plan (fused_ell.cuh)
+  bool use_ell = false; int ell_W = 0, ell_R = 0, ell_warps = 0; u32 ell_TW = 0, ell_maxA = 0, ell_lf16 = 28;
+  bool use_sort = false; int sort_LAL = 0;            // register-sort variant of the ELL path (fused_sort.cuh)   // ELL fast path plan (fused_ell.cuh)
   u32 hist_rows[34] = {};
   int fused_bps[4][16] = {};        // cached occupancy of k_fused<G> per log2(cap)
   int* user_ccol = nullptr; int64_t user_cap = 0;   // caller-provided output (device) or null -> arena
@@ -116,6 +118,10 @@ static int set_kernel_attributes(int smem_optin) {
 #define ATTR_E(Wv) ATTR((k_fused_ell<Wv, 1>)); ATTR((k_fused_ell<Wv, 2>)); ATTR((k_fused_ell<Wv, 4>)); ATTR((k_fused_ell<Wv, 8>))
   ATTR_E(4); ATTR_E(8); ATTR_E(16); ATTR_E(32);
 #undef ATTR_E
+#define ATTR_S(Wv) ATTR((k_fused_sort<Wv, 2>)); ATTR((k_fused_sort<Wv, 3>)); ATTR((k_fused_sort<Wv, 4>))
+  ATTR_S(4); ATTR_S(8); ATTR_S(16); ATTR_S(32);
+  ATTR((k_fused_sort<4, 5>)); ATTR((k_fused_sort<8, 5>)); ATTR((k_fused_sort<16, 5>));
+#undef ATTR_S
 #undef ATTR_G
 #undef ATTR
   return BSPGEMM_OK;
@@ -196,7 +202,8 @@ static bool ell_plan(bspgemm_dev* d) {
   if (h.max_len_a == 0 || h.max_len_b == 0 || h.max_len_b > 32) return false;
   int W = 4; while (W < (int)h.max_len_b) W <<= 1;
   if ((u64)a.m.Bn * (u64)W > 4ull * (u64)a.Bnnz + 4096ull && !getenv("BSPGEMM_FORCE_ELL")) return false;   // padding waste
-  const u32 TW = ell_table_limit(h.max_len_a, (u32)W);
+  u32 lf16 = 28; if (const char* e = getenv("BSPGEMM_ELL_LF16")) lf16 = (u32)std::max(16, std::min(64, atoi(e)));   // tuning knob
+  const u32 TW = ell_table_limit(h.max_len_a, (u32)W, lf16);
   if (TW > 8192u || (u64)a.m.Bm < 4ull * TW) return false;
   const size_t avail = d->smem_optin - 64 - ELL_CTA_WORDS * 4;
   const int64_t avgA = std::max<int64_t>(1, (a.Annz + a.m.An - 1) / std::max(a.m.An, 1));
@@ -208,17 +215,61 @@ static bool ell_plan(bspgemm_dev* d) {
   if (const char* e = getenv("BSPGEMM_ELL_R")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) R = v; }   // tuning knob
   const int warps = warps_for(R);
   if (warps < 4) return false;
-  d->use_ell = true; d->ell_W = W; d->ell_R = R; d->ell_TW = TW; d->ell_warps = warps; d->ell_maxA = h.max_len_a;
+  // register-sort variant: regular matrices (every row close to the padded size LA*W <= 512)
+  d->use_sort = false;
+  if (!getenv("BSPGEMM_NO_SORT")) {
+    int lal = 2; while ((1u << lal) < h.max_len_a) ++lal;
+    const int LA = 1 << lal;
+    const bool fits = lal <= 5 && LA * W <= 512;
+    const bool regular = (u64)a.Annz * 2ull >= (u64)a.m.An * (u64)LA || getenv("BSPGEMM_FORCE_SORT");
+    if (fits && regular) { d->use_sort = true; d->sort_LAL = lal; }
+  }
+  d->use_ell = true; d->ell_W = W; d->ell_R = R; d->ell_TW = TW; d->ell_warps = warps; d->ell_maxA = h.max_len_a; d->ell_lf16 = lf16;
   return true;
+}
+
+template <int W, int LAL> static int launch_sort_t(bspgemm_dev* d, int* ccol) {
+  const MulArgs& a = d->a;
+  constexpr SortGeom G = sort_geom<W, LAL>();
+  const u32 ntiles = (u32)(((size_t)a.m.An + G.R - 1) / G.R);
+  const size_t per_warp = (size_t)2 * sort_stage_words(G.R, G.LA, W) * 4;
+  const size_t avail = d->smem_optin - 64 - ELL_CTA_WORDS * 4;
+  const int warps = (int)std::min<size_t>(SORT_MAX_WARPS, avail / per_warp);
+  if (warps < 1) return fail(BSPGEMM_ERR_CUDA, "sort kernel does not fit on an SM");
+  const size_t smem = per_warp * warps + ELL_CTA_WORDS * 4;
+  const long long want = ((long long)ntiles + warps - 1) / warps;
+  const int grid = (int)std::max<long long>(1, std::min<long long>(want, d->sm_count));
+  const size_t niter = ((size_t)ntiles + (size_t)grid * warps - 1) / ((size_t)grid * warps);
+  const size_t nblocks = niter * grid + 1;
+  CKS(d->status.ensure(nblocks));
+  CK(cudaMemsetAsync(d->status.p, 0, nblocks * sizeof(u64), d->stream));
+  CK(cudaEventRecord(d->ev[3], d->stream));
+  EllArgs p{};
+  p.blk_status = d->status.p;
+  p.Arow = a.m.Arow; p.Acol = a.m.Acol; p.Bell = d->bell.p; p.An = a.m.An; p.Bn = a.m.Bn;
+  p.Bm = (u32)a.m.Bm; p.Crow = a.dCrow; p.is64 = a.is64; p.Ccol = ccol; p.sc = d->d_sc; p.ntiles = ntiles;
+  p.debug_nochain = getenv("BSPGEMM_DEBUG_NOCHAIN") ? (u32)(G.R * G.LA * W) : 0u;   // WRONG RESULTS: timing experiments only
+  d->st.rows_per_tile = G.R; d->st.variant = 2;
+  k_fused_sort<W, LAL><<<grid, warps * 32, smem, d->stream>>>(p);
+  d->launches++;
+  CK(cudaGetLastError());
+  return BSPGEMM_OK;
+}
+static int launch_sort(bspgemm_dev* d, int* ccol) {
+  const int W = d->ell_W, L = d->sort_LAL;
+#define LS(Wv) do { switch (L) { case 2: return launch_sort_t<Wv, 2>(d, ccol); case 3: return launch_sort_t<Wv, 3>(d, ccol); case 4: return launch_sort_t<Wv, 4>(d, ccol); \
+                                 default: return launch_sort_t<(Wv == 32 ? 16 : Wv), 5>(d, ccol); } } while (0)
+  switch (W) { case 4: LS(4); case 8: LS(8); case 16: LS(16); default: LS(32); }
+#undef LS
 }
 
 static int launch_ell(bspgemm_dev* d) {
   const MulArgs& a = d->a;
   int* ccol = d->user_ccol ? d->user_ccol : d->ccol.p;
   const int W = d->ell_W, R = d->ell_R;
-  CKS(d->bell.ensure((size_t)a.m.Bn * W + 4));
+  CKS(d->bell.ensure(((size_t)a.m.Bn + 1) * W + 4));
   {
-    const long long threads = (long long)a.m.Bn * (W / 4);
+    const long long threads = ((long long)a.m.Bn + 1) * (W / 4);
     const int grid = (int)((threads + 255) / 256);
     switch (W) {
       case 4:  k_build_ell<4><<<grid, 256, 0, d->stream>>>(a.m.Brow, a.m.Bcol, a.m.Bn, (u32)a.m.Bm, d->bell.p, d->d_sc); break;
@@ -229,6 +280,7 @@ static int launch_ell(bspgemm_dev* d) {
     d->launches++;
     CK(cudaGetLastError());
   }
+  if (d->use_sort) return launch_sort(d, ccol);
   const u32 ntiles = (u32)(((size_t)a.m.An + R - 1) / R);
   const int warps = d->ell_warps;
   const u32 SW = (u32)R * d->ell_maxA * (u32)W;
@@ -244,7 +296,7 @@ static int launch_ell(bspgemm_dev* d) {
   p.blk_status = d->status.p;
   p.Arow = a.m.Arow; p.Acol = a.m.Acol; p.Bell = d->bell.p; p.An = a.m.An; p.Bn = a.m.Bn;
   { const double inv = 4294967296.0 / (double)a.m.Bm * (1.0 - 1.0 / 1048576.0); float f = (float)inv; if ((double)f > inv) f = nextafterf(f, 0.0f); p.inv_bm = f; }
-  p.SW = SW;
+  p.SW = SW; p.lf16 = d->ell_lf16;
   p.TW = d->ell_TW; p.Bm = (u32)a.m.Bm; p.Crow = a.dCrow; p.is64 = a.is64; p.Ccol = ccol; p.sc = d->d_sc;
   p.ntiles = ntiles;
   p.debug_nochain = getenv("BSPGEMM_DEBUG_NOCHAIN") ? (u32)(R * d->ell_maxA * W) : 0u;   // WRONG RESULTS: timing experiments only

@@ -39,11 +39,12 @@ constexpr int ELL_QCAP = 192;            // loser-queue entries per warp (a batc
 struct EllArgs {
   const int* __restrict__ Arow;   // An+1 absolute offsets
   const int* __restrict__ Acol;
-  const u32* __restrict__ Bell;   // Bn rows of W columns, EMPTY-padded
+  const u32* __restrict__ Bell;   // Bn+1 rows of W columns, EMPTY-padded; row Bn is all EMPTY (what an absent A nonzero selects)
   int An, Bn;
   float inv_bm;                   // slightly less than 2^32 / Bm: slot = umulhi(key, floor(T_home * inv_bm)) < T_home
   u32 TW;                         // table words per output row (multiple of 128)
   u32 SW;                         // staging words per tile = R * max_len(A) * W
+  u32 lf16;                       // table sizing rule, see ell_table_limit
   u32 Bm;
   void* Crow; int is64;
   int* Ccol;
@@ -56,11 +57,11 @@ struct EllArgs {
 // Table geometry of a row with lenA nonzeros in A (cap = lenA*W >= its IP): `lim` slots, a multiple of 128 (the
 // compaction reads 128 slots per warp instruction); keys are mapped to the first lim-32 "home" slots, the last 32 only
 // take keys pushed right by collisions.  Load factor of the home slots <= 4/7.
-__host__ __device__ constexpr u32 ell_table_limit(u32 lenA, u32 W) {
+__host__ __device__ constexpr u32 ell_table_limit(u32 lenA, u32 W, u32 lf16 = 28u) {     // lf16/16 = min home slots per key
   const u32 cap = lenA * W;
   u32 lim = (2u * cap + 127u) & ~127u;
   if (lim < 128u) lim = 128u;
-  if ((lim - 32u) * 4u < cap * 7u) lim += 128u;
+  if ((lim - 32u) * 16u < cap * lf16) lim += 128u;
   return lim;
 }
 __host__ __device__ constexpr u32 ell_warp_words(u32 R, u32 TW, u32 SW) { return R * TW + SW + 2u * ELL_QCAP + 4u * 8u; }
@@ -74,7 +75,8 @@ __global__ void __launch_bounds__(256) k_build_ell(const int* __restrict__ Brow,
   const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long row = gtid / LPR;
   const int part = (int)(gtid % LPR);
-  if (row >= Bn) return;
+  if (row > Bn) return;
+  if (row == Bn) { reinterpret_cast<uint4*>(Bell)[row * LPR + part] = make_uint4(EMPTY, EMPTY, EMPTY, EMPTY); return; }   // the "no row" row
   const int bs = Brow[row], be = Brow[row + 1];
   uint4 v;
   u32 x[4];
@@ -337,16 +339,16 @@ __global__ void __launch_bounds__(ELL_MAX_WARPS * 32, 1) k_fused_ell(const EllAr
     const int nr = (int)min((long long)R, (long long)p.An - r0);
     return p.Arow[r0 + min((int)lane, nr)];
   };
-  auto load_acol = [&](int abase, int e0, int E, int& j0, int& j1) {
-    j0 = -1; j1 = -1;
+  auto load_acol = [&](int abase, int e0, int E, int& j0, int& j1) {      // absent entries select the all-EMPTY row Bn
+    j0 = p.Bn; j1 = p.Bn;
     if (e0 + (int)lane < E) j0 = p.Acol[abase + e0 + (int)lane];
     if (e0 + 32 + (int)lane < E) j1 = p.Acol[abase + e0 + 32 + (int)lane];
   };
   auto check_acol = [&](int& j0, int& j1) {
-    if ((j0 >= p.Bn) | (j1 >= p.Bn) | (j0 < -1) | (j1 < -1)) {
+    if (((u32)j0 > (u32)p.Bn) | ((u32)j1 > (u32)p.Bn)) {
       atomicOr(&p.sc->err, 1u);
-      if ((u32)j0 >= (u32)p.Bn) j0 = -1;
-      if ((u32)j1 >= (u32)p.Bn) j1 = -1;
+      if ((u32)j0 > (u32)p.Bn) j0 = p.Bn;
+      if ((u32)j1 > (u32)p.Bn) j1 = p.Bn;
     }
   };
   auto load_group = [&](int g, int j0, int j1, uint4 (&v)[NBG]) {      // the B rows of batches g .. g+NBG-1 of a chunk
@@ -354,8 +356,7 @@ __global__ void __launch_bounds__(ELL_MAX_WARPS * 32, 1) k_fused_ell(const EllAr
     for (int u = 0; u < NBG; ++u) {
       const int seg = (g + u) * NSEG + (int)sub;
       const int j = __shfl_sync(0xffffffffu, ((g + u) * NSEG < 32) ? j0 : j1, seg & 31);
-      v[u] = make_uint4(EMPTY, EMPTY, EMPTY, EMPTY);
-      if (j >= 0) v[u] = __ldg(&Bell4[(size_t)j * LPR + part]);
+      v[u] = __ldg(&Bell4[(size_t)j * LPR + part]);
     }
   };
   // commit of a finished tile: its rows are in stage[0..total), lane r holds the inclusive count of row r
@@ -373,13 +374,15 @@ __global__ void __launch_bounds__(ELL_MAX_WARPS * 32, 1) k_fused_ell(const EllAr
     __syncwarp();
   };
 
-  // ---- pipeline prologue
+  // ---- pipeline prologue: row pointers two tiles ahead, Acol one tile ahead, B rows from the end of the previous
+  // tile's inserts
   u32 tile = cta_first + warp, iter = 0;
-  int a[R + 1];
+  int a[R + 1], an[R + 1];
   {
     const int ar = load_rowptr(tile);
+    const int arn = load_rowptr(tile + stride < tile ? 0xffffffffu : tile + stride);
 #pragma unroll
-    for (int r = 0; r <= R; ++r) a[r] = __shfl_sync(0xffffffffu, ar, r);
+    for (int r = 0; r <= R; ++r) { a[r] = __shfl_sync(0xffffffffu, ar, r); an[r] = __shfl_sync(0xffffffffu, arn, r); }
   }
   int j0, j1;
   uint4 v[NBG];
@@ -390,14 +393,17 @@ __global__ void __launch_bounds__(ELL_MAX_WARPS * 32, 1) k_fused_ell(const EllAr
 
   while (tile < p.ntiles) {
     const u32 next = (tile + stride < tile) ? 0xffffffffu : tile + stride;
-    const int ar_n = load_rowptr(next);                            // in flight during the inserts
+    const u32 next2 = (next + stride < next) ? 0xffffffffu : next + stride;
+    const int ar_nn = load_rowptr(next2);                          // consumed at the end of the iteration
+    int j0n, j1n;
+    load_acol(an[0], 0, an[R] - an[0], j0n, j1n);                  // consumed after the inserts
     const int E = a[R] - a[0];
     int b[R];                                                      // first A nonzero of every row, relative to the tile
 #pragma unroll
     for (int r = 0; r < R; ++r) b[r] = a[r] - a[0];
     u32 lim[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) lim[r] = ell_table_limit((u32)(a[r + 1] - a[r]), W);
+    for (int r = 0; r < R; ++r) lim[r] = ell_table_limit((u32)(a[r + 1] - a[r]), W, p.lf16);
     if (lane < R) {
       u32 l = 128;
 #pragma unroll
@@ -451,6 +457,9 @@ __global__ void __launch_bounds__(ELL_MAX_WARPS * 32, 1) k_fused_ell(const EllAr
         }
       }
     }
+    // ---- next tile: its Acol has arrived; v[] is dead until the next iteration: start the B-row loads now
+    check_acol(j0n, j1n);
+    load_group(0, j0n, j1n, v);
     if (qn) { const u32 d = ell_drain(tab_s, queue_s, 0u, qn, TW); ovf |= d >> 16; added += d & 0xffffu; }
     ovf = __reduce_or_sync(0xffffffffu, ovf);
     u32 agg = __reduce_add_sync(0xffffffffu, added);
@@ -472,13 +481,7 @@ __global__ void __launch_bounds__(ELL_MAX_WARPS * 32, 1) k_fused_ell(const EllAr
     // ---- 3. commit the previous tile (frees the staging buffer)
     if (prev_tile != 0xffffffffu) commit(prev_tile, iter - 1u, prev_incl, prev_total);
 
-    // ---- 4. next tile: row pointers have arrived, start its Acol loads; compact this tile into the staging buffer
-    int an[R + 1];
-#pragma unroll
-    for (int r = 0; r <= R; ++r) an[r] = __shfl_sync(0xffffffffu, ar_n, r);
-    int j0n, j1n;
-    load_acol(an[0], 0, an[R] - an[0], j0n, j1n);
-
+    // ---- 4. compact this tile into the staging buffer
     u32 run = 0, incl_mine = 0;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -501,15 +504,12 @@ __global__ void __launch_bounds__(ELL_MAX_WARPS * 32, 1) k_fused_ell(const EllAr
     }
     __syncwarp();
 
-    // ---- 5. next tile: Acol has arrived, start its B-row loads (v[] is free again)
-    check_acol(j0n, j1n);
-    load_group(0, j0n, j1n, v);
     if (agent) chain_try_resolve(cc, p.blk_status, iter, iter * gridDim.x + blockIdx.x, agent - 1u);
 
     prev_tile = tile; prev_incl = incl_mine; prev_total = run;
     tile = next; ++iter;
 #pragma unroll
-    for (int r = 0; r <= R; ++r) a[r] = an[r];
+    for (int r = 0; r <= R; ++r) { a[r] = an[r]; an[r] = __shfl_sync(0xffffffffu, ar_nn, r); }
     j0 = j0n; j1 = j1n;
   }
   if (prev_tile != 0xffffffffu) commit(prev_tile, iter - 1u, prev_incl, prev_total);

@@ -1,0 +1,238 @@
+// binary-spgemm_b200/csrc/fused_sort.cuh — one-pass kernel for REGULAR short-row matrices: register sorting network.
+//
+// Replaces, like fused_ell.cuh, SpGEMM_bigslice (final/SpGEMM_mpi_omp.c:15-58: Gustavson row product + `xb` flag
+// de-duplication + per-row quickSort) and the concatenation / row-pointer fix-up of SpGEMM_omp (:111-141), for
+// matrices whose every output row has IP <= LA*W <= 512 (LA = max_len(A) rounded up to a power of two, W = ELL width
+// of B).  The hash-table kernel of fused_ell.cuh spends ~560 warp instructions and ~220 L1/shared-memory wavefronts
+// per config-3 row on atomics, collision queues, table init and compaction (profiles/r01_v6_*).  Here the candidate
+// columns never leave the registers they were loaded into:
+//   * a row occupies S lanes with K = LA*W/S <= 16 keys per lane (K/4 LDG.128 of the ELL copy of B, fused_ell.cuh
+//     k_build_ell); 32/S rows are handled by one warp pass;
+//   * a bitonic network sorts the row in place — exchanges at distance < K are register-to-register min/max, larger
+//     distances one SHFL.BFLY + one min/max per key; padding (EMPTY = 0xFFFFFFFF) sorts to the end;
+//   * duplicates are adjacent after the sort: neighbour compare, segmented warp scan, and the distinct keys go to a
+//     bank-skewed staging buffer in shared memory (the only shared-memory traffic: 1 store + 1 load per output);
+//   * no atomics, no collision chains, no overflow path: the cost of a row is a constant, whatever its columns are.
+// The scan / deferred commit / tile pipeline are those of fused_ell.cuh (CtaChain): the aggregate of a tile is posted
+// when its rows are staged, the tile is committed one tile later from the other half of a ping-pong staging buffer.
+#pragma once
+#include "fused_ell.cuh"
+
+namespace bsk {
+
+constexpr int SORT_MAX_WARPS = 24;
+
+struct SortGeom {          // compile-time geometry of k_fused_sort<W, LAL>
+  int LPR, LA, S, NQ, K, RP, R, NP;
+};
+template <int W, int LAL> __host__ __device__ constexpr SortGeom sort_geom() {
+  SortGeom g{};
+  g.LPR = W / 4;                               // lanes per B row (one uint4 each)
+  g.LA = 1 << LAL;                             // B rows per output row (A row length, rounded up)
+  const int cap = g.LA * W;                    // keys per output row (padded)
+  // up to 16 keys per lane: exchanges inside a lane cost 1 instruction per key, across lanes 3 (SHFL, min, max)
+  int s = cap / 16; if (s < g.LPR) s = g.LPR; if (s < 2) s = 2; if (s > 32) s = 32;
+  g.S = s;                                     // lanes per row
+  g.K = cap / g.S;                             // keys per lane per row
+  g.NQ = g.K / 4;                              // uint4 per lane per row
+  g.RP = 32 / g.S;                             // rows per warp pass
+  int r = 64 / g.LA; if (r > 16) r = 16; if (r < g.RP) r = g.RP;
+  const int maxnp = 32 / g.K > 0 ? 32 / g.K : 1;   // at most 32 key registers per lane in flight
+  if (r > g.RP * maxnp) r = g.RP * maxnp;
+  g.R = r;                                     // rows per tile (R * LA <= 64 A nonzeros, or one pass)
+  g.NP = g.R / g.RP;                           // passes per tile
+  return g;
+}
+// staging words of one tile: R rows of LA*W keys, plus one pad word per 32 (bank skew)
+__host__ __device__ constexpr u32 sort_stage_words(int R, int LA, int W) { const u32 n = (u32)(R * LA * W); return (n + n / 32u + 4u + 3u) & ~3u; }
+
+// In-place ascending bitonic sort of 32/S independent rows, K keys per lane, element index i = lane_in_row*K + k.
+// "Flip" formulation: every merge level starts with the mirror exchange i <-> i ^ (size-1), then half-cleaners
+// i <-> i ^ d; every comparator puts the minimum at the lower index, so exchanges inside a lane need no run-time
+// direction (min + max), exchanges between lanes cost SHFL + min + predicated max.
+template <int K, int S>
+__device__ __forceinline__ void bitonic_sort_rows(u32 (&x)[K], const u32 ll) {
+  constexpr int N = K * S;
+#pragma unroll
+  for (int size = 2; size <= N; size <<= 1) {
+    if (size <= K) {                                               // mirror inside the lane
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const int pk = k ^ (size - 1);
+        if (k < pk) { const u32 lo = min(x[k], x[pk]), hi = max(x[k], x[pk]); x[k] = lo; x[pk] = hi; }
+      }
+    } else {                                                       // mirror across lanes: register k <-> K-1-k of lane ^ (size/K-1)
+      const u32 lm = (u32)(size / K - 1);
+      const bool keepmin = (ll & (u32)(size / (2 * K))) == 0u;
+#pragma unroll
+      for (int k = 0; k < K / 2; ++k) {
+        const u32 ya = __shfl_xor_sync(0xffffffffu, x[K - 1 - k], lm);
+        const u32 yb = __shfl_xor_sync(0xffffffffu, x[k], lm);
+        x[k] = keepmin ? min(x[k], ya) : max(x[k], ya);
+        x[K - 1 - k] = keepmin ? min(x[K - 1 - k], yb) : max(x[K - 1 - k], yb);
+      }
+    }
+#pragma unroll
+    for (int d = size >> 2; d >= 1; d >>= 1) {
+      if (d >= K) {                                                // partner key lives in lane ^ (d/K)
+        const u32 ld = (u32)(d / K);
+        const bool keepmin = (ll & ld) == 0u;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const u32 y = __shfl_xor_sync(0xffffffffu, x[k], ld);
+          x[k] = keepmin ? min(x[k], y) : max(x[k], y);
+        }
+      } else {                                                     // both keys in this lane
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+          if ((k & d) == 0) { const u32 lo = min(x[k], x[k | d]), hi = max(x[k], x[k | d]); x[k] = lo; x[k | d] = hi; }
+      }
+    }
+  }
+}
+
+// Every warp is an independent worker on tiles of R consecutive rows.  Per iteration (tile t):
+//   for each pass: sort the pass's rows in registers, mark first occurrences, scan, write the distinct keys to the
+//   current staging buffer; then reload the same registers with the same pass of tile t+1;
+//   post the tile's aggregate; commit tile t-1 from the other staging buffer.
+template <int W, int LAL>
+__global__ void __launch_bounds__(SORT_MAX_WARPS * 32, 1) k_fused_sort(const EllArgs p) {
+  constexpr SortGeom G = sort_geom<W, LAL>();
+  constexpr int LPR = G.LPR, S = G.S, NQ = G.NQ, K = G.K, RP = G.RP, R = G.R, NP = G.NP;
+  constexpr u32 SWORDS = sort_stage_words(R, G.LA, W);
+  extern __shared__ __align__(16) u32 smem[];
+  const u32 warp = threadIdx.x >> 5, lane = lane_id(), nwarps = blockDim.x >> 5;
+  const u32 stage_s = (u32)__cvta_generic_to_shared(smem) + warp * (2u * SWORDS * 4u);    // ping-pong staging buffers
+  CtaChain* cc = reinterpret_cast<CtaChain*>(smem + (size_t)nwarps * 2u * SWORDS);
+  for (u32 i = threadIdx.x; i < sizeof(CtaChain) / 4; i += blockDim.x) reinterpret_cast<u32*>(cc)[i] = 0;
+  __syncthreads();                          // the only CTA-wide barrier
+  const u32 ll = lane % S, seg = lane / S;  // lane within its row, row within the pass
+  const uint4* __restrict__ Bell4 = reinterpret_cast<const uint4*>(p.Bell);
+  u32 ipc = 0;
+  const u32 stride = gridDim.x * nwarps;
+  const u32 cta_first = blockIdx.x * nwarps;
+
+  auto load_rowptr = [&](u32 t) -> int {     // lane r (r <= R) gets Arow[t*R + r], clamped to the matrix
+    if (t >= p.ntiles) return 0;
+    const long long r0 = (long long)t * R;
+    const int nr = (int)min((long long)R, (long long)p.An - r0);
+    return p.Arow[r0 + min((int)lane, nr)];
+  };
+  auto load_acol = [&](int ar, int& j0, int& j1) {                 // the tile's A nonzeros (<= 64), absent ones select row Bn
+    const int a0 = __shfl_sync(0xffffffffu, ar, 0), E = __shfl_sync(0xffffffffu, ar, R) - a0;
+    j0 = p.Bn; j1 = p.Bn;
+    if ((int)lane < E) j0 = p.Acol[a0 + (int)lane];
+    if (32 + (int)lane < E) j1 = p.Acol[a0 + 32 + (int)lane];
+  };
+  auto check_acol = [&](int& j0, int& j1) {
+    if (((u32)j0 > (u32)p.Bn) | ((u32)j1 > (u32)p.Bn)) {
+      atomicOr(&p.sc->err, 1u);
+      if ((u32)j0 > (u32)p.Bn) j0 = p.Bn;
+      if ((u32)j1 > (u32)p.Bn) j1 = p.Bn;
+    }
+  };
+  // keys of pass q of a tile: lane (seg, ll) takes uint4 number u of row q*RP+seg from B row slot u*(S/LPR) + ll/LPR
+  auto load_pass = [&](int q, int ar, int j0, int j1, u32 (&x)[K]) {
+    const int row = q * RP + (int)seg;
+    const int a0 = __shfl_sync(0xffffffffu, ar, 0);
+    const int lo = __shfl_sync(0xffffffffu, ar, row), hi = __shfl_sync(0xffffffffu, ar, row + 1);
+#pragma unroll
+    for (int u = 0; u < NQ; ++u) {
+      const int i = u * (S / LPR) + (int)(ll / LPR);
+      const int e = lo - a0 + i;
+      const int ja = __shfl_sync(0xffffffffu, j0, e & 31), jb = __shfl_sync(0xffffffffu, j1, e & 31);
+      int j = (e < 32) ? ja : jb;
+      if (i >= hi - lo) j = p.Bn;
+      const uint4 t4 = __ldg(&Bell4[(size_t)j * LPR + (ll % LPR)]);
+      x[4 * u + 0] = t4.x; x[4 * u + 1] = t4.y; x[4 * u + 2] = t4.z; x[4 * u + 3] = t4.w;
+    }
+  };
+  auto commit = [&](u32 t, u32 iter, u32 incl_mine, u32 total, u32 buf_s) {
+    const u32 blk = iter * gridDim.x + blockIdx.x;
+    const u32 expected = min(nwarps, p.ntiles - (iter * stride + cta_first));
+    const u64 excl = p.debug_nochain ? (u64)t * (u64)p.debug_nochain : chain_resolve(cc, p.blk_status, iter, warp, blk, expected);
+    const long long row0 = (long long)t * R;
+    const int nrows = (int)min((long long)R, (long long)p.An - row0);
+    if ((int)lane < nrows) st_rowptr(p.Crow, p.is64, (size_t)(row0 + lane) + 1, excl + incl_mine, &p.sc->err);
+    if (t == 0 && lane == 0) st_rowptr(p.Crow, p.is64, 0, 0, &p.sc->err);
+    if (t == p.ntiles - 1 && lane == 0) p.sc->total_nnz = excl + total;
+    int* dst = p.Ccol + excl;
+    u32 src = buf_s + 4u * lane;                                   // key q lives at word q + q/32: 33 words per 32 keys
+    for (u32 q = lane; q < total; q += 32, src += 132u) dst[q] = (int)lds32(src);
+    __syncwarp();
+  };
+
+  // ---- pipeline prologue
+  u32 tile = cta_first + warp, iter = 0;
+  int ar = load_rowptr(tile);
+  int arn = load_rowptr(tile + stride < tile ? 0xffffffffu : tile + stride);
+  int j0, j1;
+  load_acol(ar, j0, j1);
+  check_acol(j0, j1);
+  u32 x[NP][K];
+#pragma unroll
+  for (int q = 0; q < NP; ++q) load_pass(q, ar, j0, j1, x[q]);
+  u32 prev_tile = 0xffffffffu, prev_incl = 0, prev_total = 0;
+
+  while (tile < p.ntiles) {
+    const u32 next = (tile + stride < tile) ? 0xffffffffu : tile + stride;
+    const u32 next2 = (next + stride < next) ? 0xffffffffu : next + stride;
+    const int arnn = load_rowptr(next2);
+    int j0n, j1n;
+    load_acol(arn, j0n, j1n);
+    const u32 cur_s = stage_s + (iter & 1u) * (SWORDS * 4u);
+    u32 run = 0, incl_mine = 0;
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+      u32 (&k)[K] = x[q];
+#pragma unroll
+      for (int i = 0; i < K; ++i) ipc += (k[i] != EMPTY) ? 1u : 0u;
+      bitonic_sort_rows<K, S>(k, ll);
+      // first occurrences: the row is ascending along (lane, register)
+      u32 prev_last = __shfl_up_sync(0xffffffffu, k[K - 1], 1);
+      if (ll == 0) prev_last = EMPTY;                              // nothing before the row's first key (EMPTY never counts)
+      bool f[K];
+      u32 cnt = 0;
+#pragma unroll
+      for (int i = 0; i < K; ++i) { f[i] = (k[i] != EMPTY) && (k[i] != (i ? k[i - 1] : prev_last)); cnt += f[i] ? 1u : 0u; }
+      // inclusive scan of cnt inside the row's S lanes
+      u32 inc = cnt;
+#pragma unroll
+      for (int d = 1; d < S; d <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, inc, d); if ((int)ll >= d) inc += t; }
+      // rows of the pass are staged back to back, in row order
+      u32 rowbase = run;
+#pragma unroll
+      for (int sq = 0; sq < RP; ++sq) {
+        const u32 tot = __shfl_sync(0xffffffffu, inc, sq * S + S - 1);
+        if ((int)seg > sq) rowbase += tot;
+        run += tot;
+        if ((int)lane == q * RP + sq) incl_mine = run;
+      }
+      u32 o = rowbase + inc - cnt;
+#pragma unroll
+      for (int i = 0; i < K; ++i) if (f[i]) { sts32(cur_s + 4u * (o + (o >> 5)), k[i]); ++o; }
+      // the registers of this pass are free: refill them with the same pass of the next tile
+      if (q == 0) check_acol(j0n, j1n);
+      load_pass(q, arn, j0n, j1n, k);
+    }
+    __syncwarp();
+    u32 agent = 0;
+    if (!p.debug_nochain) {
+      const u32 blk_first = iter * stride + cta_first;
+      const u32 expected = min(nwarps, p.ntiles - blk_first);
+      agent = chain_post(cc, p.blk_status, iter, warp, run, expected, iter * gridDim.x + blockIdx.x);
+    }
+    if (prev_tile != 0xffffffffu) commit(prev_tile, iter - 1u, prev_incl, prev_total, stage_s + ((iter - 1u) & 1u) * (SWORDS * 4u));
+    if (agent) chain_try_resolve(cc, p.blk_status, iter, iter * gridDim.x + blockIdx.x, agent - 1u);
+    prev_tile = tile; prev_incl = incl_mine; prev_total = run;
+    tile = next; ++iter;
+    ar = arn; arn = arnn; j0 = j0n; j1 = j1n;
+  }
+  if (prev_tile != 0xffffffffu) commit(prev_tile, iter - 1u, prev_incl, prev_total, stage_s + ((iter - 1u) & 1u) * (SWORDS * 4u));
+  u64 ips = ipc;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) ips += __shfl_xor_sync(0xffffffffu, ips, d);
+  if (lane == 0 && ips) atomicAdd(&p.sc->total_ip, ips);
+}
+
+}  // namespace bsk

@@ -115,8 +115,9 @@ typedef struct bspgemm_stats {
   float   ms_main;            /* fused kernel (fused mode) or scan + S numeric kernel (two-phase) */
   float   ms_numeric;         /* M/L numeric kernels */
   int64_t algorithmic_bytes;  /* 4(An+1)+12nnzA+4IP+4nnzC+4(An+1) (8-byte terms for _i64 Crow) */
-  int32_t variant;            /* 0 = CSR-gather kernels (kernels.cuh), 1 = ELL fast path (fused_ell.cuh; then cap_s = table
-                                 words per row, group = ELL width W, ms_symbolic = the CSR->ELL re-layout of B) */
+  int32_t variant;            /* 0 = CSR-gather kernels (kernels.cuh); ELL fast paths: 1 = ordered-table kernel (fused_ell.cuh),
+                                 2 = register sorting network (fused_sort.cuh); then cap_s = table words per row, group =
+                                 ELL width W, ms_symbolic = the CSR->ELL re-layout of B */
   int32_t rows_per_tile;      /* fused kernels: consecutive rows per look-back tile */
 } bspgemm_stats;
 

@@ -328,23 +328,36 @@ def test_ell_fast_path_variants(bs, oracle, monkeypatch):
     Brow, Bcol = random_csr(rng, n, m, 2.5, sort=True, dups=False)
     cases.append(("short rows", Acol, Arow, n, Bcol, Brow, n, m))
     seen = set()
-    for name, Acol, Arow, An, Bcol, Brow, Bn, Bm in cases:
-        want_col, want_row = oracle.spgemm(Acol, Arow, An, Bcol, Brow, Bm)
-        for i64 in (False, True):
-            got_col, got_row, st = dev_multiply(bs, bs.MODE_AUTO, Acol, Arow, An, Bcol, Brow, Bn, Bm, i64=i64)
-            msg = _explain(got_col, got_row, want_col, want_row)
-            assert not msg, f"{name} i64={i64}: {msg}"
-            assert st["ip"] == oracle.intermediate_products(Acol, Arow, An, Brow), name
-            if np.diff(Brow).max() <= 32:
-                assert st["variant"] == 1, f"{name}: expected the ELL fast path, stats {st}"
-                seen.add((st["group"], st["rows_per_tile"]))
-    assert {w for w, _ in seen} == {4, 8, 16, 32}, seen
-    assert len({r for _, r in seen}) >= 3, seen
+    for kernel in ("hash", "sort"):
+        # hash: ordered-table kernel (fused_ell.cuh, variant 1); sort: register sorting network (fused_sort.cuh, variant 2)
+        monkeypatch.delenv("BSPGEMM_NO_SORT", raising=False)
+        monkeypatch.delenv("BSPGEMM_FORCE_SORT", raising=False)
+        monkeypatch.setenv("BSPGEMM_NO_SORT" if kernel == "hash" else "BSPGEMM_FORCE_SORT", "1")
+        for name, Acol, Arow, An, Bcol, Brow, Bn, Bm in cases:
+            want_col, want_row = oracle.spgemm(Acol, Arow, An, Bcol, Brow, Bm)
+            for i64 in (False, True):
+                got_col, got_row, st = dev_multiply(bs, bs.MODE_AUTO, Acol, Arow, An, Bcol, Brow, Bn, Bm, i64=i64)
+                msg = _explain(got_col, got_row, want_col, want_row)
+                assert not msg, f"{name} [{kernel}] i64={i64}: {msg}"
+                assert st["ip"] == oracle.intermediate_products(Acol, Arow, An, Brow), name
+                if np.diff(Brow).max() <= 32:
+                    la = 4
+                    while la < np.diff(Arow).max():
+                        la *= 2
+                    sortable = la <= 32 and la * st["group"] <= 512
+                    want_variant = 2 if (kernel == "sort" and sortable) else 1
+                    assert st["variant"] == want_variant, f"{name} [{kernel}]: stats {st}"
+                    seen.add((st["variant"], st["group"], st["rows_per_tile"]))
+    assert {w for v, w, _ in seen if v == 1} == {4, 8, 16, 32}, seen
+    assert {w for v, w, _ in seen if v == 2} >= {4, 8, 16}, seen
+    assert len({r for v, _, r in seen if v == 1}) >= 3, seen
 
 
-def test_ell_clustered_columns_spill_and_rebuild(bs, oracle):
+@pytest.mark.parametrize("kernel", ["hash", "sort"])
+def test_ell_clustered_columns_spill_and_rebuild(bs, oracle, monkeypatch, kernel):
     """Columns of B concentrated in a sliver of a wide [0,Bm): the global monotone slot map sends every key of a
     row to a handful of slots, chains run past the 32 spare slots, the row is rebuilt by the exact path."""
+    monkeypatch.setenv("BSPGEMM_NO_SORT" if kernel == "hash" else "BSPGEMM_FORCE_SORT", "1")
     rng = np.random.default_rng(37)
     n, Bm = 6000, 1 << 22
     Arow, Acol = random_csr(rng, n, n, 12.0, sort=True, dups=False)
@@ -356,7 +369,7 @@ def test_ell_clustered_columns_spill_and_rebuild(bs, oracle):
     got_col, got_row, st = dev_multiply(bs, bs.MODE_AUTO, Acol, Arow, n, Bcol, Brow, n, Bm)
     msg = _explain(got_col, got_row, want_col, want_row)
     assert not msg, msg
-    assert st["variant"] == 1
+    assert st["variant"] == (1 if kernel == "hash" else 2)
     # two clusters far apart + a few uniform columns: partial spills
     Bcol2 = Bcol.copy()
     sel = rng.random(len(Bcol2)) < 0.3
