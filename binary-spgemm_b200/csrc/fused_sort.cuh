@@ -30,17 +30,23 @@ template <int W, int LAL> __host__ __device__ constexpr SortGeom sort_geom() {
   g.LPR = W / 4;                               // lanes per B row (one uint4 each)
   g.LA = 1 << LAL;                             // B rows per output row (A row length, rounded up)
   const int cap = g.LA * W;                    // keys per output row (padded)
-  // up to 16 keys per lane: exchanges inside a lane cost 1 instruction per key, across lanes 3 (SHFL, min, max)
-  int s = cap / 16; if (s < g.LPR) s = g.LPR; if (s < 2) s = 2; if (s > 32) s = 32;
-  g.S = s;                                     // lanes per row
-  g.K = cap / g.S;                             // keys per lane per row
+  // As many keys per lane as possible (exchanges inside a lane cost 1 instruction per key, across lanes 3: SHFL,
+  // min, max), subject to: a row spans >= max(LPR, 2) lanes, at most 32 key registers per lane, and the rows of one
+  // warp pass own at most 64 A nonzeros (two registers of Acol per lane).
+  int k = 32;
+  while (k > 4) {
+    const int s = cap / k;
+    if (s >= (g.LPR > 2 ? g.LPR : 2) && s <= 32 && (32 / s) * g.LA <= 64) break;
+    k >>= 1;
+  }
+  g.K = k;                                     // keys per lane per row
+  g.S = cap / k;                               // lanes per row
   g.NQ = g.K / 4;                              // uint4 per lane per row
   g.RP = 32 / g.S;                             // rows per warp pass
-  int r = 64 / g.LA; if (r > 16) r = 16; if (r < g.RP) r = g.RP;
-  const int maxnp = 32 / g.K > 0 ? 32 / g.K : 1;   // at most 32 key registers per lane in flight
-  if (r > g.RP * maxnp) r = g.RP * maxnp;
-  g.R = r;                                     // rows per tile (R * LA <= 64 A nonzeros, or one pass)
-  g.NP = g.R / g.RP;                           // passes per tile
+  int np = 32 / g.K; if (np < 1) np = 1;       // passes per tile: at most 32 key registers per lane in flight,
+  while (np > 1 && (g.RP * np * g.LA > 64 || g.RP * np > 16)) np >>= 1;   // <= 64 A nonzeros and <= 16 rows per tile
+  g.NP = np;
+  g.R = g.RP * np;                             // rows per tile
   return g;
 }
 // staging words of one tile: R rows of LA*W keys, plus one pad word per 32 (bank skew)
@@ -195,22 +201,37 @@ __global__ void __launch_bounds__(SORT_MAX_WARPS * 32, 1) k_fused_sort(const Ell
       u32 cnt = 0;
 #pragma unroll
       for (int i = 0; i < K; ++i) { f[i] = (k[i] != EMPTY) && (k[i] != (i ? k[i - 1] : prev_last)); cnt += f[i] ? 1u : 0u; }
-      // inclusive scan of cnt inside the row's S lanes
-      u32 inc = cnt;
+      if (__all_sync(0xffffffffu, cnt == (u32)K)) {
+        // the usual case: no duplicate, no padding anywhere in the pass — every key's place is known in advance
+        const u32 pos = lane * (u32)K;                             // rows of the pass back to back, lane-major
+        const u32 a0s = cur_s + 4u * (run + pos + ((run + pos) >> 5));
+        if (((run + pos) & 31u) + (u32)K <= 32u || (K % 32 == 0 && ((run + pos) & 31u) == 0u)) {
 #pragma unroll
-      for (int d = 1; d < S; d <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, inc, d); if ((int)ll >= d) inc += t; }
-      // rows of the pass are staged back to back, in row order
-      u32 rowbase = run;
+          for (int i = 0; i < K; ++i) sts32(a0s + 4u * (u32)(i + i / 32), k[i]);
+        } else {
 #pragma unroll
-      for (int sq = 0; sq < RP; ++sq) {
-        const u32 tot = __shfl_sync(0xffffffffu, inc, sq * S + S - 1);
-        if ((int)seg > sq) rowbase += tot;
-        run += tot;
-        if ((int)lane == q * RP + sq) incl_mine = run;
+          for (int i = 0; i < K; ++i) { const u32 o = run + pos + (u32)i; sts32(cur_s + 4u * (o + (o >> 5)), k[i]); }
+        }
+#pragma unroll
+        for (int sq = 0; sq < RP; ++sq) { run += (u32)(K * S); if ((int)lane == q * RP + sq) incl_mine = run; }
+      } else {
+        // inclusive scan of cnt inside the row's S lanes
+        u32 inc = cnt;
+#pragma unroll
+        for (int d = 1; d < S; d <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, inc, d); if ((int)ll >= d) inc += t; }
+        // rows of the pass are staged back to back, in row order
+        u32 rowbase = run;
+#pragma unroll
+        for (int sq = 0; sq < RP; ++sq) {
+          const u32 tot = __shfl_sync(0xffffffffu, inc, sq * S + S - 1);
+          if ((int)seg > sq) rowbase += tot;
+          run += tot;
+          if ((int)lane == q * RP + sq) incl_mine = run;
+        }
+        u32 o = rowbase + inc - cnt;
+#pragma unroll
+        for (int i = 0; i < K; ++i) if (f[i]) { sts32(cur_s + 4u * (o + (o >> 5)), k[i]); ++o; }
       }
-      u32 o = rowbase + inc - cnt;
-#pragma unroll
-      for (int i = 0; i < K; ++i) if (f[i]) { sts32(cur_s + 4u * (o + (o >> 5)), k[i]); ++o; }
       // the registers of this pass are free: refill them with the same pass of the next tile
       if (q == 0) check_acol(j0n, j1n);
       load_pass(q, arn, j0n, j1n, k);
