@@ -271,12 +271,10 @@ static int launch_ell(bspgemm_dev* d) {
   {
     const long long threads = ((long long)a.m.Bn + 1) * (W / 4);
     const int grid = (int)((threads + 255) / 256);
-    switch (W) {
-      case 4:  k_build_ell<4><<<grid, 256, 0, d->stream>>>(a.m.Brow, a.m.Bcol, a.m.Bn, (u32)a.m.Bm, d->bell.p, d->d_sc); break;
-      case 8:  k_build_ell<8><<<grid, 256, 0, d->stream>>>(a.m.Brow, a.m.Bcol, a.m.Bn, (u32)a.m.Bm, d->bell.p, d->d_sc); break;
-      case 16: k_build_ell<16><<<grid, 256, 0, d->stream>>>(a.m.Brow, a.m.Bcol, a.m.Bn, (u32)a.m.Bm, d->bell.p, d->d_sc); break;
-      default: k_build_ell<32><<<grid, 256, 0, d->stream>>>(a.m.Brow, a.m.Bcol, a.m.Bn, (u32)a.m.Bm, d->bell.p, d->d_sc); break;
-    }
+#define BE(Wv) do { if (d->use_sort) k_build_ell<Wv, true><<<grid, 256, 0, d->stream>>>(a.m.Brow, a.m.Bcol, a.m.Bn, (u32)a.m.Bm, d->bell.p, d->d_sc); \
+                    else k_build_ell<Wv, false><<<grid, 256, 0, d->stream>>>(a.m.Brow, a.m.Bcol, a.m.Bn, (u32)a.m.Bm, d->bell.p, d->d_sc); } while (0)
+    switch (W) { case 4: BE(4); break; case 8: BE(8); break; case 16: BE(16); break; default: BE(32); break; }
+#undef BE
     d->launches++;
     CK(cudaGetLastError());
   }

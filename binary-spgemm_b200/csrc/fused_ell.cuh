@@ -67,18 +67,20 @@ __host__ __device__ constexpr u32 ell_table_limit(u32 lenA, u32 W, u32 lf16 = 28
 __host__ __device__ constexpr u32 ell_warp_words(u32 R, u32 TW, u32 SW) { return R * TW + SW + 2u * ELL_QCAP + 4u * 8u; }
 constexpr u32 ELL_CTA_WORDS = 160;       // CtaChain, after the warp regions
 
-// ---- B (CSR) -> ELL.  LPR = W/4 lanes write one row as uint4 each; also validates B's columns.
-template <int W>
+// ---- B (CSR) -> ELL.  LPR = W/4 lanes write one row as uint4 each; also validates B's columns.  SORTED: every ELL row
+// is sorted ascending (EMPTY padding last) by a small register network — the sorting-network kernel (fused_sort.cuh)
+// starts its merges from these runs; the reference accepts unsorted rows, so nothing may be assumed.
+template <int K, int S, int RUN> __device__ __forceinline__ void bitonic_sort_rows(u32 (&x)[K], const u32 ll);   // fused_sort.cuh
+template <int W, bool SORTED>
 __global__ void __launch_bounds__(256) k_build_ell(const int* __restrict__ Brow, const int* __restrict__ Bcol, int Bn, u32 Bm,
                                                    u32* __restrict__ Bell, DevScalars* sc) {
   constexpr int LPR = W / 4;
   const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long row = gtid / LPR;
+  long long row = gtid / LPR;
   const int part = (int)(gtid % LPR);
-  if (row > Bn) return;
-  if (row == Bn) { reinterpret_cast<uint4*>(Bell)[row * LPR + part] = make_uint4(EMPTY, EMPTY, EMPTY, EMPTY); return; }   // the "no row" row
-  const int bs = Brow[row], be = Brow[row + 1];
-  uint4 v;
+  const bool live = row <= Bn;                 // row Bn is the all-EMPTY "no row" row; lanes beyond it only take part in shuffles
+  if (!live) row = Bn;
+  const int bs = row < Bn ? Brow[row] : 0, be = row < Bn ? Brow[row + 1] : 0;
   u32 x[4];
   u32 bad = 0;
 #pragma unroll
@@ -87,8 +89,8 @@ __global__ void __launch_bounds__(256) k_build_ell(const int* __restrict__ Brow,
     x[k] = (o < be) ? (u32)__ldg(&Bcol[o]) : EMPTY;
     if (o < be && x[k] >= Bm) { bad = 1; x[k] = EMPTY; }
   }
-  v.x = x[0]; v.y = x[1]; v.z = x[2]; v.w = x[3];
-  reinterpret_cast<uint4*>(Bell)[row * LPR + part] = v;
+  if (SORTED) bitonic_sort_rows<4, LPR, 1>(x, (u32)part);          // 256 threads = whole rows: LPR divides 32
+  if (live) reinterpret_cast<uint4*>(Bell)[row * LPR + part] = make_uint4(x[0], x[1], x[2], x[3]);
   if (bad) atomicOr(&sc->err, 4u);
 }
 

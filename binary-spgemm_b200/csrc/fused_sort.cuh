@@ -56,11 +56,12 @@ __host__ __device__ constexpr u32 sort_stage_words(int R, int LA, int W) { const
 // "Flip" formulation: every merge level starts with the mirror exchange i <-> i ^ (size-1), then half-cleaners
 // i <-> i ^ d; every comparator puts the minimum at the lower index, so exchanges inside a lane need no run-time
 // direction (min + max), exchanges between lanes cost SHFL + min + predicated max.
-template <int K, int S>
+// RUN: the keys arrive as ascending runs of RUN consecutive elements (1 = unsorted): the merge levels up to RUN are skipped.
+template <int K, int S, int RUN = 1>
 __device__ __forceinline__ void bitonic_sort_rows(u32 (&x)[K], const u32 ll) {
   constexpr int N = K * S;
 #pragma unroll
-  for (int size = 2; size <= N; size <<= 1) {
+  for (int size = 2 * RUN; size <= N; size <<= 1) {
     if (size <= K) {                                               // mirror inside the lane
 #pragma unroll
       for (int k = 0; k < K; ++k) {
@@ -137,20 +138,29 @@ __global__ void __launch_bounds__(SORT_MAX_WARPS * 32, 1) k_fused_sort(const Ell
       if ((u32)j1 > (u32)p.Bn) j1 = p.Bn;
     }
   };
-  // keys of pass q of a tile: lane (seg, ll) takes uint4 number u of row q*RP+seg from B row slot u*(S/LPR) + ll/LPR
+  // keys of pass q of a tile.  The K keys of lane (seg, ll) are consecutive uint4 of the row's B rows taken in A order:
+  // uint4 number t = ll*NQ + u of the row is part t % LPR of B row slot t / LPR, so a lane holds whole (sorted) B rows,
+  // or a contiguous piece of one.
   auto load_pass = [&](int q, int ar, int j0, int j1, u32 (&x)[K]) {
     const int row = q * RP + (int)seg;
     const int a0 = __shfl_sync(0xffffffffu, ar, 0);
     const int lo = __shfl_sync(0xffffffffu, ar, row), hi = __shfl_sync(0xffffffffu, ar, row + 1);
+    constexpr int SLOTS = NQ >= LPR ? NQ / LPR : 1;                // B rows per lane
+    constexpr int PARTS = NQ >= LPR ? LPR : NQ;                    // uint4 per B row taken by this lane
 #pragma unroll
-    for (int u = 0; u < NQ; ++u) {
-      const int i = u * (S / LPR) + (int)(ll / LPR);
-      const int e = lo - a0 + i;
+    for (int g = 0; g < SLOTS; ++g) {
+      const int slot = NQ >= LPR ? (int)ll * SLOTS + g : (int)(ll * NQ) / LPR;
+      const int part0 = NQ >= LPR ? 0 : (int)(ll * NQ) % LPR;
+      const int e = lo - a0 + slot;
       const int ja = __shfl_sync(0xffffffffu, j0, e & 31), jb = __shfl_sync(0xffffffffu, j1, e & 31);
       int j = (e < 32) ? ja : jb;
-      if (i >= hi - lo) j = p.Bn;
-      const uint4 t4 = __ldg(&Bell4[(size_t)j * LPR + (ll % LPR)]);
-      x[4 * u + 0] = t4.x; x[4 * u + 1] = t4.y; x[4 * u + 2] = t4.z; x[4 * u + 3] = t4.w;
+      if (slot >= hi - lo) j = p.Bn;
+#pragma unroll
+      for (int c = 0; c < PARTS; ++c) {
+        const uint4 t4 = __ldg(&Bell4[(size_t)j * LPR + part0 + c]);
+        const int u = g * PARTS + c;
+        x[4 * u + 0] = t4.x; x[4 * u + 1] = t4.y; x[4 * u + 2] = t4.z; x[4 * u + 3] = t4.w;
+      }
     }
   };
   auto commit = [&](u32 t, u32 iter, u32 incl_mine, u32 total, u32 buf_s) {
@@ -193,7 +203,7 @@ __global__ void __launch_bounds__(SORT_MAX_WARPS * 32, 1) k_fused_sort(const Ell
       u32 (&k)[K] = x[q];
 #pragma unroll
       for (int i = 0; i < K; ++i) ipc += (k[i] != EMPTY) ? 1u : 0u;
-      bitonic_sort_rows<K, S>(k, ll);
+      bitonic_sort_rows<K, S, (W < K ? W : K)>(k, ll);     // every B row is ascending in the ELL copy (k_build_ell sorts it)
       // first occurrences: the row is ascending along (lane, register)
       u32 prev_last = __shfl_up_sync(0xffffffffu, k[K - 1], 1);
       if (ll == 0) prev_last = EMPTY;                              // nothing before the row's first key (EMPTY never counts)
