@@ -209,9 +209,9 @@ static bool ell_plan(bspgemm_dev* d) {
   const int64_t avgA = std::max<int64_t>(1, (a.Annz + a.m.An - 1) / std::max(a.m.An, 1));
   // R rows per tile: as many as keep (a) the tile's A nonzeros within one 64-entry chunk on average and (b) the CTA at
   // ELL_MAX_WARPS warps (shared memory per warp grows with R; occupancy matters more than amortising the tile overhead)
-  auto warps_for = [&](int r) { return (int)std::min<size_t>(ELL_MAX_WARPS, avail / ((size_t)ell_warp_words(r, TW, r * h.max_len_a * W) * 4)); };
+  auto warps_for = [&](int r) { return (int)std::min<size_t>(ELL_MAX_WARPS - 1, avail / ((size_t)ell_warp_words(r, TW, r * h.max_len_a * W) * 4)); };
   int R = 8;
-  while (R > 1 && ((int64_t)R * avgA > 64 || warps_for(R) < ELL_MAX_WARPS)) R >>= 1;
+  while (R > 1 && ((int64_t)R * avgA > 64 || warps_for(R) < ELL_MAX_WARPS - 1)) R >>= 1;
   if (const char* e = getenv("BSPGEMM_ELL_R")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) R = v; }   // tuning knob
   const int warps = warps_for(R);
   if (warps < 4) return false;
@@ -228,13 +228,23 @@ static bool ell_plan(bspgemm_dev* d) {
   return true;
 }
 
+// Compute warps per CTA for the persistent fused kernels (one more warp, the chain helper, is added at launch).
+// Shared memory comes out of the SM's 256 KB unified array in steps (.., 164, 196, 228 KB); what is left is L1, which
+// the gathers of B want: stay one step below the maximum unless that costs more than a fifth of the warps.
+static int pick_compute_warps(size_t per_warp, size_t fixed, int max_warps, size_t optin) {
+  auto fit = [&](size_t cap) { return cap > fixed ? (int)std::min<size_t>((size_t)max_warps, (cap - fixed) / per_warp) : 0; };
+  const int w_max = fit(optin), w_step = fit(196 * 1024 - 1024);
+  int w = (w_step * 5 >= w_max * 4) ? w_step : w_max;
+  if (const char* e = getenv("BSPGEMM_WARPS")) w = std::max(1, std::min(w_max, atoi(e)));   // tuning knob
+  return w;
+}
+
 template <int W, int LAL> static int launch_sort_t(bspgemm_dev* d, int* ccol) {
   const MulArgs& a = d->a;
   constexpr SortGeom G = sort_geom<W, LAL>();
   const u32 ntiles = (u32)(((size_t)a.m.An + G.R - 1) / G.R);
   const size_t per_warp = (size_t)2 * sort_stage_words(G.R, G.LA, W) * 4;
-  const size_t avail = d->smem_optin - 64 - ELL_CTA_WORDS * 4;
-  const int warps = (int)std::min<size_t>(SORT_MAX_WARPS, avail / per_warp);
+  const int warps = pick_compute_warps(per_warp, ELL_CTA_WORDS * 4 + 64, SORT_MAX_WARPS - 1, d->smem_optin);
   if (warps < 1) return fail(BSPGEMM_ERR_CUDA, "sort kernel does not fit on an SM");
   const size_t smem = per_warp * warps + ELL_CTA_WORDS * 4;
   const long long want = ((long long)ntiles + warps - 1) / warps;
@@ -250,7 +260,7 @@ template <int W, int LAL> static int launch_sort_t(bspgemm_dev* d, int* ccol) {
   p.Bm = (u32)a.m.Bm; p.Crow = a.dCrow; p.is64 = a.is64; p.Ccol = ccol; p.sc = d->d_sc; p.ntiles = ntiles;
   p.debug_nochain = getenv("BSPGEMM_DEBUG_NOCHAIN") ? (u32)(G.R * G.LA * W) : 0u;   // WRONG RESULTS: timing experiments only
   d->st.rows_per_tile = G.R; d->st.variant = 2;
-  k_fused_sort<W, LAL><<<grid, warps * 32, smem, d->stream>>>(p);
+  k_fused_sort<W, LAL><<<grid, (warps + 1) * 32, smem, d->stream>>>(p);        // + the chain helper warp
   d->launches++;
   CK(cudaGetLastError());
   return BSPGEMM_OK;
@@ -298,7 +308,7 @@ static int launch_ell(bspgemm_dev* d) {
   p.TW = d->ell_TW; p.Bm = (u32)a.m.Bm; p.Crow = a.dCrow; p.is64 = a.is64; p.Ccol = ccol; p.sc = d->d_sc;
   p.ntiles = ntiles;
   p.debug_nochain = getenv("BSPGEMM_DEBUG_NOCHAIN") ? (u32)(R * d->ell_maxA * W) : 0u;   // WRONG RESULTS: timing experiments only
-#define LE(Wv, Rv) k_fused_ell<Wv, Rv><<<grid, warps * 32, smem, d->stream>>>(p)
+#define LE(Wv, Rv) k_fused_ell<Wv, Rv><<<grid, (warps + 1) * 32, smem, d->stream>>>(p)   /* + the chain helper warp */
 #define LER(Wv) do { switch (R) { case 1: LE(Wv, 1); break; case 2: LE(Wv, 2); break; case 4: LE(Wv, 4); break; default: LE(Wv, 8); break; } } while (0)
   switch (W) { case 4: LER(4); break; case 8: LER(8); break; case 16: LER(16); break; default: LER(32); break; }
 #undef LER

@@ -95,50 +95,37 @@ __global__ void __launch_bounds__(256) k_build_ell(const int* __restrict__ Brow,
 }
 
 // ------------------------------------------------------------------------------------------------ hierarchical tile chain
-// Level 1 (shared memory): the warps of a CTA work on NW consecutive tiles per iteration ("block" b = iteration *
-// gridDim.x + blockIdx.x); they post their aggregates into a 4-deep ring of slots.  The last poster of a slot (the
-// agent) publishes the block total in global memory.  Level 2 (global): a flat decoupled look-back over blocks —
-// ~16 blocks per microsecond at the target rate instead of ~350 tiles, and one poller per CTA instead of one per warp
-// (3256 warps polling the same few status lines starved the L2 slices that also had to take the posts).
-// The offset of a tile is needed only one whole tile later (deferred commit), when all earlier blocks have long been
-// posted: the first warp of the CTA that needs it resolves it (CtaChain::lock), the others spin on shared memory.
+// Level 1 (shared memory): the compute warps of a CTA work on NW consecutive tiles per iteration ("block" b =
+// iteration * gridDim.x + blockIdx.x) and post their aggregates into a 4-deep ring of slots.  Level 2 (global): a flat
+// decoupled look-back over blocks — ~16 blocks per microsecond at the target rate instead of ~350 tiles, and one
+// poller per CTA instead of one per warp (3256 warps polling the same few status lines starved the L2 slices that
+// also had to take the posts).  The look-back is run by a HELPER WARP (the last warp of the CTA, no row work): as
+// soon as the block's last aggregate is posted it publishes the block total, walks back, and leaves the block's
+// offset in shared memory.  The compute warps need that offset only one whole tile later (deferred commit), so they
+// normally never wait: with the walk done lazily by the first committing warp the chain cost 12 % of config 3 and
+// 40 % of config 2 (profiles/r01_sort_nochain_sweep.txt).
 struct CtaChain {
-  u32 cnt[4];             // warps that have posted in the slot (reset two iterations ahead by the agent)
-  u32 lock[4];            // iteration+1 of the newest resolve claimed on the slot (monotone, atomicMax)
+  u32 cnt[4];             // compute warps that have posted in the slot (reset two iterations ahead by the helper)
+  u32 pad[4];
   u64 base[4];            // (tag << 48) | exclusive prefix of the block, tag = (iteration & 0xfff) + 1
   u32 agg[4][32];         // (tag << 20) | aggregate of warp w's tile
 };
 constexpr u32 CH_AGG_MASK = (1u << 20) - 1;
 constexpr u64 CH_BASE_MASK = (1ull << 48) - 1;
 
-// Publish this warp's tile aggregate for `iter`.  expected = warps of this CTA that own a tile in `iter`.
-// Returns 0, or in the block's agent (the last poster) 1 + the block total.
-__device__ __forceinline__ u32 chain_post(CtaChain* cc, u64* blk_status, u32 iter, u32 warp, u32 agg, u32 expected, u32 blk) {
-  const u32 lane = lane_id();
-  const u32 s = iter & 3u, tag = (iter & 0xfffu) + 1u;
-  u32 old = 0;
-  if (lane == 0) {
+// Publish this warp's tile aggregate for `iter` (lane 0 does the work).
+__device__ __forceinline__ void chain_post(CtaChain* cc, u32 iter, u32 warp, u32 agg) {
+  if (lane_id() == 0) {
+    const u32 s = iter & 3u, tag = (iter & 0xfffu) + 1u;
     *reinterpret_cast<volatile u32*>(&cc->agg[s][warp]) = (tag << 20) | agg;
     __threadfence_block();
-    old = atomicAdd(&cc->cnt[s], 1u);
+    atomicAdd(&cc->cnt[s], 1u);
   }
-  old = __shfl_sync(0xffffffffu, old, 0);
-  if (old + 1u != expected) return 0u;
-  // the agent: every warp of the block has posted
-  const u32 w = (lane < expected) ? (*reinterpret_cast<volatile u32*>(&cc->agg[s][lane]) & CH_AGG_MASK) : 0u;
-  const u32 total = __reduce_add_sync(0xffffffffu, w);
-  if (lane == 0) {
-    const u32 s2 = (iter + 2u) & 3u;                               // everybody has committed iteration iter-2: recycle its slot
-    cc->cnt[s2] = 0;
-    __threadfence();
-    st_status(&blk_status[blk], ST_AGG | (u64)total);
-  }
-  return total + 1u;
 }
 
-// Flat decoupled look-back over blocks: exclusive prefix of block `blk` (whole warp).  K windows of 32 blocks are
-// loaded together (one L2 round trip).  Non-blocking mode gives up (returns false) on a block that has not posted.
-__device__ __noinline__ bool chain_walk(const u64* blk_status, u32 blk, bool blocking, u64* out) {
+// Flat decoupled look-back over blocks: exclusive prefix of block `blk` (whole warp, blocking).  K windows of 32
+// blocks are loaded together (one L2 round trip).
+__device__ __noinline__ u64 chain_walk(const u64* blk_status, u32 blk) {
   constexpr int K = 5;
   const u32 lane = lane_id();
   u64 excl = 0;
@@ -155,8 +142,7 @@ __device__ __noinline__ bool chain_walk(const u64* blk_status, u32 blk, bool blo
       const u32 inc0 = __ballot_sync(0xffffffffu, (st[k] >> 62) == 2);
       const u32 first0 = inc0 ? (u32)(__ffs(inc0) - 1) : 32u;
       while (__any_sync(0xffffffffu, lane <= first0 && (st[k] >> 62) == 0)) {   // only blocks nearer than the first INC matter
-        if (!blocking) return false;
-        __nanosleep(200);
+        __nanosleep(100);
         if ((st[k] >> 62) == 0) st[k] = ld_status(&blk_status[my]);
       }
       const u32 inc_mask = __ballot_sync(0xffffffffu, lane <= first0 && (st[k] >> 62) == 2);
@@ -169,55 +155,45 @@ __device__ __noinline__ bool chain_walk(const u64* blk_status, u32 blk, bool blo
     }
     idx -= 32 * K;
   }
-  *out = excl;
-  return true;
+  return excl;
 }
 
-__device__ __forceinline__ void chain_publish(CtaChain* cc, u64* blk_status, u32 iter, u32 blk, u64 excl, u64 total) {   // lane 0
-  st_status(&blk_status[blk], ST_INC | (excl + total));
-  *reinterpret_cast<volatile u64*>(&cc->base[iter & 3u]) = ((u64)((iter & 0xfffu) + 1u) << 48) | excl;
-  __threadfence_block();
-}
-
-// The agent, some time after posting (after its compaction): resolve the block's offset if every earlier block has
-// posted by now, so that nobody waits for it at commit time.  Racing with a lazy resolver is benign: both derive the
-// same values from the same inputs (the block total always comes from the CTA's own shared-memory slots).
-__device__ __noinline__ void chain_try_resolve(CtaChain* cc, u64* blk_status, u32 iter, u32 blk, u32 total) {
-  const u32 tag = (iter & 0xfffu) + 1u;
-  if ((u32)(*reinterpret_cast<volatile u64*>(&cc->base[iter & 3u]) >> 48) == tag) return;
-  u64 excl;
-  if (!chain_walk(blk_status, blk, false, &excl)) return;
-  if (lane_id() == 0) chain_publish(cc, blk_status, iter, blk, excl, total);
-  __syncwarp();
+// The helper warp: for every iteration in which this CTA owns tiles, wait for the compute warps' aggregates, publish
+// the block total, walk back, publish the block's inclusive prefix and leave its offset in shared memory.
+// ncompute = compute warps of the CTA; tiles of iteration i: [i*stride + cta_first, ... + ncompute) clipped to ntiles.
+__device__ __noinline__ void chain_helper(CtaChain* cc, u64* blk_status, u32 ntiles, u32 stride, u32 cta_first, u32 ncompute) {
+  const u32 lane = lane_id();
+  for (u32 iter = 0;; ++iter) {
+    const unsigned long long first_tile = (unsigned long long)iter * stride + cta_first;
+    if (first_tile >= ntiles) break;
+    const u32 expected = (u32)min((unsigned long long)ncompute, (unsigned long long)ntiles - first_tile);
+    const u32 s = iter & 3u, tag = (iter & 0xfffu) + 1u, blk = iter * gridDim.x + blockIdx.x;
+    while (*reinterpret_cast<volatile u32*>(&cc->cnt[s]) != expected) __nanosleep(100);
+    __threadfence_block();
+    const u32 w = (lane < expected) ? (*reinterpret_cast<volatile u32*>(&cc->agg[s][lane]) & CH_AGG_MASK) : 0u;
+    const u32 total = __reduce_add_sync(0xffffffffu, w);
+    if (lane == 0) {
+      *reinterpret_cast<volatile u32*>(&cc->cnt[(iter + 2u) & 3u]) = 0;   // everybody has committed iteration iter-2: recycle its slot
+      __threadfence_block();
+      st_status(&blk_status[blk], ST_AGG | (u64)total);
+    }
+    const u64 excl = chain_walk(blk_status, blk);
+    if (lane == 0) {
+      st_status(&blk_status[blk], ST_INC | (excl + (u64)total));
+      *reinterpret_cast<volatile u64*>(&cc->base[s]) = ((u64)tag << 48) | excl;
+      __threadfence_block();
+    }
+    __syncwarp();
+  }
 }
 
 // Exclusive prefix of this warp's tile of iteration `iter` (whole warp).  Called one tile after chain_post(iter).
-__device__ __noinline__ u64 chain_resolve(CtaChain* cc, u64* blk_status, u32 iter, u32 warp, u32 blk, u32 expected) {
+__device__ __forceinline__ u64 chain_resolve(CtaChain* cc, u32 iter, u32 warp) {
   const u32 lane = lane_id();
   const u32 s = iter & 3u, tag = (iter & 0xfffu) + 1u;
   volatile u64* basep = &cc->base[s];
-  u64 bw = *basep;
-  if ((u32)(bw >> 48) != tag) {
-    u32 claimed = 0;
-    if (lane == 0) claimed = atomicMax(&cc->lock[s], iter + 1u) < iter + 1u ? 1u : 0u;
-    claimed = __shfl_sync(0xffffffffu, claimed, 0);
-    if (claimed) {
-      u32 w;                                                      // the block total: every warp's slot must carry this iteration's tag
-      while (true) {
-        w = (lane < expected) ? *reinterpret_cast<volatile u32*>(&cc->agg[s][lane]) : (tag << 20);
-        if (!__any_sync(0xffffffffu, (w >> 20) != tag)) break;
-        __nanosleep(200);
-      }
-      const u32 total = __reduce_add_sync(0xffffffffu, w & CH_AGG_MASK);
-      u64 excl;
-      chain_walk(blk_status, blk, true, &excl);
-      if (lane == 0) chain_publish(cc, blk_status, iter, blk, excl, total);
-      __syncwarp();
-      bw = ((u64)tag << 48) | excl;
-    } else {
-      while ((u32)((bw = *basep) >> 48) != tag) __nanosleep(500);
-    }
-  }
+  u64 bw;
+  while ((u32)((bw = *basep) >> 48) != tag) __nanosleep(200);
   const u32 w = (lane < warp) ? (*reinterpret_cast<volatile u32*>(&cc->agg[s][lane]) & CH_AGG_MASK) : 0u;
   return (bw & CH_BASE_MASK) + __reduce_add_sync(0xffffffffu, w);
 }
@@ -312,7 +288,7 @@ __global__ void __launch_bounds__(ELL_MAX_WARPS * 32, 1) k_fused_ell(const EllAr
   constexpr int NBS = 64 / NSEG;           // batches per chunk of 64 A nonzeros
   constexpr int NBG = NBS < 8 ? NBS : 8;   // batches in flight (a "group")
   extern __shared__ __align__(16) u32 smem[];
-  const u32 warp = threadIdx.x >> 5, lane = lane_id(), nwarps = blockDim.x >> 5;
+  const u32 warp = threadIdx.x >> 5, lane = lane_id(), nwarps = (blockDim.x >> 5) - 1u;   // compute warps; the last warp is the chain helper
   const u32 TW = p.TW;
   const u32 wwords = ell_warp_words(R, TW, p.SW);
   u32* tab = smem + (size_t)warp * wwords;
@@ -323,6 +299,10 @@ __global__ void __launch_bounds__(ELL_MAX_WARPS * 32, 1) k_fused_ell(const EllAr
   CtaChain* cc = reinterpret_cast<CtaChain*>(smem + (size_t)nwarps * wwords);
   for (u32 i = threadIdx.x; i < sizeof(CtaChain) / 4; i += blockDim.x) reinterpret_cast<u32*>(cc)[i] = 0;
   __syncthreads();                          // the only CTA-wide barrier
+  if (warp == nwarps) {
+    if (!p.debug_nochain) chain_helper(cc, p.blk_status, p.ntiles, gridDim.x * nwarps, blockIdx.x * nwarps, nwarps);
+    return;
+  }
   const u32 sub = lane / LPR, part = lane % LPR;
   const u32 ltmask = (1u << lane) - 1u;
   const uint4* __restrict__ Bell4 = reinterpret_cast<const uint4*>(p.Bell);
@@ -363,9 +343,7 @@ __global__ void __launch_bounds__(ELL_MAX_WARPS * 32, 1) k_fused_ell(const EllAr
   };
   // commit of a finished tile: its rows are in stage[0..total), lane r holds the inclusive count of row r
   auto commit = [&](u32 t, u32 iter, u32 incl_mine, u32 total) {
-    const u32 blk = iter * gridDim.x + blockIdx.x;
-    const u32 expected = min(nwarps, p.ntiles - (iter * stride + cta_first));
-    const u64 excl = p.debug_nochain ? (u64)t * (u64)p.debug_nochain : chain_resolve(cc, p.blk_status, iter, warp, blk, expected);
+    const u64 excl = p.debug_nochain ? (u64)t * (u64)p.debug_nochain : chain_resolve(cc, iter, warp);
     const long long row0 = (long long)t * R;
     const int nrows = (int)min((long long)R, (long long)p.An - row0);
     if ((int)lane < nrows) st_rowptr(p.Crow, p.is64, (size_t)(row0 + lane) + 1, excl + incl_mine, &p.sc->err);
@@ -474,12 +452,7 @@ __global__ void __launch_bounds__(ELL_MAX_WARPS * 32, 1) k_fused_ell(const EllAr
       for (int r = 0; r < R; ++r) if (a[r + 1] > a[r]) agg += ell_count_table(tab + r * TW, lim[r]);
     }
     // ---- 2. publish the aggregate
-    u32 agent = 0;
-    if (!p.debug_nochain) {
-      const u32 blk_first = iter * stride + cta_first;             // first tile of this CTA's block
-      const u32 expected = min(nwarps, p.ntiles - blk_first);
-      agent = chain_post(cc, p.blk_status, iter, warp, agg, expected, iter * gridDim.x + blockIdx.x);
-    }
+    if (!p.debug_nochain) chain_post(cc, iter, warp, agg);
     // ---- 3. commit the previous tile (frees the staging buffer)
     if (prev_tile != 0xffffffffu) commit(prev_tile, iter - 1u, prev_incl, prev_total);
 
@@ -505,8 +478,6 @@ __global__ void __launch_bounds__(ELL_MAX_WARPS * 32, 1) k_fused_ell(const EllAr
       if ((int)lane == r) incl_mine = run;
     }
     __syncwarp();
-
-    if (agent) chain_try_resolve(cc, p.blk_status, iter, iter * gridDim.x + blockIdx.x, agent - 1u);
 
     prev_tile = tile; prev_incl = incl_mine; prev_total = run;
     tile = next; ++iter;

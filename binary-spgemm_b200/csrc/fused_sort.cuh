@@ -108,11 +108,15 @@ __global__ void __launch_bounds__(SORT_MAX_WARPS * 32, 1) k_fused_sort(const Ell
   constexpr int LPR = G.LPR, S = G.S, NQ = G.NQ, K = G.K, RP = G.RP, R = G.R, NP = G.NP;
   constexpr u32 SWORDS = sort_stage_words(R, G.LA, W);
   extern __shared__ __align__(16) u32 smem[];
-  const u32 warp = threadIdx.x >> 5, lane = lane_id(), nwarps = blockDim.x >> 5;
+  const u32 warp = threadIdx.x >> 5, lane = lane_id(), nwarps = (blockDim.x >> 5) - 1u;   // compute warps; the last warp is the chain helper
   const u32 stage_s = (u32)__cvta_generic_to_shared(smem) + warp * (2u * SWORDS * 4u);    // ping-pong staging buffers
   CtaChain* cc = reinterpret_cast<CtaChain*>(smem + (size_t)nwarps * 2u * SWORDS);
   for (u32 i = threadIdx.x; i < sizeof(CtaChain) / 4; i += blockDim.x) reinterpret_cast<u32*>(cc)[i] = 0;
   __syncthreads();                          // the only CTA-wide barrier
+  if (warp == nwarps) {
+    if (!p.debug_nochain) chain_helper(cc, p.blk_status, p.ntiles, gridDim.x * nwarps, blockIdx.x * nwarps, nwarps);
+    return;
+  }
   const u32 ll = lane % S, seg = lane / S;  // lane within its row, row within the pass
   const uint4* __restrict__ Bell4 = reinterpret_cast<const uint4*>(p.Bell);
   u32 ipc = 0;
@@ -164,9 +168,7 @@ __global__ void __launch_bounds__(SORT_MAX_WARPS * 32, 1) k_fused_sort(const Ell
     }
   };
   auto commit = [&](u32 t, u32 iter, u32 incl_mine, u32 total, u32 buf_s) {
-    const u32 blk = iter * gridDim.x + blockIdx.x;
-    const u32 expected = min(nwarps, p.ntiles - (iter * stride + cta_first));
-    const u64 excl = p.debug_nochain ? (u64)t * (u64)p.debug_nochain : chain_resolve(cc, p.blk_status, iter, warp, blk, expected);
+    const u64 excl = p.debug_nochain ? (u64)t * (u64)p.debug_nochain : chain_resolve(cc, iter, warp);
     const long long row0 = (long long)t * R;
     const int nrows = (int)min((long long)R, (long long)p.An - row0);
     if ((int)lane < nrows) st_rowptr(p.Crow, p.is64, (size_t)(row0 + lane) + 1, excl + incl_mine, &p.sc->err);
@@ -247,14 +249,8 @@ __global__ void __launch_bounds__(SORT_MAX_WARPS * 32, 1) k_fused_sort(const Ell
       load_pass(q, arn, j0n, j1n, k);
     }
     __syncwarp();
-    u32 agent = 0;
-    if (!p.debug_nochain) {
-      const u32 blk_first = iter * stride + cta_first;
-      const u32 expected = min(nwarps, p.ntiles - blk_first);
-      agent = chain_post(cc, p.blk_status, iter, warp, run, expected, iter * gridDim.x + blockIdx.x);
-    }
+    if (!p.debug_nochain) chain_post(cc, iter, warp, run);
     if (prev_tile != 0xffffffffu) commit(prev_tile, iter - 1u, prev_incl, prev_total, stage_s + ((iter - 1u) & 1u) * (SWORDS * 4u));
-    if (agent) chain_try_resolve(cc, p.blk_status, iter, iter * gridDim.x + blockIdx.x, agent - 1u);
     prev_tile = tile; prev_incl = incl_mine; prev_total = run;
     tile = next; ++iter;
     ar = arn; arn = arnn; j0 = j0n; j1 = j1n;
