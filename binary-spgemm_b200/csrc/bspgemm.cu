@@ -243,8 +243,14 @@ template <int W, int LAL> static int launch_sort_t(bspgemm_dev* d, int* ccol) {
   const MulArgs& a = d->a;
   constexpr SortGeom G = sort_geom<W, LAL>();
   const u32 ntiles = (u32)(((size_t)a.m.An + G.R - 1) / G.R);
-  const size_t per_warp = (size_t)2 * sort_stage_words(G.R, G.LA, W) * 4;
-  const int warps = pick_compute_warps(per_warp, ELL_CTA_WORDS * 4 + 64, SORT_MAX_WARPS - 1, d->smem_optin);
+  // staging buffers per warp: 2 = commit one tile later; small tiles get up to 4 (commit lag 3) as long as that costs no warps
+  const size_t one_buf = (size_t)sort_stage_words(G.R, G.LA, W) * 4, fixed = ELL_CTA_WORDS * 4 + 64;
+  int nbuf = 2;
+  const int w2 = pick_compute_warps(2 * one_buf, fixed, SORT_MAX_WARPS - 1, d->smem_optin);
+  while (nbuf < 3 && pick_compute_warps((nbuf + 1) * one_buf, fixed, SORT_MAX_WARPS - 1, d->smem_optin) >= w2) ++nbuf;
+  if (const char* e = getenv("BSPGEMM_NBUF")) nbuf = std::max(2, std::min(4, atoi(e)));   // tuning knob
+  const size_t per_warp = (size_t)nbuf * one_buf;
+  const int warps = pick_compute_warps(per_warp, fixed, SORT_MAX_WARPS - 1, d->smem_optin);
   if (warps < 1) return fail(BSPGEMM_ERR_CUDA, "sort kernel does not fit on an SM");
   const size_t smem = per_warp * warps + ELL_CTA_WORDS * 4;
   const long long want = ((long long)ntiles + warps - 1) / warps;
@@ -257,7 +263,7 @@ template <int W, int LAL> static int launch_sort_t(bspgemm_dev* d, int* ccol) {
   EllArgs p{};
   p.blk_status = d->status.p;
   p.Arow = a.m.Arow; p.Acol = a.m.Acol; p.Bell = d->bell.p; p.An = a.m.An; p.Bn = a.m.Bn;
-  p.Bm = (u32)a.m.Bm; p.Crow = a.dCrow; p.is64 = a.is64; p.Ccol = ccol; p.sc = d->d_sc; p.ntiles = ntiles;
+  p.Bm = (u32)a.m.Bm; p.Crow = a.dCrow; p.is64 = a.is64; p.Ccol = ccol; p.sc = d->d_sc; p.ntiles = ntiles; p.nbuf = (u32)nbuf;
   p.debug_nochain = getenv("BSPGEMM_DEBUG_NOCHAIN") ? (u32)(G.R * G.LA * W) : 0u;   // WRONG RESULTS: timing experiments only
   d->st.rows_per_tile = G.R; d->st.variant = 2;
   k_fused_sort<W, LAL><<<grid, (warps + 1) * 32, smem, d->stream>>>(p);        // + the chain helper warp
@@ -350,7 +356,7 @@ static int mul_launch_probe(bspgemm_dev* d) {
   CK(cudaEventRecord(d->ev[0], d->stream));
   CK(cudaMemsetAsync(d->d_sc, 0, sizeof(DevScalars), d->stream));
   const int nmax = std::max(a.m.An, a.m.Bn);
-  k_maxlen<<<(nmax + 255) / 256, 256, 0, d->stream>>>(a.m.Arow, a.m.An, a.m.Brow, a.m.Bn, d->d_sc);
+  k_maxlen<<<std::max(1, std::min((nmax + 255) / 256, d->sm_count * 8)), 256, 0, d->stream>>>(a.m.Arow, a.m.An, a.m.Brow, a.m.Bn, d->d_sc);
   d->launches++;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(d->h_sc, d->d_sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, d->stream));

@@ -51,6 +51,7 @@ struct EllArgs {
   u64* blk_status;                // [iterations * gridDim.x] block-level look-back words, zero before the launch
   DevScalars* sc;
   u32 ntiles;
+  u32 nbuf;                       // sort kernel: staging buffers per warp (commit lag = nbuf - 1 tiles)
   u32 debug_nochain;              // timing experiments only (BSPGEMM_DEBUG_NOCHAIN): skip the scan, rows land at upper-bound offsets
 };
 
@@ -65,7 +66,7 @@ __host__ __device__ constexpr u32 ell_table_limit(u32 lenA, u32 W, u32 lf16 = 28
   return lim;
 }
 __host__ __device__ constexpr u32 ell_warp_words(u32 R, u32 TW, u32 SW) { return R * TW + SW + 2u * ELL_QCAP + 4u * 8u; }
-constexpr u32 ELL_CTA_WORDS = 160;       // CtaChain, after the warp regions
+constexpr u32 ELL_CTA_WORDS = 320;       // CtaChain, after the warp regions
 
 // ---- B (CSR) -> ELL.  LPR = W/4 lanes write one row as uint4 each; also validates B's columns.  SORTED: every ELL row
 // is sorted ascending (EMPTY padding last) by a small register network — the sorting-network kernel (fused_sort.cuh)
@@ -104,11 +105,11 @@ __global__ void __launch_bounds__(256) k_build_ell(const int* __restrict__ Brow,
 // offset in shared memory.  The compute warps need that offset only one whole tile later (deferred commit), so they
 // normally never wait: with the walk done lazily by the first committing warp the chain cost 12 % of config 3 and
 // 40 % of config 2 (profiles/r01_sort_nochain_sweep.txt).
+constexpr u32 CH_RING = 8;   // slots; supports a commit lag of up to 3 tiles (ring >= 2*lag + 2, see chain_helper)
 struct CtaChain {
-  u32 cnt[4];             // compute warps that have posted in the slot (reset two iterations ahead by the helper)
-  u32 pad[4];
-  u64 base[4];            // (tag << 48) | exclusive prefix of the block, tag = (iteration & 0xfff) + 1
-  u32 agg[4][32];         // (tag << 20) | aggregate of warp w's tile
+  u32 cnt[CH_RING];           // compute warps that have posted in the slot (recycled by the helper)
+  u64 base[CH_RING];          // (tag << 48) | exclusive prefix of the block, tag = (iteration & 0xfff) + 1
+  u32 agg[CH_RING][32];       // (tag << 20) | aggregate of warp w's tile
 };
 constexpr u32 CH_AGG_MASK = (1u << 20) - 1;
 constexpr u64 CH_BASE_MASK = (1ull << 48) - 1;
@@ -116,7 +117,7 @@ constexpr u64 CH_BASE_MASK = (1ull << 48) - 1;
 // Publish this warp's tile aggregate for `iter` (lane 0 does the work).
 __device__ __forceinline__ void chain_post(CtaChain* cc, u32 iter, u32 warp, u32 agg) {
   if (lane_id() == 0) {
-    const u32 s = iter & 3u, tag = (iter & 0xfffu) + 1u;
+    const u32 s = iter & (CH_RING - 1u), tag = (iter & 0xfffu) + 1u;
     *reinterpret_cast<volatile u32*>(&cc->agg[s][warp]) = (tag << 20) | agg;
     __threadfence_block();
     atomicAdd(&cc->cnt[s], 1u);
@@ -161,19 +162,23 @@ __device__ __noinline__ u64 chain_walk(const u64* blk_status, u32 blk) {
 // The helper warp: for every iteration in which this CTA owns tiles, wait for the compute warps' aggregates, publish
 // the block total, walk back, publish the block's inclusive prefix and leave its offset in shared memory.
 // ncompute = compute warps of the CTA; tiles of iteration i: [i*stride + cta_first, ... + ncompute) clipped to ntiles.
-__device__ __noinline__ void chain_helper(CtaChain* cc, u64* blk_status, u32 ntiles, u32 stride, u32 cta_first, u32 ncompute) {
+// lag = tiles between a compute warp's post(i) and its commit(i).  Slot recycling: when every warp has posted
+// iteration i, every warp has finished iteration i-1, i.e. committed iteration i-1-lag: that slot is reset.  Warps may
+// by then have posted up to iteration i+lag (they need base(i-1), already published), so the ring must hold
+// iterations i-lag .. i+lag plus the one being reset: CH_RING >= 2*lag + 2.
+__device__ __noinline__ void chain_helper(CtaChain* cc, u64* blk_status, u32 ntiles, u32 stride, u32 cta_first, u32 ncompute, u32 lag) {
   const u32 lane = lane_id();
   for (u32 iter = 0;; ++iter) {
     const unsigned long long first_tile = (unsigned long long)iter * stride + cta_first;
     if (first_tile >= ntiles) break;
     const u32 expected = (u32)min((unsigned long long)ncompute, (unsigned long long)ntiles - first_tile);
-    const u32 s = iter & 3u, tag = (iter & 0xfffu) + 1u, blk = iter * gridDim.x + blockIdx.x;
+    const u32 s = iter & (CH_RING - 1u), tag = (iter & 0xfffu) + 1u, blk = iter * gridDim.x + blockIdx.x;
     while (*reinterpret_cast<volatile u32*>(&cc->cnt[s]) != expected) __nanosleep(100);
     __threadfence_block();
     const u32 w = (lane < expected) ? (*reinterpret_cast<volatile u32*>(&cc->agg[s][lane]) & CH_AGG_MASK) : 0u;
     const u32 total = __reduce_add_sync(0xffffffffu, w);
     if (lane == 0) {
-      *reinterpret_cast<volatile u32*>(&cc->cnt[(iter + 2u) & 3u]) = 0;   // everybody has committed iteration iter-2: recycle its slot
+      if (iter >= 1u + lag) *reinterpret_cast<volatile u32*>(&cc->cnt[(iter - 1u - lag) & (CH_RING - 1u)]) = 0;
       __threadfence_block();
       st_status(&blk_status[blk], ST_AGG | (u64)total);
     }
@@ -187,10 +192,10 @@ __device__ __noinline__ void chain_helper(CtaChain* cc, u64* blk_status, u32 nti
   }
 }
 
-// Exclusive prefix of this warp's tile of iteration `iter` (whole warp).  Called one tile after chain_post(iter).
+// Exclusive prefix of this warp's tile of iteration `iter` (whole warp).  Called `lag` tiles after chain_post(iter).
 __device__ __forceinline__ u64 chain_resolve(CtaChain* cc, u32 iter, u32 warp) {
   const u32 lane = lane_id();
-  const u32 s = iter & 3u, tag = (iter & 0xfffu) + 1u;
+  const u32 s = iter & (CH_RING - 1u), tag = (iter & 0xfffu) + 1u;
   volatile u64* basep = &cc->base[s];
   u64 bw;
   while ((u32)((bw = *basep) >> 48) != tag) __nanosleep(200);
@@ -300,7 +305,7 @@ __global__ void __launch_bounds__(ELL_MAX_WARPS * 32, 1) k_fused_ell(const EllAr
   for (u32 i = threadIdx.x; i < sizeof(CtaChain) / 4; i += blockDim.x) reinterpret_cast<u32*>(cc)[i] = 0;
   __syncthreads();                          // the only CTA-wide barrier
   if (warp == nwarps) {
-    if (!p.debug_nochain) chain_helper(cc, p.blk_status, p.ntiles, gridDim.x * nwarps, blockIdx.x * nwarps, nwarps);
+    if (!p.debug_nochain) chain_helper(cc, p.blk_status, p.ntiles, gridDim.x * nwarps, blockIdx.x * nwarps, nwarps, 1u);
     return;
   }
   const u32 sub = lane / LPR, part = lane % LPR;

@@ -50,7 +50,8 @@ template <int W, int LAL> __host__ __device__ constexpr SortGeom sort_geom() {
   return g;
 }
 // staging words of one tile: R rows of LA*W keys, plus one pad word per 32 (bank skew)
-__host__ __device__ constexpr u32 sort_stage_words(int R, int LA, int W) { const u32 n = (u32)(R * LA * W); return (n + n / 32u + 4u + 3u) & ~3u; }
+constexpr u32 SORT_HDR = 20;             // per staging buffer: [0] total, [1] tile, [2..2+R) inclusive row counts
+__host__ __device__ constexpr u32 sort_stage_words(int R, int LA, int W) { const u32 n = (u32)(R * LA * W); return (SORT_HDR + n + n / 32u + 4u + 3u) & ~3u; }
 
 // In-place ascending bitonic sort of 32/S independent rows, K keys per lane, element index i = lane_in_row*K + k.
 // "Flip" formulation: every merge level starts with the mirror exchange i <-> i ^ (size-1), then half-cleaners
@@ -109,12 +110,13 @@ __global__ void __launch_bounds__(SORT_MAX_WARPS * 32, 1) k_fused_sort(const Ell
   constexpr u32 SWORDS = sort_stage_words(R, G.LA, W);
   extern __shared__ __align__(16) u32 smem[];
   const u32 warp = threadIdx.x >> 5, lane = lane_id(), nwarps = (blockDim.x >> 5) - 1u;   // compute warps; the last warp is the chain helper
-  const u32 stage_s = (u32)__cvta_generic_to_shared(smem) + warp * (2u * SWORDS * 4u);    // ping-pong staging buffers
-  CtaChain* cc = reinterpret_cast<CtaChain*>(smem + (size_t)nwarps * 2u * SWORDS);
+  const u32 nbuf = p.nbuf;                                                                // ring of staging buffers: commit lag = nbuf-1 tiles
+  const u32 stage_s = (u32)__cvta_generic_to_shared(smem) + warp * (nbuf * SWORDS * 4u);
+  CtaChain* cc = reinterpret_cast<CtaChain*>(smem + (size_t)nwarps * nbuf * SWORDS);
   for (u32 i = threadIdx.x; i < sizeof(CtaChain) / 4; i += blockDim.x) reinterpret_cast<u32*>(cc)[i] = 0;
   __syncthreads();                          // the only CTA-wide barrier
   if (warp == nwarps) {
-    if (!p.debug_nochain) chain_helper(cc, p.blk_status, p.ntiles, gridDim.x * nwarps, blockIdx.x * nwarps, nwarps);
+    if (!p.debug_nochain) chain_helper(cc, p.blk_status, p.ntiles, gridDim.x * nwarps, blockIdx.x * nwarps, nwarps, p.nbuf - 1u);
     return;
   }
   const u32 ll = lane % S, seg = lane / S;  // lane within its row, row within the pass
@@ -167,7 +169,10 @@ __global__ void __launch_bounds__(SORT_MAX_WARPS * 32, 1) k_fused_sort(const Ell
       }
     }
   };
-  auto commit = [&](u32 t, u32 iter, u32 incl_mine, u32 total, u32 buf_s) {
+  // commit of the tile staged in buffer buf_s during iteration `iter` (header: total, tile, inclusive row counts)
+  auto commit = [&](u32 iter, u32 buf_s) {
+    const u32 total = lds32(buf_s), t = lds32(buf_s + 4u);
+    const u32 incl_mine = lds32(buf_s + 8u + 4u * min(lane, (u32)R - 1u));
     const u64 excl = p.debug_nochain ? (u64)t * (u64)p.debug_nochain : chain_resolve(cc, iter, warp);
     const long long row0 = (long long)t * R;
     const int nrows = (int)min((long long)R, (long long)p.An - row0);
@@ -175,7 +180,7 @@ __global__ void __launch_bounds__(SORT_MAX_WARPS * 32, 1) k_fused_sort(const Ell
     if (t == 0 && lane == 0) st_rowptr(p.Crow, p.is64, 0, 0, &p.sc->err);
     if (t == p.ntiles - 1 && lane == 0) p.sc->total_nnz = excl + total;
     int* dst = p.Ccol + excl;
-    u32 src = buf_s + 4u * lane;                                   // key q lives at word q + q/32: 33 words per 32 keys
+    u32 src = buf_s + 4u * (SORT_HDR + lane);                      // key q lives at word q + q/32: 33 words per 32 keys
     for (u32 q = lane; q < total; q += 32, src += 132u) dst[q] = (int)lds32(src);
     __syncwarp();
   };
@@ -190,7 +195,7 @@ __global__ void __launch_bounds__(SORT_MAX_WARPS * 32, 1) k_fused_sort(const Ell
   u32 x[NP][K];
 #pragma unroll
   for (int q = 0; q < NP; ++q) load_pass(q, ar, j0, j1, x[q]);
-  u32 prev_tile = 0xffffffffu, prev_incl = 0, prev_total = 0;
+  u32 cur_buf = 0;                           // iter % nbuf
 
   while (tile < p.ntiles) {
     const u32 next = (tile + stride < tile) ? 0xffffffffu : tile + stride;
@@ -198,7 +203,7 @@ __global__ void __launch_bounds__(SORT_MAX_WARPS * 32, 1) k_fused_sort(const Ell
     const int arnn = load_rowptr(next2);
     int j0n, j1n;
     load_acol(arn, j0n, j1n);
-    const u32 cur_s = stage_s + (iter & 1u) * (SWORDS * 4u);
+    const u32 buf_s = stage_s + cur_buf * (SWORDS * 4u), cur_s = buf_s + 4u * SORT_HDR;
     u32 run = 0, incl_mine = 0;
 #pragma unroll
     for (int q = 0; q < NP; ++q) {
@@ -248,14 +253,18 @@ __global__ void __launch_bounds__(SORT_MAX_WARPS * 32, 1) k_fused_sort(const Ell
       if (q == 0) check_acol(j0n, j1n);
       load_pass(q, arn, j0n, j1n, k);
     }
+    if (lane == 0) sts64(buf_s, run, tile);
+    if (lane < (u32)R) sts32(buf_s + 8u + 4u * lane, incl_mine);
     __syncwarp();
     if (!p.debug_nochain) chain_post(cc, iter, warp, run);
-    if (prev_tile != 0xffffffffu) commit(prev_tile, iter - 1u, prev_incl, prev_total, stage_s + ((iter - 1u) & 1u) * (SWORDS * 4u));
-    prev_tile = tile; prev_incl = incl_mine; prev_total = run;
+    // commit the tile staged nbuf-1 iterations ago: its buffer is the next one of the ring
+    cur_buf = (cur_buf + 1u == nbuf) ? 0u : cur_buf + 1u;
+    if (iter + 1u >= nbuf) commit(iter + 1u - nbuf, stage_s + cur_buf * (SWORDS * 4u));
     tile = next; ++iter;
     ar = arn; arn = arnn; j0 = j0n; j1 = j1n;
   }
-  if (prev_tile != 0xffffffffu) commit(prev_tile, iter - 1u, prev_incl, prev_total, stage_s + ((iter - 1u) & 1u) * (SWORDS * 4u));
+  // drain: the last nbuf-1 tiles of this warp
+  for (u32 k = (iter + 1u >= nbuf) ? iter + 1u - nbuf : 0u; k < iter; ++k) commit(k, stage_s + (k % nbuf) * (SWORDS * 4u));
   u64 ips = ipc;
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) ips += __shfl_xor_sync(0xffffffffu, ips, d);

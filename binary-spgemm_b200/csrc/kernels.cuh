@@ -600,13 +600,20 @@ __global__ void __launch_bounds__(1024, 1) k_fused(Csr m, const u32* __restrict_
 // Longest row of A and of B (two streaming passes over the row pointers).  If maxA*maxB <= the S-bin capacity
 // no row can leave the S bin and Σip <= nnzA*maxB, so the work-estimation pass can be skipped entirely.
 __global__ void __launch_bounds__(256) k_maxlen(const int* __restrict__ Arow, int An, const int* __restrict__ Brow, int Bn, DevScalars* sc) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ u32 s_a, s_b;
+  if (threadIdx.x == 0) { s_a = 0; s_b = 0; }
+  __syncthreads();
   u32 la = 0, lb = 0;
-  if (i < An) la = (u32)(Arow[i + 1] - Arow[i]);
-  if (i < Bn) lb = (u32)(Brow[i + 1] - Brow[i]);
+  const long long n = max(An, Bn), step = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {   // grid-stride: one global atomic pair per CTA
+    if (i < An) la = max(la, (u32)(Arow[i + 1] - Arow[i]));
+    if (i < Bn) lb = max(lb, (u32)(Brow[i + 1] - Brow[i]));
+  }
   la = __reduce_max_sync(0xffffffffu, la);
   lb = __reduce_max_sync(0xffffffffu, lb);
-  if (lane_id() == 0) { if (la) atomicMax(&sc->max_len_a, la); if (lb) atomicMax(&sc->max_len_b, lb); }
+  if (lane_id() == 0) { if (la) atomicMax(&s_a, la); if (lb) atomicMax(&s_b, lb); }
+  __syncthreads();
+  if (threadIdx.x == 0) { if (s_a) atomicMax(&sc->max_len_a, s_a); if (s_b) atomicMax(&sc->max_len_b, s_b); }
 }
 
 // ------------------------------------------------------------------------------------------------ (2b) M bin: one CTA per row
