@@ -208,18 +208,16 @@ __global__ void __launch_bounds__(SORT_MAX_WARPS * 32, 1) k_fused_sort(const Ell
 #pragma unroll
     for (int q = 0; q < NP; ++q) {
       u32 (&k)[K] = x[q];
-#pragma unroll
-      for (int i = 0; i < K; ++i) ipc += (k[i] != EMPTY) ? 1u : 0u;
       bitonic_sort_rows<K, S, (W < K ? W : K)>(k, ll);     // every B row is ascending in the ELL copy (k_build_ell sorts it)
-      // first occurrences: the row is ascending along (lane, register)
+      // the row is ascending along (lane, register); EMPTY (padding) is the largest value
       u32 prev_last = __shfl_up_sync(0xffffffffu, k[K - 1], 1);
       if (ll == 0) prev_last = EMPTY;                              // nothing before the row's first key (EMPTY never counts)
-      bool f[K];
-      u32 cnt = 0;
+      bool plain = (k[K - 1] != EMPTY) && (k[0] != prev_last);     // no padding in this lane, no duplicate
 #pragma unroll
-      for (int i = 0; i < K; ++i) { f[i] = (k[i] != EMPTY) && (k[i] != (i ? k[i - 1] : prev_last)); cnt += f[i] ? 1u : 0u; }
-      if (__all_sync(0xffffffffu, cnt == (u32)K)) {
+      for (int i = 1; i < K; ++i) plain = plain && (k[i] != k[i - 1]);
+      if (__all_sync(0xffffffffu, plain)) {
         // the usual case: no duplicate, no padding anywhere in the pass — every key's place is known in advance
+        ipc += (u32)K;
         const u32 pos = lane * (u32)K;                             // rows of the pass back to back, lane-major
         const u32 a0s = cur_s + 4u * (run + pos + ((run + pos) >> 5));
         if (((run + pos) & 31u) + (u32)K <= 32u || (K % 32 == 0 && ((run + pos) & 31u) == 0u)) {
@@ -232,7 +230,15 @@ __global__ void __launch_bounds__(SORT_MAX_WARPS * 32, 1) k_fused_sort(const Ell
 #pragma unroll
         for (int sq = 0; sq < RP; ++sq) { run += (u32)(K * S); if ((int)lane == q * RP + sq) incl_mine = run; }
       } else {
-        // inclusive scan of cnt inside the row's S lanes
+        // first occurrences, their count, inclusive scan of the count inside the row's S lanes
+        bool f[K];
+        u32 cnt = 0;
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+          f[i] = (k[i] != EMPTY) && (k[i] != (i ? k[i - 1] : prev_last));
+          cnt += f[i] ? 1u : 0u;
+          ipc += (k[i] != EMPTY) ? 1u : 0u;
+        }
         u32 inc = cnt;
 #pragma unroll
         for (int d = 1; d < S; d <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, inc, d); if ((int)ll >= d) inc += t; }
