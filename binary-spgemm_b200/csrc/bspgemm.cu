@@ -243,14 +243,18 @@ template <int W, int LAL> static int launch_sort_t(bspgemm_dev* d, int* ccol) {
   const MulArgs& a = d->a;
   constexpr SortGeom G = sort_geom<W, LAL>();
   const u32 ntiles = (u32)(((size_t)a.m.An + G.R - 1) / G.R);
-  // staging buffers per warp: 2 = commit one tile later; small tiles get up to 4 (commit lag 3) as long as that costs no warps
+  // warps per CTA: what the kernel's register count allows (registers are allocated per SM sub-partition: 80 -> 6 warps
+  // each, 81..102 -> 5), one of them the chain helper
+  cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, k_fused_sort<W, LAL>));
+  const int max_compute = std::max(1, std::min(SORT_MAX_WARPS, fa.maxThreadsPerBlock / 32) - 1);
+  // staging buffers per warp: 2 = commit one tile later; small tiles get 3 (commit lag 2) as long as that costs no warps
   const size_t one_buf = (size_t)sort_stage_words(G.R, G.LA, W) * 4, fixed = ELL_CTA_WORDS * 4 + 64;
   int nbuf = 2;
-  const int w2 = pick_compute_warps(2 * one_buf, fixed, SORT_MAX_WARPS - 1, d->smem_optin);
-  while (nbuf < 3 && pick_compute_warps((nbuf + 1) * one_buf, fixed, SORT_MAX_WARPS - 1, d->smem_optin) >= w2) ++nbuf;
+  const int w2 = pick_compute_warps(2 * one_buf, fixed, max_compute, d->smem_optin);
+  while (nbuf < 3 && pick_compute_warps((nbuf + 1) * one_buf, fixed, max_compute, d->smem_optin) >= w2) ++nbuf;
   if (const char* e = getenv("BSPGEMM_NBUF")) nbuf = std::max(2, std::min(4, atoi(e)));   // tuning knob
   const size_t per_warp = (size_t)nbuf * one_buf;
-  const int warps = pick_compute_warps(per_warp, fixed, SORT_MAX_WARPS - 1, d->smem_optin);
+  const int warps = pick_compute_warps(per_warp, fixed, max_compute, d->smem_optin);
   if (warps < 1) return fail(BSPGEMM_ERR_CUDA, "sort kernel does not fit on an SM");
   const size_t smem = per_warp * warps + ELL_CTA_WORDS * 4;
   const long long want = ((long long)ntiles + warps - 1) / warps;
@@ -266,6 +270,11 @@ template <int W, int LAL> static int launch_sort_t(bspgemm_dev* d, int* ccol) {
   p.Bm = (u32)a.m.Bm; p.Crow = a.dCrow; p.is64 = a.is64; p.Ccol = ccol; p.sc = d->d_sc; p.ntiles = ntiles; p.nbuf = (u32)nbuf;
   p.debug_nochain = getenv("BSPGEMM_DEBUG_NOCHAIN") ? (u32)(G.R * G.LA * W) : 0u;   // WRONG RESULTS: timing experiments only
   d->st.rows_per_tile = G.R; d->st.variant = 2;
+  if (getenv("BSPGEMM_VERBOSE")) {
+    cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, k_fused_sort<W, LAL>);
+    fprintf(stderr, "k_fused_sort<%d,%d>: regs %d, maxThreadsPerBlock %d, static smem %zu, launch %d x %d threads, dyn smem %zu, nbuf %d\n",
+            W, LAL, fa.numRegs, fa.maxThreadsPerBlock, fa.sharedSizeBytes, grid, (warps + 1) * 32, smem, nbuf);
+  }
   k_fused_sort<W, LAL><<<grid, (warps + 1) * 32, smem, d->stream>>>(p);        // + the chain helper warp
   d->launches++;
   CK(cudaGetLastError());

@@ -20,7 +20,7 @@
 
 namespace bsk {
 
-constexpr int SORT_MAX_WARPS = 24;
+constexpr int SORT_MAX_WARPS = 32;        // CtaChain holds 32 warps; the launch uses what the registers of the instantiation allow
 
 struct SortGeom {          // compile-time geometry of k_fused_sort<W, LAL>
   int LPR, LA, S, NQ, K, RP, R, NP;
@@ -103,8 +103,10 @@ __device__ __forceinline__ void bitonic_sort_rows(u32 (&x)[K], const u32 ll) {
 //   for each pass: sort the pass's rows in registers, mark first occurrences, scan, write the distinct keys to the
 //   current staging buffer; then reload the same registers with the same pass of tile t+1;
 //   post the tile's aggregate; commit tile t-1 from the other staging buffer.
+// No launch bound: up to 96 registers (no spills — at 80 a reload from thrashed local memory cost 10 % of the warp
+// time); the host sizes the CTA from cudaFuncGetAttributes (registers are allocated per SM sub-partition, 16K each).
 template <int W, int LAL>
-__global__ void __launch_bounds__(SORT_MAX_WARPS * 32, 1) k_fused_sort(const EllArgs p) {
+__global__ void __maxnreg__(96) k_fused_sort(const EllArgs p) {
   constexpr SortGeom G = sort_geom<W, LAL>();
   constexpr int LPR = G.LPR, S = G.S, NQ = G.NQ, K = G.K, RP = G.RP, R = G.R, NP = G.NP;
   constexpr u32 SWORDS = sort_stage_words(R, G.LA, W);
