@@ -248,12 +248,12 @@ template <int W, int LAL> static int launch_sort_t(bspgemm_dev* d, int* ccol) {
   cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, k_fused_sort<W, LAL>));
   const int max_compute = std::max(1, std::min(SORT_MAX_WARPS, fa.maxThreadsPerBlock / 32) - 1);
   // staging buffers per warp: 2 = commit one tile later; small tiles get 3 (commit lag 2) as long as that costs no warps
-  const size_t one_buf = (size_t)sort_stage_words(G.R, G.LA, W) * 4, fixed = ELL_CTA_WORDS * 4 + 64;
+  const size_t one_buf = (size_t)sort_stage_words(G.R, G.LA, W) * 4, acol_bytes = 256, fixed = ELL_CTA_WORDS * 4 + 64;
   int nbuf = 2;
-  const int w2 = pick_compute_warps(2 * one_buf, fixed, max_compute, d->smem_optin);
-  while (nbuf < 3 && pick_compute_warps((nbuf + 1) * one_buf, fixed, max_compute, d->smem_optin) >= w2) ++nbuf;
+  const int w2 = pick_compute_warps(2 * one_buf + acol_bytes, fixed, max_compute, d->smem_optin);
+  while (nbuf < 3 && pick_compute_warps((nbuf + 1) * one_buf + acol_bytes, fixed, max_compute, d->smem_optin) >= w2) ++nbuf;
   if (const char* e = getenv("BSPGEMM_NBUF")) nbuf = std::max(2, std::min(4, atoi(e)));   // tuning knob
-  const size_t per_warp = (size_t)nbuf * one_buf;
+  const size_t per_warp = (size_t)nbuf * one_buf + acol_bytes;
   const int warps = pick_compute_warps(per_warp, fixed, max_compute, d->smem_optin);
   if (warps < 1) return fail(BSPGEMM_ERR_CUDA, "sort kernel does not fit on an SM");
   const size_t smem = per_warp * warps + ELL_CTA_WORDS * 4;

@@ -113,8 +113,10 @@ __global__ void __maxnreg__(96) k_fused_sort(const EllArgs p) {
   extern __shared__ __align__(16) u32 smem[];
   const u32 warp = threadIdx.x >> 5, lane = lane_id(), nwarps = (blockDim.x >> 5) - 1u;   // compute warps; the last warp is the chain helper
   const u32 nbuf = p.nbuf;                                                                // ring of staging buffers: commit lag = nbuf-1 tiles
-  const u32 stage_s = (u32)__cvta_generic_to_shared(smem) + warp * (nbuf * SWORDS * 4u);
-  CtaChain* cc = reinterpret_cast<CtaChain*>(smem + (size_t)nwarps * nbuf * SWORDS);
+  const u32 wwords = nbuf * SWORDS + 64u;                                                 // + the next tile's <= 64 A nonzeros
+  const u32 stage_s = (u32)__cvta_generic_to_shared(smem) + warp * (wwords * 4u);
+  const u32 acol_s = stage_s + nbuf * SWORDS * 4u;
+  CtaChain* cc = reinterpret_cast<CtaChain*>(smem + (size_t)nwarps * wwords);
   for (u32 i = threadIdx.x; i < sizeof(CtaChain) / 4; i += blockDim.x) reinterpret_cast<u32*>(cc)[i] = 0;
   __syncthreads();                          // the only CTA-wide barrier
   if (warp == nwarps) {
@@ -139,17 +141,20 @@ __global__ void __maxnreg__(96) k_fused_sort(const EllArgs p) {
     if ((int)lane < E) j0 = p.Acol[a0 + (int)lane];
     if (32 + (int)lane < E) j1 = p.Acol[a0 + 32 + (int)lane];
   };
-  auto check_acol = [&](int& j0, int& j1) {
+  auto stash_acol = [&](int j0, int j1) {                          // validate, then park them in shared memory (frees the registers)
     if (((u32)j0 > (u32)p.Bn) | ((u32)j1 > (u32)p.Bn)) {
       atomicOr(&p.sc->err, 1u);
       if ((u32)j0 > (u32)p.Bn) j0 = p.Bn;
       if ((u32)j1 > (u32)p.Bn) j1 = p.Bn;
     }
+    sts32(acol_s + 4u * lane, (u32)j0);
+    sts32(acol_s + 4u * (32u + lane), (u32)j1);
+    __syncwarp();
   };
   // keys of pass q of a tile.  The K keys of lane (seg, ll) are consecutive uint4 of the row's B rows taken in A order:
   // uint4 number t = ll*NQ + u of the row is part t % LPR of B row slot t / LPR, so a lane holds whole (sorted) B rows,
   // or a contiguous piece of one.
-  auto load_pass = [&](int q, int ar, int j0, int j1, u32 (&x)[K]) {
+  auto load_pass = [&](int q, int ar, u32 (&x)[K]) {
     const int row = q * RP + (int)seg;
     const int a0 = __shfl_sync(0xffffffffu, ar, 0);
     const int lo = __shfl_sync(0xffffffffu, ar, row), hi = __shfl_sync(0xffffffffu, ar, row + 1);
@@ -159,10 +164,8 @@ __global__ void __maxnreg__(96) k_fused_sort(const EllArgs p) {
     for (int g = 0; g < SLOTS; ++g) {
       const int slot = NQ >= LPR ? (int)ll * SLOTS + g : (int)(ll * NQ) / LPR;
       const int part0 = NQ >= LPR ? 0 : (int)(ll * NQ) % LPR;
-      const int e = lo - a0 + slot;
-      const int ja = __shfl_sync(0xffffffffu, j0, e & 31), jb = __shfl_sync(0xffffffffu, j1, e & 31);
-      int j = (e < 32) ? ja : jb;
-      if (slot >= hi - lo) j = p.Bn;
+      int j = p.Bn;
+      if (slot < hi - lo) j = (int)lds32(acol_s + 4u * (u32)(lo - a0 + slot));
 #pragma unroll
       for (int c = 0; c < PARTS; ++c) {
         const uint4 t4 = __ldg(&Bell4[(size_t)j * LPR + part0 + c]);
@@ -189,14 +192,17 @@ __global__ void __maxnreg__(96) k_fused_sort(const EllArgs p) {
 
   // ---- pipeline prologue
   u32 tile = cta_first + warp, iter = 0;
-  int ar = load_rowptr(tile);
   int arn = load_rowptr(tile + stride < tile ? 0xffffffffu : tile + stride);
-  int j0, j1;
-  load_acol(ar, j0, j1);
-  check_acol(j0, j1);
   u32 x[NP][K];
+  {
+    const int ar = load_rowptr(tile);
+    int j0, j1;
+    load_acol(ar, j0, j1);
+    stash_acol(j0, j1);
 #pragma unroll
-  for (int q = 0; q < NP; ++q) load_pass(q, ar, j0, j1, x[q]);
+    for (int q = 0; q < NP; ++q) load_pass(q, ar, x[q]);
+    __syncwarp();
+  }
   u32 cur_buf = 0;                           // iter % nbuf
 
   while (tile < p.ntiles) {
@@ -258,8 +264,8 @@ __global__ void __maxnreg__(96) k_fused_sort(const EllArgs p) {
         for (int i = 0; i < K; ++i) if (f[i]) { sts32(cur_s + 4u * (o + (o >> 5)), k[i]); ++o; }
       }
       // the registers of this pass are free: refill them with the same pass of the next tile
-      if (q == 0) check_acol(j0n, j1n);
-      load_pass(q, arn, j0n, j1n, k);
+      if (q == 0) stash_acol(j0n, j1n);
+      load_pass(q, arn, k);
     }
     if (lane == 0) sts64(buf_s, run, tile);
     if (lane < (u32)R) sts32(buf_s + 8u + 4u * lane, incl_mine);
@@ -269,7 +275,7 @@ __global__ void __maxnreg__(96) k_fused_sort(const EllArgs p) {
     cur_buf = (cur_buf + 1u == nbuf) ? 0u : cur_buf + 1u;
     if (iter + 1u >= nbuf) commit(iter + 1u - nbuf, stage_s + cur_buf * (SWORDS * 4u));
     tile = next; ++iter;
-    ar = arn; arn = arnn; j0 = j0n; j1 = j1n;
+    arn = arnn;
   }
   // drain: the last nbuf-1 tiles of this warp
   for (u32 k = (iter + 1u >= nbuf) ? iter + 1u - nbuf : 0u; k < iter; ++k) commit(k, stage_s + (k % nbuf) * (SWORDS * 4u));
