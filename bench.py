@@ -281,12 +281,13 @@ def main():
 
     mode = {"auto": bs.MODE_AUTO, "fused": bs.MODE_FUSED, "twophase": bs.MODE_TWOPHASE}[args.mode]
     h = bs.DeviceSpGEMM(local_rank, mode)
-    d_crow = torch.zeros(rows + 1, dtype=torch.int32, device=dev)
+    i64 = args.workload.startswith("rmat")          # nnz(C) of the R-MAT workloads exceeds 2^31: 64-bit row pointers
+    d_crow = torch.zeros(rows + 1, dtype=torch.int64 if i64 else torch.int32, device=dev)
     stream = torch.cuda.current_stream()
     a_row_ptr = d_row.data_ptr() + 4 * r0             # shifted Arow, absolute offsets (final/SpGEMM_mpi_omp.c:171)
 
     def step():
-        return h.multiply(d_col, a_row_ptr, rows, shard_nnz, d_col, d_row, n, n, nnzA, d_crow, stream=stream.cuda_stream)
+        return h.multiply(d_col, a_row_ptr, rows, shard_nnz, d_col, d_row, n, n, nnzA, d_crow, stream=stream.cuda_stream, crow_is_i64=i64)
 
     for _ in range(max(3, args.warmup)):
         ptr, nnz = step()
@@ -371,18 +372,25 @@ def main():
     else:
         rc = torch.from_numpy(row).pin_memory(); cc = torch.from_numpy(col).pin_memory()
         row_h, col_h = rc.numpy(), cc.numpy()
-    out_cap = int(nnz) + 16
+    out_cap = 16 if args.workload.startswith("rmat") else int(nnz) + 16
     out_pin = torch.empty(out_cap, dtype=torch.int32).pin_memory()
     out_h = out_pin.numpy()
     torch.cuda.synchronize()
     bs.init(1, devices=[local_rank])
     e2e_steps = max(1, min(args.e2e_steps, args.steps))
     a_row_h = row_h[r0:r1 + 1]
-    e2e_nnz, _ = bs.spgemm_csr_into(col_h, a_row_h, rows, col_h, row_h, n, n, out_h)       # warm-up (allocations)
+    if i64:      # nnz(C) >= 2^31: the 64-bit row-pointer operator (callee-allocated output)
+        def e2e_call():
+            cc_, cr_ = bs.spgemm_csr(col_h, a_row_h, rows, col_h, row_h, n, n, i64=True)
+            return len(cc_), cr_
+    else:
+        def e2e_call():
+            return bs.spgemm_csr_into(col_h, a_row_h, rows, col_h, row_h, n, n, out_h)
+    e2e_nnz, _ = e2e_call()                                                                # warm-up (allocations)
     barrier()
     w0 = time.perf_counter()
     for _ in range(e2e_steps):
-        e2e_nnz, crow_h = bs.spgemm_csr_into(col_h, a_row_h, rows, col_h, row_h, n, n, out_h)
+        e2e_nnz, crow_h = e2e_call()
     barrier()
     e2e_wall = time.perf_counter() - w0
     bs.finalize()
@@ -395,7 +403,7 @@ def main():
         dist.all_reduce(io, op=dist.ReduceOp.SUM)
     e2e_s = float(e2[0]) / e2e_steps
     e2e = {"value": ip_total / e2e_s, "unit": "IP/s", "h2d_bytes_per_step": int(io[0]), "d2h_bytes_per_step": int(io[1]),
-           "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "api": "bspgemm_csr_into (pinned host CSR in, pinned host CSR out)",
+           "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "api": "bspgemm_csr_i64 (pinned host CSR in, malloc'ed host CSR out)" if i64 else "bspgemm_csr_into (pinned host CSR in, pinned host CSR out)",
            "timer": "host CLOCK_MONOTONIC around the synchronous call, max over ranks"}
 
     # ---------------- CPU baseline beside it (rank 0, N=1 only)

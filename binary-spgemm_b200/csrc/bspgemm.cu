@@ -120,7 +120,7 @@ static int set_kernel_attributes(int smem_optin) {
 #undef ATTR_E
 #define ATTR_S(Wv) ATTR((k_fused_sort<Wv, 2>)); ATTR((k_fused_sort<Wv, 3>)); ATTR((k_fused_sort<Wv, 4>))
   ATTR_S(4); ATTR_S(8); ATTR_S(16); ATTR_S(32);
-  ATTR((k_fused_sort<4, 5>)); ATTR((k_fused_sort<8, 5>)); ATTR((k_fused_sort<16, 5>));
+  ATTR((k_fused_sort<4, 5>)); ATTR((k_fused_sort<8, 5>)); ATTR((k_fused_sort<16, 5>)); ATTR((k_fused_sort<32, 5>));
 #undef ATTR_S
 #undef ATTR_G
 #undef ATTR
@@ -200,6 +200,7 @@ static bool ell_plan(bspgemm_dev* d) {
   // explicit bin / estimate overrides select the CSR-gather kernels
   if (d->mode == BSPGEMM_MODE_TWOPHASE || getenv("BSPGEMM_NO_ELL") || getenv("BSPGEMM_CAP_S") || getenv("BSPGEMM_FORCE_ESTIMATE")) return false;
   if (h.max_len_a == 0 || h.max_len_b == 0 || h.max_len_b > 32) return false;
+  const bool clustered = h.span_rows > 0 && 2u * h.span_narrow > h.span_rows;   // most rows fit a 2^15-column window (k_probe_span)
   int W = 4; while (W < (int)h.max_len_b) W <<= 1;
   if ((u64)a.m.Bn * (u64)W > 4ull * (u64)a.Bnnz + 4096ull && !getenv("BSPGEMM_FORCE_ELL")) return false;   // padding waste
   u32 lf16 = 28; if (const char* e = getenv("BSPGEMM_ELL_LF16")) lf16 = (u32)std::max(16, std::min(64, atoi(e)));   // tuning knob
@@ -220,10 +221,11 @@ static bool ell_plan(bspgemm_dev* d) {
   if (!getenv("BSPGEMM_NO_SORT")) {
     int lal = 2; while ((1u << lal) < h.max_len_a) ++lal;
     const int LA = 1 << lal;
-    const bool fits = lal <= 5 && LA * W <= 512;
+    const bool fits = lal <= 5 && LA * W <= 1024;
     const bool regular = (u64)a.Annz * 2ull >= (u64)a.m.An * (u64)LA || getenv("BSPGEMM_FORCE_SORT");
     if (fits && regular) { d->use_sort = true; d->sort_LAL = lal; }
   }
+  if (clustered && !d->use_sort && !getenv("BSPGEMM_FORCE_ELL")) return false;   // narrow rows: the bitmap kernels (kernels.cuh), not the global slot map
   d->use_ell = true; d->ell_W = W; d->ell_R = R; d->ell_TW = TW; d->ell_warps = warps; d->ell_maxA = h.max_len_a; d->ell_lf16 = lf16;
   return true;
 }
@@ -283,7 +285,7 @@ template <int W, int LAL> static int launch_sort_t(bspgemm_dev* d, int* ccol) {
 static int launch_sort(bspgemm_dev* d, int* ccol) {
   const int W = d->ell_W, L = d->sort_LAL;
 #define LS(Wv) do { switch (L) { case 2: return launch_sort_t<Wv, 2>(d, ccol); case 3: return launch_sort_t<Wv, 3>(d, ccol); case 4: return launch_sort_t<Wv, 4>(d, ccol); \
-                                 default: return launch_sort_t<(Wv == 32 ? 16 : Wv), 5>(d, ccol); } } while (0)
+                                 default: return launch_sort_t<Wv, 5>(d, ccol); } } while (0)
   switch (W) { case 4: LS(4); case 8: LS(8); case 16: LS(16); default: LS(32); }
 #undef LS
 }
@@ -368,6 +370,12 @@ static int mul_launch_probe(bspgemm_dev* d) {
   k_maxlen<<<std::max(1, std::min((nmax + 255) / 256, d->sm_count * 8)), 256, 0, d->stream>>>(a.m.Arow, a.m.An, a.m.Brow, a.m.Bn, d->d_sc);
   d->launches++;
   CK(cudaGetLastError());
+  if (a.m.An > 0 && a.Bnnz > 0) {                                  // are the rows' columns clustered (banded / block-diagonal)?
+    const int nsamples = std::min(a.m.An, 2048);
+    k_probe_span<<<(nsamples * 32 + 255) / 256, 256, 0, d->stream>>>(a.m, nsamples, d->d_sc);
+    d->launches++;
+    CK(cudaGetLastError());
+  }
   CK(cudaMemcpyAsync(d->h_sc, d->d_sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, d->stream));
   d->phase = 1;
   return BSPGEMM_OK;

@@ -54,7 +54,7 @@ struct DevScalars {     // one per context, in device memory; copied to the host
   u32 n_m1, n_m2, n_l;  // list lengths (k_build_lists)
   u32 tile_counter;     // dynamic tile ids (fused kernel / scan kernel)
   u32 max_len_a, max_len_b;   // longest row of A / of B (k_maxlen)
-  u32 pad;
+  u32 span_rows, span_narrow; // k_probe_span: sampled non-empty rows / those whose candidate columns span < 2^15
 };
 
 // ------------------------------------------------------------------------------------------------ helpers
@@ -614,6 +614,27 @@ __global__ void __launch_bounds__(256) k_maxlen(const int* __restrict__ Arow, in
   if (lane_id() == 0) { if (la) atomicMax(&s_a, la); if (lb) atomicMax(&s_b, lb); }
   __syncthreads();
   if (threadIdx.x == 0) { if (s_a) atomicMax(&sc->max_len_a, s_a); if (s_b) atomicMax(&sc->max_len_b, s_b); }
+}
+
+// Column-span probe: one warp per sampled row of A gathers the row's candidate columns and records whether they fit a
+// window of 2^15 columns (banded / block-diagonal rows: the bitmap path of k_rows_warp / k_fused is the right tool, the
+// global slot map of k_fused_ell would send every key of such a row to the same few slots).
+__global__ void __launch_bounds__(256) k_probe_span(Csr m, int nsamples, DevScalars* sc) {
+  const int s = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (s >= nsamples) return;
+  const long long row = (long long)m.An * s / nsamples;
+  const u32 lane = lane_id();
+  u32 lo = EMPTY, hi = 0;
+  const int a0 = m.Arow[row], a1 = m.Arow[row + 1];
+  for (int jj = a0; jj < a1 && jj < a0 + 64; ++jj) {                 // first 64 A nonzeros are enough for a verdict
+    const int j = m.Acol[jj];
+    if ((u32)j >= (u32)m.Bn) continue;
+    const int b0 = m.Brow[j], b1 = m.Brow[j + 1];
+    for (int o = b0 + (int)lane; o < b1 && o < b0 + 256; o += 32) { const u32 v = (u32)m.Bcol[o]; lo = min(lo, v); hi = max(hi, v); }
+  }
+  lo = __reduce_min_sync(0xffffffffu, lo);
+  hi = __reduce_max_sync(0xffffffffu, hi);
+  if (lane == 0 && lo != EMPTY) { atomicAdd(&sc->span_rows, 1u); if (hi - lo < (1u << 15)) atomicAdd(&sc->span_narrow, 1u); }
 }
 
 // ------------------------------------------------------------------------------------------------ (2b) M bin: one CTA per row

@@ -344,7 +344,7 @@ def test_ell_fast_path_variants(bs, oracle, monkeypatch):
                     la = 4
                     while la < np.diff(Arow).max():
                         la *= 2
-                    sortable = la <= 32 and la * st["group"] <= 512
+                    sortable = la <= 32 and la * st["group"] <= 1024
                     want_variant = 2 if (kernel == "sort" and sortable) else 1
                     assert st["variant"] == want_variant, f"{name} [{kernel}]: stats {st}"
                     seen.add((st["variant"], st["group"], st["rows_per_tile"]))
@@ -358,6 +358,7 @@ def test_ell_clustered_columns_spill_and_rebuild(bs, oracle, monkeypatch, kernel
     """Columns of B concentrated in a sliver of a wide [0,Bm): the global monotone slot map sends every key of a
     row to a handful of slots, chains run past the 32 spare slots, the row is rebuilt by the exact path."""
     monkeypatch.setenv("BSPGEMM_NO_SORT" if kernel == "hash" else "BSPGEMM_FORCE_SORT", "1")
+    monkeypatch.setenv("BSPGEMM_FORCE_ELL", "1")     # the span probe would route clustered rows to the bitmap kernels
     rng = np.random.default_rng(37)
     n, Bm = 6000, 1 << 22
     Arow, Acol = random_csr(rng, n, n, 12.0, sort=True, dups=False)
