@@ -154,10 +154,27 @@ __global__ void __maxnreg__(96) k_fused_sort(const EllArgs p) {
   // keys of pass q of a tile.  The K keys of lane (seg, ll) are consecutive uint4 of the row's B rows taken in A order:
   // uint4 number t = ll*NQ + u of the row is part t % LPR of B row slot t / LPR, so a lane holds whole (sorted) B rows,
   // or a contiguous piece of one.
+  // XPOSE (the config-3 geometry: 4 lanes per B row, 8 lanes and 32 keys per lane per output row): the loads are issued
+  // quad-coalesced instead — load u of lane (quad qd, part pp) is part pp of B row slot 2u+qd, a whole 64-byte row per
+  // quad and instruction: 8 instead of 32 lines per LDG.128 and no dependence on L1 — and the lane-per-B-row layout is
+  // produced when the keys are consumed, by transpose_pass() through the (still unused) staging area of the tile.
+  constexpr bool XPOSE = (LPR == 4 && S == 8 && K == 32);
   auto load_pass = [&](int q, int ar, u32 (&x)[K]) {
     const int row = q * RP + (int)seg;
     const int a0 = __shfl_sync(0xffffffffu, ar, 0);
     const int lo = __shfl_sync(0xffffffffu, ar, row), hi = __shfl_sync(0xffffffffu, ar, row + 1);
+    if (XPOSE) {
+      const int qd = (int)(ll >> 2), pp = (int)(ll & 3u);
+#pragma unroll
+      for (int u = 0; u < NQ; ++u) {
+        const int slot = 2 * u + qd;
+        int j = p.Bn;
+        if (slot < hi - lo) j = (int)lds32(acol_s + 4u * (u32)(lo - a0 + slot));
+        const uint4 t4 = __ldcg(&Bell4[(size_t)j * LPR + pp]);        // every sector is used exactly once: keep it out of L1
+        x[4 * u + 0] = t4.x; x[4 * u + 1] = t4.y; x[4 * u + 2] = t4.z; x[4 * u + 3] = t4.w;
+      }
+      return;
+    }
     constexpr int SLOTS = NQ >= LPR ? NQ / LPR : 1;                // B rows per lane
     constexpr int PARTS = NQ >= LPR ? LPR : NQ;                    // uint4 per B row taken by this lane
 #pragma unroll
@@ -173,6 +190,26 @@ __global__ void __maxnreg__(96) k_fused_sort(const EllArgs p) {
         x[4 * u + 0] = t4.x; x[4 * u + 1] = t4.y; x[4 * u + 2] = t4.z; x[4 * u + 3] = t4.w;
       }
     }
+  };
+  // XPOSE: quad-coalesced -> lane-per-B-row.  uint4 (row seg, slot, part) lives at seg*64 + (slot>>1)*8 + ((4*(slot&1) +
+  // part) ^ (slot>>1)) of the scratch: the XOR makes both the writes (fixed u: the 8 lanes of a row cover one 128-byte
+  // line) and the reads (fixed (g,c): the 8 lanes of a row hit 8 different 16-byte bank columns) conflict-free.
+  auto transpose_pass = [&](u32 (&x)[K], u32 scratch_s) {
+    if (!XPOSE) return;
+    const u32 qd = ll >> 2, pp = ll & 3u, rowbase = scratch_s + seg * 1024u;
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      sts128(rowbase + 16u * ((u32)u * 8u + ((4u * qd + pp) ^ (u32)u)), x[4 * u], x[4 * u + 1], x[4 * u + 2], x[4 * u + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int g = 0; g < 2; ++g)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint4 t4 = lds128(rowbase + 16u * (ll * 8u + ((u32)(4 * g + c) ^ ll)));
+        const int u = g * 4 + c;
+        x[4 * u + 0] = t4.x; x[4 * u + 1] = t4.y; x[4 * u + 2] = t4.z; x[4 * u + 3] = t4.w;
+      }
+    __syncwarp();
   };
   // commit of the tile staged in buffer buf_s during iteration `iter` (header: total, tile, inclusive row counts)
   auto commit = [&](u32 iter, u32 buf_s) {
@@ -216,6 +253,7 @@ __global__ void __maxnreg__(96) k_fused_sort(const EllArgs p) {
 #pragma unroll
     for (int q = 0; q < NP; ++q) {
       u32 (&k)[K] = x[q];
+      transpose_pass(k, cur_s);
       bitonic_sort_rows<K, S, (W < K ? W : K)>(k, ll);     // every B row is ascending in the ELL copy (k_build_ell sorts it)
       // the row is ascending along (lane, register); EMPTY (padding) is the largest value
       u32 prev_last = __shfl_up_sync(0xffffffffu, k[K - 1], 1);
