@@ -106,7 +106,7 @@ __device__ __forceinline__ void bitonic_sort_rows(u32 (&x)[K], const u32 ll) {
 // No launch bound: up to 96 registers (no spills — at 80 a reload from thrashed local memory cost 10 % of the warp
 // time); the host sizes the CTA from cudaFuncGetAttributes (registers are allocated per SM sub-partition, 16K each).
 template <int W, int LAL>
-__global__ void __maxnreg__(96) k_fused_sort(const EllArgs p) {
+__global__ void __maxnreg__((sort_geom<W, LAL>().K >= 32 ? 96 : 80)) k_fused_sort(const EllArgs p) {
   constexpr SortGeom G = sort_geom<W, LAL>();
   constexpr int LPR = G.LPR, S = G.S, NQ = G.NQ, K = G.K, RP = G.RP, R = G.R, NP = G.NP;
   constexpr u32 SWORDS = sort_stage_words(R, G.LA, W);
