@@ -209,7 +209,29 @@ def cpu_reference_run(row, col, n, target_seconds: float, steps: int = 1, warmup
 
 
 # ------------------------------------------------------------------------------------------------ main
+_RESULT_FD = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version line on the GPU
+    boxes): keep a private copy of the real stdout for the result line and point fd 1 at stderr for everything else."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -246,7 +268,7 @@ def main():
                 "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": res["value"], "unit": "IP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "out_nnz_per_s": res["out_nnz_per_s"], "gpu_launches": 0}
-        print(json.dumps(line))
+        _emit(line)
         return 0
 
     import torch
@@ -429,7 +451,7 @@ def main():
                          "launches_per_step": stats[-1]["launches"]},
             "wall_ms_per_step": wall_max / args.steps * 1e3, "setup_s": gen_s,
         }
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -15,6 +15,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <strings.h>
 #include <stdarg.h>
 #include <math.h>
 #include <algorithm>
@@ -661,6 +662,9 @@ static Global g;
 static std::mutex g_mu;
 
 static int nccl_load(Nccl& n) {
+  // NCCL prints its version line to stdout at NCCL_DEBUG=VERSION (set on some boxes): the drivers' stdout is the CSV line
+  const char* dbg = getenv("NCCL_DEBUG");
+  if (!dbg || !strcasecmp(dbg, "VERSION")) setenv("NCCL_DEBUG", "WARN", 1);
   const char* names[] = {"libnccl.so.2", "libnccl.so"};
   for (const char* nm : names) { n.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (n.lib) break; }
   if (!n.lib) return fail(BSPGEMM_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
