@@ -110,6 +110,8 @@ struct CtaChain {
   u32 cnt[CH_RING];           // compute warps that have posted in the slot (recycled by the helper)
   u64 base[CH_RING];          // (tag << 48) | exclusive prefix of the block, tag = (iteration & 0xfff) + 1
   u32 agg[CH_RING][32];       // (tag << 20) | aggregate of warp w's tile
+  u32 blkid[CH_RING];         // dynamic block assignment (chain_helper_dyn): block id of the CTA's iteration ...
+  u32 blkit[CH_RING];         // ... valid when this holds iteration + 1
 };
 constexpr u32 CH_AGG_MASK = (1u << 20) - 1;
 constexpr u64 CH_BASE_MASK = (1ull << 48) - 1;
@@ -190,6 +192,56 @@ __device__ __noinline__ void chain_helper(CtaChain* cc, u64* blk_status, u32 nti
     }
     __syncwarp();
   }
+}
+
+// Dynamic variant: the CTA's block of iteration i is not i*gridDim.x + blockIdx.x but the next id of a global counter,
+// claimed four iterations ahead (the compute warps prefetch two tiles ahead).  An SM that runs slower than the others
+// (the static deal made every CTA process the same number of blocks: the kernel ran at the pace of the slowest SM and
+// the warps of the others spent 9 % of their time waiting for offsets, profiles/r01_sort_cfg3_static_blocks.txt) then
+// simply takes fewer blocks.  Ids are consecutive in time, so neighbours in the chain still run at the same time.
+__device__ __noinline__ void chain_helper_dyn(CtaChain* cc, u64* blk_status, u32* counter, u32 ntiles, u32 ncompute, u32 lag) {
+  const u32 lane = lane_id();
+  const u32 nblocks = (ntiles + ncompute - 1u) / ncompute;
+  auto claim = [&](u32 it) {
+    if (lane == 0) {
+      const u32 id = atomicAdd(counter, 1u);
+      *reinterpret_cast<volatile u32*>(&cc->blkid[it & (CH_RING - 1u)]) = id;
+      __threadfence_block();
+      *reinterpret_cast<volatile u32*>(&cc->blkit[it & (CH_RING - 1u)]) = it + 1u;
+    }
+  };
+  for (u32 it = 0; it < 4u; ++it) claim(it);
+  __syncwarp();
+  for (u32 iter = 0;; ++iter) {
+    const u32 s = iter & (CH_RING - 1u), tag = (iter & 0xfffu) + 1u;
+    const u32 blk = *reinterpret_cast<volatile u32*>(&cc->blkid[s]);
+    if (blk >= nblocks) break;
+    const u32 expected = min(ncompute, ntiles - blk * ncompute);
+    while (*reinterpret_cast<volatile u32*>(&cc->cnt[s]) != expected) __nanosleep(100);
+    __threadfence_block();
+    const u32 w = (lane < expected) ? (*reinterpret_cast<volatile u32*>(&cc->agg[s][lane]) & CH_AGG_MASK) : 0u;
+    const u32 total = __reduce_add_sync(0xffffffffu, w);
+    if (lane == 0) {
+      if (iter >= 1u + lag) *reinterpret_cast<volatile u32*>(&cc->cnt[(iter - 1u - lag) & (CH_RING - 1u)]) = 0;
+      __threadfence_block();
+      st_status(&blk_status[blk], ST_AGG | (u64)total);
+    }
+    claim(iter + 4u);                        // every warp has posted `iter`: nobody reads the ids of iterations <= iter-4 any more
+    const u64 excl = chain_walk(blk_status, blk);
+    if (lane == 0) {
+      st_status(&blk_status[blk], ST_INC | (excl + (u64)total));
+      *reinterpret_cast<volatile u64*>(&cc->base[s]) = ((u64)tag << 48) | excl;
+      __threadfence_block();
+    }
+    __syncwarp();
+  }
+}
+// Block id of the CTA's iteration `it` (compute warps; normally already there).
+__device__ __forceinline__ u32 chain_block_of(CtaChain* cc, u32 it) {
+  const u32 s = it & (CH_RING - 1u);
+  while (*reinterpret_cast<volatile u32*>(&cc->blkit[s]) != it + 1u) __nanosleep(100);
+  __threadfence_block();
+  return *reinterpret_cast<volatile u32*>(&cc->blkid[s]);
 }
 
 // Exclusive prefix of this warp's tile of iteration `iter` (whole warp).  Called `lag` tiles after chain_post(iter).

@@ -120,7 +120,7 @@ __global__ void __maxnreg__((sort_geom<W, LAL>().K >= 32 ? 96 : 80)) k_fused_sor
   for (u32 i = threadIdx.x; i < sizeof(CtaChain) / 4; i += blockDim.x) reinterpret_cast<u32*>(cc)[i] = 0;
   __syncthreads();                          // the only CTA-wide barrier
   if (warp == nwarps) {
-    if (!p.debug_nochain) chain_helper(cc, p.blk_status, p.ntiles, gridDim.x * nwarps, blockIdx.x * nwarps, nwarps, p.nbuf - 1u);
+    if (!p.debug_nochain) chain_helper_dyn(cc, p.blk_status, &p.sc->tile_counter, p.ntiles, nwarps, p.nbuf - 1u);
     return;
   }
   const u32 ll = lane % S, seg = lane / S;  // lane within its row, row within the pass
@@ -228,8 +228,17 @@ __global__ void __maxnreg__((sort_geom<W, LAL>().K >= 32 ? 96 : 80)) k_fused_sor
   };
 
   // ---- pipeline prologue
-  u32 tile = cta_first + warp, iter = 0;
-  int arn = load_rowptr(tile + stride < tile ? 0xffffffffu : tile + stride);
+  // tile of this warp in the CTA's iteration `it`: block ids come from the chain helper (dynamic deal, see chain_helper_dyn)
+  const u32 nblocks = (p.ntiles + nwarps - 1u) / nwarps;
+  auto tile_of = [&](u32 it) -> u32 {
+    if (p.debug_nochain) { const unsigned long long t = (unsigned long long)it * stride + cta_first + warp; return t < p.ntiles ? (u32)t : 0xffffffffu; }
+    const u32 blk = chain_block_of(cc, it);
+    if (blk >= nblocks) return 0xffffffffu;
+    const u32 t = blk * nwarps + warp;
+    return t < p.ntiles ? t : 0xffffffffu;
+  };
+  u32 tile = tile_of(0), iter = 0;
+  int arn = load_rowptr(tile_of(1));
   u32 x[NP][K];
   {
     const int ar = load_rowptr(tile);
@@ -243,9 +252,8 @@ __global__ void __maxnreg__((sort_geom<W, LAL>().K >= 32 ? 96 : 80)) k_fused_sor
   u32 cur_buf = 0;                           // iter % nbuf
 
   while (tile < p.ntiles) {
-    const u32 next = (tile + stride < tile) ? 0xffffffffu : tile + stride;
-    const u32 next2 = (next + stride < next) ? 0xffffffffu : next + stride;
-    const int arnn = load_rowptr(next2);
+    const u32 next = tile_of(iter + 1u);
+    const int arnn = load_rowptr(tile_of(iter + 2u));
     int j0n, j1n;
     load_acol(arn, j0n, j1n);
     const u32 buf_s = stage_s + cur_buf * (SWORDS * 4u), cur_s = buf_s + 4u * SORT_HDR;
