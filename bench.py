@@ -44,6 +44,8 @@ WORKLOADS = {
     "cfg3": ("gen_uniform", ((1 << 22), 16, 1), "uniform random boolean n=2^22 d=16 seed=1, C=A*A"),
     "rmat20": ("gen_rmat", (20, 16, 0.45, 0.22, 0.22, 1), "R-MAT (.45,.22,.22,.11) scale 20 edge factor 16, C=A*A"),
     "banded22": ("gen_banded", ((1 << 22), 32), "banded n=2^22 d=32, C=A*A"),
+    "cfg4": ("gen_rmat", (22, 16, 0.45, 0.22, 0.22, 1), "BASELINE config 4: R-MAT (.45,.22,.22,.11) scale 22 edge factor 16, C=A*A (int64 row pointers)"),
+    "cfg5": ("gen_banded", ((1 << 24), 32), "BASELINE config 5: banded n=2^24 d=32, C=A*A"),
     "small": ("gen_uniform", ((1 << 16), 8, 1), "uniform random boolean n=2^16 d=8 seed=1, C=A*A"),
 }
 
@@ -303,7 +305,7 @@ def main():
 
     mode = {"auto": bs.MODE_AUTO, "fused": bs.MODE_FUSED, "twophase": bs.MODE_TWOPHASE}[args.mode]
     h = bs.DeviceSpGEMM(local_rank, mode)
-    i64 = args.workload.startswith("rmat")          # nnz(C) of the R-MAT workloads exceeds 2^31: 64-bit row pointers
+    i64 = args.workload.startswith("rmat") or args.workload == "cfg4"          # nnz(C) of the R-MAT workloads exceeds 2^31: 64-bit row pointers
     d_crow = torch.zeros(rows + 1, dtype=torch.int64 if i64 else torch.int32, device=dev)
     stream = torch.cuda.current_stream()
     a_row_ptr = d_row.data_ptr() + 4 * r0             # shifted Arow, absolute offsets (final/SpGEMM_mpi_omp.c:171)
@@ -394,7 +396,7 @@ def main():
     else:
         rc = torch.from_numpy(row).pin_memory(); cc = torch.from_numpy(col).pin_memory()
         row_h, col_h = rc.numpy(), cc.numpy()
-    out_cap = 16 if args.workload.startswith("rmat") else int(nnz) + 16
+    out_cap = 16 if i64 else int(nnz) + 16
     out_pin = torch.empty(out_cap, dtype=torch.int32).pin_memory()
     out_h = out_pin.numpy()
     torch.cuda.synchronize()
