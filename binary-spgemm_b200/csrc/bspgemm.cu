@@ -9,6 +9,7 @@
 #include "kernels.cuh"
 #include "fused_ell.cuh"
 #include "fused_sort.cuh"
+#include "rows_window.cuh"
 
 #include <nccl.h>      // types only; the library itself is dlopen'ed so libbspgemm.so loads without it
 #include <dlfcn.h>
@@ -91,6 +92,7 @@ struct bspgemm_dev {
   int used_mode = 0, G = 16, launches = 0;
   u32 cap_s = 0, cap_m1 = 0, cap_m2 = 0;
   bool have_m = false, have_m2 = false, have_l = false;
+  bool use_window = false;          // M/L bins: windowed shared-memory bitmap (rows_window.cuh) instead of table / global bitmap
   u32 bm_words = 0; int l_grid = 0;
   bool skip_estimate = false; u32 row_ip_bound = 0, max_len_b = 0;
   bool use_ell = false; int ell_W = 0, ell_R = 0, ell_warps = 0; u32 ell_TW = 0, ell_maxA = 0, ell_lf16 = 28;
@@ -116,6 +118,7 @@ static int set_kernel_attributes(int smem_optin) {
 #define ATTR_G(Gv) ATTR((k_rows_warp<Gv, MODE_COUNT>)); ATTR((k_rows_warp<Gv, MODE_FILL>)); ATTR((k_fused<Gv, true>)); ATTR((k_fused<Gv, false>))
   ATTR_G(4); ATTR_G(8); ATTR_G(16); ATTR_G(32);
   ATTR(k_rows_cta<MODE_COUNT>); ATTR(k_rows_cta<MODE_FILL>);
+  ATTR(k_rows_window<MODE_COUNT>); ATTR(k_rows_window<MODE_FILL>);
 #define ATTR_E(Wv) ATTR((k_fused_ell<Wv, 1>)); ATTR((k_fused_ell<Wv, 2>)); ATTR((k_fused_ell<Wv, 4>)); ATTR((k_fused_ell<Wv, 8>))
   ATTR_E(4); ATTR_E(8); ATTR_E(16); ATTR_E(32);
 #undef ATTR_E
@@ -174,6 +177,21 @@ template <int MODE> static int launch_bins_ml(bspgemm_dev* d) {
   int* ccol = d->user_ccol ? d->user_ccol : d->ccol.p;
   const size_t An = (size_t)a.m.An;
   u32* l1 = d->lists.p, *l2 = d->lists.p + An, *l3 = d->lists.p + 2 * An;
+  if (d->use_window) {
+    // windowed shared-memory bitmap (rows_window.cuh): largest rows first, rows handed out dynamically
+    const size_t smem = (size_t)WIN_WORDS * 4;
+    u32* ctr = d->d_sc->win_ctr + (MODE == MODE_FILL ? 3 : 0);
+    const u32* nl[3] = { &d->d_sc->n_l, &d->d_sc->n_m2, &d->d_sc->n_m1 };
+    u32* ls[3] = { l3, l2, l1 };
+    const bool have[3] = { d->have_l, d->have_m2, d->have_m };
+    for (int b = 0; b < 3; ++b) {
+      if (!have[b]) continue;
+      k_rows_window<MODE><<<d->sm_count, 1024, smem, d->stream>>>(a.m, ls[b], nl[b], ctr + b, d->cnt.p, d->G, WIN_WORDS, a.dCrow, a.is64, ccol, d->d_sc);
+      d->launches++;
+      CK(cudaGetLastError());
+    }
+    return BSPGEMM_OK;
+  }
   if (d->have_m) {
     k_rows_cta<MODE><<<d->sm_count * 4, 256, 3ull * CAP_M1 * 4, d->stream>>>(a.m, l1, &d->d_sc->n_m1, d->ip.p, d->cnt.p, CAP_M1, d->G, a.dCrow, a.is64, ccol, d->d_sc);
     d->launches++;
@@ -471,7 +489,9 @@ static int mul_launch_main(bspgemm_dev* d) {
     d->launches++;
     CK(cudaGetLastError());
   }
-  if (d->have_l) {
+  // Matrices of up to WIN_MAX_WINDOWS windows of columns: every big row goes through the windowed bitmap kernel
+  d->use_window = (u64)a.m.Bm <= (u64)WIN_MAX_WINDOWS * WIN_WORDS * 32ull && !getenv("BSPGEMM_NO_WINDOW");
+  if (d->have_l && !d->use_window) {
     d->bm_words = (u32)(((size_t)a.m.Bm + 31) / 32);
     d->l_grid = d->sm_count;
     const size_t need = (size_t)d->l_grid * d->bm_words;

@@ -53,51 +53,7 @@ template <int W, int LAL> __host__ __device__ constexpr SortGeom sort_geom() {
 constexpr u32 SORT_HDR = 20;             // per staging buffer: [0] total, [1] tile, [2..2+R) inclusive row counts
 __host__ __device__ constexpr u32 sort_stage_words(int R, int LA, int W) { const u32 n = (u32)(R * LA * W); return (SORT_HDR + n + n / 32u + 4u + 3u) & ~3u; }
 
-// In-place ascending bitonic sort of 32/S independent rows, K keys per lane, element index i = lane_in_row*K + k.
-// "Flip" formulation: every merge level starts with the mirror exchange i <-> i ^ (size-1), then half-cleaners
-// i <-> i ^ d; every comparator puts the minimum at the lower index, so exchanges inside a lane need no run-time
-// direction (min + max), exchanges between lanes cost SHFL + min + predicated max.
-// RUN: the keys arrive as ascending runs of RUN consecutive elements (1 = unsorted): the merge levels up to RUN are skipped.
-template <int K, int S, int RUN = 1>
-__device__ __forceinline__ void bitonic_sort_rows(u32 (&x)[K], const u32 ll) {
-  constexpr int N = K * S;
-#pragma unroll
-  for (int size = 2 * RUN; size <= N; size <<= 1) {
-    if (size <= K) {                                               // mirror inside the lane
-#pragma unroll
-      for (int k = 0; k < K; ++k) {
-        const int pk = k ^ (size - 1);
-        if (k < pk) { const u32 lo = min(x[k], x[pk]), hi = max(x[k], x[pk]); x[k] = lo; x[pk] = hi; }
-      }
-    } else {                                                       // mirror across lanes: register k <-> K-1-k of lane ^ (size/K-1)
-      const u32 lm = (u32)(size / K - 1);
-      const bool keepmin = (ll & (u32)(size / (2 * K))) == 0u;
-#pragma unroll
-      for (int k = 0; k < K / 2; ++k) {
-        const u32 ya = __shfl_xor_sync(0xffffffffu, x[K - 1 - k], lm);
-        const u32 yb = __shfl_xor_sync(0xffffffffu, x[k], lm);
-        x[k] = keepmin ? min(x[k], ya) : max(x[k], ya);
-        x[K - 1 - k] = keepmin ? min(x[K - 1 - k], yb) : max(x[K - 1 - k], yb);
-      }
-    }
-#pragma unroll
-    for (int d = size >> 2; d >= 1; d >>= 1) {
-      if (d >= K) {                                                // partner key lives in lane ^ (d/K)
-        const u32 ld = (u32)(d / K);
-        const bool keepmin = (ll & ld) == 0u;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-          const u32 y = __shfl_xor_sync(0xffffffffu, x[k], ld);
-          x[k] = keepmin ? min(x[k], y) : max(x[k], y);
-        }
-      } else {                                                     // both keys in this lane
-#pragma unroll
-        for (int k = 0; k < K; ++k)
-          if ((k & d) == 0) { const u32 lo = min(x[k], x[k | d]), hi = max(x[k], x[k | d]); x[k] = lo; x[k | d] = hi; }
-      }
-    }
-  }
-}
+// (bitonic_sort_rows, the register sorting network, lives in kernels.cuh: the warp-per-row kernels use it too)
 
 // Every warp is an independent worker on tiles of R consecutive rows.  Per iteration (tile t):
 //   for each pass: sort the pass's rows in registers, mark first occurrences, scan, write the distinct keys to the

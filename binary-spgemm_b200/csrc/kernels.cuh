@@ -55,6 +55,7 @@ struct DevScalars {     // one per context, in device memory; copied to the host
   u32 tile_counter;     // dynamic tile ids (fused kernel / scan kernel)
   u32 max_len_a, max_len_b;   // longest row of A / of B (k_maxlen)
   u32 span_rows, span_narrow; // k_probe_span: sampled non-empty rows / those whose candidate columns span < 2^15
+  u32 win_ctr[8];             // k_rows_window: next list entry, one counter per launch (3 lists x COUNT/FILL)
 };
 
 // ------------------------------------------------------------------------------------------------ helpers
@@ -110,6 +111,52 @@ __device__ __forceinline__ u64 lookback_exclusive(u64* status, u32 tile, u64 agg
   }
   if (lane == 0) st_status(&status[tile], ST_INC | (excl + aggregate));
   return excl;
+}
+
+// In-place ascending bitonic sort of 32/S independent rows, K keys per lane, element index i = lane_in_row*K + k.
+// "Flip" formulation: every merge level starts with the mirror exchange i <-> i ^ (size-1), then half-cleaners
+// i <-> i ^ d; every comparator puts the minimum at the lower index, so exchanges inside a lane need no run-time
+// direction (min + max), exchanges between lanes cost SHFL + min + predicated max.
+// RUN: the keys arrive as ascending runs of RUN consecutive elements (1 = unsorted): the merge levels up to RUN are skipped.
+template <int K, int S, int RUN = 1>
+__device__ __forceinline__ void bitonic_sort_rows(u32 (&x)[K], const u32 ll) {
+  constexpr int N = K * S;
+#pragma unroll
+  for (int size = 2 * RUN; size <= N; size <<= 1) {
+    if (size <= K) {                                               // mirror inside the lane
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const int pk = k ^ (size - 1);
+        if (k < pk) { const u32 lo = min(x[k], x[pk]), hi = max(x[k], x[pk]); x[k] = lo; x[pk] = hi; }
+      }
+    } else {                                                       // mirror across lanes: register k <-> K-1-k of lane ^ (size/K-1)
+      const u32 lm = (u32)(size / K - 1);
+      const bool keepmin = (ll & (u32)(size / (2 * K))) == 0u;
+#pragma unroll
+      for (int k = 0; k < K / 2; ++k) {
+        const u32 ya = __shfl_xor_sync(0xffffffffu, x[K - 1 - k], lm);
+        const u32 yb = __shfl_xor_sync(0xffffffffu, x[k], lm);
+        x[k] = keepmin ? min(x[k], ya) : max(x[k], ya);
+        x[K - 1 - k] = keepmin ? min(x[K - 1 - k], yb) : max(x[K - 1 - k], yb);
+      }
+    }
+#pragma unroll
+    for (int d = size >> 2; d >= 1; d >>= 1) {
+      if (d >= K) {                                                // partner key lives in lane ^ (d/K)
+        const u32 ld = (u32)(d / K);
+        const bool keepmin = (ll & ld) == 0u;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const u32 y = __shfl_xor_sync(0xffffffffu, x[k], ld);
+          x[k] = keepmin ? min(x[k], y) : max(x[k], y);
+        }
+      } else {                                                     // both keys in this lane
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+          if ((k & d) == 0) { const u32 lo = min(x[k], x[k | d]), hi = max(x[k], x[k | d]); x[k] = lo; x[k | d] = hi; }
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ (1) work estimation
@@ -192,6 +239,7 @@ struct RowTable {
   u32 span;      // bitmap: number of words; ordered table: largest occupied slot
   u32 count;     // distinct columns
   u32 bitmap;    // 1 = bitmap over [lo,hi], 0 = ordered table
+  u32 sorted;    // 1 = the distinct columns already stand ascending in the row's staging area (register sort)
   u32 ok;        // 0 = the optimistic build failed (bad lo/hi hint or spill overflow): rebuild exactly
 };
 
@@ -201,14 +249,43 @@ __device__ __forceinline__ void table_init_empty(u32* tab, u32 words) {      // 
   for (u32 q = lane_id(); q < words / 4; q += 32) t4[q] = e;
 }
 
-// Exact build from staged candidates stage[0..ipr): lo/hi by reduction, then
-//   narrow span (hi-lo < 32*tabw): bitmap over [lo,hi];
-//   wide span: ordered table.  Attempt 0: T = 2*IP home slots + 32 spill slots (overflow detected);
-//   attempt 1: T = tabw-IP home slots + IP spill slots, which cannot overflow (a key is pushed right past
-//   at most IP-1 smaller distinct keys).  range > 32*tabw > T  =>  the slot scale fits 32 bits.
-__device__ __noinline__ RowTable build_staged(const u32* stage, const u32 ipr, u32* tab, const u32 tabw, const u32 Bm, u32* err) {
+// Sort + de-duplicate the staged candidates of one row in registers (one warp, K keys per lane, 32*K >= ipr): the row's
+// distinct columns end up ascending in stage[0..count).  The cost is a constant of the (padded) row size — it does not
+// depend on how the columns are distributed, unlike an order-preserving slot map, which degenerates into long
+// collision chains on power-law rows (R-MAT: most candidates of every row sit on the same few hub columns).
+template <int K>
+__device__ __noinline__ u32 sort_dedup_staged(u32* stage, const u32 ipr, const u32 Bm, u32* err) {
   const u32 lane = lane_id();
-  RowTable t; t.ok = 1; t.count = 0; t.span = 0; t.bitmap = 0;
+  u32 x[K];
+  u32 vmax = 0;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {                       // any order will do: lane-interleaved = conflict-free
+    const u32 i = (u32)k * 32u + lane;
+    x[k] = EMPTY;
+    if (i < ipr) { x[k] = stage[i]; vmax = max(vmax, x[k]); }
+  }
+  if (__reduce_max_sync(0xffffffffu, vmax) >= Bm) { if (lane == 0) atomicOr(err, 4u); return 0u; }   // B column outside [0,Bm): refuse
+  __syncwarp();
+  bitonic_sort_rows<K, 32, 1>(x, lane);
+  u32 prev = __shfl_up_sync(0xffffffffu, x[K - 1], 1);
+  if (lane == 0) prev = EMPTY;
+  u32 c = 0, f = 0;
+#pragma unroll
+  for (int k = 0; k < K; ++k) { const bool fk = (x[k] != EMPTY) && (x[k] != (k ? x[k - 1] : prev)); f |= fk ? (1u << k) : 0u; c += fk ? 1u : 0u; }
+  const u32 inc = warp_incl_scan(c);
+  u32 o = inc - c;
+#pragma unroll
+  for (int k = 0; k < K; ++k) if ((f >> k) & 1u) stage[o++] = x[k];
+  __syncwarp();
+  return __shfl_sync(0xffffffffu, inc, 31);
+}
+
+// Exact build from staged candidates stage[0..ipr): lo/hi by reduction, then
+//   narrow span (hi-lo < 32*tabw): bitmap over [lo,hi] in tab[] (emit_sorted reads it back);
+//   wide span: register sort (sort_dedup_staged): the sorted distinct row is left in stage[] (t.sorted = 1).
+__device__ __noinline__ RowTable build_staged(u32* stage, const u32 ipr, u32* tab, const u32 tabw, const u32 Bm, u32* err) {
+  const u32 lane = lane_id();
+  RowTable t; t.ok = 1; t.count = 0; t.span = 0; t.bitmap = 0; t.sorted = 0;
   u32 vmin = EMPTY, vmax = 0;
 #pragma unroll 4
   for (u32 p = lane; p < ipr; p += 32) { const u32 v = stage[p]; vmin = min(vmin, v); vmax = max(vmax, v); }
@@ -232,30 +309,12 @@ __device__ __noinline__ RowTable build_staged(const u32* stage, const u32 ipr, u
     t.bitmap = 1; t.span = nW; t.count = __reduce_add_sync(0xffffffffu, added);
     return t;
   }
-  u32 added = 0, max_slot = 0;
-  for (int attempt = 0;; ++attempt) {
-    const u32 T = attempt ? tabw - ipr : 2 * ipr;
-    const u32 limit = attempt ? tabw : T + 32;
-    const u32 scale = slot_scale(T, range);
-    table_init_empty(tab, 128u * (((limit + 127) >> 7) | 1u));
-    __syncwarp();
-    added = 0; max_slot = 0;
-    u32 ovf = 0;
-    for (u32 p = lane; p < ipr; p += 32) {
-      u32 x = stage[p], s = __umulhi(x - lo, scale);
-      while (true) {
-        if (s >= limit) { ovf = 1; break; }
-        const u32 old = atomicMin(&tab[s], x);
-        if (old == EMPTY) { ++added; max_slot = max(max_slot, s); break; }
-        if (old == x) break;
-        x = max(old, x); ++s;
-      }
-    }
-    __syncwarp();
-    if (!__any_sync(0xffffffffu, ovf)) break;
-  }
-  t.span = __reduce_max_sync(0xffffffffu, max_slot);
-  t.count = __reduce_add_sync(0xffffffffu, added);
+  t.sorted = 1;
+  if (ipr <= 64u)       t.count = sort_dedup_staged<2>(stage, ipr, Bm, err);
+  else if (ipr <= 128u) t.count = sort_dedup_staged<4>(stage, ipr, Bm, err);
+  else if (ipr <= 256u) t.count = sort_dedup_staged<8>(stage, ipr, Bm, err);
+  else if (ipr <= 512u) t.count = sort_dedup_staged<16>(stage, ipr, Bm, err);
+  else                  t.count = sort_dedup_staged<32>(stage, ipr, Bm, err);     // cap_s <= 1024
   return t;
 }
 
@@ -355,7 +414,7 @@ __global__ void __launch_bounds__(WARPS_S * 32) k_rows_warp(Csr m, const u32* __
       const RowTable t = build_staged(stage, ipr, tab, tab_words(cap), (u32)m.Bm, &sc->err);
       c = t.count;
       if (MODE == MODE_FILL && c) {
-        emit_sorted(tab, t, stage);
+        if (!t.sorted) emit_sorted(tab, t, stage);
         const u64 base = ld_rowptr(Crow, is64, (size_t)row);
         for (u32 p = lane; p < c; p += 32) Ccol[base + p] = (int)stage[p];
       }
@@ -509,7 +568,7 @@ __global__ void __launch_bounds__(1024, 1) k_fused(Csr m, const u32* __restrict_
       u32* out = stage + r * cap;
       bool need_exact = !fast;
       u32 ipr = 0;
-      RowTable t; t.ok = 0; t.count = 0; t.bitmap = 0; t.lo = 0; t.span = 0;
+      RowTable t; t.ok = 0; t.count = 0; t.bitmap = 0; t.sorted = 0; t.lo = 0; t.span = 0;
       if (fast) {
         u32 Sa = S[0], Sb = S[1], lo = lo_r[0], hi = hi_r[0]; int e0 = a[0], e1 = a[1];
 #pragma unroll
@@ -529,29 +588,7 @@ __global__ void __launch_bounds__(1024, 1) k_fused(Csr m, const u32* __restrict_
             direct_insert_loop<G, NOTAIL, true>(m, desc, e0, e1, tab, out, lo, range, 0u, added, max_slot, bad, qn);
             __syncwarp();
             t.bitmap = 1; t.span = nW;
-          } else {
-            const u32 T = 2 * ipr, limit = T + 32;
-            const u32 scale = slot_scale(T, range);
-            table_init_empty(tab, 128u * (((limit + 127) >> 7) | 1u));
-            __syncwarp();
-            if (lane == 0) *qn = 0;
-            __syncwarp();
-            direct_insert_loop<G, NOTAIL, false>(m, desc, e0, e1, tab, out, lo, range, scale, added, max_slot, bad, qn);
-            __syncwarp();
-            const u32 nq = *qn;
-            for (u32 i = lane; i < nq; i += 32) {                   // drain the collision queue, all lanes busy
-              u32 x = out[i], s = __umulhi(x - lo, scale);
-              while (true) {
-                if (s >= limit) { bad = 1; break; }
-                const u32 old = atomicMin(&tab[s], x);
-                if (old == EMPTY) { ++added; max_slot = max(max_slot, s); break; }
-                if (old == x) break;
-                x = max(old, x); ++s;
-              }
-            }
-            __syncwarp();
-            t.span = __reduce_max_sync(0xffffffffu, max_slot);
-          }
+          } else bad = 1;                                   // wide span: staged gather + register sort (build_staged)
           t.count = __reduce_add_sync(0xffffffffu, added);
           t.ok = __any_sync(0xffffffffu, bad) ? 0u : 1u;
           need_exact = !t.ok;
@@ -564,7 +601,7 @@ __global__ void __launch_bounds__(1024, 1) k_fused(Csr m, const u32* __restrict_
       }
       if (!fast) { ip_sum += ipr; ip_max = max(ip_max, ipr); }
       if (ipr > cap) c = cnt_big[row0 + r];
-      else if (ipr > 0 && t.ok && t.count) { emit_sorted(tab, t, out); c = t.count; mine_mask |= 1u << r; }
+      else if (ipr > 0 && t.ok && t.count) { if (!t.sorted) emit_sorted(tab, t, out); c = t.count; mine_mask |= 1u << r; }
       if ((int)lane == r) c_mine = c;
     }
     if (fast) { ip_sum += S[R] - S[0]; 

@@ -379,3 +379,64 @@ def test_ell_clustered_columns_spill_and_rebuild(bs, oracle, monkeypatch, kernel
     got_col, got_row, st = dev_multiply(bs, bs.MODE_AUTO, Acol, Arow, n, Bcol2, Brow, n, Bm)
     msg = _explain(got_col, got_row, want_col, want_row)
     assert not msg, msg
+
+
+def test_power_law_rows_sort_and_window_bins(bs, oracle):
+    """R-MAT (no vertex permutation): the candidates of every row pile up on the hub columns.  Small rows go through the
+    register sort of the warp bin, big rows through the windowed shared-memory bitmap (rows_window.cuh), hub rows of B
+    through the warp-per-long-row loop."""
+    row, col = bs.gen_rmat(15, 16, 0.45, 0.22, 0.22, 3)
+    n = len(row) - 1
+    want_col, want_row = oracle.spgemm(col, row, n, col, row, n)
+    for mode in (bs.MODE_FUSED, bs.MODE_TWOPHASE):
+        got_col, got_row, st = dev_multiply(bs, mode, col, row, n, col, row, n, n, i64=True)
+        msg = _explain(got_col, got_row, want_col, want_row)
+        assert not msg, f"mode {mode}: {msg}"
+        assert st["rows_m"] > 0 and st["rows_l"] > 0 and st["rows_s"] > 0
+    # a steeper one (Graph500 parameters): longer hub rows
+    row, col = bs.gen_rmat(13, 16, 0.57, 0.19, 0.19, 5)
+    n = len(row) - 1
+    want_col, want_row = oracle.spgemm(col, row, n, col, row, n)
+    got_col, got_row, st = dev_multiply(bs, bs.MODE_FUSED, col, row, n, col, row, n, n, i64=True)
+    msg = _explain(got_col, got_row, want_col, want_row)
+    assert not msg, msg
+
+
+def test_window_bins_many_windows_unsorted_rows(bs, oracle, monkeypatch):
+    """Big rows whose columns span several bitmap windows (Bm = 6M columns = 4 windows), with gaps, with B rows that are
+    NOT ascending (the first-window guess is wrong: restart path) and with repeated columns."""
+    rng = np.random.default_rng(29)
+    Bm = 6_000_000
+    k = 3000
+    blen = rng.integers(1, 30, k)
+    blen[:40] = 2500                                  # long B rows (warp-per-row loop)
+    Brow = np.concatenate([[0], np.cumsum(blen)]).astype(np.int32)
+    parts = []
+    for i, l in enumerate(blen):
+        if i % 3 == 0:   c = rng.integers(0, Bm, l)                                   # anywhere, unsorted, may repeat
+        elif i % 3 == 1: c = rng.integers(4_000_000, 4_000_000 + 5000, l)             # a cluster in window 2
+        else:            c = np.sort(rng.integers(5_900_000, Bm, l))                  # the last columns
+        parts.append(c)
+    Bcol = np.concatenate(parts).astype(np.int32)
+    rows = [np.arange(0, 40), np.arange(1, 2000, 3), np.arange(2, 2000, 3), np.arange(40, 1500), np.arange(0, k),
+            rng.choice(k, 200, replace=False), np.arange(41, 3000, 3)]
+    for _ in range(50):
+        rows.append(rng.choice(np.arange(40, k), int(rng.integers(0, 10)), replace=False))
+    Arow = np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.int32)
+    Acol = np.concatenate(rows).astype(np.int32)
+    An = len(rows)
+    want_col, want_row = oracle.spgemm(Acol, Arow, An, Bcol, Brow, Bm)
+    for cap in (None, "32"):
+        if cap: monkeypatch.setenv("BSPGEMM_CAP_S", cap)
+        for mode in (bs.MODE_FUSED, bs.MODE_TWOPHASE):
+            got_col, got_row, st = dev_multiply(bs, mode, Acol, Arow, An, Bcol, Brow, k, Bm)
+            msg = _explain(got_col, got_row, want_col, want_row)
+            assert not msg, f"cap {cap} mode {mode}: {msg}"
+            assert st["rows_m"] > 0 and st["rows_l"] > 0
+
+
+def test_wide_matrices_keep_table_and_global_bitmap_bins(bs, oracle, monkeypatch):
+    """BSPGEMM_NO_WINDOW: the ordered-table CTA kernels and the global-bitmap kernel (the route of matrices with more
+    than WIN_MAX_WINDOWS windows of columns) still match."""
+    monkeypatch.setenv("BSPGEMM_NO_WINDOW", "1")
+    test_every_bin_is_exercised(bs, oracle)
