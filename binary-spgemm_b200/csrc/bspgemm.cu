@@ -10,6 +10,7 @@
 #include "fused_ell.cuh"
 #include "fused_sort.cuh"
 #include "rows_window.cuh"
+#include "band.cuh"
 
 #include <nccl.h>      // types only; the library itself is dlopen'ed so libbspgemm.so loads without it
 #include <dlfcn.h>
@@ -92,6 +93,7 @@ struct bspgemm_dev {
   int used_mode = 0, G = 16, launches = 0;
   u32 cap_s = 0, cap_m1 = 0, cap_m2 = 0;
   bool have_m = false, have_m2 = false, have_l = false;
+  bool use_band = false, no_band = false;   // run/bitmap kernel for banded matrices (band.cuh); no_band: it failed on this input, redo generally
   bool use_window = false;          // M/L bins: windowed shared-memory bitmap (rows_window.cuh) instead of table / global bitmap
   u32 bm_words = 0; int l_grid = 0;
   bool skip_estimate = false; u32 row_ip_bound = 0, max_len_b = 0;
@@ -309,6 +311,34 @@ static int launch_sort(bspgemm_dev* d, int* ccol) {
 #undef LS
 }
 
+// Banded / block-diagonal fast path (band.cuh): B rows become (first, len) descriptors, output rows 128-bit bitmaps.
+static int launch_band(bspgemm_dev* d) {
+  const MulArgs& a = d->a;
+  int* ccol = d->user_ccol ? d->user_ccol : d->ccol.p;
+  CKS(d->bell.ensure(((size_t)a.m.Bn + 1) * 2 + 4));
+  uint2* desc = reinterpret_cast<uint2*>(d->bell.p);
+  {
+    const long long threads = (((long long)a.m.Bn + 31) / 32) * 32;
+    k_build_desc<<<(int)((threads + 255) / 256), 256, 0, d->stream>>>(a.m.Brow, a.m.Bcol, a.m.Bn, (u32)a.m.Bm, desc, d->d_sc);
+    d->launches++;
+    CK(cudaGetLastError());
+  }
+  const u32 ntiles = (u32)(((size_t)a.m.An + BAND_THREADS - 1) / BAND_THREADS);
+  CKS(d->status.ensure((size_t)ntiles + 1));
+  CK(cudaMemsetAsync(d->status.p, 0, ((size_t)ntiles + 1) * sizeof(u64), d->stream));
+  CK(cudaEventRecord(d->ev[3], d->stream));
+  int bps = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_band, BAND_THREADS, 0));
+  const int grid = (int)std::max<long long>(1, std::min<long long>((long long)ntiles, (long long)d->sm_count * std::max(bps, 1)));
+  BandArgs p{};
+  p.Arow = a.m.Arow; p.Acol = a.m.Acol; p.desc = desc; p.An = a.m.An; p.Bn = a.m.Bn;
+  p.Crow = a.dCrow; p.is64 = a.is64; p.Ccol = ccol; p.status = d->status.p; p.sc = d->d_sc; p.ntiles = ntiles;
+  k_band<<<grid, BAND_THREADS, 0, d->stream>>>(p);
+  d->launches++;
+  CK(cudaGetLastError());
+  return BSPGEMM_OK;
+}
+
 static int launch_ell(bspgemm_dev* d) {
   const MulArgs& a = d->a;
   int* ccol = d->user_ccol ? d->user_ccol : d->ccol.p;
@@ -411,6 +441,11 @@ static int mul_launch_estimate(bspgemm_dev* d) {
   d->max_len_b = h.max_len_b;
   d->skip_estimate = d->mode != BSPGEMM_MODE_TWOPHASE && bound <= (u64)g_cap_s_max() && !getenv("BSPGEMM_FORCE_ESTIMATE");
   if (ell_plan(d)) d->skip_estimate = true;
+  // every sampled row is a union of runs of consecutive columns inside a 128-column window: banded / block-diagonal
+  d->use_band = !d->no_band && d->mode != BSPGEMM_MODE_TWOPHASE && h.span_rows > 0 && h.span_runs == h.span_rows &&
+                !getenv("BSPGEMM_NO_BAND") && !getenv("BSPGEMM_NO_ELL") && !getenv("BSPGEMM_CAP_S") && !getenv("BSPGEMM_FORCE_ESTIMATE") &&
+                !getenv("BSPGEMM_FORCE_ELL") && !getenv("BSPGEMM_FORCE_SORT") && !getenv("BSPGEMM_NO_SORT");
+  if (d->use_band) d->skip_estimate = true;
   d->row_ip_bound = (u32)std::min<u64>(bound, 0xfffffffeull);
   CK(cudaEventRecord(d->ev[6], d->stream));
   if (!d->skip_estimate) {
@@ -429,6 +464,34 @@ static int mul_launch_main(bspgemm_dev* d) {
   const size_t An = (size_t)a.m.An;
   u64 ip_bound;                      // upper bound of nnz(C) used to size the fused output arena
   u32 max_ip;
+  if (d->use_band) {
+    ip_bound = std::min<u64>((u64)a.Annz * (u64)d->max_len_b, (u64)a.m.An * (u64)BAND_BITS);   // an output row has at most BAND_BITS columns
+    bool fits;
+    if (d->user_ccol) fits = (u64)d->user_cap >= ip_bound;
+    else if (ip_bound <= (u64)d->ccol.cap) fits = true;
+    else { size_t fr = 0, tot = 0; CK(cudaMemGetInfo(&fr, &tot)); fits = ip_bound * 4ull + (u64)a.m.Bn * 8ull <= (u64)d->ccol.cap * 4ull + (u64)(fr / 2); }
+    if (fits) {
+      d->cap_s = BAND_BITS; d->G = 1; d->have_m = d->have_m2 = d->have_l = false;
+      d->st.cap_s = (int)BAND_BITS; d->st.group = 1; d->st.variant = 3; d->st.rows_per_tile = BAND_THREADS;
+      d->used_mode = BSPGEMM_MODE_FUSED; d->st.mode = BSPGEMM_MODE_FUSED;
+      CK(cudaEventRecord(d->ev[2], d->stream));
+      if (!d->user_ccol) CKS(d->ccol.ensure((size_t)std::max<u64>(ip_bound, 1)));
+      CKS(launch_band(d));                              // records ev[3] between the descriptor build and the band kernel
+      CK(cudaEventRecord(d->ev[4], d->stream));
+      CK(cudaEventRecord(d->ev[5], d->stream));
+      CK(cudaMemcpyAsync(d->h_sc, d->d_sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, d->stream));
+      d->phase = 3;
+      return BSPGEMM_OK;
+    }
+    d->use_band = false;
+    if (!d->use_ell) {
+      d->skip_estimate = false;
+      CKS(launch_estimate_kernel(d));
+      CK(cudaMemcpyAsync(d->h_sc, d->d_sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, d->stream));
+      CK(cudaEventRecord(d->ev[1], d->stream));
+      return mul_launch_main(d);
+    }
+  }
   if (d->use_ell) {
     // ELL fast path: every row fits one warp's table by construction; needs the Σip bound to fit the output arena
     ip_bound = (u64)a.Annz * (u64)d->max_len_b;
@@ -552,6 +615,17 @@ static int mul_launch_fill(bspgemm_dev* d) {
   CK(cudaSetDevice(d->device));
   CK(cudaStreamSynchronize(d->stream));
   const DevScalars& h = *d->h_sc;
+  if (d->use_band && h.band_fail) {
+    // the optimistic run/bitmap kernel met a B row that is not a run of consecutive columns, or an output row wider than
+    // its register bitmap: nothing it wrote is used — the whole product is redone by the general kernels
+    d->no_band = true;
+    int rc = mul_launch_probe(d);
+    if (rc == BSPGEMM_OK) rc = mul_launch_estimate(d);
+    if (rc == BSPGEMM_OK) rc = mul_launch_main(d);
+    if (rc == BSPGEMM_OK) rc = mul_launch_fill(d);
+    d->no_band = false;
+    return rc;
+  }
   if (h.err & 1u) return fail(BSPGEMM_ERR_BADARG, "a column index of A is outside [0,Bn=%d)", a.m.Bn);
   if (h.err & 4u) return fail(BSPGEMM_ERR_BADARG, "a column index of B is outside [0,Bm=%d)", a.m.Bm);
   if (h.err & 2u) return fail(BSPGEMM_ERR_OVERFLOW32, "nnz(C) = %llu does not fit 32-bit row pointers", (unsigned long long)h.total_nnz);

@@ -56,6 +56,8 @@ struct DevScalars {     // one per context, in device memory; copied to the host
   u32 max_len_a, max_len_b;   // longest row of A / of B (k_maxlen)
   u32 span_rows, span_narrow; // k_probe_span: sampled non-empty rows / those whose candidate columns span < 2^15
   u32 win_ctr[8];             // k_rows_window: next list entry, one counter per launch (3 lists x COUNT/FILL)
+  u32 span_runs;              // k_probe_span: sampled rows whose B rows are all runs of consecutive columns
+  u32 band_fail;              // band.cuh: bit0 = a B row is not a run / an output row is wider than the register bitmap
 };
 
 // ------------------------------------------------------------------------------------------------ helpers
@@ -661,17 +663,26 @@ __global__ void __launch_bounds__(256) k_probe_span(Csr m, int nsamples, DevScal
   if (s >= nsamples) return;
   const long long row = (long long)m.An * s / nsamples;
   const u32 lane = lane_id();
-  u32 lo = EMPTY, hi = 0;
+  u32 lo = EMPTY, hi = 0, runs = 1;
   const int a0 = m.Arow[row], a1 = m.Arow[row + 1];
   for (int jj = a0; jj < a1 && jj < a0 + 64; ++jj) {                 // first 64 A nonzeros are enough for a verdict
     const int j = m.Acol[jj];
     if ((u32)j >= (u32)m.Bn) continue;
     const int b0 = m.Brow[j], b1 = m.Brow[j + 1];
-    for (int o = b0 + (int)lane; o < b1 && o < b0 + 256; o += 32) { const u32 v = (u32)m.Bcol[o]; lo = min(lo, v); hi = max(hi, v); }
+    const u32 first = b1 > b0 ? (u32)m.Bcol[b0] : 0u;
+    for (int o = b0 + (int)lane; o < b1 && o < b0 + 256; o += 32) {
+      const u32 v = (u32)m.Bcol[o]; lo = min(lo, v); hi = max(hi, v);
+      if (v != first + (u32)(o - b0)) runs = 0;
+    }
   }
   lo = __reduce_min_sync(0xffffffffu, lo);
   hi = __reduce_max_sync(0xffffffffu, hi);
-  if (lane == 0 && lo != EMPTY) { atomicAdd(&sc->span_rows, 1u); if (hi - lo < (1u << 15)) atomicAdd(&sc->span_narrow, 1u); }
+  runs = __all_sync(0xffffffffu, runs);
+  if (lane == 0 && lo != EMPTY) {
+    atomicAdd(&sc->span_rows, 1u);
+    if (hi - lo < (1u << 15)) atomicAdd(&sc->span_narrow, 1u);
+    if (runs && hi - lo < 128u) atomicAdd(&sc->span_runs, 1u);       // candidate for the run/bitmap kernel (band.cuh)
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ (2b) M bin: one CTA per row

@@ -188,8 +188,9 @@ def test_every_bin_is_exercised(bs, oracle):
         assert st["rows_m"] > 0 and st["rows_l"] > 0 and st["rows_s"] > 0
 
 
-def test_narrow_span_rows_use_bitmap_and_match(gpu_ctx, oracle):
+def test_narrow_span_rows_use_bitmap_and_match(gpu_ctx, oracle, monkeypatch):
     """Clustered columns (banded / block-diagonal): the [lo,hi] bitmap path inside the warp and CTA bins."""
+    monkeypatch.setenv("BSPGEMM_NO_BAND", "1")       # not the run/bitmap kernel of band.cuh (tested on its own)
     for gen, args in ((gpu_ctx.gen_banded, (3000, 32)), (gpu_ctx.gen_blockdiag, (3000, 32)), (gpu_ctx.gen_banded, (500, 8))):
         row, col = gen(*args)
         n = len(row) - 1
@@ -440,3 +441,65 @@ def test_wide_matrices_keep_table_and_global_bitmap_bins(bs, oracle, monkeypatch
     than WIN_MAX_WINDOWS windows of columns) still match."""
     monkeypatch.setenv("BSPGEMM_NO_WINDOW", "1")
     test_every_bin_is_exercised(bs, oracle)
+
+
+def _band_csr(n, m, below, above):
+    """Row i holds the run of columns [i-below, i+above] clipped to [0,m)."""
+    lo = np.clip(np.arange(n) - below, 0, m)
+    hi = np.clip(np.arange(n) + above + 1, 0, m)
+    hi = np.maximum(hi, lo)
+    row = np.concatenate([[0], np.cumsum(hi - lo)]).astype(np.int32)
+    col = np.concatenate([np.arange(a, b) for a, b in zip(lo, hi)]).astype(np.int32) if row[-1] else np.zeros(0, np.int32)
+    return row, col
+
+
+def test_band_kernel_runs_and_register_bitmap(bs, oracle):
+    """BASELINE config 5 shapes (banded, block-diagonal): B rows as (first,len) runs, output rows as 128-bit bitmaps."""
+    cases = [("banded d=32", *bs.gen_banded(5000, 32)), ("blockdiag d=32", *bs.gen_blockdiag(5000, 32)), ("banded d=8", *bs.gen_banded(777, 8))]
+    for name, row, col in cases:
+        n = len(row) - 1
+        want_col, want_row = oracle.spgemm(col, row, n, col, row, n)
+        got_col, got_row, st = dev_multiply(bs, bs.MODE_AUTO, col, row, n, col, row, n, n)
+        msg = _explain(got_col, got_row, want_col, want_row)
+        assert not msg, f"{name}: {msg}"
+        assert st["variant"] == 3, f"{name}: variant {st['variant']}"
+        assert st["ip"] == oracle.intermediate_products(col, row, n, row)
+    # rectangular, A rows longer than a warp (40 runs per row), empty rows of A and of B
+    Arow, Acol = _band_csr(3000, 2500, 20, 19)
+    Brow, Bcol = _band_csr(2500, 4000, 10, 9)
+    keep = np.ones(len(Arow) - 1, bool); keep[100:140] = False; keep[2999] = False          # empty rows of A
+    lens = np.diff(Arow) * keep
+    Acol = np.concatenate([Acol[Arow[i]:Arow[i + 1]] for i in np.nonzero(keep)[0]]).astype(np.int32)
+    Arow = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    want_col, want_row = oracle.spgemm(Acol, Arow, 3000, Bcol, Brow, 4000)
+    got_col, got_row, st = dev_multiply(bs, bs.MODE_AUTO, Acol, Arow, 3000, Bcol, Brow, 2500, 4000)
+    msg = _explain(got_col, got_row, want_col, want_row)
+    assert not msg, msg
+    assert st["variant"] == 3
+
+
+def test_band_kernel_falls_back_when_a_row_is_not_a_run(bs, oracle):
+    """The probe samples rows; a defect elsewhere (a B row with a gap, an output row wider than the bitmap) must be caught
+    by the kernels themselves and the product redone by the general path — same result."""
+    n = 100_000
+    Arow, Acol = _band_csr(n, n, 16, 15)
+    # (1) B row 20 (not visited by the sampled rows 0, 48, 97, ...) has a gap
+    Brow, Bcol = _band_csr(n, n, 16, 15)
+    Bcol = Bcol.copy(); Bcol[Brow[20] + 3] += 0      # still a run
+    want_col, want_row = oracle.spgemm(Acol, Arow, n, Bcol, Brow, n)
+    got_col, got_row, st = dev_multiply(bs, bs.MODE_AUTO, Acol, Arow, n, Bcol, Brow, n, n)
+    assert not _explain(got_col, got_row, want_col, want_row) and st["variant"] == 3
+    Bcol[Brow[20 + 1] - 1] += 40                     # last entry of row 20 jumps: not a run any more
+    want_col, want_row = oracle.spgemm(Acol, Arow, n, Bcol, Brow, n)
+    got_col, got_row, st = dev_multiply(bs, bs.MODE_AUTO, Acol, Arow, n, Bcol, Brow, n, n)
+    msg = _explain(got_col, got_row, want_col, want_row)
+    assert not msg, msg
+    assert st["variant"] != 3
+    # (2) every B row is a run, but row 7 of A also selects a far-away B row: its output spans more than 128 columns
+    Brow, Bcol = _band_csr(n, n, 16, 15)
+    A2col = Acol.copy(); A2col[Arow[7 + 1] - 1] = 5000
+    want_col, want_row = oracle.spgemm(A2col, Arow, n, Bcol, Brow, n)
+    got_col, got_row, st = dev_multiply(bs, bs.MODE_AUTO, A2col, Arow, n, Bcol, Brow, n, n)
+    msg = _explain(got_col, got_row, want_col, want_row)
+    assert not msg, msg
+    assert st["variant"] != 3
