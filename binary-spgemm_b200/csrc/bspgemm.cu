@@ -10,6 +10,7 @@
 #include "fused_ell.cuh"
 #include "fused_sort.cuh"
 #include "rows_window.cuh"
+#include "rows_sort.cuh"
 #include "band.cuh"
 
 #include <nccl.h>      // types only; the library itself is dlopen'ed so libbspgemm.so loads without it
@@ -90,7 +91,7 @@ struct bspgemm_dev {
   // per-call state
   MulArgs a{};
   int phase = 0;                    // 0 idle, 1 estimate in flight, 2 main in flight, 3 fill in flight, 4 done
-  int used_mode = 0, G = 16, launches = 0;
+  int used_mode = 0, G = 16, G_big = 16, launches = 0;   // G: lanes per B row from mean len(B); G_big: from the mean length of the SELECTED B rows (Σip / nnzA)
   u32 cap_s = 0, cap_m1 = 0, cap_m2 = 0;
   bool have_m = false, have_m2 = false, have_l = false;
   bool use_band = false, no_band = false;   // run/bitmap kernel for banded matrices (band.cuh); no_band: it failed on this input, redo generally
@@ -119,7 +120,8 @@ static int set_kernel_attributes(int smem_optin) {
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - (int)fa_.sharedSizeBytes)); } while (0)
 #define ATTR_G(Gv) ATTR((k_rows_warp<Gv, MODE_COUNT>)); ATTR((k_rows_warp<Gv, MODE_FILL>)); ATTR((k_fused<Gv, true>)); ATTR((k_fused<Gv, false>))
   ATTR_G(4); ATTR_G(8); ATTR_G(16); ATTR_G(32);
-  ATTR(k_rows_cta<MODE_COUNT>); ATTR(k_rows_cta<MODE_FILL>);
+  ATTR((k_rows_sort<32, 512, MODE_COUNT>)); ATTR((k_rows_sort<32, 512, MODE_FILL>));
+  ATTR((k_rows_sort<8, 256, MODE_COUNT>)); ATTR((k_rows_sort<8, 256, MODE_FILL>));
   ATTR(k_rows_window<MODE_COUNT>); ATTR(k_rows_window<MODE_FILL>);
 #define ATTR_E(Wv) ATTR((k_fused_ell<Wv, 1>)); ATTR((k_fused_ell<Wv, 2>)); ATTR((k_fused_ell<Wv, 4>)); ATTR((k_fused_ell<Wv, 8>))
   ATTR_E(4); ATTR_E(8); ATTR_E(16); ATTR_E(32);
@@ -179,33 +181,28 @@ template <int MODE> static int launch_bins_ml(bspgemm_dev* d) {
   int* ccol = d->user_ccol ? d->user_ccol : d->ccol.p;
   const size_t An = (size_t)a.m.An;
   u32* l1 = d->lists.p, *l2 = d->lists.p + An, *l3 = d->lists.p + 2 * An;
-  if (d->use_window) {
-    // windowed shared-memory bitmap (rows_window.cuh): largest rows first, rows handed out dynamically
-    const size_t smem = (size_t)WIN_WORDS * 4;
-    u32* ctr = d->d_sc->win_ctr + (MODE == MODE_FILL ? 3 : 0);
-    const u32* nl[3] = { &d->d_sc->n_l, &d->d_sc->n_m2, &d->d_sc->n_m1 };
-    u32* ls[3] = { l3, l2, l1 };
-    const bool have[3] = { d->have_l, d->have_m2, d->have_m };
-    for (int b = 0; b < 3; ++b) {
-      if (!have[b]) continue;
-      k_rows_window<MODE><<<d->sm_count, 1024, smem, d->stream>>>(a.m, ls[b], nl[b], ctr + b, d->cnt.p, d->G, WIN_WORDS, a.dCrow, a.is64, ccol, d->d_sc);
-      d->launches++;
-      CK(cudaGetLastError());
-    }
-    return BSPGEMM_OK;
-  }
-  if (d->have_m) {
-    k_rows_cta<MODE><<<d->sm_count * 4, 256, 3ull * CAP_M1 * 4, d->stream>>>(a.m, l1, &d->d_sc->n_m1, d->ip.p, d->cnt.p, CAP_M1, d->G, a.dCrow, a.is64, ccol, d->d_sc);
-    d->launches++;
-    CK(cudaGetLastError());
-  }
-  if (d->have_m2) {
-    k_rows_cta<MODE><<<d->sm_count, 1024, 3ull * CAP_M2 * 4, d->stream>>>(a.m, l2, &d->d_sc->n_m2, d->ip.p, d->cnt.p, CAP_M2, d->G, a.dCrow, a.is64, ccol, d->d_sc);
-    d->launches++;
-    CK(cudaGetLastError());
-  }
+  u32* ctr = d->d_sc->win_ctr + (MODE == MODE_FILL ? 3 : 0);
+  int bps = 0;
+  // largest rows first; rows are handed out dynamically inside every kernel
   if (d->have_l) {
-    k_rows_gbitmap<MODE><<<d->l_grid, 1024, 0, d->stream>>>(a.m, l3, &d->d_sc->n_l, d->cnt.p, d->G, d->bitmaps.p, d->bm_words, a.dCrow, a.is64, ccol, d->d_sc);
+    if (d->use_window)   // windowed shared-memory bitmap (rows_window.cuh)
+      k_rows_window<MODE><<<d->sm_count, 1024, (size_t)WIN_WORDS * 4, d->stream>>>(a.m, l3, &d->d_sc->n_l, ctr + 0, d->cnt.p, d->G_big, WIN_WORDS, a.dCrow, a.is64, ccol, d->d_sc);
+    else                 // matrices with more columns than WIN_MAX_WINDOWS windows: bitmap over [0,Bm) in global memory
+      k_rows_gbitmap<MODE><<<d->l_grid, 1024, 0, d->stream>>>(a.m, l3, &d->d_sc->n_l, d->cnt.p, d->G_big, d->bitmaps.p, d->bm_words, a.dCrow, a.is64, ccol, d->d_sc);
+    d->launches++;
+    CK(cudaGetLastError());
+  }
+  if (d->have_m2) {      // 2048 < IP <= 16384: 512 threads, up to 32 keys per thread (rows_sort.cuh)
+    const size_t smem = (size_t)CAP_M2 * 4;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_rows_sort<32, 512, MODE>, 512, smem));
+    k_rows_sort<32, 512, MODE><<<d->sm_count * std::max(bps, 1), 512, smem, d->stream>>>(a.m, l2, &d->d_sc->n_m2, ctr + 1, d->ip.p, d->cnt.p, d->G_big, a.dCrow, a.is64, ccol, d->d_sc);
+    d->launches++;
+    CK(cudaGetLastError());
+  }
+  if (d->have_m) {       // cap_s < IP <= 2048: 256 threads, up to 8 keys per thread
+    const size_t smem = (size_t)CAP_M1 * 4;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_rows_sort<8, 256, MODE>, 256, smem));
+    k_rows_sort<8, 256, MODE><<<d->sm_count * std::max(bps, 1), 256, smem, d->stream>>>(a.m, l1, &d->d_sc->n_m1, ctr + 2, d->ip.p, d->cnt.p, d->G_big, a.dCrow, a.is64, ccol, d->d_sc);
     d->launches++;
     CK(cudaGetLastError());
   }
@@ -540,6 +537,7 @@ static int mul_launch_main(bspgemm_dev* d) {
   while (cap < max_ip && cap < cap_max) cap <<= 1;
   d->cap_s = cap;
   d->G = pick_group(a.Bnnz, a.m.Bn);
+  d->G_big = d->skip_estimate ? d->G : std::max(d->G, pick_group((int64_t)ip_bound, a.Annz));   // power-law: long B rows are selected more often
   d->have_m = max_ip > cap;
   d->have_m2 = max_ip > CAP_M1;
   d->have_l = max_ip > CAP_M2;

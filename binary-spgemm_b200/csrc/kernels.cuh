@@ -7,8 +7,9 @@
 //
 // Design: rows are binned by their intermediate-product count IP_i (k_estimate):
 //   S  (IP <= cap_s)  one warp per row, table in shared memory              k_rows_warp<G,MODE>
-//   M  (IP <= cap_m)  one CTA per row, table in shared memory               k_rows_cta<MODE>
-//   L  (larger)       one CTA per row, bitmap over [0,Bm) in global memory  k_rows_gbitmap<MODE>
+//   M  (IP <= 16384)  one CTA per row, CTA-wide register sort               k_rows_sort<K,T,MODE>   (rows_sort.cuh)
+//   L  (larger)       one CTA per row, windowed shared-memory bitmap        k_rows_window<MODE>     (rows_window.cuh)
+//                     (matrices with very many columns: bitmap over [0,Bm) in global memory, k_rows_gbitmap<MODE>)
 // De-duplication AND sorting are one step: an *ordered* open-addressing table.  Keys are placed by a
 // monotone map slot = floor((k-lo)*T/(hi-lo+1)) and collisions are resolved with atomicMin + "the larger
 // key moves one slot right" (no wrap-around).  The final table, read left to right, is the sorted set of
@@ -730,88 +731,6 @@ __device__ __forceinline__ u32 block_excl_scan(u32 v, u32* s_red, u32* total) {
   *total = s_red[32];
   __syncthreads();
   return r;
-}
-
-// Shared memory: tab[3*cap] words.  The B rows are walked twice (lo/hi pass, insert pass); the second
-// walk hits L1/L2.  COUNT writes cnt[row]; FILL compacts the table straight into Ccol at Crow[row].
-template <int MODE>
-__global__ void __launch_bounds__(1024) k_rows_cta(Csr m, const u32* __restrict__ list, const u32* __restrict__ nlist,
-                                                   const u32* __restrict__ ip, u32* __restrict__ cnt, u32 cap, int G,
-                                                   const void* __restrict__ Crow, int is64, int* __restrict__ Ccol,
-                                                   DevScalars* sc) {
-  extern __shared__ __align__(16) u32 tab[];
-  __shared__ u32 s_red[33];
-  __shared__ u32 s_lo, s_hi, s_maxslot;
-  const u32 n = *nlist;
-  for (u32 idx = blockIdx.x; idx < n; idx += gridDim.x) {
-    const int row = (int)list[idx];
-    const u32 ipr = ip[row];
-    const int a0 = m.Arow[row], a1 = m.Arow[row + 1];
-    if (threadIdx.x == 0) { s_lo = EMPTY; s_hi = 0; s_maxslot = 0; }
-    __syncthreads();
-    u32 vmin = EMPTY, vmax = 0;
-    cta_for_each_product(m, a0, a1, G, [&](u32 v) { vmin = min(vmin, v); vmax = max(vmax, v); });
-    vmin = __reduce_min_sync(0xffffffffu, vmin);
-    vmax = __reduce_max_sync(0xffffffffu, vmax);
-    if (lane_id() == 0) { atomicMin(&s_lo, vmin); atomicMax(&s_hi, vmax); }
-    __syncthreads();
-    const u32 lo = s_lo, hi = s_hi;
-    if (hi >= (u32)m.Bm) { if (threadIdx.x == 0) { atomicOr(&sc->err, 4u); if (MODE == MODE_COUNT) cnt[row] = 0; } __syncthreads(); continue; }
-    const u32 range = hi - lo + 1;
-    const u64 base = (MODE == MODE_FILL) ? ld_rowptr(Crow, is64, (size_t)row) : 0;
-    if (range <= 32u * 3u * cap) {
-      const u32 nW = (range + 31) >> 5;
-      for (u32 w = threadIdx.x; w < nW; w += blockDim.x) tab[w] = 0;
-      __syncthreads();
-      u32 added = 0;
-      cta_for_each_product(m, a0, a1, G, [&](u32 v) {
-        v -= lo; const u32 bit = 1u << (v & 31);
-        const u32 old = atomicOr(&tab[v >> 5], bit);
-        added += (old & bit) ? 0u : 1u;
-      });
-      __syncthreads();
-      if (MODE == MODE_COUNT) {
-        const u32 c = block_reduce_add(added, s_red);
-        if (threadIdx.x == 0) cnt[row] = c;
-      } else {
-        u32 done = 0;
-        for (u32 w0 = 0; w0 < nW; w0 += blockDim.x) {
-          const u32 w = w0 + threadIdx.x;
-          u32 word = (w < nW) ? tab[w] : 0u, tot;
-          u32 o = done + block_excl_scan(__popc(word), s_red, &tot);
-          const u32 b0 = lo + (w << 5);
-          while (word) { const u32 b = __ffs(word) - 1; word &= word - 1; Ccol[base + o++] = (int)(b0 + b); }
-          done += tot;
-        }
-      }
-    } else {
-      const u32 T = 2 * ipr, limit = T + ipr;
-      const u32 scale = slot_scale(T, range);
-      for (u32 q = threadIdx.x; q < limit; q += blockDim.x) tab[q] = EMPTY;
-      __syncthreads();
-      u32 added = 0, max_slot = 0;
-      cta_for_each_product(m, a0, a1, G, [&](u32 x) { added += ordered_insert(tab, __umulhi(x - lo, scale), x, max_slot); });
-      if (MODE == MODE_COUNT) {
-        const u32 c = block_reduce_add(added, s_red);
-        if (threadIdx.x == 0) cnt[row] = c;
-      } else {
-        max_slot = __reduce_max_sync(0xffffffffu, max_slot);
-        if (lane_id() == 0) atomicMax(&s_maxslot, max_slot);
-        __syncthreads();
-        const u32 ms = s_maxslot;
-        u32 done = 0;
-        for (u32 s0 = 0; s0 <= ms; s0 += blockDim.x) {
-          const u32 s = s0 + threadIdx.x;
-          const u32 v = (s <= ms) ? tab[s] : EMPTY;
-          u32 tot;
-          const u32 o = done + block_excl_scan(v != EMPTY ? 1u : 0u, s_red, &tot);
-          if (v != EMPTY) Ccol[base + o] = (int)v;
-          done += tot;
-        }
-      }
-    }
-    __syncthreads();
-  }
 }
 
 // ------------------------------------------------------------------------------------------------ (2c) L bin: global bitmap

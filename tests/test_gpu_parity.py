@@ -437,8 +437,8 @@ def test_window_bins_many_windows_unsorted_rows(bs, oracle, monkeypatch):
 
 
 def test_wide_matrices_keep_table_and_global_bitmap_bins(bs, oracle, monkeypatch):
-    """BSPGEMM_NO_WINDOW: the ordered-table CTA kernels and the global-bitmap kernel (the route of matrices with more
-    than WIN_MAX_WINDOWS windows of columns) still match."""
+    """BSPGEMM_NO_WINDOW: the global-bitmap kernel of the L bin (the route of matrices with more than WIN_MAX_WINDOWS
+    windows of columns) still matches."""
     monkeypatch.setenv("BSPGEMM_NO_WINDOW", "1")
     test_every_bin_is_exercised(bs, oracle)
 
