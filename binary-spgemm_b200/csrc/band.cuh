@@ -40,14 +40,27 @@ __global__ void __launch_bounds__(256) k_build_desc(const int* __restrict__ Brow
   if (be > bs) first = (u32)__ldg(&Bcol[bs]);
   u32 ok_mine = 1;
   const int nr = (int)min(32ll, (long long)Bn - r0);
-#pragma unroll 4
-  for (int r = 0; r < nr; ++r) {
-    const int s = __shfl_sync(0xffffffffu, bs, r), e = __shfl_sync(0xffffffffu, be, r);
-    const u32 f = __shfl_sync(0xffffffffu, first, r);
-    u32 good = 1;
-    for (int o = s + (int)lane; o < e; o += 32) good &= ((u32)__ldg(&Bcol[o]) == f + (u32)(o - s)) ? 1u : 0u;
-    good = __all_sync(0xffffffffu, good);
-    if ((int)lane == r) ok_mine = good;
+  constexpr int RB = 8;                               // rows whose loads are issued together
+#pragma unroll 1
+  for (int rb = 0; rb < nr; rb += RB) {
+    int s[RB], len[RB];
+    u32 v[RB];
+#pragma unroll
+    for (int q = 0; q < RB; ++q) {
+      s[q] = __shfl_sync(0xffffffffu, bs, (rb + q) & 31);
+      len[q] = __shfl_sync(0xffffffffu, be, (rb + q) & 31) - s[q];
+      if (rb + q >= nr) len[q] = 0;
+    }
+#pragma unroll
+    for (int q = 0; q < RB; ++q) v[q] = ((int)lane < len[q]) ? (u32)__ldg(&Bcol[s[q] + (int)lane]) : 0u;
+#pragma unroll
+    for (int q = 0; q < RB; ++q) {
+      const u32 f = __shfl_sync(0xffffffffu, first, (rb + q) & 31);
+      u32 good = ((int)lane >= len[q] || v[q] == f + lane) ? 1u : 0u;
+      for (int o = 32 + (int)lane; o < len[q]; o += 32) good &= ((u32)__ldg(&Bcol[s[q] + o]) == f + (u32)o) ? 1u : 0u;   // rows longer than a warp
+      good = __all_sync(0xffffffffu, good);
+      if ((int)lane == rb + q) ok_mine = good;
+    }
   }
   const u32 len = (u32)(be - bs);
   u32 bad_col = 0;
@@ -94,58 +107,76 @@ __global__ void __launch_bounds__(BAND_THREADS) k_band(const BandArgs p) {
     const int ar = p.Arow[min(row0 + (long long)lane, (long long)p.An)];
     const int arE = p.Arow[min(row0 + 32ll, (long long)p.An)];
     u32 mylo = 0, m0 = 0, m1 = 0, m2 = 0, m3 = 0;
-#pragma unroll 4
-    for (int r = 0; r < 32; ++r) {
-      const int a0 = __shfl_sync(0xffffffffu, ar, r);
-      const int a1 = (r < 31) ? __shfl_sync(0xffffffffu, ar, r + 1) : arE;
-      if (a1 <= a0) continue;                                   // empty row (or past the end of A): uniform in the warp
-      u32 f = EMPTY, l = 0;
-      u32 lo, hi;
-      if (a1 - a0 <= 32) {
-        if ((int)lane < a1 - a0) {
-          const int j = p.Acol[a0 + (int)lane];
-          if ((u32)j < (u32)p.Bn) { const uint2 d = p.desc[j]; f = d.x; l = d.y & ~BAND_CONTIG; if (!(d.y & BAND_CONTIG)) fail = 1; if (!l) f = EMPTY; }
-          else bad_a = 1;
+    // blocks of RB rows: all Acol loads of the block are issued together, then all descriptor gathers, then the bitmaps
+    // are built (two dependent round trips per RB rows instead of per row)
+    constexpr int RB = 8;
+#pragma unroll 1
+    for (int rb = 0; rb < 32; rb += RB) {
+      int a0[RB], la[RB], j[RB];
+#pragma unroll
+      for (int q = 0; q < RB; ++q) {
+        a0[q] = __shfl_sync(0xffffffffu, ar, rb + q);
+        const int a1 = (rb + q < 31) ? __shfl_sync(0xffffffffu, ar, (rb + q + 1) & 31) : arE;
+        la[q] = a1 - a0[q];
+      }
+#pragma unroll
+      for (int q = 0; q < RB; ++q) j[q] = ((int)lane < la[q] && la[q] <= 32) ? p.Acol[a0[q] + (int)lane] : -1;
+      uint2 dsc[RB];
+#pragma unroll
+      for (int q = 0; q < RB; ++q) {
+        dsc[q] = make_uint2(EMPTY, BAND_CONTIG);
+        if (j[q] >= 0) { if (j[q] < p.Bn) dsc[q] = p.desc[j[q]]; else bad_a = 1; }
+      }
+#pragma unroll
+      for (int q = 0; q < RB; ++q) {
+        const int r = rb + q;
+        if (la[q] <= 0) continue;                                 // empty row (or past the end of A): uniform in the warp
+        if (la[q] <= 32) {
+          u32 f = dsc[q].x;
+          const u32 l = dsc[q].y & ~BAND_CONTIG;
+          if (!(dsc[q].y & BAND_CONTIG)) fail = 1;
+          if (!l) f = EMPTY;
+          ips += l;
+          const u32 lo = __reduce_min_sync(0xffffffffu, f);
+          const u32 hi = __reduce_max_sync(0xffffffffu, l ? f + l : 0u);    // one past the last column
+          if (lo == EMPTY) continue;                              // only empty B rows
+          if (hi - lo > BAND_BITS) { fail = 1; continue; }
+          const u32 s = f - lo, e = s + l;
+          const u32 w0 = __reduce_or_sync(0xffffffffu, l ? run_word(s, e, 0) : 0u);
+          const u32 w1 = __reduce_or_sync(0xffffffffu, l ? run_word(s, e, 1) : 0u);
+          const u32 w2 = __reduce_or_sync(0xffffffffu, l ? run_word(s, e, 2) : 0u);
+          const u32 w3 = __reduce_or_sync(0xffffffffu, l ? run_word(s, e, 3) : 0u);
+          if ((int)lane == r) { mylo = lo; m0 = w0; m1 = w1; m2 = w2; m3 = w3; }
+        } else {                                                  // long A row: first the window, then the runs
+          const int b0 = a0[q], b1 = a0[q] + la[q];
+          u32 vlo = EMPTY, vhi = 0;
+          for (int jj = b0 + (int)lane; jj < b1; jj += 32) {
+            const int jx = p.Acol[jj];
+            if ((u32)jx >= (u32)p.Bn) { bad_a = 1; continue; }
+            const uint2 d = p.desc[jx];
+            const u32 ll = d.y & ~BAND_CONTIG;
+            if (!(d.y & BAND_CONTIG)) fail = 1;
+            ips += ll;
+            if (ll) { vlo = min(vlo, d.x); vhi = max(vhi, d.x + ll); }
+          }
+          const u32 lo = __reduce_min_sync(0xffffffffu, vlo);
+          const u32 hi = __reduce_max_sync(0xffffffffu, vhi);
+          if (lo == EMPTY) continue;
+          if (hi - lo > BAND_BITS) { fail = 1; continue; }
+          u32 w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+          for (int jj = b0 + (int)lane; jj < b1; jj += 32) {
+            const int jx = p.Acol[jj];
+            if ((u32)jx >= (u32)p.Bn) continue;
+            const uint2 d = p.desc[jx];
+            const u32 ll = d.y & ~BAND_CONTIG;
+            if (!ll) continue;
+            const u32 s = d.x - lo, e = s + ll;
+            w0 |= run_word(s, e, 0); w1 |= run_word(s, e, 1); w2 |= run_word(s, e, 2); w3 |= run_word(s, e, 3);
+          }
+          w0 = __reduce_or_sync(0xffffffffu, w0); w1 = __reduce_or_sync(0xffffffffu, w1);
+          w2 = __reduce_or_sync(0xffffffffu, w2); w3 = __reduce_or_sync(0xffffffffu, w3);
+          if ((int)lane == r) { mylo = lo; m0 = w0; m1 = w1; m2 = w2; m3 = w3; }
         }
-        ips += l;
-        lo = __reduce_min_sync(0xffffffffu, f);
-        hi = __reduce_max_sync(0xffffffffu, l ? f + l : 0u);    // one past the last column
-        if (lo == EMPTY) continue;                              // only empty B rows
-        if (hi - lo > BAND_BITS) { fail = 1; continue; }
-        const u32 s = f - lo, e = s + l;
-        const u32 w0 = __reduce_or_sync(0xffffffffu, l ? run_word(s, e, 0) : 0u);
-        const u32 w1 = __reduce_or_sync(0xffffffffu, l ? run_word(s, e, 1) : 0u);
-        const u32 w2 = __reduce_or_sync(0xffffffffu, l ? run_word(s, e, 2) : 0u);
-        const u32 w3 = __reduce_or_sync(0xffffffffu, l ? run_word(s, e, 3) : 0u);
-        if ((int)lane == r) { mylo = lo; m0 = w0; m1 = w1; m2 = w2; m3 = w3; }
-      } else {                                                  // long A row: first the window, then the runs
-        u32 vlo = EMPTY, vhi = 0;
-        for (int jj = a0 + (int)lane; jj < a1; jj += 32) {
-          const int j = p.Acol[jj];
-          if ((u32)j >= (u32)p.Bn) { bad_a = 1; continue; }
-          const uint2 d = p.desc[j];
-          const u32 ll = d.y & ~BAND_CONTIG;
-          if (!(d.y & BAND_CONTIG)) fail = 1;
-          ips += ll;
-          if (ll) { vlo = min(vlo, d.x); vhi = max(vhi, d.x + ll); }
-        }
-        lo = __reduce_min_sync(0xffffffffu, vlo);
-        hi = __reduce_max_sync(0xffffffffu, vhi);
-        if (lo == EMPTY) continue;
-        if (hi - lo > BAND_BITS) { fail = 1; continue; }
-        u32 w0 = 0, w1 = 0, w2 = 0, w3 = 0;
-        for (int jj = a0 + (int)lane; jj < a1; jj += 32) {
-          const int j = p.Acol[jj];
-          if ((u32)j >= (u32)p.Bn) continue;
-          const uint2 d = p.desc[j];
-          const u32 ll = d.y & ~BAND_CONTIG;
-          if (!ll) continue;
-          const u32 s = d.x - lo, e = s + ll;
-          w0 |= run_word(s, e, 0); w1 |= run_word(s, e, 1); w2 |= run_word(s, e, 2); w3 |= run_word(s, e, 3);
-        }
-        w0 = __reduce_or_sync(0xffffffffu, w0); w1 = __reduce_or_sync(0xffffffffu, w1);
-        w2 = __reduce_or_sync(0xffffffffu, w2); w3 = __reduce_or_sync(0xffffffffu, w3);
-        if ((int)lane == r) { mylo = lo; m0 = w0; m1 = w1; m2 = w2; m3 = w3; }
       }
     }
     // thread t holds row tile*128 + t: scan the counts, chain the tile, stage, stream out

@@ -85,6 +85,8 @@ struct bspgemm_dev {
   DevBuf<u32> ip, cnt, lists, bitmaps, bell;
   DevBuf<u64> status;
   DevBuf<int> ccol;                 // output arena
+  DevBuf<int> temp;                 // staging arena of the big rows (MODE_STAGE): Σ IP of the M/L rows
+  DevBuf<u64> tofs;                 // per row: offset of its staged columns in temp
   DevScalars* d_sc = nullptr;
   DevScalars* h_sc = nullptr;       // pinned
   cudaEvent_t ev[8] = {};
@@ -95,6 +97,7 @@ struct bspgemm_dev {
   u32 cap_s = 0, cap_m1 = 0, cap_m2 = 0;
   bool have_m = false, have_m2 = false, have_l = false;
   bool use_band = false, no_band = false;   // run/bitmap kernel for banded matrices (band.cuh); no_band: it failed on this input, redo generally
+  bool staged = false;              // big rows went through the staging arena (one pass) in the last multiply
   bool use_window = false;          // M/L bins: windowed shared-memory bitmap (rows_window.cuh) instead of table / global bitmap
   u32 bm_words = 0; int l_grid = 0;
   bool skip_estimate = false; u32 row_ip_bound = 0, max_len_b = 0;
@@ -120,9 +123,9 @@ static int set_kernel_attributes(int smem_optin) {
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - (int)fa_.sharedSizeBytes)); } while (0)
 #define ATTR_G(Gv) ATTR((k_rows_warp<Gv, MODE_COUNT>)); ATTR((k_rows_warp<Gv, MODE_FILL>)); ATTR((k_fused<Gv, true>)); ATTR((k_fused<Gv, false>))
   ATTR_G(4); ATTR_G(8); ATTR_G(16); ATTR_G(32);
-  ATTR((k_rows_sort<32, 512, MODE_COUNT>)); ATTR((k_rows_sort<32, 512, MODE_FILL>));
-  ATTR((k_rows_sort<8, 256, MODE_COUNT>)); ATTR((k_rows_sort<8, 256, MODE_FILL>));
-  ATTR(k_rows_window<MODE_COUNT>); ATTR(k_rows_window<MODE_FILL>);
+  ATTR((k_rows_sort<32, 512, MODE_COUNT>)); ATTR((k_rows_sort<32, 512, MODE_FILL>)); ATTR((k_rows_sort<32, 512, MODE_STAGE>));
+  ATTR((k_rows_sort<8, 256, MODE_COUNT>)); ATTR((k_rows_sort<8, 256, MODE_FILL>)); ATTR((k_rows_sort<8, 256, MODE_STAGE>));
+  ATTR(k_rows_window<MODE_COUNT>); ATTR(k_rows_window<MODE_FILL>); ATTR(k_rows_window<MODE_STAGE>);
 #define ATTR_E(Wv) ATTR((k_fused_ell<Wv, 1>)); ATTR((k_fused_ell<Wv, 2>)); ATTR((k_fused_ell<Wv, 4>)); ATTR((k_fused_ell<Wv, 8>))
   ATTR_E(4); ATTR_E(8); ATTR_E(16); ATTR_E(32);
 #undef ATTR_E
@@ -183,10 +186,15 @@ template <int MODE> static int launch_bins_ml(bspgemm_dev* d) {
   u32* l1 = d->lists.p, *l2 = d->lists.p + An, *l3 = d->lists.p + 2 * An;
   u32* ctr = d->d_sc->win_ctr + (MODE == MODE_FILL ? 3 : 0);
   int bps = 0;
+  const u64* tofs = d->tofs.p;
+  if (MODE == MODE_STAGE) {
+    if (d->have_l && !d->use_window) return fail(BSPGEMM_ERR_CUDA, "internal: the global-bitmap kernel has no staged mode");
+    ccol = d->temp.p;               // the kernels write row i at temp[tofs[i] ..)
+  }
   // largest rows first; rows are handed out dynamically inside every kernel
   if (d->have_l) {
     if (d->use_window)   // windowed shared-memory bitmap (rows_window.cuh)
-      k_rows_window<MODE><<<d->sm_count, 1024, (size_t)WIN_WORDS * 4, d->stream>>>(a.m, l3, &d->d_sc->n_l, ctr + 0, d->cnt.p, d->G_big, WIN_WORDS, a.dCrow, a.is64, ccol, d->d_sc);
+      k_rows_window<MODE><<<d->sm_count, 1024, (size_t)WIN_WORDS * 4, d->stream>>>(a.m, l3, &d->d_sc->n_l, ctr + 0, d->cnt.p, d->G_big, WIN_WORDS, a.dCrow, a.is64, ccol, tofs, d->d_sc);
     else                 // matrices with more columns than WIN_MAX_WINDOWS windows: bitmap over [0,Bm) in global memory
       k_rows_gbitmap<MODE><<<d->l_grid, 1024, 0, d->stream>>>(a.m, l3, &d->d_sc->n_l, d->cnt.p, d->G_big, d->bitmaps.p, d->bm_words, a.dCrow, a.is64, ccol, d->d_sc);
     d->launches++;
@@ -195,14 +203,31 @@ template <int MODE> static int launch_bins_ml(bspgemm_dev* d) {
   if (d->have_m2) {      // 2048 < IP <= 16384: 512 threads, up to 32 keys per thread (rows_sort.cuh)
     const size_t smem = (size_t)CAP_M2 * 4;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_rows_sort<32, 512, MODE>, 512, smem));
-    k_rows_sort<32, 512, MODE><<<d->sm_count * std::max(bps, 1), 512, smem, d->stream>>>(a.m, l2, &d->d_sc->n_m2, ctr + 1, d->ip.p, d->cnt.p, d->G_big, a.dCrow, a.is64, ccol, d->d_sc);
+    k_rows_sort<32, 512, MODE><<<d->sm_count * std::max(bps, 1), 512, smem, d->stream>>>(a.m, l2, &d->d_sc->n_m2, ctr + 1, d->ip.p, d->cnt.p, d->G_big, a.dCrow, a.is64, ccol, tofs, d->d_sc);
     d->launches++;
     CK(cudaGetLastError());
   }
   if (d->have_m) {       // cap_s < IP <= 2048: 256 threads, up to 8 keys per thread
     const size_t smem = (size_t)CAP_M1 * 4;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_rows_sort<8, 256, MODE>, 256, smem));
-    k_rows_sort<8, 256, MODE><<<d->sm_count * std::max(bps, 1), 256, smem, d->stream>>>(a.m, l1, &d->d_sc->n_m1, ctr + 2, d->ip.p, d->cnt.p, d->G_big, a.dCrow, a.is64, ccol, d->d_sc);
+    k_rows_sort<8, 256, MODE><<<d->sm_count * std::max(bps, 1), 256, smem, d->stream>>>(a.m, l1, &d->d_sc->n_m1, ctr + 2, d->ip.p, d->cnt.p, d->G_big, a.dCrow, a.is64, ccol, tofs, d->d_sc);
+    d->launches++;
+    CK(cudaGetLastError());
+  }
+  return BSPGEMM_OK;
+}
+
+// MODE_STAGE epilogue: staged big rows -> their final position in Ccol
+static int launch_copy_rows(bspgemm_dev* d) {
+  const MulArgs& a = d->a;
+  int* ccol = d->user_ccol ? d->user_ccol : d->ccol.p;
+  const size_t An = (size_t)a.m.An;
+  u32* ls[3] = { d->lists.p + 2 * An, d->lists.p + An, d->lists.p };
+  const u32* nl[3] = { &d->d_sc->n_l, &d->d_sc->n_m2, &d->d_sc->n_m1 };
+  const bool have[3] = { d->have_l, d->have_m2, d->have_m };
+  for (int b = 0; b < 3; ++b) {
+    if (!have[b]) continue;
+    k_copy_rows<<<d->sm_count * 8, 256, 0, d->stream>>>(ls[b], nl[b], d->cnt.p, d->tofs.p, d->temp.p, a.dCrow, a.is64, ccol);
     d->launches++;
     CK(cudaGetLastError());
   }
@@ -545,8 +570,9 @@ static int mul_launch_main(bspgemm_dev* d) {
   CKS(d->cnt.ensure(An + 1));
   if (d->have_m) {
     CKS(d->lists.ensure(3 * An + 3));
+    CKS(d->tofs.ensure(An + 1));
     k_build_lists<<<(int)((An + 255) / 256), 256, 0, d->stream>>>(d->ip.p, a.m.An, cap, CAP_M1, CAP_M2,
-        d->lists.p, d->lists.p + An, d->lists.p + 2 * An, d->d_sc);
+        d->lists.p, d->lists.p + An, d->lists.p + 2 * An, d->tofs.p, d->d_sc);
     d->launches++;
     CK(cudaGetLastError());
   }
@@ -580,16 +606,29 @@ static int mul_launch_main(bspgemm_dev* d) {
   d->used_mode = mode; d->st.mode = mode;
   CK(cudaEventRecord(d->ev[2], d->stream));
   if (mode == BSPGEMM_MODE_FUSED) {
-    if (d->have_m) CKS(launch_bins_ml<MODE_COUNT>(d));
-    CK(cudaEventRecord(d->ev[3], d->stream));
     if (!d->user_ccol) CKS(d->ccol.ensure((size_t)std::max<u64>(ip_bound, 1)));
+    // Big rows in ONE pass when memory allows: count + sorted row into a staging arena (Σ of their IP <= Σip words), moved to
+    // Ccol once the fused kernel has produced the row pointers — instead of a symbolic and a numeric pass that both gather
+    // and de-duplicate the row.
+    bool staged = false;
+    if (d->have_m && (!d->have_l || d->use_window) && !getenv("BSPGEMM_NO_STAGE")) {
+      const size_t need = (size_t)std::max<u64>(ip_bound, 1);
+      if (d->temp.cap >= need) staged = true;
+      else {
+        size_t fr = 0, tot = 0; CK(cudaMemGetInfo(&fr, &tot));
+        if ((u64)fr + (u64)d->temp.cap * 4ull >= (u64)need * 4ull + (2ull << 30)) { d->temp.release(); if (d->temp.ensure(need) == BSPGEMM_OK) staged = true; }
+      }
+    }
+    d->staged = staged;
+    if (d->have_m) CKS(staged ? launch_bins_ml<MODE_STAGE>(d) : launch_bins_ml<MODE_COUNT>(d));
+    CK(cudaEventRecord(d->ev[3], d->stream));
     const u32 rows_per_tile = FUSED_R;
     const u32 ntiles = (u32)((An + rows_per_tile - 1) / rows_per_tile);
     CKS(d->status.ensure(ntiles + 1));
     CK(cudaMemsetAsync(d->status.p, 0, (size_t)ntiles * sizeof(u64), d->stream));
     CKS(launch_fused(d, ntiles, d->skip_estimate ? 1 : 0));
     CK(cudaEventRecord(d->ev[4], d->stream));
-    if (d->have_m) CKS(launch_bins_ml<MODE_FILL>(d));
+    if (d->have_m) CKS(staged ? launch_copy_rows(d) : launch_bins_ml<MODE_FILL>(d));
     CK(cudaEventRecord(d->ev[5], d->stream));
   } else {
     CKS(launch_rows_warp<MODE_COUNT>(d));
@@ -703,7 +742,7 @@ static void dev_destroy(bspgemm_dev* d) {
   if (!d) return;
   cudaSetDevice(d->device);
   cudaStreamSynchronize(d->stream);
-  d->ip.release(); d->cnt.release(); d->lists.release(); d->bitmaps.release(); d->status.release(); d->ccol.release();
+  d->ip.release(); d->cnt.release(); d->lists.release(); d->bitmaps.release(); d->status.release(); d->ccol.release(); d->temp.release(); d->tofs.release();
   d->in_arow.release(); d->in_acol.release(); d->in_brow.release(); d->in_bcol.release(); d->crow_dev.release(); d->crow_tmp.release();
   if (d->d_sc) cudaFree(d->d_sc);
   if (d->h_sc) cudaFreeHost(d->h_sc);

@@ -30,6 +30,7 @@ constexpr u32 EMPTY = 0xFFFFFFFFu;
 constexpr int MODE_COUNT = 0;   // symbolic: cnt[row] = nnz(C_row)
 constexpr int MODE_FILL  = 1;   // numeric : Ccol[Crow[row]..] = sorted distinct columns
 constexpr int MODE_FUSED = 2;   // symbolic + scan + numeric in one pass (tiles of consecutive rows)
+constexpr int MODE_STAGE = 3;   // big rows, one pass: cnt[row] AND the sorted row at temp[tofs[row]..] (k_copy_rows moves it to Ccol)
 
 constexpr int WARPS_S = 8;      // warps per CTA in the warp-per-row kernel (= rows per tile in MODE_FUSED)
 
@@ -59,6 +60,7 @@ struct DevScalars {     // one per context, in device memory; copied to the host
   u32 win_ctr[8];             // k_rows_window: next list entry, one counter per launch (3 lists x COUNT/FILL)
   u32 span_runs;              // k_probe_span: sampled rows whose B rows are all runs of consecutive columns
   u32 band_fail;              // band.cuh: bit0 = a B row is not a run / an output row is wider than the register bitmap
+  u64 temp_used;              // k_build_lists: words of the staging arena handed to big rows (Σ of their IP)
 };
 
 // ------------------------------------------------------------------------------------------------ helpers
@@ -201,17 +203,45 @@ __global__ void __launch_bounds__(256) k_estimate(Csr m, u32* __restrict__ ip, D
   if (threadIdx.x == 0) { if (s_sum) atomicAdd(&sc->total_ip, s_sum); atomicMax(&sc->max_ip, s_max); }
 }
 
-// Row lists for the CTA-per-row bins (order inside a list is irrelevant).
+// Row lists for the CTA-per-row bins (order inside a list is irrelevant).  tofs (optional): every listed row also gets
+// IP words of the staging arena (MODE_STAGE), handed out with one 64-bit atomic per warp.
 __global__ void __launch_bounds__(256) k_build_lists(const u32* __restrict__ ip, int An, u32 cap_s, u32 cap_m1, u32 cap_m2,
                                                      u32* __restrict__ list_m1, u32* __restrict__ list_m2,
-                                                     u32* __restrict__ list_l, DevScalars* sc) {
+                                                     u32* __restrict__ list_l, u64* __restrict__ tofs, DevScalars* sc) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= An) return;
-  const u32 v = ip[i];
-  if (v <= cap_s) return;
+  const u32 v = (i < An) ? ip[i] : 0u;
+  const bool big = v > cap_s;
+  if (tofs) {
+    const u32 mine = big ? v : 0u;
+    u64 inc = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const u64 t = __shfl_up_sync(0xffffffffu, inc, d); if ((int)lane_id() >= d) inc += t; }
+    const u64 tot = __shfl_sync(0xffffffffu, inc, 31);
+    u64 base = 0;
+    if (lane_id() == 0 && tot) base = atomicAdd(&sc->temp_used, tot);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (big) tofs[i] = base + inc - mine;
+  }
+  if (!big) return;
   if (v <= cap_m1)      list_m1[atomicAdd(&sc->n_m1, 1u)] = (u32)i;
   else if (v <= cap_m2) list_m2[atomicAdd(&sc->n_m2, 1u)] = (u32)i;
   else                  list_l[atomicAdd(&sc->n_l, 1u)] = (u32)i;
+}
+
+// MODE_STAGE epilogue: the staged rows go to their final place, Ccol[Crow[row] ..) (Crow is complete once the fused kernel
+// has run).  One CTA per listed row, grid-stride.
+__global__ void __launch_bounds__(256) k_copy_rows(const u32* __restrict__ list, const u32* __restrict__ nlist, const u32* __restrict__ cnt,
+                                                   const u64* __restrict__ tofs, const int* __restrict__ temp,
+                                                   const void* __restrict__ Crow, int is64, int* __restrict__ Ccol) {
+  const u32 n = *nlist;
+  for (u32 idx = blockIdx.x; idx < n; idx += gridDim.x) {
+    const u32 row = list[idx];
+    const u32 c = cnt[row];
+    const int* __restrict__ src = temp + tofs[row];
+    int* __restrict__ dst = Ccol + ld_rowptr(Crow, is64, (size_t)row);
+#pragma unroll 4
+    for (u32 i = threadIdx.x; i < c; i += 256) dst[i] = __ldcs(&src[i]);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ ordered table primitives

@@ -109,7 +109,7 @@ __device__ __forceinline__ u32 cta_sort_dedup(u32* buf, const u32 ipr, const u32
   if (bad) *bad_out = 1;
   u32 tot;
   const u32 off = block_excl_scan(c, s_red, &tot);
-  if (MODE == MODE_FILL) {
+  if (MODE != MODE_COUNT) {
     u32 o = off;
 #pragma unroll
     for (int k = 0; k < K; ++k) if ((f >> k) & 1u) buf[o++] = x[k];
@@ -125,7 +125,8 @@ __device__ __forceinline__ u32 cta_sort_dedup(u32* buf, const u32 ipr, const u32
 template <int KMAX, int T, int MODE>
 __global__ void __maxnreg__(64) k_rows_sort(Csr m, const u32* __restrict__ list, const u32* __restrict__ nlist, u32* __restrict__ ctr,
                                                  const u32* __restrict__ ip, u32* __restrict__ cnt, int G,
-                                                 const void* __restrict__ Crow, int is64, int* __restrict__ Ccol, DevScalars* sc) {
+                                                 const void* __restrict__ Crow, int is64, int* __restrict__ Ccol,
+                                                 const u64* __restrict__ tofs, DevScalars* sc) {
   extern __shared__ __align__(16) u32 buf[];                 // KMAX*T words
   __shared__ u32 s_red[33], s_last[32];
   __shared__ u32 s_idx, s_pos, s_nlong, s_bad;
@@ -184,12 +185,12 @@ __global__ void __maxnreg__(64) k_rows_sort(Csr m, const u32* __restrict__ list,
     }
     __syncthreads();
     // ---- sort, de-duplicate, count / write
-    int* dst = (MODE == MODE_FILL) ? Ccol + ld_rowptr(Crow, is64, (size_t)row) : nullptr;
+    int* dst = (MODE == MODE_FILL) ? Ccol + ld_rowptr(Crow, is64, (size_t)row) : (MODE == MODE_STAGE) ? Ccol + tofs[row] : nullptr;   // STAGE: Ccol is the staging arena
     u32 c;
     if (ipr <= (u32)(KMAX / 4) * T)      c = cta_sort_dedup<KMAX / 4, T, MODE>(buf, ipr, (u32)m.Bm, dst, s_red, s_last, &s_bad);
     else if (ipr <= (u32)(KMAX / 2) * T) c = cta_sort_dedup<KMAX / 2, T, MODE>(buf, ipr, (u32)m.Bm, dst, s_red, s_last, &s_bad);
     else                                 c = cta_sort_dedup<KMAX, T, MODE>(buf, ipr, (u32)m.Bm, dst, s_red, s_last, &s_bad);
-    if (MODE == MODE_COUNT && t == 0) cnt[row] = c;
+    if (MODE != MODE_FILL && t == 0) cnt[row] = c;
   }
   __syncthreads();
   if (t == 0 && s_bad) atomicOr(&sc->err, 4u);

@@ -27,7 +27,7 @@ template <int MODE>
 __global__ void __launch_bounds__(1024, 1) k_rows_window(Csr m, const u32* __restrict__ list, const u32* __restrict__ nlist,
                                                          u32* __restrict__ ctr, u32* __restrict__ cnt, int G, u32 wwords,
                                                          const void* __restrict__ Crow, int is64, int* __restrict__ Ccol,
-                                                         DevScalars* sc) {
+                                                         const u64* __restrict__ tofs, DevScalars* sc) {
   extern __shared__ __align__(16) u32 bm[];
   __shared__ u32 s_red[33];
   __shared__ u32 s_idx, s_guess, s_above, s_below, s_wlo, s_whi, s_bad, s_long;
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(1024, 1) k_rows_window(Csr m, const u32* __res
     u32 start = s_guess;
     u32 added = 0;
     u64 done = 0;
-    const u64 base = (MODE == MODE_FILL) ? ld_rowptr(Crow, is64, (size_t)row) : 0;
+    const u64 base = (MODE == MODE_FILL) ? ld_rowptr(Crow, is64, (size_t)row) : (MODE == MODE_STAGE) ? tofs[row] : 0;   // STAGE: Ccol is the staging arena
     bool first = true;
     if (start != EMPTY && start < (u32)m.Bm) {
       start &= ~31u;
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(1024, 1) k_rows_window(Csr m, const u32* __res
         if (!restart) added += add;
         if (w_lo != EMPTY) {
           const u32 q0 = w_lo >> 2, q1 = w_hi >> 2;
-          if (MODE == MODE_FILL && !restart) {
+          if (MODE != MODE_COUNT && !restart) {
             for (u32 qb = q0; qb <= q1; qb += nthr) {
               const u32 q = qb + tid;
               uint4 v = make_uint4(0u, 0u, 0u, 0u);
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(1024, 1) k_rows_window(Csr m, const u32* __res
     } else if (start != EMPTY) {
       if (tid == 0) s_bad = 1;                               // first entry of a B row outside [0,Bm)
     }
-    if (MODE == MODE_COUNT) {
+    if (MODE != MODE_FILL) {
       const u32 c = block_reduce_add(added, s_red);
       if (tid == 0) cnt[row] = c;
     }

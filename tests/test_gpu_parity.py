@@ -382,6 +382,18 @@ def test_ell_clustered_columns_spill_and_rebuild(bs, oracle, monkeypatch, kernel
     assert not msg, msg
 
 
+def test_big_rows_two_pass_when_staging_is_off(bs, oracle, monkeypatch):
+    """BSPGEMM_NO_STAGE: M/L rows counted, then filled (the route taken when the staging arena does not fit in memory)."""
+    monkeypatch.setenv("BSPGEMM_NO_STAGE", "1")
+    test_every_bin_is_exercised(bs, oracle)
+    row, col = bs.gen_rmat(13, 16, 0.57, 0.19, 0.19, 7)
+    n = len(row) - 1
+    want_col, want_row = oracle.spgemm(col, row, n, col, row, n)
+    got_col, got_row, st = dev_multiply(bs, bs.MODE_FUSED, col, row, n, col, row, n, n)
+    msg = _explain(got_col, got_row, want_col, want_row)
+    assert not msg, msg
+
+
 def test_power_law_rows_sort_and_window_bins(bs, oracle):
     """R-MAT (no vertex permutation): the candidates of every row pile up on the hub columns.  Small rows go through the
     register sort of the warp bin, big rows through the windowed shared-memory bitmap (rows_window.cuh), hub rows of B
