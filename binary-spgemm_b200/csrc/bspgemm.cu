@@ -129,9 +129,12 @@ static int set_kernel_attributes(int smem_optin) {
 #define ATTR_E(Wv) ATTR((k_fused_ell<Wv, 1>)); ATTR((k_fused_ell<Wv, 2>)); ATTR((k_fused_ell<Wv, 4>)); ATTR((k_fused_ell<Wv, 8>))
   ATTR_E(4); ATTR_E(8); ATTR_E(16); ATTR_E(32);
 #undef ATTR_E
-#define ATTR_S(Wv) ATTR((k_fused_sort<Wv, 2>)); ATTR((k_fused_sort<Wv, 3>)); ATTR((k_fused_sort<Wv, 4>))
+#define ATTR_S(Wv) ATTR((k_fused_sort<Wv, 2>)); ATTR((k_fused_sort<Wv, 3>)); ATTR((k_fused_sort<Wv, 4>)); \
+                   ATTR((k_fused_sort_async<Wv, 2>)); ATTR((k_fused_sort_async<Wv, 3>)); ATTR((k_fused_sort_async<Wv, 4>))
   ATTR_S(4); ATTR_S(8); ATTR_S(16); ATTR_S(32);
   ATTR((k_fused_sort<4, 5>)); ATTR((k_fused_sort<8, 5>)); ATTR((k_fused_sort<16, 5>)); ATTR((k_fused_sort<32, 5>));
+  ATTR((k_fused_sort_async<16, 4, 16>));
+  ATTR((k_fused_sort_async<4, 5>)); ATTR((k_fused_sort_async<8, 5>)); ATTR((k_fused_sort_async<16, 5>)); ATTR((k_fused_sort_async<32, 5>));
 #undef ATTR_S
 #undef ATTR_G
 #undef ATTR
@@ -284,21 +287,24 @@ static int pick_compute_warps(size_t per_warp, size_t fixed, int max_warps, size
   return w;
 }
 
-template <int W, int LAL> static int launch_sort_t(bspgemm_dev* d, int* ccol) {
+template <int W, int LAL, bool ASYNC, int KMAX = 32> static int launch_sort_t(bspgemm_dev* d, int* ccol) {
   const MulArgs& a = d->a;
-  constexpr SortGeom G = sort_geom<W, LAL>();
+  constexpr SortGeom G = sort_geom<W, LAL, KMAX>();
   const u32 ntiles = (u32)(((size_t)a.m.An + G.R - 1) / G.R);
   // warps per CTA: what the kernel's register count allows (registers are allocated per SM sub-partition: 80 -> 6 warps
   // each, 81..102 -> 5), one of them the chain helper
-  cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, k_fused_sort<W, LAL>));
+  auto kern = ASYNC ? k_fused_sort_async<W, LAL, KMAX> : k_fused_sort<W, LAL>;
+  cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, kern));
   const int max_compute = std::max(1, std::min(SORT_MAX_WARPS, fa.maxThreadsPerBlock / 32) - 1);
   // staging buffers per warp: 2 = commit one tile later; small tiles get 3 (commit lag 2) as long as that costs no warps
-  const size_t one_buf = (size_t)sort_stage_words(G.R, G.LA, W) * 4, acol_bytes = 256, fixed = ELL_CTA_WORDS * 4 + 64;
+  // ASYNC: one of the buffers is the (unpadded) input buffer the cp.async copies land in, the other nbuf-1 are staging buffers
+  const size_t one_buf = (size_t)sort_stage_words(G.R, G.LA, W) * 4, in_buf = (size_t)sort_input_words(G.R, G.LA, W) * 4, fixed = ELL_CTA_WORDS * 4 + 64;
+  auto warp_bytes = [&](int nb) { return (ASYNC ? in_buf + (size_t)(nb - 1) * one_buf : (size_t)nb * one_buf) + 256; };   // + the next tile's <= 64 B-row ids
   int nbuf = 2;
-  const int w2 = pick_compute_warps(2 * one_buf + acol_bytes, fixed, max_compute, d->smem_optin);
-  while (nbuf < 3 && pick_compute_warps((nbuf + 1) * one_buf + acol_bytes, fixed, max_compute, d->smem_optin) >= w2) ++nbuf;
+  const int w2 = pick_compute_warps(warp_bytes(2), fixed, max_compute, d->smem_optin);
+  while (nbuf < 3 && pick_compute_warps(warp_bytes(nbuf + 1), fixed, max_compute, d->smem_optin) >= w2) ++nbuf;
   if (const char* e = getenv("BSPGEMM_NBUF")) nbuf = std::max(2, std::min(4, atoi(e)));   // tuning knob
-  const size_t per_warp = (size_t)nbuf * one_buf + acol_bytes;
+  const size_t per_warp = warp_bytes(nbuf);
   const int warps = pick_compute_warps(per_warp, fixed, max_compute, d->smem_optin);
   if (warps < 1) return fail(BSPGEMM_ERR_CUDA, "sort kernel does not fit on an SM");
   const size_t smem = per_warp * warps + ELL_CTA_WORDS * 4;
@@ -316,20 +322,23 @@ template <int W, int LAL> static int launch_sort_t(bspgemm_dev* d, int* ccol) {
   p.debug_nochain = getenv("BSPGEMM_DEBUG_NOCHAIN") ? (u32)(G.R * G.LA * W) : 0u;   // WRONG RESULTS: timing experiments only
   d->st.rows_per_tile = G.R; d->st.variant = 2;
   if (getenv("BSPGEMM_VERBOSE")) {
-    cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, k_fused_sort<W, LAL>);
-    fprintf(stderr, "k_fused_sort<%d,%d>: regs %d, maxThreadsPerBlock %d, static smem %zu, launch %d x %d threads, dyn smem %zu, nbuf %d\n",
-            W, LAL, fa.numRegs, fa.maxThreadsPerBlock, fa.sharedSizeBytes, grid, (warps + 1) * 32, smem, nbuf);
+    fprintf(stderr, "k_fused_sort%s<%d,%d>: regs %d, maxThreadsPerBlock %d, static smem %zu, launch %d x %d threads, dyn smem %zu, nbuf %d\n",
+            ASYNC ? "_async" : "", W, LAL, fa.numRegs, fa.maxThreadsPerBlock, fa.sharedSizeBytes, grid, (warps + 1) * 32, smem, nbuf);
   }
-  k_fused_sort<W, LAL><<<grid, (warps + 1) * 32, smem, d->stream>>>(p);        // + the chain helper warp
+  kern<<<grid, (warps + 1) * 32, smem, d->stream>>>(p);        // + the chain helper warp
   d->launches++;
   CK(cudaGetLastError());
   return BSPGEMM_OK;
 }
 static int launch_sort(bspgemm_dev* d, int* ccol) {
   const int W = d->ell_W, L = d->sort_LAL;
-#define LS(Wv) do { switch (L) { case 2: return launch_sort_t<Wv, 2>(d, ccol); case 3: return launch_sort_t<Wv, 3>(d, ccol); case 4: return launch_sort_t<Wv, 4>(d, ccol); \
-                                 default: return launch_sort_t<Wv, 5>(d, ccol); } } while (0)
-  switch (W) { case 4: LS(4); case 8: LS(8); case 16: LS(16); default: LS(32); }
+#define LS(Wv, As) do { switch (L) { case 2: return launch_sort_t<Wv, 2, As>(d, ccol); case 3: return launch_sort_t<Wv, 3, As>(d, ccol); \
+                                     case 4: return launch_sort_t<Wv, 4, As>(d, ccol); default: return launch_sort_t<Wv, 5, As>(d, ccol); } } while (0)
+  if (getenv("BSPGEMM_SORT_K16") && W == 16 && L == 4) return launch_sort_t<16, 4, true, 16>(d, ccol);   // experiment: 16 keys per lane, 2-row tiles
+  if (getenv("BSPGEMM_SORT_SYNC")) {          // A/B knob: the register-prefetch kernel instead of the cp.async one
+    switch (W) { case 4: LS(4, false); case 8: LS(8, false); case 16: LS(16, false); default: LS(32, false); }
+  }
+  switch (W) { case 4: LS(4, true); case 8: LS(8, true); case 16: LS(16, true); default: LS(32, true); }
 #undef LS
 }
 

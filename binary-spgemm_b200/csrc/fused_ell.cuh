@@ -195,7 +195,7 @@ __device__ __noinline__ void chain_helper(CtaChain* cc, u64* blk_status, u32 nti
 }
 
 // Dynamic variant: the CTA's block of iteration i is not i*gridDim.x + blockIdx.x but the next id of a global counter,
-// claimed four iterations ahead (the compute warps prefetch two tiles ahead).  An SM that runs slower than the others
+// claimed five iterations ahead (the compute warps look up to three tiles ahead).  An SM that runs slower than the others
 // (the static deal made every CTA process the same number of blocks: the kernel ran at the pace of the slowest SM and
 // the warps of the others spent 9 % of their time waiting for offsets, profiles/r01_sort_cfg3_static_blocks.txt) then
 // simply takes fewer blocks.  Ids are consecutive in time, so neighbours in the chain still run at the same time.
@@ -210,7 +210,7 @@ __device__ __noinline__ void chain_helper_dyn(CtaChain* cc, u64* blk_status, u32
       *reinterpret_cast<volatile u32*>(&cc->blkit[it & (CH_RING - 1u)]) = it + 1u;
     }
   };
-  for (u32 it = 0; it < 4u; ++it) claim(it);
+  for (u32 it = 0; it < 5u; ++it) claim(it);
   __syncwarp();
   for (u32 iter = 0;; ++iter) {
     const u32 s = iter & (CH_RING - 1u), tag = (iter & 0xfffu) + 1u;
@@ -226,7 +226,7 @@ __device__ __noinline__ void chain_helper_dyn(CtaChain* cc, u64* blk_status, u32
       __threadfence_block();
       st_status(&blk_status[blk], ST_AGG | (u64)total);
     }
-    claim(iter + 4u);                        // every warp has posted `iter`: nobody reads the ids of iterations <= iter-4 any more
+    claim(iter + 5u);                        // every warp has posted `iter`: nobody reads the ids of iterations <= iter any more (ring of 8)
     const u64 excl = chain_walk(blk_status, blk);
     if (lane == 0) {
       st_status(&blk_status[blk], ST_INC | (excl + (u64)total));

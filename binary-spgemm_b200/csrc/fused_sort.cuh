@@ -25,7 +25,7 @@ constexpr int SORT_MAX_WARPS = 32;        // CtaChain holds 32 warps; the launch
 struct SortGeom {          // compile-time geometry of k_fused_sort<W, LAL>
   int LPR, LA, S, NQ, K, RP, R, NP;
 };
-template <int W, int LAL> __host__ __device__ constexpr SortGeom sort_geom() {
+template <int W, int LAL, int KMAX = 32> __host__ __device__ constexpr SortGeom sort_geom() {
   SortGeom g{};
   g.LPR = W / 4;                               // lanes per B row (one uint4 each)
   g.LA = 1 << LAL;                             // B rows per output row (A row length, rounded up)
@@ -33,7 +33,7 @@ template <int W, int LAL> __host__ __device__ constexpr SortGeom sort_geom() {
   // As many keys per lane as possible (exchanges inside a lane cost 1 instruction per key, across lanes 3: SHFL,
   // min, max), subject to: a row spans >= max(LPR, 2) lanes, at most 32 key registers per lane, and the rows of one
   // warp pass own at most 64 A nonzeros (two registers of Acol per lane).
-  int k = 32;
+  int k = KMAX;
   while (k > 4) {
     const int s = cap / k;
     if (s >= (g.LPR > 2 ? g.LPR : 2) && s <= 32 && (32 / s) * g.LA <= 64) break;
@@ -43,7 +43,7 @@ template <int W, int LAL> __host__ __device__ constexpr SortGeom sort_geom() {
   g.S = cap / k;                               // lanes per row
   g.NQ = g.K / 4;                              // uint4 per lane per row
   g.RP = 32 / g.S;                             // rows per warp pass
-  int np = 32 / g.K; if (np < 1) np = 1;       // passes per tile: at most 32 key registers per lane in flight,
+  int np = 32 / g.K; if (np < 1 || KMAX < 32) np = 1;   // passes per tile: at most 32 key registers per lane in flight (small-tile variant: one),
   while (np > 1 && (g.RP * np * g.LA > 64 || g.RP * np > 16)) np >>= 1;   // <= 64 A nonzeros and <= 16 rows per tile
   g.NP = np;
   g.R = g.RP * np;                             // rows per tile
@@ -281,6 +281,223 @@ __global__ void __maxnreg__((sort_geom<W, LAL>().K >= 32 ? 96 : 80)) k_fused_sor
   }
   // drain: the last nbuf-1 tiles of this warp
   for (u32 k = (iter + 1u >= nbuf) ? iter + 1u - nbuf : 0u; k < iter; ++k) commit(k, stage_s + (k % nbuf) * (SWORDS * 4u));
+  u64 ips = ipc;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) ips += __shfl_xor_sync(0xffffffffu, ips, d);
+  if (lane == 0 && ips) atomicAdd(&p.sc->total_ip, ips);
+}
+
+// ---------------------------------------------------------------------------------------------- asynchronous-input variant
+// k_fused_sort keeps the next tile's B rows in flight in the key registers, so the gather can only be issued after the
+// current tile has been sorted and staged: its DRAM latency is covered by the commit alone and the warp then waits
+// (long-scoreboard stalls: 22 % of the warp time at config 3, profiles/r01_sort_cfg3_ncu_summary.txt).  Here the B rows of
+// tile t+1 are copied global -> shared memory with cp.async (LDGSTS.128, L1 bypassed, no destination registers) right
+// after tile t has been read into registers, i.e. the gather is in flight during the whole sort of tile t:
+//   iteration t:  wait for the copies of tile t; keys <- input buffer (LDS.128); park the B-row table of tile t+1; issue
+//                 the Acol loads of tile t+2 and the row pointers of tile t+3; issue the copies of tile t+1 into the (now
+//                 free) input buffer; sort; commit tile t-LAG from the staging buffer tile t is about to use; stage; post.
+// The copies land directly in the lane-per-B-row layout the network wants (16-byte piece pr of the pass goes to
+// L*NQ + (c ^ swz(L)), L = pr / NQ the consuming lane, c = pr % NQ): the copy instructions are row-coalesced (LPR lanes
+// per B row) and both the LDGSTS writes and the LDS.128 reads are bank-conflict-free, so the register -> shared -> register
+// transpose of k_fused_sort is gone too.  One input buffer + LAG staging buffers per warp: same shared memory as before.
+__device__ __forceinline__ void cp_async16(u32 dst_s, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst_s), "l"(src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__host__ __device__ constexpr u32 sort_input_words(int R, int LA, int W) { return (u32)(R * LA * W); }
+
+template <int W, int LAL, int KMAX = 32>
+__global__ void __maxnreg__((sort_geom<W, LAL, KMAX>().K >= 32 ? 96 : KMAX < 32 ? 64 : 80)) k_fused_sort_async(const EllArgs p) {
+  constexpr SortGeom G = sort_geom<W, LAL, KMAX>();
+  constexpr int LPR = G.LPR, LA = G.LA, S = G.S, NQ = G.NQ, K = G.K, RP = G.RP, R = G.R, NP = G.NP;
+  constexpr u32 SWORDS = sort_stage_words(R, LA, W), IWORDS = sort_input_words(R, LA, W);
+  constexpr int SH = NQ >= 8 ? 0 : NQ == 4 ? 1 : NQ == 2 ? 2 : 3;     // swz(L) = (L >> SH) & (NQ-1): 8 consecutive lanes hit 8 different 16-byte bank columns
+  static_assert(NQ <= 8 && R * LA <= 64, "geometry");
+  extern __shared__ __align__(16) u32 smem[];
+  const u32 warp = threadIdx.x >> 5, lane = lane_id(), nwarps = (blockDim.x >> 5) - 1u;   // compute warps; the last warp is the chain helper
+  const u32 lag = p.nbuf - 1u;                                                            // staging buffers = commit lag in tiles
+  const u32 wwords = IWORDS + lag * SWORDS + 64u;                                         // input, staging ring, B-row table of the next tile
+  const u32 in_s = (u32)__cvta_generic_to_shared(smem) + warp * (wwords * 4u);
+  const u32 stage_s = in_s + IWORDS * 4u;
+  const u32 jtab_s = stage_s + lag * SWORDS * 4u;
+  CtaChain* cc = reinterpret_cast<CtaChain*>(smem + (size_t)nwarps * wwords);
+  for (u32 i = threadIdx.x; i < sizeof(CtaChain) / 4; i += blockDim.x) reinterpret_cast<u32*>(cc)[i] = 0;
+  __syncthreads();                          // the only CTA-wide barrier
+  if (warp == nwarps) {
+    if (!p.debug_nochain) chain_helper_dyn(cc, p.blk_status, &p.sc->tile_counter, p.ntiles, nwarps, lag);
+    return;
+  }
+  const u32 ll = lane % S;                  // lane within its row
+  const uint4* __restrict__ Bell4 = reinterpret_cast<const uint4*>(p.Bell);
+  u32 ipc = 0;
+  const u32 stride = gridDim.x * nwarps;
+  const u32 cta_first = blockIdx.x * nwarps;
+
+  auto load_rowptr = [&](u32 t) -> int {     // lane r (r <= R) gets Arow[t*R + r], clamped to the matrix
+    if (t >= p.ntiles) return 0;
+    const long long r0 = (long long)t * R;
+    const int nr = (int)min((long long)R, (long long)p.An - r0);
+    return p.Arow[r0 + min((int)lane, nr)];
+  };
+  // B-row table of a tile: entry e = row*LA + slot is the B row the slot gathers, Bn (the all-EMPTY row) when the A row
+  // is shorter.  Lane l loads entries l and l+32 straight from Acol (whole rows: the same coalesced accesses).
+  auto load_jtab = [&](int ar, int& j0, int& j1) {
+    j0 = p.Bn; j1 = p.Bn;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int e = h * 32 + (int)lane, row = e / LA, slot = e % LA;
+      const int lo = __shfl_sync(0xffffffffu, ar, row & 31), hi = __shfl_sync(0xffffffffu, ar, (row + 1) & 31);
+      if (row < R && slot < hi - lo) { const int j = p.Acol[lo + slot]; if (h) j1 = j; else j0 = j; }
+    }
+  };
+  auto stash_jtab = [&](int j0, int j1) {                          // validate, then park the table in shared memory
+    if (((u32)j0 > (u32)p.Bn) | ((u32)j1 > (u32)p.Bn)) {
+      atomicOr(&p.sc->err, 1u);
+      if ((u32)j0 > (u32)p.Bn) j0 = p.Bn;
+      if ((u32)j1 > (u32)p.Bn) j1 = p.Bn;
+    }
+    sts32(jtab_s + 4u * lane, (u32)j0);
+    sts32(jtab_s + 4u * (32u + lane), (u32)j1);
+    __syncwarp();
+  };
+  // copies of a whole tile: NP*NQ LDGSTS.128 per lane.  Copy u of lane l is piece gp = (u % NQ)*32 + l of pass u / NQ:
+  // part l % LPR of table entry pass*RP*LA + gp / LPR.
+  auto issue_tile = [&]() {
+#pragma unroll
+    for (int u = 0; u < NP * NQ; ++u) {
+      const int q = u / NQ, v = u % NQ;
+      const u32 e = (u32)(q * RP * LA + v * (32 / LPR)) + lane / (u32)LPR;
+      const u32 j = lds32(jtab_s + 4u * e);
+      const u32 L = (u32)(v * (32 / NQ)) + lane / (u32)NQ, c = lane % (u32)NQ;
+      const u32 pos = (u32)(q * 32 * NQ) + L * (u32)NQ + (c ^ ((L >> SH) & (u32)(NQ - 1)));
+      cp_async16(in_s + 16u * pos, &Bell4[(size_t)j * LPR + (lane % (u32)LPR)]);
+    }
+    cp_async_commit();
+  };
+  auto read_pass = [&](int q, u32 (&x)[K]) {
+#pragma unroll
+    for (int c = 0; c < NQ; ++c) {
+      const uint4 t4 = lds128(in_s + 16u * ((u32)(q * 32 * NQ) + lane * (u32)NQ + ((u32)c ^ ((lane >> SH) & (u32)(NQ - 1)))));
+      x[4 * c + 0] = t4.x; x[4 * c + 1] = t4.y; x[4 * c + 2] = t4.z; x[4 * c + 3] = t4.w;
+    }
+  };
+  // commit of the tile staged in buffer buf_s during iteration `iter` (header: total, tile, inclusive row counts)
+  auto commit = [&](u32 iter, u32 buf_s) {
+    const u32 total = lds32(buf_s), t = lds32(buf_s + 4u);
+    const u32 incl_mine = lds32(buf_s + 8u + 4u * min(lane, (u32)R - 1u));
+    const u64 excl = p.debug_nochain ? (u64)t * (u64)p.debug_nochain : chain_resolve(cc, iter, warp);
+    const long long row0 = (long long)t * R;
+    const int nrows = (int)min((long long)R, (long long)p.An - row0);
+    if ((int)lane < nrows) st_rowptr(p.Crow, p.is64, (size_t)(row0 + lane) + 1, excl + incl_mine, &p.sc->err);
+    if (t == 0 && lane == 0) st_rowptr(p.Crow, p.is64, 0, 0, &p.sc->err);
+    if (t == p.ntiles - 1 && lane == 0) p.sc->total_nnz = excl + total;
+    int* dst = p.Ccol + excl;
+    u32 src = buf_s + 4u * (SORT_HDR + lane);                      // key q lives at word q + q/32: 33 words per 32 keys
+    for (u32 q = lane; q < total; q += 32, src += 132u) dst[q] = (int)lds32(src);
+    __syncwarp();
+  };
+
+  // tile of this warp in the CTA's iteration `it`: block ids come from the chain helper (dealt 5 iterations ahead)
+  const u32 nblocks = (p.ntiles + nwarps - 1u) / nwarps;
+  auto tile_of = [&](u32 it) -> u32 {
+    if (p.debug_nochain) { const unsigned long long t = (unsigned long long)it * stride + cta_first + warp; return t < p.ntiles ? (u32)t : 0xffffffffu; }
+    const u32 blk = chain_block_of(cc, it);
+    if (blk >= nblocks) return 0xffffffffu;
+    const u32 t = blk * nwarps + warp;
+    return t < p.ntiles ? t : 0xffffffffu;
+  };
+  // ---- pipeline prologue: copies of tile 0 in flight, table of tile 1 in registers, row pointers of tile 2
+  u32 tile = tile_of(0), iter = 0;
+  int j0n, j1n, ar2;
+  {
+    int j0, j1;
+    load_jtab(load_rowptr(tile), j0, j1);
+    stash_jtab(j0, j1);
+    issue_tile();
+    load_jtab(load_rowptr(tile_of(1)), j0n, j1n);
+    ar2 = load_rowptr(tile_of(2));
+  }
+  u32 cur_buf = 0;                           // iter % lag
+
+  while (tile < p.ntiles) {
+    const u32 next = tile_of(iter + 1u);
+    const int ar3 = load_rowptr(tile_of(iter + 3u));
+    u32 x[NP][K];
+    cp_async_wait_all();
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < NP; ++q) read_pass(q, x[q]);
+    __syncwarp();                            // every lane has read the input buffer and the old table
+    stash_jtab(j0n, j1n);                    // table of tile t+1
+    issue_tile();                            // ... and its copies, in flight during the sort
+    load_jtab(ar2, j0n, j1n);                // table of tile t+2
+    const u32 buf_s = stage_s + cur_buf * (SWORDS * 4u), cur_s = buf_s + 4u * SORT_HDR;
+    u32 run = 0, incl_mine = 0;
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+      u32 (&k)[K] = x[q];
+      bitonic_sort_rows<K, S, (W < K ? W : K)>(k, ll);     // every B row is ascending in the ELL copy (k_build_ell sorts it)
+      if (q == 0 && iter >= lag) commit(iter - lag, buf_s);        // frees the staging buffer this tile is about to use
+      // the row is ascending along (lane, register); EMPTY (padding) is the largest value
+      u32 prev_last = __shfl_up_sync(0xffffffffu, k[K - 1], 1);
+      if (ll == 0) prev_last = EMPTY;                              // nothing before the row's first key (EMPTY never counts)
+      bool plain = (k[K - 1] != EMPTY) && (k[0] != prev_last);     // no padding in this lane, no duplicate
+#pragma unroll
+      for (int i = 1; i < K; ++i) plain = plain && (k[i] != k[i - 1]);
+      if (__all_sync(0xffffffffu, plain)) {
+        // the usual case: no duplicate, no padding anywhere in the pass — every key's place is known in advance
+        ipc += (u32)K;
+        const u32 pos = lane * (u32)K;                             // rows of the pass back to back, lane-major
+        const u32 a0s = cur_s + 4u * (run + pos + ((run + pos) >> 5));
+        if (((run + pos) & 31u) + (u32)K <= 32u || (K % 32 == 0 && ((run + pos) & 31u) == 0u)) {
+#pragma unroll
+          for (int i = 0; i < K; ++i) sts32(a0s + 4u * (u32)(i + i / 32), k[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < K; ++i) { const u32 o = run + pos + (u32)i; sts32(cur_s + 4u * (o + (o >> 5)), k[i]); }
+        }
+#pragma unroll
+        for (int sq = 0; sq < RP; ++sq) { run += (u32)(K * S); if ((int)lane == q * RP + sq) incl_mine = run; }
+      } else {
+        // first occurrences, their count, inclusive scan of the count inside the row's S lanes
+        const u32 seg = lane / S;
+        bool f[K];
+        u32 cnt = 0;
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+          f[i] = (k[i] != EMPTY) && (k[i] != (i ? k[i - 1] : prev_last));
+          cnt += f[i] ? 1u : 0u;
+          ipc += (k[i] != EMPTY) ? 1u : 0u;
+        }
+        u32 inc = cnt;
+#pragma unroll
+        for (int d = 1; d < S; d <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, inc, d); if ((int)ll >= d) inc += t; }
+        // rows of the pass are staged back to back, in row order
+        u32 rowbase = run;
+#pragma unroll
+        for (int sq = 0; sq < RP; ++sq) {
+          const u32 tot = __shfl_sync(0xffffffffu, inc, sq * S + S - 1);
+          if ((int)seg > sq) rowbase += tot;
+          run += tot;
+          if ((int)lane == q * RP + sq) incl_mine = run;
+        }
+        u32 o = rowbase + inc - cnt;
+#pragma unroll
+        for (int i = 0; i < K; ++i) if (f[i]) { sts32(cur_s + 4u * (o + (o >> 5)), k[i]); ++o; }
+      }
+    }
+    if (lane == 0) sts64(buf_s, run, tile);
+    if (lane < (u32)R) sts32(buf_s + 8u + 4u * lane, incl_mine);
+    __syncwarp();
+    if (!p.debug_nochain) chain_post(cc, iter, warp, run);
+    cur_buf = (cur_buf + 1u == lag) ? 0u : cur_buf + 1u;
+    tile = next; ++iter;
+    ar2 = ar3;
+  }
+  cp_async_wait_all();
+  // drain: the last `lag` tiles of this warp
+  for (u32 k = (iter >= lag) ? iter - lag : 0u; k < iter; ++k) commit(k, stage_s + (k % lag) * (SWORDS * 4u));
   u64 ips = ipc;
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) ips += __shfl_xor_sync(0xffffffffu, ips, d);

@@ -8,7 +8,7 @@
 constexpr int WARPS = 8, ITERS = 2048, CH = 16;
 
 template <int OP>
-__global__ void __launch_bounds__(WARPS * 32) k(uint32_t* out, long long* clk, uint32_t seed, uint32_t one) {
+__global__ void __launch_bounds__(WARPS * 32) k(uint32_t* out, long long* clk, uint32_t seed, uint32_t one, uint32_t mone) {
   uint32_t x[CH], y[CH];
 #pragma unroll
   for (int c = 0; c < CH; ++c) { x[c] = seed * (threadIdx.x + 1) + c * 977u; y[c] = x[c] ^ (0x9e3779b9u * (c + 1)); }
@@ -26,6 +26,14 @@ __global__ void __launch_bounds__(WARPS * 32) k(uint32_t* out, long long* clk, u
       else if (OP == 5) x[c] = (x[c] & y[c]) ^ seed;                             // LOP3
       else if (OP == 6) { const uint32_t t = __shfl_xor_sync(0xffffffffu, x[c], 1); x[c] = p ? min(x[c], t) : max(x[c], t); }  // the cross-lane exchange
       else if (OP == 7) { const uint32_t lo = min(x[c], y[c]), hi = max(x[c], y[c]); x[c] = lo; y[c] = hi; }                  // the in-lane exchange
+      else if (OP == 8 || (OP == 9 && c % 3 != 0) || (OP == 10 && (c & 1))) {                                                   // in-lane exchange, max formed on the FMA pipe
+        const uint32_t lo = min(x[c], y[c]); uint32_t s, hi;
+        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(s) : "r"(x[c]), "r"(one), "r"(y[c]));
+        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(hi) : "r"(lo), "r"(mone), "r"(s));
+        x[c] = lo; y[c] = hi;
+      }
+      else if (OP == 9 || OP == 10) { const uint32_t lo = min(x[c], y[c]), hi = max(x[c], y[c]); x[c] = lo; y[c] = hi; }
+      else if (OP == 11) { x[c] = min(x[c], y[c] + i); }                                                                          // VIMNMX + IADD3-or-IMAD.IADD (ptxas' choice)
     }
     if (OP == 0) {
 #pragma unroll
@@ -43,8 +51,8 @@ __global__ void __launch_bounds__(WARPS * 32) k(uint32_t* out, long long* clk, u
 template <int OP> void run(const char* name, int sms, double ops_per_iter) {
   uint32_t* out; long long* clk; cudaMalloc(&out, 4); cudaMalloc(&clk, 8);
   const int grid = sms * 4;
-  k<OP><<<grid, WARPS * 32>>>(out, clk, 3, 1); cudaDeviceSynchronize();
-  k<OP><<<grid, WARPS * 32>>>(out, clk, 3, 1); cudaDeviceSynchronize();
+  k<OP><<<grid, WARPS * 32>>>(out, clk, 3, 1, 0xffffffffu); cudaDeviceSynchronize();
+  k<OP><<<grid, WARPS * 32>>>(out, clk, 3, 1, 0xffffffffu); cudaDeviceSynchronize();
   long long cyc; cudaMemcpy(&cyc, clk, 8, cudaMemcpyDeviceToHost);
   const double warp_ops_per_smsp = 8.0 * ITERS * ops_per_iter;      // 32 warps per SM = 8 per sub-partition
   printf("%-44s block0 cycles %10lld -> %.2f cycles per warp instruction per SM sub-partition\n", name, cyc, (double)cyc / warp_ops_per_smsp);
@@ -62,5 +70,10 @@ int main() {
   run<5>("LOP3", p.multiProcessorCount, CH);
   run<6>("SHFL + VIMNMX + @p VIMNMX (3 instr)", p.multiProcessorCount, 3 * CH);
   run<7>("VIMNMX min + VIMNMX max (2 instr)", p.multiProcessorCount, 2 * CH);
+  run<7>("exchange: min + max          (per exchange)", p.multiProcessorCount, CH);
+  run<8>("exchange: min + IMAD + IMAD  (per exchange)", p.multiProcessorCount, CH);
+  run<9>("exchange: 2 of 3 IMAD form   (per exchange)", p.multiProcessorCount, CH);
+  run<10>("exchange: 1 of 2 IMAD form   (per exchange)", p.multiProcessorCount, CH);
+  run<11>("VIMNMX + add (2 instr)", p.multiProcessorCount, 2 * CH);
   return 0;
 }
