@@ -133,7 +133,6 @@ static int set_kernel_attributes(int smem_optin) {
                    ATTR((k_fused_sort_async<Wv, 2>)); ATTR((k_fused_sort_async<Wv, 3>)); ATTR((k_fused_sort_async<Wv, 4>))
   ATTR_S(4); ATTR_S(8); ATTR_S(16); ATTR_S(32);
   ATTR((k_fused_sort<4, 5>)); ATTR((k_fused_sort<8, 5>)); ATTR((k_fused_sort<16, 5>)); ATTR((k_fused_sort<32, 5>));
-  ATTR((k_fused_sort_async<16, 4, 16>));
   ATTR((k_fused_sort_async<4, 5>)); ATTR((k_fused_sort_async<8, 5>)); ATTR((k_fused_sort_async<16, 5>)); ATTR((k_fused_sort_async<32, 5>));
 #undef ATTR_S
 #undef ATTR_G
@@ -287,25 +286,29 @@ static int pick_compute_warps(size_t per_warp, size_t fixed, int max_warps, size
   return w;
 }
 
-template <int W, int LAL, bool ASYNC, int KMAX = 32> static int launch_sort_t(bspgemm_dev* d, int* ccol) {
+template <int W, int LAL, bool ASYNC> static int launch_sort_t(bspgemm_dev* d, int* ccol) {
   const MulArgs& a = d->a;
-  constexpr SortGeom G = sort_geom<W, LAL, KMAX>();
+  constexpr SortGeom G = sort_geom<W, LAL>();
   const u32 ntiles = (u32)(((size_t)a.m.An + G.R - 1) / G.R);
   // warps per CTA: what the kernel's register count allows (registers are allocated per SM sub-partition: 80 -> 6 warps
   // each, 81..102 -> 5), one of them the chain helper
-  auto kern = ASYNC ? k_fused_sort_async<W, LAL, KMAX> : k_fused_sort<W, LAL>;
+  auto kern = ASYNC ? k_fused_sort_async<W, LAL> : k_fused_sort<W, LAL>;
   cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, kern));
   const int max_compute = std::max(1, std::min(SORT_MAX_WARPS, fa.maxThreadsPerBlock / 32) - 1);
-  // staging buffers per warp: 2 = commit one tile later; small tiles get 3 (commit lag 2) as long as that costs no warps
-  // ASYNC: one of the buffers is the (unpadded) input buffer the cp.async copies land in, the other nbuf-1 are staging buffers
+  // staging buffers per warp: 2 = commit one tile later; small tiles get 3 (commit lag 2) as long as that costs no warps.
+  // ASYNC: the input buffer the cp.async copies land in + 2 staging buffers (the commit of tile t-2 comes before tile t is
+  // staged, see fused_sort.cuh); nothing is kept back for L1, which the copies bypass.
   const size_t one_buf = (size_t)sort_stage_words(G.R, G.LA, W) * 4, in_buf = (size_t)sort_input_words(G.R, G.LA, W) * 4, fixed = ELL_CTA_WORDS * 4 + 64;
   auto warp_bytes = [&](int nb) { return (ASYNC ? in_buf + (size_t)(nb - 1) * one_buf : (size_t)nb * one_buf) + 256; };   // + the next tile's <= 64 B-row ids
-  int nbuf = 2;
-  const int w2 = pick_compute_warps(warp_bytes(2), fixed, max_compute, d->smem_optin);
-  while (nbuf < 3 && pick_compute_warps(warp_bytes(nbuf + 1), fixed, max_compute, d->smem_optin) >= w2) ++nbuf;
+  int nbuf = ASYNC ? 3 : 2;
+  if (!ASYNC) {
+    const int w2 = pick_compute_warps(warp_bytes(2), fixed, max_compute, d->smem_optin);
+    while (nbuf < 3 && pick_compute_warps(warp_bytes(nbuf + 1), fixed, max_compute, d->smem_optin) >= w2) ++nbuf;
+  }
   if (const char* e = getenv("BSPGEMM_NBUF")) nbuf = std::max(2, std::min(4, atoi(e)));   // tuning knob
   const size_t per_warp = warp_bytes(nbuf);
-  const int warps = pick_compute_warps(per_warp, fixed, max_compute, d->smem_optin);
+  int warps = pick_compute_warps(per_warp, fixed, max_compute, d->smem_optin);
+  if (ASYNC && !getenv("BSPGEMM_WARPS")) warps = (int)std::min<size_t>((size_t)max_compute, (d->smem_optin - fixed) / per_warp);
   if (warps < 1) return fail(BSPGEMM_ERR_CUDA, "sort kernel does not fit on an SM");
   const size_t smem = per_warp * warps + ELL_CTA_WORDS * 4;
   const long long want = ((long long)ntiles + warps - 1) / warps;
@@ -332,14 +335,15 @@ template <int W, int LAL, bool ASYNC, int KMAX = 32> static int launch_sort_t(bs
 }
 static int launch_sort(bspgemm_dev* d, int* ccol) {
   const int W = d->ell_W, L = d->sort_LAL;
-#define LS(Wv, As) do { switch (L) { case 2: return launch_sort_t<Wv, 2, As>(d, ccol); case 3: return launch_sort_t<Wv, 3, As>(d, ccol); \
-                                     case 4: return launch_sort_t<Wv, 4, As>(d, ccol); default: return launch_sort_t<Wv, 5, As>(d, ccol); } } while (0)
-  if (getenv("BSPGEMM_SORT_K16") && W == 16 && L == 4) return launch_sort_t<16, 4, true, 16>(d, ccol);   // experiment: 16 keys per lane, 2-row tiles
-  if (getenv("BSPGEMM_SORT_SYNC")) {          // A/B knob: the register-prefetch kernel instead of the cp.async one
-    switch (W) { case 4: LS(4, false); case 8: LS(8, false); case 16: LS(16, false); default: LS(32, false); }
-  }
-  switch (W) { case 4: LS(4, true); case 8: LS(8, true); case 16: LS(16, true); default: LS(32, true); }
+  // Big tiles (32 keys per lane, one pass per tile: config 3) take the cp.async kernel, the others the register-prefetch
+  // one (config 2: 0.205 ms against 0.24 ms).  BSPGEMM_SORT_SYNC / BSPGEMM_SORT_ASYNC force one of them (A/B runs, tests).
+  const bool force_sync = getenv("BSPGEMM_SORT_SYNC") != nullptr, force_async = getenv("BSPGEMM_SORT_ASYNC") != nullptr;
+#define LS1(Wv, Lv) do { constexpr SortGeom g_ = sort_geom<Wv, Lv>(); \
+    return (force_async || (!force_sync && g_.K == 32 && g_.NP == 1)) ? launch_sort_t<Wv, Lv, true>(d, ccol) : launch_sort_t<Wv, Lv, false>(d, ccol); } while (0)
+#define LS(Wv) do { switch (L) { case 2: LS1(Wv, 2); case 3: LS1(Wv, 3); case 4: LS1(Wv, 4); default: LS1(Wv, 5); } } while (0)
+  switch (W) { case 4: LS(4); case 8: LS(8); case 16: LS(16); default: LS(32); }
 #undef LS
+#undef LS1
 }
 
 // Banded / block-diagonal fast path (band.cuh): B rows become (first, len) descriptors, output rows 128-bit bitmaps.

@@ -217,7 +217,7 @@ __device__ __noinline__ void chain_helper_dyn(CtaChain* cc, u64* blk_status, u32
     const u32 blk = *reinterpret_cast<volatile u32*>(&cc->blkid[s]);
     if (blk >= nblocks) break;
     const u32 expected = min(ncompute, ntiles - blk * ncompute);
-    while (*reinterpret_cast<volatile u32*>(&cc->cnt[s]) != expected) __nanosleep(100);
+    while (*reinterpret_cast<volatile u32*>(&cc->cnt[s]) != expected) __nanosleep(400);   // (at 100 ns this spin was 38 % of the SM's issued instructions)
     __threadfence_block();
     const u32 w = (lane < expected) ? (*reinterpret_cast<volatile u32*>(&cc->agg[s][lane]) & CH_AGG_MASK) : 0u;
     const u32 total = __reduce_add_sync(0xffffffffu, w);

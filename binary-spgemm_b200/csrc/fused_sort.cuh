@@ -25,7 +25,7 @@ constexpr int SORT_MAX_WARPS = 32;        // CtaChain holds 32 warps; the launch
 struct SortGeom {          // compile-time geometry of k_fused_sort<W, LAL>
   int LPR, LA, S, NQ, K, RP, R, NP;
 };
-template <int W, int LAL, int KMAX = 32> __host__ __device__ constexpr SortGeom sort_geom() {
+template <int W, int LAL> __host__ __device__ constexpr SortGeom sort_geom() {
   SortGeom g{};
   g.LPR = W / 4;                               // lanes per B row (one uint4 each)
   g.LA = 1 << LAL;                             // B rows per output row (A row length, rounded up)
@@ -33,7 +33,7 @@ template <int W, int LAL, int KMAX = 32> __host__ __device__ constexpr SortGeom 
   // As many keys per lane as possible (exchanges inside a lane cost 1 instruction per key, across lanes 3: SHFL,
   // min, max), subject to: a row spans >= max(LPR, 2) lanes, at most 32 key registers per lane, and the rows of one
   // warp pass own at most 64 A nonzeros (two registers of Acol per lane).
-  int k = KMAX;
+  int k = 32;
   while (k > 4) {
     const int s = cap / k;
     if (s >= (g.LPR > 2 ? g.LPR : 2) && s <= 32 && (32 / s) * g.LA <= 64) break;
@@ -43,7 +43,7 @@ template <int W, int LAL, int KMAX = 32> __host__ __device__ constexpr SortGeom 
   g.S = cap / k;                               // lanes per row
   g.NQ = g.K / 4;                              // uint4 per lane per row
   g.RP = 32 / g.S;                             // rows per warp pass
-  int np = 32 / g.K; if (np < 1 || KMAX < 32) np = 1;   // passes per tile: at most 32 key registers per lane in flight (small-tile variant: one),
+  int np = 32 / g.K; if (np < 1) np = 1;       // passes per tile: at most 32 key registers per lane in flight,
   while (np > 1 && (g.RP * np * g.LA > 64 || g.RP * np > 16)) np >>= 1;   // <= 64 A nonzeros and <= 16 rows per tile
   g.NP = np;
   g.R = g.RP * np;                             // rows per tile
@@ -296,10 +296,20 @@ __global__ void __maxnreg__((sort_geom<W, LAL>().K >= 32 ? 96 : 80)) k_fused_sor
 //   iteration t:  wait for the copies of tile t; keys <- input buffer (LDS.128); park the B-row table of tile t+1; issue
 //                 the Acol loads of tile t+2 and the row pointers of tile t+3; issue the copies of tile t+1 into the (now
 //                 free) input buffer; sort; commit tile t-LAG from the staging buffer tile t is about to use; stage; post.
+// (Measured alternatives, profiles/r01_sort_async_sweeps.txt: committing at the top of the iteration, where no key register
+// is live, costs 9 % — the copies' DEPBAR then also waits for the commit's stores; forcing the LDGSTS into a block of their
+// own instead of letting ptxas spread them over the first half of the network changes nothing.)
 // The copies land directly in the lane-per-B-row layout the network wants (16-byte piece pr of the pass goes to
 // L*NQ + (c ^ swz(L)), L = pr / NQ the consuming lane, c = pr % NQ): the copy instructions are row-coalesced (LPR lanes
 // per B row) and both the LDGSTS writes and the LDS.128 reads are bank-conflict-free, so the register -> shared -> register
-// transpose of k_fused_sort is gone too.  One input buffer + LAG staging buffers per warp: same shared memory as before.
+// transpose of k_fused_sort is gone too.
+// Shared memory per warp: the input buffer + LAG staging buffers.  A tile can only be committed once the offsets of ALL
+// earlier tiles of the grid are known (the chain), about one iteration after it was posted, and here the commit of tile
+// t-LAG comes before tile t is staged: with LAG = 1 the warps wait for the chain in every iteration (config 3: 3.64 ms,
+// 2.61 ms with the scan switched off), so the host launches LAG = 2 — 13 KB per warp at config 3, 17 warps per SM where
+// the registers would allow 19 (3.11 ms).  Tried and dropped (profiles/r01_sort_async_sweeps.txt): a CTA-wide pool of
+// staging buffers shared by 19 warps (3.52 ms: the warps that find the pool empty hold back the whole CTA), tiles of 2
+// rows with 16 keys per lane and 31 warps (3.15 ms: 128 more SHFL per 1024 keys).
 __device__ __forceinline__ void cp_async16(u32 dst_s, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst_s), "l"(src));
 }
@@ -307,9 +317,9 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __host__ __device__ constexpr u32 sort_input_words(int R, int LA, int W) { return (u32)(R * LA * W); }
 
-template <int W, int LAL, int KMAX = 32>
-__global__ void __maxnreg__((sort_geom<W, LAL, KMAX>().K >= 32 ? 96 : KMAX < 32 ? 64 : 80)) k_fused_sort_async(const EllArgs p) {
-  constexpr SortGeom G = sort_geom<W, LAL, KMAX>();
+template <int W, int LAL>
+__global__ void __maxnreg__((sort_geom<W, LAL>().K >= 32 ? 96 : 80)) k_fused_sort_async(const EllArgs p) {
+  constexpr SortGeom G = sort_geom<W, LAL>();
   constexpr int LPR = G.LPR, LA = G.LA, S = G.S, NQ = G.NQ, K = G.K, RP = G.RP, R = G.R, NP = G.NP;
   constexpr u32 SWORDS = sort_stage_words(R, LA, W), IWORDS = sort_input_words(R, LA, W);
   constexpr int SH = NQ >= 8 ? 0 : NQ == 4 ? 1 : NQ == 2 ? 2 : 3;     // swz(L) = (L >> SH) & (NQ-1): 8 consecutive lanes hit 8 different 16-byte bank columns
@@ -393,8 +403,17 @@ __global__ void __maxnreg__((sort_geom<W, LAL, KMAX>().K >= 32 ? 96 : KMAX < 32 
     if (t == 0 && lane == 0) st_rowptr(p.Crow, p.is64, 0, 0, &p.sc->err);
     if (t == p.ntiles - 1 && lane == 0) p.sc->total_nnz = excl + total;
     int* dst = p.Ccol + excl;
-    u32 src = buf_s + 4u * (SORT_HDR + lane);                      // key q lives at word q + q/32: 33 words per 32 keys
-    for (u32 q = lane; q < total; q += 32, src += 132u) dst[q] = (int)lds32(src);
+    const u32 src = buf_s + 4u * (SORT_HDR + lane);                // key q lives at word q + q/32: 33 words per 32 keys
+    constexpr u32 FULL = (u32)(R * LA * W), UN = FULL / 32u < 8u ? FULL / 32u : 8u;      // loads in flight per lane
+    u32 q = 0;
+    for (; q + 32u * UN <= total; q += 32u * UN) {
+      u32 v[UN];
+#pragma unroll
+      for (u32 i = 0; i < UN; ++i) v[i] = lds32(src + 132u * (q / 32u + i));
+#pragma unroll
+      for (u32 i = 0; i < UN; ++i) dst[q + 32u * i + lane] = (int)v[i];
+    }
+    for (q += lane; q < total; q += 32u) dst[q] = (int)lds32(src + 132u * (q / 32u));
     __syncwarp();
   };
 
@@ -423,6 +442,7 @@ __global__ void __maxnreg__((sort_geom<W, LAL, KMAX>().K >= 32 ? 96 : KMAX < 32 
   while (tile < p.ntiles) {
     const u32 next = tile_of(iter + 1u);
     const int ar3 = load_rowptr(tile_of(iter + 3u));
+    const u32 buf_s = stage_s + cur_buf * (SWORDS * 4u), cur_s = buf_s + 4u * SORT_HDR;
     u32 x[NP][K];
     cp_async_wait_all();
     __syncwarp();
@@ -430,9 +450,8 @@ __global__ void __maxnreg__((sort_geom<W, LAL, KMAX>().K >= 32 ? 96 : KMAX < 32 
     for (int q = 0; q < NP; ++q) read_pass(q, x[q]);
     __syncwarp();                            // every lane has read the input buffer and the old table
     stash_jtab(j0n, j1n);                    // table of tile t+1
-    issue_tile();                            // ... and its copies, in flight during the sort
+    issue_tile();                            // ... and its copies, in flight during the sort (a tile that does not exist copies the EMPTY row)
     load_jtab(ar2, j0n, j1n);                // table of tile t+2
-    const u32 buf_s = stage_s + cur_buf * (SWORDS * 4u), cur_s = buf_s + 4u * SORT_HDR;
     u32 run = 0, incl_mine = 0;
 #pragma unroll
     for (int q = 0; q < NP; ++q) {

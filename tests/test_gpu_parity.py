@@ -329,11 +329,16 @@ def test_ell_fast_path_variants(bs, oracle, monkeypatch):
     Brow, Bcol = random_csr(rng, n, m, 2.5, sort=True, dups=False)
     cases.append(("short rows", Acol, Arow, n, Bcol, Brow, n, m))
     seen = set()
-    for kernel in ("hash", "sort"):
-        # hash: ordered-table kernel (fused_ell.cuh, variant 1); sort: register sorting network (fused_sort.cuh, variant 2)
-        monkeypatch.delenv("BSPGEMM_NO_SORT", raising=False)
-        monkeypatch.delenv("BSPGEMM_FORCE_SORT", raising=False)
+    for kernel in ("hash", "sort", "sort-sync", "sort-async"):
+        # hash: ordered-table kernel (fused_ell.cuh, variant 1); sort: register sorting network (fused_sort.cuh, variant 2),
+        # as dispatched / k_fused_sort (register prefetch) for every geometry / k_fused_sort_async (cp.async) for every geometry
+        for v in ("BSPGEMM_NO_SORT", "BSPGEMM_FORCE_SORT", "BSPGEMM_SORT_SYNC", "BSPGEMM_SORT_ASYNC"):
+            monkeypatch.delenv(v, raising=False)
         monkeypatch.setenv("BSPGEMM_NO_SORT" if kernel == "hash" else "BSPGEMM_FORCE_SORT", "1")
+        if kernel == "sort-sync":
+            monkeypatch.setenv("BSPGEMM_SORT_SYNC", "1")
+        if kernel == "sort-async":
+            monkeypatch.setenv("BSPGEMM_SORT_ASYNC", "1")
         for name, Acol, Arow, An, Bcol, Brow, Bn, Bm in cases:
             want_col, want_row = oracle.spgemm(Acol, Arow, An, Bcol, Brow, Bm)
             for i64 in (False, True):
@@ -346,7 +351,7 @@ def test_ell_fast_path_variants(bs, oracle, monkeypatch):
                     while la < np.diff(Arow).max():
                         la *= 2
                     sortable = la <= 32 and la * st["group"] <= 1024
-                    want_variant = 2 if (kernel == "sort" and sortable) else 1
+                    want_variant = 2 if (kernel != "hash" and sortable) else 1
                     assert st["variant"] == want_variant, f"{name} [{kernel}]: stats {st}"
                     seen.add((st["variant"], st["group"], st["rows_per_tile"]))
     assert {w for v, w, _ in seen if v == 1} == {4, 8, 16, 32}, seen
