@@ -17,7 +17,7 @@ from pathlib import Path
 import numpy as np
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libbspgemm.so"
+LIB_PATH = Path(os.environ["BSPGEMM_LIB"]) if os.environ.get("BSPGEMM_LIB") else _HERE / "libbspgemm.so"   # override: A/B builds of the same ABI
 HOST_LIB_PATH = _HERE / "libbspgemm_host.so"
 
 OK, ERR_CUDA, ERR_NCCL, ERR_OOM, ERR_OVERFLOW32, ERR_BADARG, ERR_NOGPU, ERR_CAPACITY, ERR_STATE = range(9)

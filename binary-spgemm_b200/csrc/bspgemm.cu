@@ -299,7 +299,7 @@ template <int W, int LAL, bool ASYNC> static int launch_sort_t(bspgemm_dev* d, i
   // ASYNC: the input buffer the cp.async copies land in + 2 staging buffers (the commit of tile t-2 comes before tile t is
   // staged, see fused_sort.cuh); nothing is kept back for L1, which the copies bypass.
   const size_t one_buf = (size_t)sort_stage_words(G.R, G.LA, W) * 4, in_buf = (size_t)sort_input_words(G.R, G.LA, W) * 4, fixed = ELL_CTA_WORDS * 4 + 64;
-  auto warp_bytes = [&](int nb) { return (ASYNC ? in_buf + (size_t)(nb - 1) * one_buf : (size_t)nb * one_buf) + 256; };   // + the next tile's <= 64 B-row ids
+  auto warp_bytes = [&](int nb) { return ASYNC ? in_buf + (size_t)(nb - 1) * one_buf : (size_t)nb * one_buf + 256; };   // sync: + the next tile's <= 64 A nonzeros
   int nbuf = ASYNC ? 3 : 2;
   if (!ASYNC) {
     const int w2 = pick_compute_warps(warp_bytes(2), fixed, max_compute, d->smem_optin);

@@ -303,7 +303,7 @@ __global__ void __maxnreg__((sort_geom<W, LAL>().K >= 32 ? 96 : 80)) k_fused_sor
 // L*NQ + (c ^ swz(L)), L = pr / NQ the consuming lane, c = pr % NQ): the copy instructions are row-coalesced (LPR lanes
 // per B row) and both the LDGSTS writes and the LDS.128 reads are bank-conflict-free, so the register -> shared -> register
 // transpose of k_fused_sort is gone too.
-// Shared memory per warp: the input buffer + LAG staging buffers.  A tile can only be committed once the offsets of ALL
+// Shared memory per warp: the input buffer + LAG staging buffers (the tile's B-row table stays in registers).  A tile can only be committed once the offsets of ALL
 // earlier tiles of the grid are known (the chain), about one iteration after it was posted, and here the commit of tile
 // t-LAG comes before tile t is staged: with LAG = 1 the warps wait for the chain in every iteration (config 3: 3.64 ms,
 // 2.61 ms with the scan switched off), so the host launches LAG = 2 — 13 KB per warp at config 3, 17 warps per SM where
@@ -327,10 +327,9 @@ __global__ void __maxnreg__((sort_geom<W, LAL>().K >= 32 ? 96 : 80)) k_fused_sor
   extern __shared__ __align__(16) u32 smem[];
   const u32 warp = threadIdx.x >> 5, lane = lane_id(), nwarps = (blockDim.x >> 5) - 1u;   // compute warps; the last warp is the chain helper
   const u32 lag = p.nbuf - 1u;                                                            // staging buffers = commit lag in tiles
-  const u32 wwords = IWORDS + lag * SWORDS + 64u;                                         // input, staging ring, B-row table of the next tile
+  const u32 wwords = IWORDS + lag * SWORDS;                                               // input buffer, staging ring
   const u32 in_s = (u32)__cvta_generic_to_shared(smem) + warp * (wwords * 4u);
   const u32 stage_s = in_s + IWORDS * 4u;
-  const u32 jtab_s = stage_s + lag * SWORDS * 4u;
   CtaChain* cc = reinterpret_cast<CtaChain*>(smem + (size_t)nwarps * wwords);
   for (u32 i = threadIdx.x; i < sizeof(CtaChain) / 4; i += blockDim.x) reinterpret_cast<u32*>(cc)[i] = 0;
   __syncthreads();                          // the only CTA-wide barrier
@@ -361,24 +360,22 @@ __global__ void __maxnreg__((sort_geom<W, LAL>().K >= 32 ? 96 : 80)) k_fused_sor
       if (row < R && slot < hi - lo) { const int j = p.Acol[lo + slot]; if (h) j1 = j; else j0 = j; }
     }
   };
-  auto stash_jtab = [&](int j0, int j1) {                          // validate, then park the table in shared memory
+  auto check_jtab = [&](int& j0, int& j1) {                        // an A column outside [0,Bn): flag it, gather nothing
     if (((u32)j0 > (u32)p.Bn) | ((u32)j1 > (u32)p.Bn)) {
       atomicOr(&p.sc->err, 1u);
       if ((u32)j0 > (u32)p.Bn) j0 = p.Bn;
       if ((u32)j1 > (u32)p.Bn) j1 = p.Bn;
     }
-    sts32(jtab_s + 4u * lane, (u32)j0);
-    sts32(jtab_s + 4u * (32u + lane), (u32)j1);
-    __syncwarp();
   };
   // copies of a whole tile: NP*NQ LDGSTS.128 per lane.  Copy u of lane l is piece gp = (u % NQ)*32 + l of pass u / NQ:
-  // part l % LPR of table entry pass*RP*LA + gp / LPR.
-  auto issue_tile = [&]() {
+  // part l % LPR of table entry e = pass*RP*LA + gp / LPR, which lane e % 32 holds in j0 (e < 32) or j1: the table never
+  // leaves the registers (one SHFL per copy; in shared memory it cost 256 bytes per warp — the 18th warp of config 3).
+  auto issue_tile = [&](int j0, int j1) {
 #pragma unroll
     for (int u = 0; u < NP * NQ; ++u) {
       const int q = u / NQ, v = u % NQ;
-      const u32 e = (u32)(q * RP * LA + v * (32 / LPR)) + lane / (u32)LPR;
-      const u32 j = lds32(jtab_s + 4u * e);
+      const int c0 = q * RP * LA + v * (32 / LPR);                 // multiple of 32/LPR: e >= 32 iff c0 >= 32
+      const u32 j = (u32)__shfl_sync(0xffffffffu, c0 >= 32 ? j1 : j0, (c0 & 31) + (int)(lane / (u32)LPR));
       const u32 L = (u32)(v * (32 / NQ)) + lane / (u32)NQ, c = lane % (u32)NQ;
       const u32 pos = (u32)(q * 32 * NQ) + L * (u32)NQ + (c ^ ((L >> SH) & (u32)(NQ - 1)));
       cp_async16(in_s + 16u * pos, &Bell4[(size_t)j * LPR + (lane % (u32)LPR)]);
@@ -403,17 +400,29 @@ __global__ void __maxnreg__((sort_geom<W, LAL>().K >= 32 ? 96 : 80)) k_fused_sor
     if (t == 0 && lane == 0) st_rowptr(p.Crow, p.is64, 0, 0, &p.sc->err);
     if (t == p.ntiles - 1 && lane == 0) p.sc->total_nnz = excl + total;
     int* dst = p.Ccol + excl;
-    const u32 src = buf_s + 4u * (SORT_HDR + lane);                // key q lives at word q + q/32: 33 words per 32 keys
-    constexpr u32 FULL = (u32)(R * LA * W), UN = FULL / 32u < 8u ? FULL / 32u : 8u;      // loads in flight per lane
-    u32 q = 0;
-    for (; q + 32u * UN <= total; q += 32u * UN) {
-      u32 v[UN];
-#pragma unroll
-      for (u32 i = 0; i < UN; ++i) v[i] = lds32(src + 132u * (q / 32u + i));
-#pragma unroll
-      for (u32 i = 0; i < UN; ++i) dst[q + 32u * i + lane] = (int)v[i];
+    // 16-byte stores: `head` keys up to the first 16-byte boundary of Ccol, then chunks of 4 keys (4 LDS.32 at the skewed
+    // staging addresses — conflict-free, the skew moves every 8th lane to the next bank — and one STG.128: a warp instruction
+    // writes 512 contiguous bytes), then the `tail` keys.  40 instead of 64 memory instructions per 1024-key tile
+    // (config 3, same box: 3.16 -> 3.11 ms).
+    const u32 head = min(total, (u32)(((16u - ((u32)(size_t)dst & 15u)) & 15u) >> 2));
+    const u32 body = (total - head) >> 2, tail = (total - head) & 3u;
+    auto key_s = [&](u32 q) { return buf_s + 4u * (SORT_HDR + q + (q >> 5)); };
+    if (lane < head) dst[lane] = (int)lds32(key_s(lane));
+    if (lane < tail) dst[head + 4u * body + lane] = (int)lds32(key_s(head + 4u * body + lane));
+    int4* dst4 = reinterpret_cast<int4*>(dst + head);
+    u32 c = lane;
+    for (; c + 32u < body; c += 64u) {
+      const u32 q0 = head + 4u * c, q1 = q0 + 128u;
+      const u32 a0 = lds32(key_s(q0)), a1 = lds32(key_s(q0 + 1u)), a2 = lds32(key_s(q0 + 2u)), a3 = lds32(key_s(q0 + 3u));
+      const u32 b0 = lds32(key_s(q1)), b1 = lds32(key_s(q1 + 1u)), b2 = lds32(key_s(q1 + 2u)), b3 = lds32(key_s(q1 + 3u));
+      dst4[c] = make_int4((int)a0, (int)a1, (int)a2, (int)a3);
+      dst4[c + 32u] = make_int4((int)b0, (int)b1, (int)b2, (int)b3);
     }
-    for (q += lane; q < total; q += 32u) dst[q] = (int)lds32(src + 132u * (q / 32u));
+    for (; c < body; c += 32u) {
+      const u32 q0 = head + 4u * c;
+      const u32 a0 = lds32(key_s(q0)), a1 = lds32(key_s(q0 + 1u)), a2 = lds32(key_s(q0 + 2u)), a3 = lds32(key_s(q0 + 3u));
+      dst4[c] = make_int4((int)a0, (int)a1, (int)a2, (int)a3);
+    }
     __syncwarp();
   };
 
@@ -432,8 +441,8 @@ __global__ void __maxnreg__((sort_geom<W, LAL>().K >= 32 ? 96 : 80)) k_fused_sor
   {
     int j0, j1;
     load_jtab(load_rowptr(tile), j0, j1);
-    stash_jtab(j0, j1);
-    issue_tile();
+    check_jtab(j0, j1);
+    issue_tile(j0, j1);
     load_jtab(load_rowptr(tile_of(1)), j0n, j1n);
     ar2 = load_rowptr(tile_of(2));
   }
@@ -448,9 +457,9 @@ __global__ void __maxnreg__((sort_geom<W, LAL>().K >= 32 ? 96 : 80)) k_fused_sor
     __syncwarp();
 #pragma unroll
     for (int q = 0; q < NP; ++q) read_pass(q, x[q]);
-    __syncwarp();                            // every lane has read the input buffer and the old table
-    stash_jtab(j0n, j1n);                    // table of tile t+1
-    issue_tile();                            // ... and its copies, in flight during the sort (a tile that does not exist copies the EMPTY row)
+    __syncwarp();                            // every lane has read the input buffer
+    check_jtab(j0n, j1n);                    // table of tile t+1
+    issue_tile(j0n, j1n);                    // ... and its copies, in flight during the sort (a tile that does not exist copies the EMPTY row)
     load_jtab(ar2, j0n, j1n);                // table of tile t+2
     u32 run = 0, incl_mine = 0;
 #pragma unroll
