@@ -32,9 +32,10 @@ ABI_SYMBOLS = [
     "bspgemm_SpGEMM_mpi", "bspgemm_SpGEMM_omp", "bspgemm_SpGEMM_bigslice",
     "bspgemm_dev_create", "bspgemm_dev_destroy", "bspgemm_dev_set_mode",
     "bspgemm_dev_multiply", "bspgemm_dev_get_stats",
+    "bspgemm_coo2csc", "bspgemm_coo2csc_dev",
 ]
 HOST_SYMBOLS = [
-    "readCOO", "readCOO_status", "coo2csc", "tictoc", "bs_time_stats",
+    "readCOO", "readCOO_status", "readCOO_convert", "coo2csc", "tictoc", "bs_time_stats",
     "bs_gen_uniform", "bs_gen_rmat", "bs_gen_banded", "bs_gen_blockdiag", "bs_write_mtx",
     "mm_read_banner", "mm_read_mtx_crd_size", "mm_write_banner", "mm_write_mtx_crd_size",
     "mm_is_valid", "mm_typecode_to_str",
@@ -107,6 +108,8 @@ def lib() -> C.CDLL:
                                            C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64,
                                            C.c_void_p, C.c_int, C.POINTER(C.c_void_p), _I64P]
         L.bspgemm_dev_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        L.bspgemm_coo2csc.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
+        L.bspgemm_coo2csc_dev.argtypes = [C.c_void_p] + L.bspgemm_coo2csc.argtypes
         _lib = L
     return _lib
 
@@ -169,6 +172,19 @@ def readCOO(path: str):
     return _take(row, N.value + 1, np.uint32), _take(col, nnz.value, np.uint32), M.value, N.value, nnz.value
 
 
+def readCOO_gpu(path: str):
+    """readCOO_convert with bspgemm_coo2csc: the host tokenizer, then the stable sort on the GPU."""
+    H, L = host(), lib()
+    row, col = _U32P(), _U32P()
+    M, N, nnz = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    H.readCOO_convert.argtypes = [C.c_char_p, C.POINTER(_U32P), C.POINTER(_U32P), _U32P, _U32P, _U32P, C.c_void_p]
+    rc = H.readCOO_convert(os.fsencode(path), C.byref(row), C.byref(col), C.byref(M), C.byref(N), C.byref(nnz),
+                           C.cast(L.bspgemm_coo2csc, C.c_void_p))
+    if rc != 0:
+        raise OSError(f"readCOO_convert({path!r}) failed with status {rc}: {L.bspgemm_last_error().decode()}")
+    return _take(row, N.value + 1, np.uint32), _take(col, nnz.value, np.uint32), M.value, N.value, nnz.value
+
+
 def coo2csc(row_coo, col_coo, n: int, is_one_based: int = 0):
     """coo2csc (final/coo2csc.c:22-64): returns (row_indices[nnz], col_pointers[n+1])."""
     H = host()
@@ -177,6 +193,18 @@ def coo2csc(row_coo, col_coo, n: int, is_one_based: int = 0):
     out_row = np.empty(max(len(r), 1), dtype=np.uint32)
     out_col = np.empty(n + 1, dtype=np.uint32)
     H.coo2csc(out_row.ctypes.data, out_col.ctypes.data, r.ctypes.data, c.ctypes.data, len(r), n, is_one_based)
+    return out_row[: len(r)], out_col
+
+
+def coo2csc_gpu(row_coo, col_coo, n: int, is_one_based: int = 0):
+    """bspgemm_coo2csc: the same conversion on the current CUDA device (stable radix sort, csrc/coo2csc.cuh)."""
+    L = lib()
+    r = np.ascontiguousarray(row_coo, dtype=np.uint32)
+    c = np.ascontiguousarray(col_coo, dtype=np.uint32)
+    out_row = np.empty(max(len(r), 1), dtype=np.uint32)
+    out_col = np.empty(n + 1, dtype=np.uint32)
+    _check(L.bspgemm_coo2csc(out_row.ctypes.data, out_col.ctypes.data, r.ctypes.data, c.ctypes.data, len(r), n, is_one_based),
+           "bspgemm_coo2csc")
     return out_row[: len(r)], out_col
 
 

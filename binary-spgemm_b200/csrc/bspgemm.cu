@@ -12,6 +12,7 @@
 #include "rows_window.cuh"
 #include "rows_sort.cuh"
 #include "band.cuh"
+#include "coo2csc.cuh"
 
 #include <nccl.h>      // types only; the library itself is dlopen'ed so libbspgemm.so loads without it
 #include <dlfcn.h>
@@ -1046,4 +1047,97 @@ extern "C" void bspgemm_SpGEMM_bigslice(int* Acol, int* Arow, int An, int* Bcol,
   die_on(bspgemm_csr_slice(Acol, Arow, An, Bcol, Brow, derive_bn(Acol, Arow + start_row, end_row - start_row), Bm, &fresh, Crow, start_row, end_row), "SpGEMM_bigslice");
   if (Ccol) { free(*Ccol); *Ccol = fresh; } else free(fresh);
   if (Csize) *Csize = Crow[end_row - start_row];
+}
+
+// ------------------------------------------------------------------------------------------------ COO -> CSC on the device
+// Replaces final/coo2csc.c:22-64 (see coo2csc.cuh).  Works on the current device, needs no bspgemm_init.
+namespace {
+struct C2cTemps {
+  u32 *keys[2] = {nullptr, nullptr}, *vals[2] = {nullptr, nullptr}, *hist = nullptr, *cnt = nullptr;
+  int* pos = nullptr; u64* status = nullptr; DevScalars* sc = nullptr;
+  ~C2cTemps() { for (void* q : {(void*)keys[0], (void*)keys[1], (void*)vals[0], (void*)vals[1], (void*)hist, (void*)cnt, (void*)pos, (void*)status, (void*)sc}) if (q) cudaFree(q); }
+};
+static int c2c_scan(const u32* in, size_t len, int* out, C2cTemps& t, cudaStream_t st) {      // out[0..len]: exclusive prefix, out[len] = total
+  const u32 ntiles = (u32)((len + (size_t)SCAN_THREADS * SCAN_ITEMS - 1) / ((size_t)SCAN_THREADS * SCAN_ITEMS));
+  CK(cudaMemsetAsync(t.status, 0, (size_t)ntiles * sizeof(u64), st));
+  CK(cudaMemsetAsync(t.sc, 0, sizeof(DevScalars), st));
+  if (ntiles == 0) { CK(cudaMemsetAsync(out, 0, sizeof(int), st)); return BSPGEMM_OK; }
+  k_scan<<<ntiles, SCAN_THREADS, 0, st>>>(in, (int)len, out, 0, t.status, t.sc, ntiles);
+  CK(cudaGetLastError());
+  return BSPGEMM_OK;
+}
+}  // namespace
+
+extern "C" int bspgemm_coo2csc_dev(void* stream, uint32_t* d_row, uint32_t* d_col, const uint32_t* d_row_coo, const uint32_t* d_col_coo,
+                                   uint32_t nnz, uint32_t n, uint32_t isOneBased) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(BSPGEMM_ERR_NOGPU, "no CUDA device"); }
+  if (!d_col || (nnz && (!d_row || !d_row_coo || !d_col_coo))) return fail(BSPGEMM_ERR_BADARG, "coo2csc: null pointer");
+  if (nnz > 0x7fffffffu || n > 0x7ffffff0u || isOneBased > 1u) return fail(BSPGEMM_ERR_BADARG, "coo2csc: nnz and n must be below 2^31, isOneBased 0 or 1");
+  cudaStream_t st = (cudaStream_t)stream;
+  C2cTemps t;
+  const u32 nblocks = (u32)(((size_t)nnz + C2C_CHUNK - 1) / C2C_CHUNK);
+  const size_t hlen = (size_t)256 * nblocks, slen = std::max<size_t>(hlen, (size_t)n);
+  if (hlen > 0x7fffffffull) return fail(BSPGEMM_ERR_BADARG, "coo2csc: too many entries");
+  const size_t stiles = (slen + (size_t)SCAN_THREADS * SCAN_ITEMS - 1) / ((size_t)SCAN_THREADS * SCAN_ITEMS) + 1;
+  CK(cudaMalloc((void**)&t.cnt, ((size_t)n + 1) * sizeof(u32)));
+  CK(cudaMalloc((void**)&t.status, stiles * sizeof(u64)));
+  CK(cudaMalloc((void**)&t.sc, sizeof(DevScalars)));
+  // pointer array: per-column counts, then their scan straight into col[0..n]
+  CK(cudaMemsetAsync(t.cnt, 0, ((size_t)n + 1) * sizeof(u32), st));
+  CK(cudaMemsetAsync(t.sc, 0, sizeof(DevScalars), st));
+  u32* d_err = &t.sc->err;
+  if (nnz) {
+    k_c2c_count<<<(int)std::min<size_t>(((size_t)nnz + 255) / 256, 148 * 16), 256, 0, st>>>(d_col_coo, nnz, n, isOneBased, t.cnt, d_err);
+    CK(cudaGetLastError());
+    u32 h_err = 0;
+    CK(cudaMemcpyAsync(&h_err, d_err, sizeof(u32), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (h_err) return fail(BSPGEMM_ERR_BADARG, "coo2csc: a column index lies outside [0,n) (the reference's behaviour is undefined there)");
+  }
+  CKS(c2c_scan(t.cnt, n, (int*)d_col, t, st));
+  if (nnz == 0) { CK(cudaStreamSynchronize(st)); return BSPGEMM_OK; }
+  // stable LSD radix sort of (col_coo, row_coo) by the key's low `bits` bits
+  int bits = 1; while (bits < 32 && (1ull << bits) < (unsigned long long)n) ++bits;
+  const int passes = (bits + 7) / 8;
+  CK(cudaMalloc((void**)&t.hist, hlen * sizeof(u32)));
+  CK(cudaMalloc((void**)&t.pos, (hlen + 1) * sizeof(int)));
+  if (passes > 1) for (int i = 0; i < 2; ++i) {
+    CK(cudaMalloc((void**)&t.keys[i], (size_t)nnz * sizeof(u32)));
+    CK(cudaMalloc((void**)&t.vals[i], (size_t)nnz * sizeof(u32)));
+  }
+  const u32 *kin = d_col_coo, *vin = d_row_coo;
+  u32 base = isOneBased;
+  for (int pass = 0; pass < passes; ++pass) {
+    const bool last = pass == passes - 1;
+    u32* kout = last ? nullptr : t.keys[pass & 1];
+    u32* vout = last ? d_row : t.vals[pass & 1];
+    k_c2c_hist<<<nblocks, 32 * C2C_WARPS, 0, st>>>(kin, nnz, base, 8 * pass, t.hist, nblocks);
+    CK(cudaGetLastError());
+    CKS(c2c_scan(t.hist, hlen, t.pos, t, st));
+    k_c2c_scatter<<<nblocks, 32 * C2C_WARPS, 0, st>>>(kin, vin, nnz, base, base, 8 * pass, t.pos, nblocks, kout, vout);
+    CK(cudaGetLastError());
+    kin = kout; vin = vout; base = 0;
+  }
+  CK(cudaStreamSynchronize(st));
+  return BSPGEMM_OK;
+}
+
+extern "C" int bspgemm_coo2csc(uint32_t* row, uint32_t* col, const uint32_t* row_coo, const uint32_t* col_coo,
+                               uint32_t nnz, uint32_t n, uint32_t isOneBased) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(BSPGEMM_ERR_NOGPU, "no CUDA device"); }
+  if (!col || (nnz && (!row || !row_coo || !col_coo))) return fail(BSPGEMM_ERR_BADARG, "coo2csc: null pointer");
+  struct Bufs { u32 *I = nullptr, *J = nullptr, *r = nullptr, *c = nullptr; ~Bufs() { for (u32* q : {I, J, r, c}) if (q) cudaFree(q); } } b;
+  const size_t eb = std::max<size_t>(1, nnz) * sizeof(u32);
+  CK(cudaMalloc((void**)&b.I, eb)); CK(cudaMalloc((void**)&b.J, eb)); CK(cudaMalloc((void**)&b.r, eb));
+  CK(cudaMalloc((void**)&b.c, ((size_t)n + 1) * sizeof(u32)));
+  if (nnz) {
+    CK(cudaMemcpy(b.I, row_coo, (size_t)nnz * sizeof(u32), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(b.J, col_coo, (size_t)nnz * sizeof(u32), cudaMemcpyHostToDevice));
+  }
+  CKS(bspgemm_coo2csc_dev(nullptr, b.r, b.c, b.I, b.J, nnz, n, isOneBased));
+  if (nnz) CK(cudaMemcpy(row, b.r, (size_t)nnz * sizeof(u32), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(col, b.c, ((size_t)n + 1) * sizeof(u32), cudaMemcpyDeviceToHost));
+  return BSPGEMM_OK;
 }

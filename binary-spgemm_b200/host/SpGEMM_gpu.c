@@ -8,7 +8,8 @@
  *   tasks,threads,tasks*threads,block,path,An,Annz,Cnnz,mean,median,fastest        (:336)
  * "tasks" is the number of GPUs (BSPGEMM_GPUS, default 1 — stands in for `mpirun -n`); block_size and
  * threads are echoed for CSV compatibility (they only shape the CPU slices in the reference, :77).
- * A second line with GPU-side metrics goes to stderr so stdout stays byte-compatible. */
+ * A second line with GPU-side metrics goes to stderr so stdout stays byte-compatible.
+ * BSPGEMM_GPU_COO2CSC=1: the reader's COO -> CSC step runs on the GPU too (readCOO_convert + bspgemm_coo2csc). */
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -30,7 +31,12 @@ int main(int argc, char const *argv[])
     const int numtasks = bspgemm_num_gpus();
 
     uint32_t *Arow, *Acol, M, N, Annz;
-    readCOO(argv[1], &Arow, &Acol, &M, &N, &Annz);
+    if (getenv("BSPGEMM_GPU_COO2CSC")) {          /* tokenizer on the host, COO -> CSC on the GPU (bspgemm_coo2csc) */
+        int rc = readCOO_convert(argv[1], &Arow, &Acol, &M, &N, &Annz, bspgemm_coo2csc);
+        if (rc) { fprintf(stderr, "SpGEMM_gpu: cannot read %s (status %d): %s\n", argv[1], rc, bspgemm_last_error()); exit(1); }
+    } else {
+        readCOO(argv[1], &Arow, &Acol, &M, &N, &Annz);
+    }
     const int An = (int)N;                       /* pointers are indexed by the file's column (transpose-on-read) */
     if (M != N) { fprintf(stderr, "SpGEMM_gpu: C = A*A needs a square matrix (%u x %u)\n", M, N); exit(1); }
 

@@ -28,7 +28,7 @@ static inline void skip_token(const char **pp, const char *end)
     *pp = p;
 }
 
-int readCOO_status(const char *mat, uint32_t **row, uint32_t **col, uint32_t *M, uint32_t *N, uint32_t *nnz)
+int readCOO_convert(const char *mat, uint32_t **row, uint32_t **col, uint32_t *M, uint32_t *N, uint32_t *nnz, bs_coo2csc_fn convert)
 {
     MM_typecode code;
     int m = 0, n = 0, nz = 0, rc = 0;
@@ -71,9 +71,19 @@ int readCOO_status(const char *mat, uint32_t **row, uint32_t **col, uint32_t *M,
     *row = (uint32_t *)malloc(((size_t)n + 1) * sizeof(uint32_t));
     *col = (uint32_t *)malloc(((size_t)nz + 1) * sizeof(uint32_t));
     if (!*row || !*col) { free(I); free(J); return MM_COULD_NOT_READ_FILE; }
-    coo2csc(*col, *row, I, J, (uint32_t)nz, (uint32_t)n, 0);
+    if (convert) {                                     /* e.g. bspgemm_coo2csc: the same stable sort on the GPU */
+        if (convert(*col, *row, I, J, (uint32_t)nz, (uint32_t)n, 0) != 0) rc = MM_UNSUPPORTED_TYPE;
+    } else {
+        coo2csc(*col, *row, I, J, (uint32_t)nz, (uint32_t)n, 0);
+    }
     free(I); free(J);
-    return 0;
+    if (rc) { free(*row); free(*col); *row = *col = NULL; }
+    return rc;
+}
+
+int readCOO_status(const char *mat, uint32_t **row, uint32_t **col, uint32_t *M, uint32_t *N, uint32_t *nnz)
+{
+    return readCOO_convert(mat, row, col, M, N, nnz, NULL);
 }
 
 void readCOO(const char *mat, uint32_t **row, uint32_t **col, uint32_t *M, uint32_t *N, uint32_t *nnz)

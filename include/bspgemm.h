@@ -131,6 +131,16 @@ int bspgemm_dev_multiply(bspgemm_dev *h, void *stream,
                          int **dCcol_out, int64_t *nnz_out);
 int bspgemm_dev_get_stats(bspgemm_dev *h, bspgemm_stats *out);
 
+/* ---- COO -> CSC/CSR on the device.  Replaces coo2csc (final/coo2csc.c:22-64, final/coo2csc.h:5-13): same
+ * argument list and the same result — col[0..n] pointers by `col_coo`, row[] = the `row_coo` values of each column in INPUT
+ * ORDER (stable), indices made 0-based — plus a status.  A key outside [0,n) is BSPGEMM_ERR_BADARG (undefined behaviour in the
+ * reference).  nnz, n < 2^31.  Runs on the current CUDA device, no bspgemm_init needed; the _dev form takes device pointers
+ * (row_coo/col_coo are not modified) and returns after the stream has been synchronised. */
+int bspgemm_coo2csc(uint32_t *row, uint32_t *col, const uint32_t *row_coo, const uint32_t *col_coo,
+                    uint32_t nnz, uint32_t n, uint32_t isOneBased);
+int bspgemm_coo2csc_dev(void *stream, uint32_t *d_row, uint32_t *d_col, const uint32_t *d_row_coo, const uint32_t *d_col_coo,
+                        uint32_t nnz, uint32_t n, uint32_t isOneBased);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,6 +29,11 @@ extern "C" {
 void readCOO(const char *mat, uint32_t **row, uint32_t **col, uint32_t *M, uint32_t *N, uint32_t *nnz);
 /* Same, returning a status instead of exiting (0 = ok). */
 int readCOO_status(const char *mat, uint32_t **row, uint32_t **col, uint32_t *M, uint32_t *N, uint32_t *nnz);
+/* Same, with the COO -> CSC step done by `convert` (coo2csc's argument list, 0 = ok; NULL = the host coo2csc below).
+ * libbspgemm.so's bspgemm_coo2csc (include/bspgemm.h) fits: parse on the host, sort on the GPU. */
+typedef int (*bs_coo2csc_fn)(uint32_t *row, uint32_t *col, const uint32_t *row_coo, const uint32_t *col_coo,
+                             uint32_t nnz, uint32_t n, uint32_t isOneBased);
+int readCOO_convert(const char *mat, uint32_t **row, uint32_t **col, uint32_t *M, uint32_t *N, uint32_t *nnz, bs_coo2csc_fn convert);
 
 /* Stable counting sort of COO entries by col_coo (final/coo2csc.c:22-64).  `row`: nnz indices out,
  * `col`: n+1 pointers out.  Same parameter order and meaning as the reference. */

@@ -47,6 +47,9 @@ def test_no_cpu_fallback_without_gpu(bs):
     assert e.value.status == bs.ERR_NOGPU
     with pytest.raises(bs.BSpGEMMError):
         bs.DeviceSpGEMM(0)
+    with pytest.raises(bs.BSpGEMMError) as e:
+        bs.coo2csc_gpu([0, 1], [1, 0], 2, 0)          # the GPU converter does not fall back to the host coo2csc either
+    assert e.value.status == bs.ERR_NOGPU
 
 
 def test_product_does_not_link_oracle(bs):

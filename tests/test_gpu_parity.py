@@ -520,3 +520,44 @@ def test_band_kernel_falls_back_when_a_row_is_not_a_run(bs, oracle):
     msg = _explain(got_col, got_row, want_col, want_row)
     assert not msg, msg
     assert st["variant"] != 3
+
+
+def test_gpu_coo2csc_is_the_stable_counting_sort(bs, oracle):
+    """bspgemm_coo2csc (csrc/coo2csc.cuh) against the host coo2csc and the oracle's restatement of
+    final/coo2csc.c:22-64: identical pointers, identical (stable: input order inside a column) index array.  Unsorted entries,
+    repeated coordinates, both index bases, n from one radix pass (<= 256) to three, ragged tails of the 4096-entry chunks."""
+    rng = np.random.default_rng(77)
+    cases = [(1, 0), (1, 1), (7, 50), (200, 5000), (256, 4096), (257, 4097), (5000, 123457), (1 << 16, 300001),
+             ((1 << 20) + 3, 2_000_003), (1 << 22, 6_000_000)]
+    for n, nnz in cases:
+        for one in (0, 1):
+            I = rng.integers(0, n, nnz, dtype=np.uint32) + one
+            J = rng.integers(0, n, nnz, dtype=np.uint32) + one
+            if nnz > 10:                                   # a heavy column and exact duplicates
+                J[rng.integers(0, nnz, nnz // 7)] = J[0]
+                I[1], J[1] = I[0], J[0]
+            want_row, want_col = bs.coo2csc(I, J, n, one)
+            got_row, got_col = bs.coo2csc_gpu(I, J, n, one)
+            assert (got_col == want_col).all(), (n, nnz, one)
+            assert (got_row == want_row).all(), (n, nnz, one)
+            if nnz <= 200000:
+                o_row, o_col = oracle.coo2csc(I, J, n, one)
+                assert (got_col == o_col).all() and (got_row == o_row).all(), (n, nnz, one)
+    # a key outside [0,n) is an error, not a silent drop or an out-of-bounds write
+    with pytest.raises(bs.BSpGEMMError) as e:
+        bs.coo2csc_gpu(np.array([0, 1], np.uint32), np.array([0, 9], np.uint32), 4, 0)
+    assert e.value.status == bs.ERR_BADARG
+
+
+def test_gpu_coo2csc_feeds_the_product(bs, oracle, tmp_path):
+    """Matrix Market text -> host tokenizer -> GPU coo2csc (readCOO_convert + bspgemm_coo2csc) gives the arrays readCOO
+    gives, and the GPU product of them matches the oracle."""
+    row, col = bs.gen_uniform(3000, 6, 9)
+    path = tmp_path / "m.mtx"
+    bs.write_mtx(str(path), row, col)
+    want = bs.readCOO(str(path))
+    got = bs.readCOO_gpu(str(path))
+    assert got[2:] == want[2:]
+    assert (got[0] == want[0]).all() and (got[1] == want[1]).all()
+    Arow, Acol, N = got[0].astype(np.int32), got[1].astype(np.int32), got[3]
+    check(bs, oracle, Acol, Arow, N, Acol, Arow, N, N)
