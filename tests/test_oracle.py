@@ -97,3 +97,23 @@ def test_oracle_readCOO_matches_reference(oracle, ref, tmp_path):
         pytest.skip("fixture copy not present")
     a, b = oracle.readCOO(fx), ref.readCOO(fx)
     assert (a[0] == b[0]).all() and (a[1] == b[1]).all() and a[2:] == b[2:]
+
+
+def test_reference_runs_with_several_tasks_through_the_shm_mpi_shim():
+    """oracle/mpi_shm/mpi.h: the unmodified reference drivers with 4 forked tasks — the reference's own
+    `make test` command line (mpirun -n 4 … validity_test.mtx 6250 2, final/Makefile:11-12) — agree with their serial run, and
+    the performance driver's CSV line carries tasks=4 and the fixture's sizes (50000, 25000 -> 12502)."""
+    import os
+    import subprocess
+    from pathlib import Path
+    ref = Path(__file__).resolve().parents[1] / "oracle" / "_ref"
+    if not (ref / "SpGEMM_mpi_omp_validity_shm").exists():
+        pytest.skip("oracle/_ref/*_shm not built (make -C oracle ref)")
+    env = dict(os.environ, MPI_SHIM_TASKS="4", OMP_NUM_THREADS="2")
+    out = subprocess.run([str(ref / "SpGEMM_mpi_omp_validity_shm"), "validity_test.mtx", "6250", "2"], cwd=ref, env=env,
+                         capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "Results of serial and multricore are the same!" in out.stdout, out.stdout + out.stderr
+    out = subprocess.run([str(ref / "SpGEMM_mpi_omp_shm"), "validity_test.mtx", "6250", "2", "2"], cwd=ref, env=env,
+                         capture_output=True, text=True, timeout=120)
+    f = out.stdout.strip().split(",")
+    assert out.returncode == 0 and f[:4] == ["4", "2", "8", "6250"] and f[5:8] == ["50000", "25000", "12502"], out.stdout + out.stderr
