@@ -381,7 +381,7 @@ static int launch_ell(bspgemm_dev* d) {
   const int W = d->ell_W, R = d->ell_R;
   CKS(d->bell.ensure(((size_t)a.m.Bn + 1) * W + 4));
   {
-    const long long threads = ((long long)a.m.Bn + 1) * (W / 4);
+    const long long threads = (((long long)a.m.Bn + ELL_RPT) / ELL_RPT) * (W / 4);     // ELL_RPT rows per thread
     const int grid = (int)((threads + 255) / 256);
 #define BE(Wv) do { if (d->use_sort) k_build_ell<Wv, true><<<grid, 256, 0, d->stream>>>(a.m.Brow, a.m.Bcol, a.m.Bn, (u32)a.m.Bm, d->bell.p, d->d_sc); \
                     else k_build_ell<Wv, false><<<grid, 256, 0, d->stream>>>(a.m.Brow, a.m.Bcol, a.m.Bn, (u32)a.m.Bm, d->bell.p, d->d_sc); } while (0)

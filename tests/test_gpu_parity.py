@@ -561,3 +561,29 @@ def test_gpu_coo2csc_feeds_the_product(bs, oracle, tmp_path):
     assert (got[0] == want[0]).all() and (got[1] == want[1]).all()
     Arow, Acol, N = got[0].astype(np.int32), got[1].astype(np.int32), got[3]
     check(bs, oracle, Acol, Arow, N, Acol, Arow, N, N)
+
+
+@pytest.mark.parametrize("kernel", ["BSPGEMM_SORT_ASYNC", "BSPGEMM_SORT_SYNC"])
+def test_sort_kernels_on_tiny_and_ragged_shapes(bs, oracle, monkeypatch, kernel):
+    """Both sorting-network kernels (fused_sort.cuh) where the tile pipeline has nothing to chew on: fewer rows than one tile,
+    fewer tiles than warps, a last tile that is cut short, empty A rows, rectangular B."""
+    monkeypatch.setenv("BSPGEMM_FORCE_ELL", "1")
+    monkeypatch.setenv("BSPGEMM_FORCE_SORT", "1")
+    monkeypatch.setenv(kernel, "1")
+    rng = np.random.default_rng(91)
+    for An, Bn, Bm, da, db in ((1, 40, 1000, 16, 16), (3, 64, 1 << 20, 16, 16), (5, 300, 70000, 12, 14), (17, 1000, 1 << 22, 16, 16),
+                               (149, 500, 5000, 7, 6), (2663, 4000, 1 << 21, 16, 16), (4099, 9000, 123457, 30, 30)):
+        Arow, Acol = random_csr(rng, An, Bn, float(da), sort=False, dups=True)
+        Brow, Bcol = random_csr(rng, Bn, Bm, float(db), sort=False, dups=False)
+        if np.diff(Brow).max() > 32 or np.diff(Arow).max() > 32:
+            keep_b = np.minimum(np.diff(Brow), 32)
+            Bcol = np.concatenate([Bcol[Brow[i]:Brow[i] + keep_b[i]] for i in range(Bn)]).astype(np.int32)
+            Brow = np.concatenate([[0], np.cumsum(keep_b)]).astype(np.int32)
+            keep_a = np.minimum(np.diff(Arow), 32)
+            Acol = np.concatenate([Acol[Arow[i]:Arow[i] + keep_a[i]] for i in range(An)]).astype(np.int32)
+            Arow = np.concatenate([[0], np.cumsum(keep_a)]).astype(np.int32)
+        want_col, want_row = oracle.spgemm(Acol, Arow, An, Bcol, Brow, Bm)
+        for i64 in (False, True):
+            got_col, got_row, st = dev_multiply(bs, bs.MODE_AUTO, Acol, Arow, An, Bcol, Brow, Bn, Bm, i64=i64)
+            msg = _explain(got_col, got_row, want_col, want_row)
+            assert not msg, f"An={An} Bn={Bn} Bm={Bm} [{kernel}] i64={i64} variant={st['variant']}: {msg}"
