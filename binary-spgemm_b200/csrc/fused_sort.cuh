@@ -53,6 +53,33 @@ template <int W, int LAL> __host__ __device__ constexpr SortGeom sort_geom() {
 constexpr u32 SORT_HDR = 20;             // per staging buffer: [0] total, [1] tile, [2..2+R) inclusive row counts
 __host__ __device__ constexpr u32 sort_stage_words(int R, int LA, int W) { const u32 n = (u32)(R * LA * W); return (SORT_HDR + n + n / 32u + 4u + 3u) & ~3u; }
 
+// Staged keys (key q at word q + q/32 after the SORT_HDR header words: 33 words per 32 keys) -> dst[0..total), whole warp.
+// 16-byte stores: `head` keys up to the first 16-byte boundary of dst, then chunks of 4 keys (4 LDS.32 at the skewed staging
+// addresses — conflict-free, the skew moves every 8th lane to the next bank — and one STG.128: a warp instruction writes 512
+// contiguous bytes), then the `tail` keys: 40 instead of 64 memory instructions per 1024-key tile (config 3, same box: 3.16 -> 3.11 ms).
+__device__ __forceinline__ void commit_keys(int* dst, const u32 buf_s, const u32 total) {
+  const u32 lane = lane_id();
+  const u32 head = min(total, (u32)(((16u - ((u32)(size_t)dst & 15u)) & 15u) >> 2));
+  const u32 body = (total - head) >> 2, tail = (total - head) & 3u;
+  auto key_s = [&](u32 q) { return buf_s + 4u * (SORT_HDR + q + (q >> 5)); };
+  if (lane < head) dst[lane] = (int)lds32(key_s(lane));
+  if (lane < tail) dst[head + 4u * body + lane] = (int)lds32(key_s(head + 4u * body + lane));
+  int4* dst4 = reinterpret_cast<int4*>(dst + head);
+  u32 c = lane;
+  for (; c + 32u < body; c += 64u) {
+    const u32 q0 = head + 4u * c, q1 = q0 + 128u;
+    const u32 a0 = lds32(key_s(q0)), a1 = lds32(key_s(q0 + 1u)), a2 = lds32(key_s(q0 + 2u)), a3 = lds32(key_s(q0 + 3u));
+    const u32 b0 = lds32(key_s(q1)), b1 = lds32(key_s(q1 + 1u)), b2 = lds32(key_s(q1 + 2u)), b3 = lds32(key_s(q1 + 3u));
+    dst4[c] = make_int4((int)a0, (int)a1, (int)a2, (int)a3);
+    dst4[c + 32u] = make_int4((int)b0, (int)b1, (int)b2, (int)b3);
+  }
+  for (; c < body; c += 32u) {
+    const u32 q0 = head + 4u * c;
+    const u32 a0 = lds32(key_s(q0)), a1 = lds32(key_s(q0 + 1u)), a2 = lds32(key_s(q0 + 2u)), a3 = lds32(key_s(q0 + 3u));
+    dst4[c] = make_int4((int)a0, (int)a1, (int)a2, (int)a3);
+  }
+}
+
 // (bitonic_sort_rows, the register sorting network, lives in kernels.cuh: the warp-per-row kernels use it too)
 
 // Every warp is an independent worker on tiles of R consecutive rows.  Per iteration (tile t):
@@ -179,7 +206,7 @@ __global__ void __maxnreg__((sort_geom<W, LAL>().K >= 32 ? 96 : 80)) k_fused_sor
     if (t == p.ntiles - 1 && lane == 0) p.sc->total_nnz = excl + total;
     int* dst = p.Ccol + excl;
     u32 src = buf_s + 4u * (SORT_HDR + lane);                      // key q lives at word q + q/32: 33 words per 32 keys
-    for (u32 q = lane; q < total; q += 32, src += 132u) dst[q] = (int)lds32(src);
+    for (u32 q = lane; q < total; q += 32, src += 132u) dst[q] = (int)lds32(src);   // (commit_keys' 16-byte stores: 0.214 vs 0.210 ms at config 2)
     __syncwarp();
   };
 
@@ -400,29 +427,7 @@ __global__ void __maxnreg__((sort_geom<W, LAL>().K >= 32 ? 96 : 80)) k_fused_sor
     if (t == 0 && lane == 0) st_rowptr(p.Crow, p.is64, 0, 0, &p.sc->err);
     if (t == p.ntiles - 1 && lane == 0) p.sc->total_nnz = excl + total;
     int* dst = p.Ccol + excl;
-    // 16-byte stores: `head` keys up to the first 16-byte boundary of Ccol, then chunks of 4 keys (4 LDS.32 at the skewed
-    // staging addresses — conflict-free, the skew moves every 8th lane to the next bank — and one STG.128: a warp instruction
-    // writes 512 contiguous bytes), then the `tail` keys.  40 instead of 64 memory instructions per 1024-key tile
-    // (config 3, same box: 3.16 -> 3.11 ms).
-    const u32 head = min(total, (u32)(((16u - ((u32)(size_t)dst & 15u)) & 15u) >> 2));
-    const u32 body = (total - head) >> 2, tail = (total - head) & 3u;
-    auto key_s = [&](u32 q) { return buf_s + 4u * (SORT_HDR + q + (q >> 5)); };
-    if (lane < head) dst[lane] = (int)lds32(key_s(lane));
-    if (lane < tail) dst[head + 4u * body + lane] = (int)lds32(key_s(head + 4u * body + lane));
-    int4* dst4 = reinterpret_cast<int4*>(dst + head);
-    u32 c = lane;
-    for (; c + 32u < body; c += 64u) {
-      const u32 q0 = head + 4u * c, q1 = q0 + 128u;
-      const u32 a0 = lds32(key_s(q0)), a1 = lds32(key_s(q0 + 1u)), a2 = lds32(key_s(q0 + 2u)), a3 = lds32(key_s(q0 + 3u));
-      const u32 b0 = lds32(key_s(q1)), b1 = lds32(key_s(q1 + 1u)), b2 = lds32(key_s(q1 + 2u)), b3 = lds32(key_s(q1 + 3u));
-      dst4[c] = make_int4((int)a0, (int)a1, (int)a2, (int)a3);
-      dst4[c + 32u] = make_int4((int)b0, (int)b1, (int)b2, (int)b3);
-    }
-    for (; c < body; c += 32u) {
-      const u32 q0 = head + 4u * c;
-      const u32 a0 = lds32(key_s(q0)), a1 = lds32(key_s(q0 + 1u)), a2 = lds32(key_s(q0 + 2u)), a3 = lds32(key_s(q0 + 3u));
-      dst4[c] = make_int4((int)a0, (int)a1, (int)a2, (int)a3);
-    }
+    commit_keys(dst, buf_s, total);
     __syncwarp();
   };
 
