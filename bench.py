@@ -364,7 +364,7 @@ def main():
     if last["mode"] != bs.MODE_FUSED:
         kernel_name = "scan + k_rows_warp<G,MODE_FILL>"
     elif last.get("variant", 0) == 2:
-        kernel_name = "k_fused_sort<W=%d> (%d rows per tile)" % (last["group"], last["rows_per_tile"])
+        kernel_name = "k_fused_sort%s<W=%d> (%d rows per tile)" % ("_async" if last.get("kernel_flags", 0) & 1 else "", last["group"], last["rows_per_tile"])
     elif last.get("variant", 0) == 3:
         kernel_name = "k_band (%d rows per tile, 128-bit register bitmap per row)" % last["rows_per_tile"]
     elif last.get("variant", 0) == 1:

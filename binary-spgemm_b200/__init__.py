@@ -57,7 +57,7 @@ class Stats(C.Structure):
         ("ms_total", C.c_float), ("ms_estimate", C.c_float), ("ms_symbolic", C.c_float),
         ("ms_main", C.c_float), ("ms_numeric", C.c_float),
         ("algorithmic_bytes", C.c_int64),
-        ("variant", C.c_int32), ("rows_per_tile", C.c_int32),
+        ("variant", C.c_int32), ("rows_per_tile", C.c_int32), ("kernel_flags", C.c_int32),
     ]
 
     def as_dict(self):

@@ -119,6 +119,7 @@ typedef struct bspgemm_stats {
                                  2 = register sorting network (fused_sort.cuh); then cap_s = table words per row, group =
                                  ELL width W, ms_symbolic = the CSR->ELL re-layout of B */
   int32_t rows_per_tile;      /* fused kernels: consecutive rows per look-back tile */
+  int32_t kernel_flags;       /* bit 0: variant 2 ran k_fused_sort_async (cp.async input) rather than k_fused_sort */
 } bspgemm_stats;
 
 int bspgemm_dev_create(bspgemm_dev **h, int device);
