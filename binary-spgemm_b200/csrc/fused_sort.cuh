@@ -320,9 +320,9 @@ __global__ void __maxnreg__((sort_geom<W, LAL>().K >= 32 ? 96 : 80)) k_fused_sor
 // (long-scoreboard stalls: 22 % of the warp time at config 3, profiles/r01_sort_cfg3_ncu_summary.txt).  Here the B rows of
 // tile t+1 are copied global -> shared memory with cp.async (LDGSTS.128, L1 bypassed, no destination registers) right
 // after tile t has been read into registers, i.e. the gather is in flight during the whole sort of tile t:
-//   iteration t:  wait for the copies of tile t; keys <- input buffer (LDS.128); park the B-row table of tile t+1; issue
-//                 the Acol loads of tile t+2 and the row pointers of tile t+3; issue the copies of tile t+1 into the (now
-//                 free) input buffer; sort; commit tile t-LAG from the staging buffer tile t is about to use; stage; post.
+//   iteration t:  wait for the copies of tile t; keys <- input buffer (LDS.128); issue the copies of tile t+1 into the (now
+//                 free) input buffer, the Acol loads of tile t+2 (its B-row table) and the row pointers of tile t+3; sort;
+//                 commit tile t-LAG from the staging buffer tile t is about to use; stage; post.
 // (Measured alternatives, profiles/r01_sort_async_sweeps.txt: committing at the top of the iteration, where no key register
 // is live, costs 9 % — the copies' DEPBAR then also waits for the commit's stores; forcing the LDGSTS into a block of their
 // own instead of letting ptxas spread them over the first half of the network changes nothing.)
@@ -330,13 +330,14 @@ __global__ void __maxnreg__((sort_geom<W, LAL>().K >= 32 ? 96 : 80)) k_fused_sor
 // L*NQ + (c ^ swz(L)), L = pr / NQ the consuming lane, c = pr % NQ): the copy instructions are row-coalesced (LPR lanes
 // per B row) and both the LDGSTS writes and the LDS.128 reads are bank-conflict-free, so the register -> shared -> register
 // transpose of k_fused_sort is gone too.
-// Shared memory per warp: the input buffer + LAG staging buffers (the tile's B-row table stays in registers).  A tile can only be committed once the offsets of ALL
-// earlier tiles of the grid are known (the chain), about one iteration after it was posted, and here the commit of tile
-// t-LAG comes before tile t is staged: with LAG = 1 the warps wait for the chain in every iteration (config 3: 3.64 ms,
-// 2.61 ms with the scan switched off), so the host launches LAG = 2 — 13 KB per warp at config 3, 17 warps per SM where
-// the registers would allow 19 (3.11 ms).  Tried and dropped (profiles/r01_sort_async_sweeps.txt): a CTA-wide pool of
-// staging buffers shared by 19 warps (3.52 ms: the warps that find the pool empty hold back the whole CTA), tiles of 2
-// rows with 16 keys per lane and 31 warps (3.15 ms: 128 more SHFL per 1024 keys).
+// Shared memory per warp: the input buffer + LAG staging buffers (the tile's B-row table stays in registers).  A tile can
+// only be committed once the offsets of ALL earlier tiles of the grid are known (the chain), about one iteration after it
+// was posted, and here the commit of tile t-LAG comes before tile t is staged: with LAG = 1 the warps wait for the chain in
+// every iteration (config 3: 3.64 ms, 2.61 ms with the scan switched off), so the host launches LAG = 2 — 12.7 KB per warp
+// at config 3, 18 warps per SM where the registers would allow 19 (3.11 ms).  Tried and dropped
+// (profiles/r01_sort_async_sweeps.txt): a CTA-wide pool of staging buffers shared by 19 warps (3.52 ms: the warps that find
+// the pool empty hold back the whole CTA), tiles of 2 rows with 16 keys per lane and 31 warps (3.15 ms: 128 more SHFL per
+// 1024 keys), the commit done by the helper warp (6.06 ms: one warp cannot copy 18 tiles per iteration).
 __device__ __forceinline__ void cp_async16(u32 dst_s, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst_s), "l"(src));
 }
