@@ -325,6 +325,7 @@ template <int W, int LAL, bool ASYNC> static int launch_sort_t(bspgemm_dev* d, i
   p.Bm = (u32)a.m.Bm; p.Crow = a.dCrow; p.is64 = a.is64; p.Ccol = ccol; p.sc = d->d_sc; p.ntiles = ntiles; p.nbuf = (u32)nbuf;
   p.debug_nochain = getenv("BSPGEMM_DEBUG_NOCHAIN") ? (u32)(G.R * G.LA * W) : 0u;   // WRONG RESULTS: timing experiments only
   d->st.rows_per_tile = G.R; d->st.variant = 2; d->st.kernel_flags = ASYNC ? 1 : 0;
+  p.one = 1u; p.mone = 0xffffffffu;
   if (getenv("BSPGEMM_VERBOSE")) {
     fprintf(stderr, "k_fused_sort%s<%d,%d>: regs %d, maxThreadsPerBlock %d, static smem %zu, launch %d x %d threads, dyn smem %zu, nbuf %d\n",
             ASYNC ? "_async" : "", W, LAL, fa.numRegs, fa.maxThreadsPerBlock, fa.sharedSizeBytes, grid, (warps + 1) * 32, smem, nbuf);

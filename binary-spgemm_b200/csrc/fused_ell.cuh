@@ -53,6 +53,7 @@ struct EllArgs {
   u32 ntiles;
   u32 nbuf;                       // sort kernel: staging buffers per warp (commit lag = nbuf - 1 tiles)
   u32 debug_nochain;              // timing experiments only (BSPGEMM_DEBUG_NOCHAIN): skip the scan, rows land at upper-bound offsets
+  u32 one, mone;                  // 1 and 0xFFFFFFFF as run-time values (IMAD-form comparators, see cmpx in kernels.cuh)
 };
 
 // Table geometry of a row with lenA nonzeros in A (cap = lenA*W >= its IP): `lim` slots, a multiple of 128 (the
@@ -71,7 +72,6 @@ constexpr u32 ELL_CTA_WORDS = 320;       // CtaChain, after the warp regions
 // ---- B (CSR) -> ELL.  LPR = W/4 lanes write one row as uint4 each; also validates B's columns.  SORTED: every ELL row
 // is sorted ascending (EMPTY padding last) by a small register network — the sorting-network kernel (fused_sort.cuh)
 // starts its merges from these runs; the reference accepts unsorted rows, so nothing may be assumed.
-template <int K, int S, int RUN> __device__ __forceinline__ void bitonic_sort_rows(u32 (&x)[K], const u32 ll);   // fused_sort.cuh
 // Every thread converts its 16-byte part of ELL_RPT rows (row, row + H, ...: H rows apart, so that a warp still reads and writes
 // contiguous spans): the Brow loads of all of them, then the Bcol loads of all of them are in flight together — with one row per
 // thread the two dependent load phases left half of the memory latency uncovered (4.1 TB/s; config 3: 0.134 ms per call).
@@ -235,7 +235,7 @@ __device__ __noinline__ void chain_helper_dyn(CtaChain* cc, u64* blk_status, u32
     const u32 blk = *reinterpret_cast<volatile u32*>(&cc->blkid[s]);
     if (blk >= nblocks) break;
     const u32 expected = min(ncompute, ntiles - blk * ncompute);
-    while (*reinterpret_cast<volatile u32*>(&cc->cnt[s]) != expected) __nanosleep(400);   // (at 100 ns this spin was 38 % of the SM's issued instructions)
+    while (*reinterpret_cast<volatile u32*>(&cc->cnt[s]) != expected) __nanosleep(400);   // (shorter sleeps here and in chain_resolve: 3.14 ms against 3.11 at config 3)
     __threadfence_block();
     const u32 w = (lane < expected) ? (*reinterpret_cast<volatile u32*>(&cc->agg[s][lane]) & CH_AGG_MASK) : 0u;
     const u32 total = __reduce_add_sync(0xffffffffu, w);

@@ -471,7 +471,9 @@ __global__ void __maxnreg__((sort_geom<W, LAL>().K >= 32 ? 96 : 80)) k_fused_sor
 #pragma unroll
     for (int q = 0; q < NP; ++q) {
       u32 (&k)[K] = x[q];
-      bitonic_sort_rows<K, S, (W < K ? W : K)>(k, ll);     // every B row is ascending in the ELL copy (k_build_ell sorts it)
+      // every B row is ascending in the ELL copy (k_build_ell sorts it); big tiles: two of three in-lane maxima on the FMA pipe
+      // (cmpx, kernels.cuh: config 3, same box, 3.115 -> 3.072 ms)
+      bitonic_sort_rows<K, S, (W < K ? W : K), (K >= 32 ? 1 : 0)>(k, ll, p.one, p.mone);
       if (q == 0 && iter >= lag) commit(iter - lag, buf_s);        // frees the staging buffer this tile is about to use
       // the row is ascending along (lane, register); EMPTY (padding) is the largest value
       u32 prev_last = __shfl_up_sync(0xffffffffu, k[K - 1], 1);

@@ -123,8 +123,24 @@ __device__ __forceinline__ u64 lookback_exclusive(u64* status, u32 tile, u64 agg
 // i <-> i ^ d; every comparator puts the minimum at the lower index, so exchanges inside a lane need no run-time
 // direction (min + max), exchanges between lanes cost SHFL + min + predicated max.
 // RUN: the keys arrive as ascending runs of RUN consecutive elements (1 = unsorted): the merge levels up to RUN are skipped.
-template <int K, int S, int RUN = 1>
-__device__ __forceinline__ void bitonic_sort_rows(u32 (&x)[K], const u32 ll) {
+// MIX = 1: two of three in-lane comparators form the maximum on the FMA pipe (hi = a + b - lo as two IMADs whose multipliers
+// `one` = 1 and `mone` = -1 are run-time values, so that ptxas cannot fold them back into an ALU-pipe IADD3): 1 ALU + 2 FMA-pipe
+// instructions instead of 2 ALU — for kernels whose limiter is the ALU pipe.
+template <int MIX>
+__device__ __forceinline__ void cmpx(u32& a, u32& b, const int c, const u32 one, const u32 mone) {
+  const u32 lo = min(a, b);
+  u32 hi;
+  if (MIX == 1 && c % 3 != 0) {
+    u32 s;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(s) : "r"(a), "r"(one), "r"(b));
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(hi) : "r"(lo), "r"(mone), "r"(s));
+  } else {
+    hi = max(a, b);
+  }
+  a = lo; b = hi;
+}
+template <int K, int S, int RUN = 1, int MIX = 0>
+__device__ __forceinline__ void bitonic_sort_rows(u32 (&x)[K], const u32 ll, const u32 one = 1u, const u32 mone = 0xffffffffu) {
   constexpr int N = K * S;
 #pragma unroll
   for (int size = 2 * RUN; size <= N; size <<= 1) {
@@ -132,7 +148,7 @@ __device__ __forceinline__ void bitonic_sort_rows(u32 (&x)[K], const u32 ll) {
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         const int pk = k ^ (size - 1);
-        if (k < pk) { const u32 lo = min(x[k], x[pk]), hi = max(x[k], x[pk]); x[k] = lo; x[pk] = hi; }
+        if (k < pk) cmpx<MIX>(x[k], x[pk], k, one, mone);
       }
     } else {                                                       // mirror across lanes: register k <-> K-1-k of lane ^ (size/K-1)
       const u32 lm = (u32)(size / K - 1);
@@ -157,8 +173,8 @@ __device__ __forceinline__ void bitonic_sort_rows(u32 (&x)[K], const u32 ll) {
         }
       } else {                                                     // both keys in this lane
 #pragma unroll
-        for (int k = 0; k < K; ++k)
-          if ((k & d) == 0) { const u32 lo = min(x[k], x[k | d]), hi = max(x[k], x[k | d]); x[k] = lo; x[k | d] = hi; }
+        for (int k = 0, c = 0; k < K; ++k)
+          if ((k & d) == 0) { cmpx<MIX>(x[k], x[k | d], c, one, mone); ++c; }
       }
     }
   }
