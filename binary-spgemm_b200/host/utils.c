@@ -1,12 +1,16 @@
 /* host/utils.c — Matrix Market reader, stopwatch, timing statistics for the drivers.
  * Interface and observable behaviour follow final/utils.c:47-113 and final/SpGEMM_mpi_omp.c:330-333;
- * the implementation is new (whole-file read + hand tokenizer instead of one fscanf per entry). */
+ * the implementation is new (whole-file read + hand tokenizer, run by all host threads when the file is one entry per line,
+ * instead of one fscanf per entry). */
 #define _POSIX_C_SOURCE 200809L
 #include "utils.h"
 #include "mmio_compat.h"
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 /* parse the next unsigned integer token; returns 0 at end of buffer, 2 on a non-numeric token */
 static inline int next_uint(const char **pp, const char *end, uint64_t *out)
@@ -26,6 +30,83 @@ static inline void skip_token(const char **pp, const char *end)
     while (p < end && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) ++p;
     while (p < end && !(*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) ++p;
     *pp = p;
+}
+
+static inline int is_ws(char c) { return c == ' ' || c == '\n' || c == '\t' || c == '\r'; }
+
+/* Parallel tokenizer for the regular case — one entry per line, `2 + extra` tokens on it, every index in range: the buffer is cut
+ * into one piece per thread at line ends, the pieces' non-blank lines are counted, a prefix sum gives every piece its first entry
+ * number, then the pieces are parsed independently.  Returns 1 when the nz entries were read; 0 when anything at all is unusual
+ * (fewer lines than entries, a short / long / non-numeric line, an index out of range): the caller then runs the sequential
+ * tokenizer, whose verdict (and error code) stays the single definition of the format. */
+static int parse_entries_parallel(const char *buf, size_t len, int nz, int m, int n, int extra, uint32_t *I, uint32_t *J)
+{
+#ifdef _OPENMP
+    int T = omp_get_max_threads();
+    if (T > 64) T = 64;
+    if (T < 4 || len < ((size_t)4 << 20)) return 0;       /* two passes over the text: pays from four threads on */
+    size_t cut[65], first[65];
+    cut[0] = 0; cut[T] = len;
+    for (int t = 1; t < T; ++t) {
+        size_t p = len / (size_t)T * (size_t)t;
+        while (p < len && buf[p] != '\n') ++p;
+        cut[t] = p < len ? p + 1 : len;
+    }
+    size_t lines[64];
+#pragma omp parallel for num_threads(T) schedule(static, 1)
+    for (int t = 0; t < T; ++t) {
+        size_t c = 0;
+        int blank = 1;
+        for (size_t p = cut[t]; p < cut[t + 1]; ++p) {
+            if (buf[p] == '\n') { c += !blank; blank = 1; }
+            else if (!is_ws(buf[p])) blank = 0;
+        }
+        c += !blank;                                  /* last line of the buffer without a newline */
+        lines[t] = c;
+    }
+    first[0] = 0;
+    for (int t = 0; t < T; ++t) first[t + 1] = first[t] + lines[t];
+    if (first[T] < (size_t)nz) return 0;
+    int odd = 0;
+#pragma omp parallel for num_threads(T) schedule(static, 1) reduction(|:odd)
+    for (int t = 0; t < T; ++t) {
+        const char *p = buf + cut[t], *end = buf + cut[t + 1];
+        size_t e = first[t];
+        while (p < end && e < (size_t)nz && !odd) {
+            const char *eol = p;
+            while (eol < end && *eol != '\n') ++eol;
+            const char *q = p;
+            while (q < eol && is_ws(*q)) ++q;
+            if (q < eol) {                             /* a non-blank line: exactly one entry */
+                uint64_t v[2];
+                for (int k = 0; k < 2; ++k) {
+                    while (q < eol && is_ws(*q)) ++q;
+                    if (q >= eol || *q < '0' || *q > '9') { odd = 1; break; }
+                    uint64_t x = 0;
+                    while (q < eol && *q >= '0' && *q <= '9') x = x * 10 + (uint64_t)(*q++ - '0');
+                    if (q < eol && !is_ws(*q)) { odd = 1; break; }
+                    v[k] = x;
+                }
+                if (odd) break;
+                for (int k = 0; k < extra; ++k) {      /* value columns: present, skipped */
+                    while (q < eol && is_ws(*q)) ++q;
+                    if (q >= eol) { odd = 1; break; }
+                    while (q < eol && !is_ws(*q)) ++q;
+                }
+                while (q < eol && is_ws(*q)) ++q;
+                if (odd || q != eol || v[0] < 1 || v[0] > (uint64_t)m || v[1] < 1 || v[1] > (uint64_t)n) { odd = 1; break; }
+                I[e] = (uint32_t)(v[0] - 1);
+                J[e] = (uint32_t)(v[1] - 1);
+                ++e;
+            }
+            p = eol < end ? eol + 1 : end;
+        }
+    }
+    return !odd;
+#else
+    (void)buf; (void)len; (void)nz; (void)m; (void)n; (void)extra; (void)I; (void)J;
+    return 0;
+#endif
 }
 
 int readCOO_convert(const char *mat, uint32_t **row, uint32_t **col, uint32_t *M, uint32_t *N, uint32_t *nnz, bs_coo2csc_fn convert)
@@ -55,7 +136,8 @@ int readCOO_convert(const char *mat, uint32_t **row, uint32_t **col, uint32_t *M
      * every stored entry is `true` (the reference reads pairs only, final/utils.c:68) */
     const int extra = mm_is_pattern(code) ? 0 : mm_is_complex(code) ? 2 : 1;
     const char *p = buf, *end = buf + got;
-    for (int e = 0; e < nz; ++e) {
+    const int fast = parse_entries_parallel(buf, got, nz, m, n, extra, I, J);     /* all threads; 0 = let the loop below decide */
+    for (int e = fast ? nz : 0; e < nz; ++e) {
         uint64_t i = 0, j = 0;
         if (next_uint(&p, end, &i) != 1 || next_uint(&p, end, &j) != 1) { rc = MM_PREMATURE_EOF; break; }
         for (int k = 0; k < extra; ++k) skip_token(&p, end);

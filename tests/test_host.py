@@ -143,3 +143,41 @@ def test_generators(bs, tmp_path):
     bs.write_mtx(str(p), row, col)
     rr, cc, M, N, nnz = bs.readCOO(str(p))
     assert (rr == row).all() and (cc == col).all()
+
+
+def test_readCOO_parallel_tokenizer_matches_the_oracle_reader(bs, oracle, tmp_path):
+    """Files above 4 MB are tokenized by all host threads (host/utils.c parse_entries_parallel) when they are one entry per
+    line; anything unusual (blank lines, two entries on a line, values) must give what the sequential tokenizer / the
+    reference's fscanf loop give.  Compared with the oracle's restatement of readCOO (final/utils.c:47-81) and, when built,
+    the compiled reference."""
+    row, col = bs.gen_uniform(1 << 16, 8, 5)
+    p = tmp_path / "big.mtx"
+    bs.write_mtx(str(p), row, col)
+    assert p.stat().st_size > (4 << 20)
+    got = bs.readCOO(str(p))
+    want = oracle.readCOO(p)
+    assert got[2:] == want[2:] and (got[0] == want[0]).all() and (got[1] == want[1]).all()
+    from oracle.oracle import Ref, have_ref
+    if have_ref():
+        ref = Ref().readCOO(p)
+        assert (got[0] == ref[0]).all() and (got[1] == ref[1]).all()
+    # the same entries in an irregular layout: CRLF, blank lines, two entries on one line -> sequential tokenizer, same arrays
+    lines = p.read_text().splitlines()
+    head = [l for l in lines if l.startswith("%")] + [next(l for l in lines if not l.startswith("%"))]
+    body = lines[len(head):]
+    odd = head + ["", body[0] + " " + body[1]] + body[2:1000] + ["   "] + [l + "\r" for l in body[1000:]]
+    q = tmp_path / "odd.mtx"
+    q.write_text("\n".join(odd) + "\n")
+    got2 = bs.readCOO(str(q))
+    assert (got2[0] == got[0]).all() and (got2[1] == got[1]).all()
+    # real-valued file above the threshold: the value column is skipped by both tokenizers
+    r = tmp_path / "real.mtx"
+    r.write_text("\n".join([head[0].replace("pattern", "real")] + head[1:] + [l + " 1.5e0" for l in body]) + "\n")
+    got3 = bs.readCOO(str(r))
+    assert (got3[0] == got[0]).all() and (got3[1] == got[1]).all()
+    # an index out of range somewhere in the middle is still an error
+    bad = list(body); bad[len(bad) // 2] = "99999999 1"
+    b = tmp_path / "bad.mtx"
+    b.write_text("\n".join(head + bad) + "\n")
+    with pytest.raises(OSError):
+        bs.readCOO(str(b))
