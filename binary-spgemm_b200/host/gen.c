@@ -155,7 +155,22 @@ int bs_write_mtx(const char *path, uint32_t n, const int32_t *row, const int32_t
     mm_write_banner(f, t);
     fprintf(f, "%% in-memory CSR row r / column c is stored as the entry (c+1, r+1): readCOO transposes on read\n");
     mm_write_mtx_crd_size(f, (int)n, (int)n, row[n]);
-    for (uint32_t r = 0; r < n; ++r)
-        for (int32_t p = row[r]; p < row[r + 1]; ++p) fprintf(f, "%d %u\n", col[p] + 1, r + 1);
-    return fclose(f) == 0 ? 0 : 1;
+    /* "c+1 r+1\n" per entry, digits produced by hand into a 1 MB chunk (fprintf: 1.9 s for 8.4e6 entries) */
+    static char out[(1 << 20) + 64];
+    size_t used = 0;
+    int ok = 1;
+    for (uint32_t r = 0; r < n && ok; ++r)
+        for (int32_t p = row[r]; p < row[r + 1]; ++p) {
+            uint32_t v[2] = { (uint32_t)col[p] + 1u, r + 1u };
+            for (int k = 0; k < 2; ++k) {
+                char tmp[12]; int len = 0;
+                uint32_t x = v[k];
+                do { tmp[len++] = (char)('0' + x % 10u); x /= 10u; } while (x);
+                while (len) out[used++] = tmp[--len];
+                out[used++] = k ? '\n' : ' ';
+            }
+            if (used >= (1u << 20)) { if (fwrite(out, 1, used, f) != used) { ok = 0; break; } used = 0; }
+        }
+    if (ok && used && fwrite(out, 1, used, f) != used) ok = 0;
+    return (fclose(f) == 0 && ok) ? 0 : 1;
 }
