@@ -5,39 +5,19 @@
 //   Global ctx  the "communicator": G DevCtx + NCCL comms (dlopen'ed) for the B broadcast
 //   C ABI       host-pointer operators (upload / shard / gather) and the device-resident operator
 // No CPU fallback anywhere: every failure is returned as a status code.
-#include "../../include/bspgemm.h"
-#include "kernels.cuh"
-#include "fused_ell.cuh"
-#include "fused_sort.cuh"
+#include "ctx.h"
+#include "fused_ell.cuh"       // ELL_CTA_WORDS, ell_table_limit (planning only: the ELL kernels are instantiated in tu_ell.cu / tu_sort_w*.cu)
 #include "rows_window.cuh"
 #include "rows_sort.cuh"
 #include "band.cuh"
 #include "coo2csc.cuh"
 
-#include <nccl.h>      // types only; the library itself is dlopen'ed so libbspgemm.so loads without it
-#include <dlfcn.h>
-#include <stdio.h>
-#include <stdlib.h>
-#include <string.h>
-#include <strings.h>
-#include <stdarg.h>
-#include <math.h>
-#include <algorithm>
-#include <vector>
-#include <mutex>
-
-using namespace bsk;
-
 // ------------------------------------------------------------------------------------------------ errors
 static thread_local char g_err[512] = "";
-static int fail(int code, const char* fmt, ...) {
+int fail(int code, const char* fmt, ...) {
   va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
   return code;
 }
-#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
-  return fail(e_ == cudaErrorMemoryAllocation ? BSPGEMM_ERR_OOM : BSPGEMM_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
-#define CKS(expr) do { int s_ = (expr); if (s_ != BSPGEMM_OK) return s_; } while (0)
-
 extern "C" const char* bspgemm_strerror(int s) {
   switch (s) {
     case BSPGEMM_OK: return "ok";
@@ -55,89 +35,22 @@ extern "C" const char* bspgemm_strerror(int s) {
 extern "C" const char* bspgemm_last_error(void) { return g_err; }
 extern "C" const char* bspgemm_version(void) { return "bspgemm-b200 0.1 (sm_100a)"; }
 
-// ------------------------------------------------------------------------------------------------ per-GPU context
-template <class T> struct DevBuf {
-  T* p = nullptr; size_t cap = 0;
-  int ensure(size_t n, bool keep = false) {           // grow-only; contents dropped unless keep
-    if (n <= cap) return BSPGEMM_OK;
-    size_t want = n + n / 16 + 64;
-    T* q = nullptr;
-    cudaError_t e = cudaMalloc((void**)&q, want * sizeof(T));
-    if (e != cudaSuccess) { want = n; e = cudaMalloc((void**)&q, want * sizeof(T)); }
-    if (e != cudaSuccess) { cudaGetLastError(); return fail(BSPGEMM_ERR_OOM, "cudaMalloc of %zu bytes failed: %s", want * sizeof(T), cudaGetErrorString(e)); }
-    if (keep && p && cap) cudaMemcpy(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice);
-    if (p) cudaFree(p);
-    p = q; cap = want;
-    return BSPGEMM_OK;
-  }
-  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-};
-
-struct MulArgs {
-  Csr m; int64_t Annz, Bnnz; void* dCrow; int is64;
-};
-
-struct bspgemm_dev {
-  int device = 0, sm_count = 0;
-  size_t smem_optin = 0;
-  cudaStream_t own_stream = nullptr, stream = nullptr;
-  int mode = BSPGEMM_MODE_AUTO;
-  // workspace
-  DevBuf<u32> ip, cnt, lists, bitmaps, bell;
-  DevBuf<u64> status;
-  DevBuf<int> ccol;                 // output arena
-  DevBuf<int> temp;                 // staging arena of the big rows (MODE_STAGE): Σ IP of the M/L rows
-  DevBuf<u64> tofs;                 // per row: offset of its staged columns in temp
-  DevScalars* d_sc = nullptr;
-  DevScalars* h_sc = nullptr;       // pinned
-  cudaEvent_t ev[8] = {};
-  // per-call state
-  MulArgs a{};
-  int phase = 0;                    // 0 idle, 1 estimate in flight, 2 main in flight, 3 fill in flight, 4 done
-  int used_mode = 0, G = 16, G_big = 16, launches = 0;   // G: lanes per B row from mean len(B); G_big: from the mean length of the SELECTED B rows (Σip / nnzA)
-  u32 cap_s = 0, cap_m1 = 0, cap_m2 = 0;
-  bool have_m = false, have_m2 = false, have_l = false;
-  bool use_band = false, no_band = false;   // run/bitmap kernel for banded matrices (band.cuh); no_band: it failed on this input, redo generally
-  bool staged = false;              // big rows went through the staging arena (one pass) in the last multiply
-  bool use_window = false;          // M/L bins: windowed shared-memory bitmap (rows_window.cuh) instead of table / global bitmap
-  u32 bm_words = 0; int l_grid = 0;
-  bool skip_estimate = false; u32 row_ip_bound = 0, max_len_b = 0;
-  bool use_ell = false; int ell_W = 0, ell_R = 0, ell_warps = 0; u32 ell_TW = 0, ell_maxA = 0, ell_lf16 = 28;
-  bool use_sort = false; int sort_LAL = 0;            // register-sort variant of the ELL path (fused_sort.cuh)   // ELL fast path plan (fused_ell.cuh)
-  u32 hist_rows[34] = {};
-  int fused_bps[4][16] = {};        // cached occupancy of k_fused<G> per log2(cap)
-  int* user_ccol = nullptr; int64_t user_cap = 0;   // caller-provided output (device) or null -> arena
-  bspgemm_stats st{};
-  // input staging for the host-pointer API
-  DevBuf<int> in_arow, in_acol, in_brow, in_bcol;
-  DevBuf<char> crow_dev;            // device row pointers for the host API
-  DevBuf<char> crow_tmp;
-};
 
 static int g_cap_s_max() { const char* e = getenv("BSPGEMM_CAP_S"); int v = e ? atoi(e) : 512; if (v < 32) v = 32; if (v > 1024) v = 1024; int p = 32; while (p < v) p <<= 1; return p; }
 static const u32 CAP_M1 = 2048, CAP_M2 = 16384;
 
-// Every kernel that uses dynamic shared memory gets the opt-in maximum once, at context creation.
+// Every kernel that uses dynamic shared memory gets the opt-in maximum once, at context creation (BSP_ATTR, ctx.h).
 static int set_kernel_attributes(int smem_optin) {
-  // dynamic + static shared memory must stay within the opt-in limit
-#define ATTR(k) do { cudaFuncAttributes fa_; CK(cudaFuncGetAttributes(&fa_, k)); \
-    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - (int)fa_.sharedSizeBytes)); } while (0)
+#define ATTR(k) BSP_ATTR(k)
 #define ATTR_G(Gv) ATTR((k_rows_warp<Gv, MODE_COUNT>)); ATTR((k_rows_warp<Gv, MODE_FILL>)); ATTR((k_fused<Gv, true>)); ATTR((k_fused<Gv, false>))
   ATTR_G(4); ATTR_G(8); ATTR_G(16); ATTR_G(32);
   ATTR((k_rows_sort<32, 512, MODE_COUNT>)); ATTR((k_rows_sort<32, 512, MODE_FILL>)); ATTR((k_rows_sort<32, 512, MODE_STAGE>));
   ATTR((k_rows_sort<8, 256, MODE_COUNT>)); ATTR((k_rows_sort<8, 256, MODE_FILL>)); ATTR((k_rows_sort<8, 256, MODE_STAGE>));
   ATTR(k_rows_window<MODE_COUNT>); ATTR(k_rows_window<MODE_FILL>); ATTR(k_rows_window<MODE_STAGE>);
-#define ATTR_E(Wv) ATTR((k_fused_ell<Wv, 1>)); ATTR((k_fused_ell<Wv, 2>)); ATTR((k_fused_ell<Wv, 4>)); ATTR((k_fused_ell<Wv, 8>))
-  ATTR_E(4); ATTR_E(8); ATTR_E(16); ATTR_E(32);
-#undef ATTR_E
-#define ATTR_S(Wv) ATTR((k_fused_sort<Wv, 2>)); ATTR((k_fused_sort<Wv, 3>)); ATTR((k_fused_sort<Wv, 4>)); \
-                   ATTR((k_fused_sort_async<Wv, 2>)); ATTR((k_fused_sort_async<Wv, 3>)); ATTR((k_fused_sort_async<Wv, 4>))
-  ATTR_S(4); ATTR_S(8); ATTR_S(16); ATTR_S(32);
-  ATTR((k_fused_sort<4, 5>)); ATTR((k_fused_sort<8, 5>)); ATTR((k_fused_sort<16, 5>)); ATTR((k_fused_sort<32, 5>));
-  ATTR((k_fused_sort_async<4, 5>)); ATTR((k_fused_sort_async<8, 5>)); ATTR((k_fused_sort_async<16, 5>)); ATTR((k_fused_sort_async<32, 5>));
-#undef ATTR_S
 #undef ATTR_G
 #undef ATTR
+  CKS(set_attrs_ell(smem_optin));
+  CKS(set_attrs_sort_w4(smem_optin)); CKS(set_attrs_sort_w8(smem_optin)); CKS(set_attrs_sort_w16(smem_optin)); CKS(set_attrs_sort_w32(smem_optin));
   return BSPGEMM_OK;
 }
 
@@ -276,78 +189,6 @@ static bool ell_plan(bspgemm_dev* d) {
   return true;
 }
 
-// Compute warps per CTA for the persistent fused kernels (one more warp, the chain helper, is added at launch).
-// Shared memory comes out of the SM's 256 KB unified array in steps (.., 164, 196, 228 KB); what is left is L1, which
-// the gathers of B want: stay one step below the maximum unless that costs more than a fifth of the warps.
-static int pick_compute_warps(size_t per_warp, size_t fixed, int max_warps, size_t optin) {
-  auto fit = [&](size_t cap) { return cap > fixed ? (int)std::min<size_t>((size_t)max_warps, (cap - fixed) / per_warp) : 0; };
-  const int w_max = fit(optin), w_step = fit(196 * 1024 - 1024);
-  int w = (w_step * 5 >= w_max * 4) ? w_step : w_max;
-  if (const char* e = getenv("BSPGEMM_WARPS")) w = std::max(1, std::min(w_max, atoi(e)));   // tuning knob
-  return w;
-}
-
-template <int W, int LAL, bool ASYNC> static int launch_sort_t(bspgemm_dev* d, int* ccol) {
-  const MulArgs& a = d->a;
-  constexpr SortGeom G = sort_geom<W, LAL>();
-  const u32 ntiles = (u32)(((size_t)a.m.An + G.R - 1) / G.R);
-  // warps per CTA: what the kernel's register count allows (registers are allocated per SM sub-partition: 80 -> 6 warps
-  // each, 81..102 -> 5), one of them the chain helper
-  auto kern = ASYNC ? k_fused_sort_async<W, LAL> : k_fused_sort<W, LAL>;
-  cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, kern));
-  const int max_compute = std::max(1, std::min(SORT_MAX_WARPS, fa.maxThreadsPerBlock / 32) - 1);
-  // staging buffers per warp: 2 = commit one tile later; small tiles get 3 (commit lag 2) as long as that costs no warps.
-  // ASYNC: the input buffer the cp.async copies land in + 2 staging buffers (the commit of tile t-2 comes before tile t is
-  // staged, see fused_sort.cuh); nothing is kept back for L1, which the copies bypass.
-  const size_t one_buf = (size_t)sort_stage_words(G.R, G.LA, W) * 4, in_buf = (size_t)sort_input_words(G.R, G.LA, W) * 4, fixed = ELL_CTA_WORDS * 4 + 64;
-  auto warp_bytes = [&](int nb) { return ASYNC ? in_buf + (size_t)(nb - 1) * one_buf : (size_t)nb * one_buf + 256; };   // sync: + the next tile's <= 64 A nonzeros
-  int nbuf = ASYNC ? 3 : 2;
-  if (!ASYNC) {
-    const int w2 = pick_compute_warps(warp_bytes(2), fixed, max_compute, d->smem_optin);
-    while (nbuf < 3 && pick_compute_warps(warp_bytes(nbuf + 1), fixed, max_compute, d->smem_optin) >= w2) ++nbuf;
-  }
-  if (const char* e = getenv("BSPGEMM_NBUF")) nbuf = std::max(2, std::min(4, atoi(e)));   // tuning knob
-  const size_t per_warp = warp_bytes(nbuf);
-  int warps = pick_compute_warps(per_warp, fixed, max_compute, d->smem_optin);
-  if (ASYNC && !getenv("BSPGEMM_WARPS")) warps = (int)std::min<size_t>((size_t)max_compute, (d->smem_optin - fixed) / per_warp);
-  if (warps < 1) return fail(BSPGEMM_ERR_CUDA, "sort kernel does not fit on an SM");
-  const size_t smem = per_warp * warps + ELL_CTA_WORDS * 4;
-  const long long want = ((long long)ntiles + warps - 1) / warps;
-  const int grid = (int)std::max<long long>(1, std::min<long long>(want, d->sm_count));
-  const size_t niter = ((size_t)ntiles + (size_t)grid * warps - 1) / ((size_t)grid * warps);
-  const size_t nblocks = niter * grid + 1;
-  CKS(d->status.ensure(nblocks));
-  CK(cudaMemsetAsync(d->status.p, 0, nblocks * sizeof(u64), d->stream));
-  CK(cudaEventRecord(d->ev[3], d->stream));
-  EllArgs p{};
-  p.blk_status = d->status.p;
-  p.Arow = a.m.Arow; p.Acol = a.m.Acol; p.Bell = d->bell.p; p.An = a.m.An; p.Bn = a.m.Bn;
-  p.Bm = (u32)a.m.Bm; p.Crow = a.dCrow; p.is64 = a.is64; p.Ccol = ccol; p.sc = d->d_sc; p.ntiles = ntiles; p.nbuf = (u32)nbuf;
-  p.debug_nochain = getenv("BSPGEMM_DEBUG_NOCHAIN") ? (u32)(G.R * G.LA * W) : 0u;   // WRONG RESULTS: timing experiments only
-  d->st.rows_per_tile = G.R; d->st.variant = 2; d->st.kernel_flags = ASYNC ? 1 : 0;
-  p.one = 1u; p.mone = 0xffffffffu;
-  if (getenv("BSPGEMM_VERBOSE")) {
-    fprintf(stderr, "k_fused_sort%s<%d,%d>: regs %d, maxThreadsPerBlock %d, static smem %zu, launch %d x %d threads, dyn smem %zu, nbuf %d\n",
-            ASYNC ? "_async" : "", W, LAL, fa.numRegs, fa.maxThreadsPerBlock, fa.sharedSizeBytes, grid, (warps + 1) * 32, smem, nbuf);
-  }
-  kern<<<grid, (warps + 1) * 32, smem, d->stream>>>(p);        // + the chain helper warp
-  d->launches++;
-  CK(cudaGetLastError());
-  return BSPGEMM_OK;
-}
-static int launch_sort(bspgemm_dev* d, int* ccol) {
-  const int W = d->ell_W, L = d->sort_LAL;
-  // Big tiles (32 keys per lane, one pass per tile: config 3) take the cp.async kernel, the others the register-prefetch
-  // one (config 2: 0.205 ms against 0.24 ms).  BSPGEMM_SORT_SYNC / BSPGEMM_SORT_ASYNC force one of them (A/B runs, tests).
-  const bool force_sync = getenv("BSPGEMM_SORT_SYNC") != nullptr, force_async = getenv("BSPGEMM_SORT_ASYNC") != nullptr;
-#define LS1(Wv, Lv) do { constexpr SortGeom g_ = sort_geom<Wv, Lv>(); \
-    return (force_async || (!force_sync && g_.K == 32 && g_.NP == 1)) ? launch_sort_t<Wv, Lv, true>(d, ccol) : launch_sort_t<Wv, Lv, false>(d, ccol); } while (0)
-#define LS(Wv) do { switch (L) { case 2: LS1(Wv, 2); case 3: LS1(Wv, 3); case 4: LS1(Wv, 4); default: LS1(Wv, 5); } } while (0)
-  switch (W) { case 4: LS(4); case 8: LS(8); case 16: LS(16); default: LS(32); }
-#undef LS
-#undef LS1
-}
-
 // Banded / block-diagonal fast path (band.cuh): B rows become (first, len) descriptors, output rows 128-bit bitmaps.
 static int launch_band(bspgemm_dev* d) {
   const MulArgs& a = d->a;
@@ -371,51 +212,6 @@ static int launch_band(bspgemm_dev* d) {
   p.Arow = a.m.Arow; p.Acol = a.m.Acol; p.desc = desc; p.An = a.m.An; p.Bn = a.m.Bn;
   p.Crow = a.dCrow; p.is64 = a.is64; p.Ccol = ccol; p.status = d->status.p; p.sc = d->d_sc; p.ntiles = ntiles;
   k_band<<<grid, BAND_THREADS, 0, d->stream>>>(p);
-  d->launches++;
-  CK(cudaGetLastError());
-  return BSPGEMM_OK;
-}
-
-static int launch_ell(bspgemm_dev* d) {
-  const MulArgs& a = d->a;
-  int* ccol = d->user_ccol ? d->user_ccol : d->ccol.p;
-  const int W = d->ell_W, R = d->ell_R;
-  CKS(d->bell.ensure(((size_t)a.m.Bn + 1) * W + 4));
-  {
-    const long long threads = (((long long)a.m.Bn + ELL_RPT) / ELL_RPT) * (W / 4);     // ELL_RPT rows per thread
-    const int grid = (int)((threads + 255) / 256);
-#define BE(Wv) do { if (d->use_sort) k_build_ell<Wv, true><<<grid, 256, 0, d->stream>>>(a.m.Brow, a.m.Bcol, a.m.Bn, (u32)a.m.Bm, d->bell.p, d->d_sc); \
-                    else k_build_ell<Wv, false><<<grid, 256, 0, d->stream>>>(a.m.Brow, a.m.Bcol, a.m.Bn, (u32)a.m.Bm, d->bell.p, d->d_sc); } while (0)
-    switch (W) { case 4: BE(4); break; case 8: BE(8); break; case 16: BE(16); break; default: BE(32); break; }
-#undef BE
-    d->launches++;
-    CK(cudaGetLastError());
-  }
-  if (d->use_sort) return launch_sort(d, ccol);
-  const u32 ntiles = (u32)(((size_t)a.m.An + R - 1) / R);
-  const int warps = d->ell_warps;
-  const u32 SW = (u32)R * d->ell_maxA * (u32)W;
-  const size_t smem = ((size_t)ell_warp_words(R, d->ell_TW, SW) * warps + ELL_CTA_WORDS) * 4;
-  const long long want = ((long long)ntiles + warps - 1) / warps;
-  const int grid = (int)std::max<long long>(1, std::min<long long>(want, d->sm_count));
-  const size_t niter = ((size_t)ntiles + (size_t)grid * warps - 1) / ((size_t)grid * warps);
-  const size_t nblocks = niter * grid + 1;
-  CKS(d->status.ensure(nblocks));
-  CK(cudaMemsetAsync(d->status.p, 0, nblocks * sizeof(u64), d->stream));
-  CK(cudaEventRecord(d->ev[3], d->stream));
-  EllArgs p{};
-  p.blk_status = d->status.p;
-  p.Arow = a.m.Arow; p.Acol = a.m.Acol; p.Bell = d->bell.p; p.An = a.m.An; p.Bn = a.m.Bn;
-  { const double inv = 4294967296.0 / (double)a.m.Bm * (1.0 - 1.0 / 1048576.0); float f = (float)inv; if ((double)f > inv) f = nextafterf(f, 0.0f); p.inv_bm = f; }
-  p.SW = SW; p.lf16 = d->ell_lf16;
-  p.TW = d->ell_TW; p.Bm = (u32)a.m.Bm; p.Crow = a.dCrow; p.is64 = a.is64; p.Ccol = ccol; p.sc = d->d_sc;
-  p.ntiles = ntiles;
-  p.debug_nochain = getenv("BSPGEMM_DEBUG_NOCHAIN") ? (u32)(R * d->ell_maxA * W) : 0u;   // WRONG RESULTS: timing experiments only
-#define LE(Wv, Rv) k_fused_ell<Wv, Rv><<<grid, (warps + 1) * 32, smem, d->stream>>>(p)   /* + the chain helper warp */
-#define LER(Wv) do { switch (R) { case 1: LE(Wv, 1); break; case 2: LE(Wv, 2); break; case 4: LE(Wv, 4); break; default: LE(Wv, 8); break; } } while (0)
-  switch (W) { case 4: LER(4); break; case 8: LER(8); break; case 16: LER(16); break; default: LER(32); break; }
-#undef LER
-#undef LE
   d->launches++;
   CK(cudaGetLastError());
   return BSPGEMM_OK;
@@ -778,7 +574,10 @@ extern "C" int bspgemm_dev_multiply(bspgemm_dev* h, void* stream,
                                     void* dCrow, int crow_is_i64, int** dCcol_out, int64_t* nnz_out) {
   if (!h || !dArow || !dBrow || !dCrow || An < 0 || Bn < 0 || Bm < 0 || Annz < 0 || Bnnz < 0) return fail(BSPGEMM_ERR_BADARG, "null pointer or negative size");
   if ((Annz > 0 && !dAcol) || (Bnnz > 0 && !dBcol)) return fail(BSPGEMM_ERR_BADARG, "null column array");
-  h->stream = stream ? (cudaStream_t)stream : h->own_stream;
+  // NULL is the CUDA legacy default stream (what torch's default stream reports): the launches are then ordered after the
+  // caller's earlier work on it (the kernels that produced dArow/dAcol, the fill of dCrow); the handle's private
+  // non-blocking stream is only used by the host-pointer operators, which own their buffers.
+  h->stream = stream ? (cudaStream_t)stream : cudaStreamLegacy;
   h->a.m = Csr{dArow, dAcol, dBrow, dBcol, An, Bn, Bm};
   h->a.Annz = Annz; h->a.Bnnz = Bnnz; h->a.dCrow = dCrow; h->a.is64 = crow_is_i64 ? 1 : 0;
   h->user_ccol = nullptr; h->user_cap = 0;
@@ -809,8 +608,9 @@ static std::mutex g_mu;
 
 static int nccl_load(Nccl& n) {
   // NCCL prints its version line to stdout at NCCL_DEBUG=VERSION (set on some boxes): the drivers' stdout is the CSV line
-  const char* dbg = getenv("NCCL_DEBUG");
-  if (!dbg || !strcasecmp(dbg, "VERSION")) setenv("NCCL_DEBUG", "WARN", 1);
+  // (WARN still prints it: levels are NONE < VERSION < WARN < INFO).  Whatever level the environment asks for, NCCL's own
+  // messages go to stderr unless the caller chose a file.
+  if (!getenv("NCCL_DEBUG_FILE")) setenv("NCCL_DEBUG_FILE", "/dev/stderr", 1);
   const char* names[] = {"libnccl.so.2", "libnccl.so"};
   for (const char* nm : names) { n.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (n.lib) break; }
   if (!n.lib) return fail(BSPGEMM_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
@@ -837,9 +637,17 @@ static int init_devices_locked(const int* devices, int ngpus) {
     g.devs.push_back(d);
   }
   if (ngpus > 1) {
-    CKS(nccl_load(g.nccl));
-    g.comms.resize(ngpus);
-    NK(g.nccl.CommInitAll(g.comms.data(), ngpus, ids.data()));
+    int s = nccl_load(g.nccl);
+    if (s == BSPGEMM_OK) {
+      g.comms.assign(ngpus, nullptr);
+      const ncclResult_t r = g.nccl.CommInitAll(g.comms.data(), ngpus, ids.data());
+      if (r != ncclSuccess) s = fail(BSPGEMM_ERR_NCCL, "ncclCommInitAll failed: %s", g.nccl.GetErrorString ? g.nccl.GetErrorString(r) : "?");
+    }
+    if (s != BSPGEMM_OK) {            // nothing half-built stays behind: a later bspgemm_init(1) starts from scratch
+      for (auto* x : g.devs) dev_destroy(x);
+      g.devs.clear(); g.comms.clear();
+      return s;
+    }
   }
   g.inited = true;
   return BSPGEMM_OK;
@@ -876,8 +684,10 @@ static int host_multiply(const int* Acol, const int* Arow, int An, const int* Bc
                          int** Ccol_malloc, int* Ccol_buf, int64_t capacity, void* Crow, int is64, int64_t* nnz_out, int ng_limit) {
   if (!Arow || !Brow || !Crow || An < 0 || Bn < 0 || Bm < 0) return fail(BSPGEMM_ERR_BADARG, "null pointer or negative size");
   CKS(ensure_init());
-  int ng = std::min<int>((int)g.devs.size(), ng_limit);
-  if (An < ng) ng = std::max(1, An);
+  // Every GPU of the communicator takes part (a collective on a subset of its ranks never completes): with fewer rows than
+  // GPUs the surplus shards are empty — they join the broadcast of B and skip the product.  ng_limit == 1 (slice form) runs
+  // on GPU 0 alone and issues no collective.
+  const int ng = std::min<int>((int)g.devs.size(), ng_limit);
   const int64_t a_base = Arow[0], Annz = (int64_t)Arow[An] - a_base;
   const int64_t b_base = Brow[0], Bnnz = (int64_t)Brow[Bn] - b_base;
   if (Annz < 0 || Bnnz < 0 || b_base != 0) return fail(BSPGEMM_ERR_BADARG, "row pointers not monotone / Brow[0] != 0");

@@ -52,9 +52,16 @@ struct EllArgs {
   DevScalars* sc;
   u32 ntiles;
   u32 nbuf;                       // sort kernel: staging buffers per warp (commit lag = nbuf - 1 tiles)
-  u32 debug_nochain;              // timing experiments only (BSPGEMM_DEBUG_NOCHAIN): skip the scan, rows land at upper-bound offsets
+  u32 debug_nochain;              // timing experiments only, builds with -DBSPGEMM_DEBUG_KNOBS (env BSPGEMM_DEBUG_NOCHAIN): skip the scan, rows land at upper-bound offsets
   u32 one, mone;                  // 1 and 0xFFFFFFFF as run-time values (IMAD-form comparators, see cmpx in kernels.cuh)
 };
+
+// The "no chain" timing knob produces WRONG RESULTS by design; release builds compile it out (the field is ignored).
+#ifdef BSPGEMM_DEBUG_KNOBS
+#define DBG_NOCHAIN(p) ((p).debug_nochain)
+#else
+#define DBG_NOCHAIN(p) 0u
+#endif
 
 // Table geometry of a row with lenA nonzeros in A (cap = lenA*W >= its IP): `lim` slots, a multiple of 128 (the
 // compaction reads 128 slots per warp instruction); keys are mapped to the first lim-32 "home" slots, the last 32 only
@@ -68,6 +75,10 @@ __host__ __device__ constexpr u32 ell_table_limit(u32 lenA, u32 W, u32 lf16 = 28
 }
 __host__ __device__ constexpr u32 ell_warp_words(u32 R, u32 TW, u32 SW) { return R * TW + SW + 2u * ELL_QCAP + 4u * 8u; }
 constexpr u32 ELL_CTA_WORDS = 320;       // CtaChain, after the warp regions
+
+// An entry loaded from Acol must lie in [0,Bn): Bn itself is the internal "no row" sentinel of absent slots, so a stored Bn (or
+// anything beyond) becomes 0xFFFFFFFF here, which the `> Bn` test of the kernels flags as BSPGEMM_ERR_BADARG like k_estimate does.
+__device__ __forceinline__ int acol_checked(int j, int Bn) { return (u32)j < (u32)Bn ? j : -1; }
 
 // ---- B (CSR) -> ELL.  LPR = W/4 lanes write one row as uint4 each; also validates B's columns.  SORTED: every ELL row
 // is sorted ascending (EMPTY padding last) by a small register network — the sorting-network kernel (fused_sort.cuh)
@@ -146,7 +157,7 @@ __device__ __forceinline__ void chain_post(CtaChain* cc, u32 iter, u32 warp, u32
 
 // Flat decoupled look-back over blocks: exclusive prefix of block `blk` (whole warp, blocking).  K windows of 32
 // blocks are loaded together (one L2 round trip).
-__device__ __noinline__ u64 chain_walk(const u64* blk_status, u32 blk) {
+static __device__ __noinline__ u64 chain_walk(const u64* blk_status, u32 blk) {
   constexpr int K = 5;
   const u32 lane = lane_id();
   u64 excl = 0;
@@ -186,7 +197,7 @@ __device__ __noinline__ u64 chain_walk(const u64* blk_status, u32 blk) {
 // iteration i, every warp has finished iteration i-1, i.e. committed iteration i-1-lag: that slot is reset.  Warps may
 // by then have posted up to iteration i+lag (they need base(i-1), already published), so the ring must hold
 // iterations i-lag .. i+lag plus the one being reset: CH_RING >= 2*lag + 2.
-__device__ __noinline__ void chain_helper(CtaChain* cc, u64* blk_status, u32 ntiles, u32 stride, u32 cta_first, u32 ncompute, u32 lag) {
+static __device__ __noinline__ void chain_helper(CtaChain* cc, u64* blk_status, u32 ntiles, u32 stride, u32 cta_first, u32 ncompute, u32 lag) {
   const u32 lane = lane_id();
   for (u32 iter = 0;; ++iter) {
     const unsigned long long first_tile = (unsigned long long)iter * stride + cta_first;
@@ -217,7 +228,7 @@ __device__ __noinline__ void chain_helper(CtaChain* cc, u64* blk_status, u32 nti
 // (the static deal made every CTA process the same number of blocks: the kernel ran at the pace of the slowest SM and
 // the warps of the others spent 9 % of their time waiting for offsets, profiles/r01_sort_cfg3_static_blocks.txt) then
 // simply takes fewer blocks.  Ids are consecutive in time, so neighbours in the chain still run at the same time.
-__device__ __noinline__ void chain_helper_dyn(CtaChain* cc, u64* blk_status, u32* counter, u32 ntiles, u32 ncompute, u32 lag) {
+static __device__ __noinline__ void chain_helper_dyn(CtaChain* cc, u64* blk_status, u32* counter, u32 ntiles, u32 ncompute, u32 lag) {
   const u32 lane = lane_id();
   const u32 nblocks = (ntiles + ncompute - 1u) / ncompute;
   auto claim = [&](u32 it) {
@@ -297,7 +308,7 @@ __device__ __forceinline__ void sts128(u32 saddr, u32 a, u32 b, u32 c, u32 d) {
 // Queue entry: (key, y) with y = next slot (shared byte address, 18 bits) | (lim/128) << 18 | row << 24.
 // Re-insert the queued losers [lo,hi) in rounds of 32 (one entry per lane, every lane walks its collision chain).
 // Returns (rows whose table spilled past its limit) << 16 | (#keys that found an EMPTY slot).
-__device__ __noinline__ u32 ell_drain(u32 tab_s, u32 queue_s, u32 lo, u32 hi, u32 TW) {
+static __device__ __noinline__ u32 ell_drain(u32 tab_s, u32 queue_s, u32 lo, u32 hi, u32 TW) {
   u32 ovf = 0, added = 0;
   __syncwarp();
   for (u32 i = lo + lane_id(); i < hi; i += 32) {
@@ -343,7 +354,7 @@ __device__ __noinline__ void ell_rebuild_row(const int* __restrict__ Acol, const
   __syncwarp();
 }
 
-__device__ __noinline__ u32 ell_count_table(const u32* tabr, u32 lim) {     // occupied slots (after a rebuild)
+static __device__ __noinline__ u32 ell_count_table(const u32* tabr, u32 lim) {     // occupied slots (after a rebuild)
   u32 c = 0;
   for (u32 q = lane_id(); q < lim; q += 32) c += (tabr[q] != EMPTY) ? 1u : 0u;
   return __reduce_add_sync(0xffffffffu, c);
@@ -375,7 +386,7 @@ __global__ void __launch_bounds__(ELL_MAX_WARPS * 32, 1) k_fused_ell(const EllAr
   for (u32 i = threadIdx.x; i < sizeof(CtaChain) / 4; i += blockDim.x) reinterpret_cast<u32*>(cc)[i] = 0;
   __syncthreads();                          // the only CTA-wide barrier
   if (warp == nwarps) {
-    if (!p.debug_nochain) chain_helper(cc, p.blk_status, p.ntiles, gridDim.x * nwarps, blockIdx.x * nwarps, nwarps, 1u);
+    if (!DBG_NOCHAIN(p)) chain_helper(cc, p.blk_status, p.ntiles, gridDim.x * nwarps, blockIdx.x * nwarps, nwarps, 1u);
     return;
   }
   const u32 sub = lane / LPR, part = lane % LPR;
@@ -398,8 +409,8 @@ __global__ void __launch_bounds__(ELL_MAX_WARPS * 32, 1) k_fused_ell(const EllAr
   };
   auto load_acol = [&](int abase, int e0, int E, int& j0, int& j1) {      // absent entries select the all-EMPTY row Bn
     j0 = p.Bn; j1 = p.Bn;
-    if (e0 + (int)lane < E) j0 = p.Acol[abase + e0 + (int)lane];
-    if (e0 + 32 + (int)lane < E) j1 = p.Acol[abase + e0 + 32 + (int)lane];
+    if (e0 + (int)lane < E) j0 = acol_checked(p.Acol[abase + e0 + (int)lane], p.Bn);
+    if (e0 + 32 + (int)lane < E) j1 = acol_checked(p.Acol[abase + e0 + 32 + (int)lane], p.Bn);
   };
   auto check_acol = [&](int& j0, int& j1) {
     if (((u32)j0 > (u32)p.Bn) | ((u32)j1 > (u32)p.Bn)) {
@@ -418,7 +429,7 @@ __global__ void __launch_bounds__(ELL_MAX_WARPS * 32, 1) k_fused_ell(const EllAr
   };
   // commit of a finished tile: its rows are in stage[0..total), lane r holds the inclusive count of row r
   auto commit = [&](u32 t, u32 iter, u32 incl_mine, u32 total) {
-    const u64 excl = p.debug_nochain ? (u64)t * (u64)p.debug_nochain : chain_resolve(cc, iter, warp);
+    const u64 excl = DBG_NOCHAIN(p) ? (u64)t * (u64)DBG_NOCHAIN(p) : chain_resolve(cc, iter, warp);
     const long long row0 = (long long)t * R;
     const int nrows = (int)min((long long)R, (long long)p.An - row0);
     if ((int)lane < nrows) st_rowptr(p.Crow, p.is64, (size_t)(row0 + lane) + 1, excl + incl_mine, &p.sc->err);
@@ -527,7 +538,7 @@ __global__ void __launch_bounds__(ELL_MAX_WARPS * 32, 1) k_fused_ell(const EllAr
       for (int r = 0; r < R; ++r) if (a[r + 1] > a[r]) agg += ell_count_table(tab + r * TW, lim[r]);
     }
     // ---- 2. publish the aggregate
-    if (!p.debug_nochain) chain_post(cc, iter, warp, agg);
+    if (!DBG_NOCHAIN(p)) chain_post(cc, iter, warp, agg);
     // ---- 3. commit the previous tile (frees the staging buffer)
     if (prev_tile != 0xffffffffu) commit(prev_tile, iter - 1u, prev_incl, prev_total);
 

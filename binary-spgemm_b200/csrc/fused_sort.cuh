@@ -103,7 +103,7 @@ __global__ void __maxnreg__((sort_geom<W, LAL>().K >= 32 ? 96 : 80)) k_fused_sor
   for (u32 i = threadIdx.x; i < sizeof(CtaChain) / 4; i += blockDim.x) reinterpret_cast<u32*>(cc)[i] = 0;
   __syncthreads();                          // the only CTA-wide barrier
   if (warp == nwarps) {
-    if (!p.debug_nochain) chain_helper_dyn(cc, p.blk_status, &p.sc->tile_counter, p.ntiles, nwarps, p.nbuf - 1u);
+    if (!DBG_NOCHAIN(p)) chain_helper_dyn(cc, p.blk_status, &p.sc->tile_counter, p.ntiles, nwarps, p.nbuf - 1u);
     return;
   }
   const u32 ll = lane % S, seg = lane / S;  // lane within its row, row within the pass
@@ -121,8 +121,8 @@ __global__ void __maxnreg__((sort_geom<W, LAL>().K >= 32 ? 96 : 80)) k_fused_sor
   auto load_acol = [&](int ar, int& j0, int& j1) {                 // the tile's A nonzeros (<= 64), absent ones select row Bn
     const int a0 = __shfl_sync(0xffffffffu, ar, 0), E = __shfl_sync(0xffffffffu, ar, R) - a0;
     j0 = p.Bn; j1 = p.Bn;
-    if ((int)lane < E) j0 = p.Acol[a0 + (int)lane];
-    if (32 + (int)lane < E) j1 = p.Acol[a0 + 32 + (int)lane];
+    if ((int)lane < E) j0 = acol_checked(p.Acol[a0 + (int)lane], p.Bn);
+    if (32 + (int)lane < E) j1 = acol_checked(p.Acol[a0 + 32 + (int)lane], p.Bn);
   };
   auto stash_acol = [&](int j0, int j1) {                          // validate, then park them in shared memory (frees the registers)
     if (((u32)j0 > (u32)p.Bn) | ((u32)j1 > (u32)p.Bn)) {
@@ -198,7 +198,7 @@ __global__ void __maxnreg__((sort_geom<W, LAL>().K >= 32 ? 96 : 80)) k_fused_sor
   auto commit = [&](u32 iter, u32 buf_s) {
     const u32 total = lds32(buf_s), t = lds32(buf_s + 4u);
     const u32 incl_mine = lds32(buf_s + 8u + 4u * min(lane, (u32)R - 1u));
-    const u64 excl = p.debug_nochain ? (u64)t * (u64)p.debug_nochain : chain_resolve(cc, iter, warp);
+    const u64 excl = DBG_NOCHAIN(p) ? (u64)t * (u64)DBG_NOCHAIN(p) : chain_resolve(cc, iter, warp);
     const long long row0 = (long long)t * R;
     const int nrows = (int)min((long long)R, (long long)p.An - row0);
     if ((int)lane < nrows) st_rowptr(p.Crow, p.is64, (size_t)(row0 + lane) + 1, excl + incl_mine, &p.sc->err);
@@ -214,7 +214,7 @@ __global__ void __maxnreg__((sort_geom<W, LAL>().K >= 32 ? 96 : 80)) k_fused_sor
   // tile of this warp in the CTA's iteration `it`: block ids come from the chain helper (dynamic deal, see chain_helper_dyn)
   const u32 nblocks = (p.ntiles + nwarps - 1u) / nwarps;
   auto tile_of = [&](u32 it) -> u32 {
-    if (p.debug_nochain) { const unsigned long long t = (unsigned long long)it * stride + cta_first + warp; return t < p.ntiles ? (u32)t : 0xffffffffu; }
+    if (DBG_NOCHAIN(p)) { const unsigned long long t = (unsigned long long)it * stride + cta_first + warp; return t < p.ntiles ? (u32)t : 0xffffffffu; }
     const u32 blk = chain_block_of(cc, it);
     if (blk >= nblocks) return 0xffffffffu;
     const u32 t = blk * nwarps + warp;
@@ -299,7 +299,7 @@ __global__ void __maxnreg__((sort_geom<W, LAL>().K >= 32 ? 96 : 80)) k_fused_sor
     if (lane == 0) sts64(buf_s, run, tile);
     if (lane < (u32)R) sts32(buf_s + 8u + 4u * lane, incl_mine);
     __syncwarp();
-    if (!p.debug_nochain) chain_post(cc, iter, warp, run);
+    if (!DBG_NOCHAIN(p)) chain_post(cc, iter, warp, run);
     // commit the tile staged nbuf-1 iterations ago: its buffer is the next one of the ring
     cur_buf = (cur_buf + 1u == nbuf) ? 0u : cur_buf + 1u;
     if (iter + 1u >= nbuf) commit(iter + 1u - nbuf, stage_s + cur_buf * (SWORDS * 4u));
@@ -362,7 +362,7 @@ __global__ void __maxnreg__((sort_geom<W, LAL>().K >= 32 ? 96 : 80)) k_fused_sor
   for (u32 i = threadIdx.x; i < sizeof(CtaChain) / 4; i += blockDim.x) reinterpret_cast<u32*>(cc)[i] = 0;
   __syncthreads();                          // the only CTA-wide barrier
   if (warp == nwarps) {
-    if (!p.debug_nochain) chain_helper_dyn(cc, p.blk_status, &p.sc->tile_counter, p.ntiles, nwarps, lag);
+    if (!DBG_NOCHAIN(p)) chain_helper_dyn(cc, p.blk_status, &p.sc->tile_counter, p.ntiles, nwarps, lag);
     return;
   }
   const u32 ll = lane % S;                  // lane within its row
@@ -385,7 +385,7 @@ __global__ void __maxnreg__((sort_geom<W, LAL>().K >= 32 ? 96 : 80)) k_fused_sor
     for (int h = 0; h < 2; ++h) {
       const int e = h * 32 + (int)lane, row = e / LA, slot = e % LA;
       const int lo = __shfl_sync(0xffffffffu, ar, row & 31), hi = __shfl_sync(0xffffffffu, ar, (row + 1) & 31);
-      if (row < R && slot < hi - lo) { const int j = p.Acol[lo + slot]; if (h) j1 = j; else j0 = j; }
+      if (row < R && slot < hi - lo) { const int j = acol_checked(p.Acol[lo + slot], p.Bn); if (h) j1 = j; else j0 = j; }
     }
   };
   auto check_jtab = [&](int& j0, int& j1) {                        // an A column outside [0,Bn): flag it, gather nothing
@@ -421,7 +421,7 @@ __global__ void __maxnreg__((sort_geom<W, LAL>().K >= 32 ? 96 : 80)) k_fused_sor
   auto commit = [&](u32 iter, u32 buf_s) {
     const u32 total = lds32(buf_s), t = lds32(buf_s + 4u);
     const u32 incl_mine = lds32(buf_s + 8u + 4u * min(lane, (u32)R - 1u));
-    const u64 excl = p.debug_nochain ? (u64)t * (u64)p.debug_nochain : chain_resolve(cc, iter, warp);
+    const u64 excl = DBG_NOCHAIN(p) ? (u64)t * (u64)DBG_NOCHAIN(p) : chain_resolve(cc, iter, warp);
     const long long row0 = (long long)t * R;
     const int nrows = (int)min((long long)R, (long long)p.An - row0);
     if ((int)lane < nrows) st_rowptr(p.Crow, p.is64, (size_t)(row0 + lane) + 1, excl + incl_mine, &p.sc->err);
@@ -435,7 +435,7 @@ __global__ void __maxnreg__((sort_geom<W, LAL>().K >= 32 ? 96 : 80)) k_fused_sor
   // tile of this warp in the CTA's iteration `it`: block ids come from the chain helper (dealt 5 iterations ahead)
   const u32 nblocks = (p.ntiles + nwarps - 1u) / nwarps;
   auto tile_of = [&](u32 it) -> u32 {
-    if (p.debug_nochain) { const unsigned long long t = (unsigned long long)it * stride + cta_first + warp; return t < p.ntiles ? (u32)t : 0xffffffffu; }
+    if (DBG_NOCHAIN(p)) { const unsigned long long t = (unsigned long long)it * stride + cta_first + warp; return t < p.ntiles ? (u32)t : 0xffffffffu; }
     const u32 blk = chain_block_of(cc, it);
     if (blk >= nblocks) return 0xffffffffu;
     const u32 t = blk * nwarps + warp;
@@ -526,7 +526,7 @@ __global__ void __maxnreg__((sort_geom<W, LAL>().K >= 32 ? 96 : 80)) k_fused_sor
     if (lane == 0) sts64(buf_s, run, tile);
     if (lane < (u32)R) sts32(buf_s + 8u + 4u * lane, incl_mine);
     __syncwarp();
-    if (!p.debug_nochain) chain_post(cc, iter, warp, run);
+    if (!DBG_NOCHAIN(p)) chain_post(cc, iter, warp, run);
     cur_buf = (cur_buf + 1u == lag) ? 0u : cur_buf + 1u;
     tile = next; ++iter;
     ar2 = ar3;

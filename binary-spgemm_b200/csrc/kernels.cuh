@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(256) k_estimate(Csr m, u32* __restrict__ ip, D
 
 // Row lists for the CTA-per-row bins (order inside a list is irrelevant).  tofs (optional): every listed row also gets
 // IP words of the staging arena (MODE_STAGE), handed out with one 64-bit atomic per warp.
-__global__ void __launch_bounds__(256) k_build_lists(const u32* __restrict__ ip, int An, u32 cap_s, u32 cap_m1, u32 cap_m2,
+static __global__ void __launch_bounds__(256) k_build_lists(const u32* __restrict__ ip, int An, u32 cap_s, u32 cap_m1, u32 cap_m2,
                                                      u32* __restrict__ list_m1, u32* __restrict__ list_m2,
                                                      u32* __restrict__ list_l, u64* __restrict__ tofs, DevScalars* sc) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(256) k_build_lists(const u32* __restrict__ ip,
 
 // MODE_STAGE epilogue: the staged rows go to their final place, Ccol[Crow[row] ..) (Crow is complete once the fused kernel
 // has run).  One CTA per listed row, grid-stride.
-__global__ void __launch_bounds__(256) k_copy_rows(const u32* __restrict__ list, const u32* __restrict__ nlist, const u32* __restrict__ cnt,
+static __global__ void __launch_bounds__(256) k_copy_rows(const u32* __restrict__ list, const u32* __restrict__ nlist, const u32* __restrict__ cnt,
                                                    const u64* __restrict__ tofs, const int* __restrict__ temp,
                                                    const void* __restrict__ Crow, int is64, int* __restrict__ Ccol) {
   const u32 n = *nlist;
@@ -332,7 +332,7 @@ __device__ __noinline__ u32 sort_dedup_staged(u32* stage, const u32 ipr, const u
 // Exact build from staged candidates stage[0..ipr): lo/hi by reduction, then
 //   narrow span (hi-lo < 32*tabw): bitmap over [lo,hi] in tab[] (emit_sorted reads it back);
 //   wide span: register sort (sort_dedup_staged): the sorted distinct row is left in stage[] (t.sorted = 1).
-__device__ __noinline__ RowTable build_staged(u32* stage, const u32 ipr, u32* tab, const u32 tabw, const u32 Bm, u32* err) {
+static __device__ __noinline__ RowTable build_staged(u32* stage, const u32 ipr, u32* tab, const u32 tabw, const u32 Bm, u32* err) {
   const u32 lane = lane_id();
   RowTable t; t.ok = 1; t.count = 0; t.span = 0; t.bitmap = 0; t.sorted = 0;
   u32 vmin = EMPTY, vmax = 0;
@@ -369,7 +369,7 @@ __device__ __noinline__ RowTable build_staged(u32* stage, const u32 ipr, u32* ta
 
 // Sorted distinct columns of a built table -> out[0..count).  Bitmap: popc/ffs per word.  Ordered table:
 // lane l owns 4*S consecutive slots (S odd -> conflict-free LDS.128), one warp scan gives its offset.
-__device__ __noinline__ void emit_sorted(const u32* tab, const RowTable t, u32* out) {
+static __device__ __noinline__ void emit_sorted(const u32* tab, const RowTable t, u32* out) {
   const u32 lane = lane_id();
   if (t.bitmap) {
     u32 cnt = 0;
@@ -685,7 +685,7 @@ __global__ void __launch_bounds__(1024, 1) k_fused(Csr m, const u32* __restrict_
 
 // Longest row of A and of B (two streaming passes over the row pointers).  If maxA*maxB <= the S-bin capacity
 // no row can leave the S bin and Σip <= nnzA*maxB, so the work-estimation pass can be skipped entirely.
-__global__ void __launch_bounds__(256) k_maxlen(const int* __restrict__ Arow, int An, const int* __restrict__ Brow, int Bn, DevScalars* sc) {
+static __global__ void __launch_bounds__(256) k_maxlen(const int* __restrict__ Arow, int An, const int* __restrict__ Brow, int Bn, DevScalars* sc) {
   __shared__ u32 s_a, s_b;
   if (threadIdx.x == 0) { s_a = 0; s_b = 0; }
   __syncthreads();
@@ -707,7 +707,7 @@ __global__ void __launch_bounds__(256) k_maxlen(const int* __restrict__ Arow, in
 // Column-span probe: one warp per sampled row of A gathers the row's candidate columns and records whether they fit a
 // window of 2^15 columns (banded / block-diagonal rows: the bitmap path of k_rows_warp / k_fused is the right tool, the
 // global slot map of k_fused_ell would send every key of such a row to the same few slots).
-__global__ void __launch_bounds__(256) k_probe_span(Csr m, int nsamples, DevScalars* sc) {
+static __global__ void __launch_bounds__(256) k_probe_span(Csr m, int nsamples, DevScalars* sc) {
   const int s = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   if (s >= nsamples) return;
   const long long row = (long long)m.An * s / nsamples;
@@ -840,7 +840,7 @@ __global__ void __launch_bounds__(1024) k_rows_gbitmap(Csr m, const u32* __restr
 // Crow[i+1] = Σ_{r<=i} cnt[r], Crow[0] = 0 — single pass, decoupled look-back over tiles of
 // SCAN_THREADS*SCAN_ITEMS counts.  Replaces the serial fix-up loops (final/SpGEMM_mpi_omp.c:135-141, :215-221).
 constexpr int SCAN_THREADS = 256, SCAN_ITEMS = 8;
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan(const u32* __restrict__ cnt, int An, void* __restrict__ Crow, int is64,
+static __global__ void __launch_bounds__(SCAN_THREADS) k_scan(const u32* __restrict__ cnt, int An, void* __restrict__ Crow, int is64,
                                                        u64* __restrict__ status, DevScalars* sc, u32 ntiles) {
   __shared__ u32 s_tile;
   __shared__ u64 s_wsum[SCAN_THREADS / 32];
@@ -883,7 +883,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(const u32* __restrict__ c
 // ------------------------------------------------------------------------------------------------ multi-GPU helper
 // Adds a shard's displacement to its slice-relative row pointers while copying them into the gathered
 // array (replaces the root's fix-up loop final/SpGEMM_mpi_omp.c:211-223).
-__global__ void k_offset_rowptr(const void* __restrict__ src, void* __restrict__ dst, int is64, long long n, long long disp) {
+static __global__ void k_offset_rowptr(const void* __restrict__ src, void* __restrict__ dst, int is64, long long n, long long disp) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   if (is64) ((long long*)dst)[i] = ((const long long*)src)[i] + disp;
