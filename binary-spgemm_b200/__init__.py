@@ -31,7 +31,7 @@ ABI_SYMBOLS = [
     "bspgemm_intermediate_products",
     "bspgemm_SpGEMM_mpi", "bspgemm_SpGEMM_omp", "bspgemm_SpGEMM_bigslice",
     "bspgemm_dev_create", "bspgemm_dev_destroy", "bspgemm_dev_set_mode",
-    "bspgemm_dev_multiply", "bspgemm_dev_get_stats",
+    "bspgemm_dev_multiply", "bspgemm_dev_get_stats", "bspgemm_dev_prepare_b", "bspgemm_dev_forget_b",
     "bspgemm_coo2csc", "bspgemm_coo2csc_dev",
 ]
 HOST_SYMBOLS = [
@@ -58,6 +58,7 @@ class Stats(C.Structure):
         ("ms_main", C.c_float), ("ms_numeric", C.c_float),
         ("algorithmic_bytes", C.c_int64),
         ("variant", C.c_int32), ("rows_per_tile", C.c_int32), ("kernel_flags", C.c_int32),
+        ("b_prepared", C.c_int32), ("plan_cached", C.c_int32),
     ]
 
     def as_dict(self):
@@ -108,6 +109,8 @@ def lib() -> C.CDLL:
                                            C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64,
                                            C.c_void_p, C.c_int, C.POINTER(C.c_void_p), _I64P]
         L.bspgemm_dev_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        L.bspgemm_dev_prepare_b.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64]
+        L.bspgemm_dev_forget_b.argtypes = [C.c_void_p]
         L.bspgemm_coo2csc.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
         L.bspgemm_coo2csc_dev.argtypes = [C.c_void_p] + L.bspgemm_coo2csc.argtypes
         _lib = L
@@ -358,6 +361,14 @@ class DeviceSpGEMM:
                                           self._p(dCrow), 1 if crow_is_i64 else 0, C.byref(out), C.byref(nnz)),
                "bspgemm_dev_multiply")
         return out.value or 0, nnz.value
+
+    def prepare_b(self, dBcol, dBrow, Bn, Bm, Bnnz, stream=None):
+        """bspgemm_dev_prepare_b: B resident once (re-layout + plan) for the products that follow with the same B."""
+        _check(lib().bspgemm_dev_prepare_b(self._h, C.c_void_p(stream or 0), self._p(dBcol), self._p(dBrow), Bn, Bm, Bnnz),
+               "bspgemm_dev_prepare_b")
+
+    def forget_b(self):
+        _check(lib().bspgemm_dev_forget_b(self._h), "bspgemm_dev_forget_b")
 
     def stats(self) -> dict:
         s = Stats()

@@ -86,8 +86,8 @@ static int launch_fused(bspgemm_dev* d, u32 ntiles, int acc_ip) {
   const int grid = (int)std::max<long long>(1, std::min<long long>(want, d->sm_count));
   const bool notail = d->max_len_b <= (u32)d->G;
 #define LF(Gv) do { \
-    if (notail) k_fused<Gv, true><<<grid, warps * 32, smem, d->stream>>>(a.m, d->cnt.p, d->cap_s, a.dCrow, a.is64, ccol, d->status.p, d->d_sc, ntiles, acc_ip); \
-    else        k_fused<Gv, false><<<grid, warps * 32, smem, d->stream>>>(a.m, d->cnt.p, d->cap_s, a.dCrow, a.is64, ccol, d->status.p, d->d_sc, ntiles, acc_ip); } while (0)
+    if (notail) k_fused<Gv, true><<<grid, warps * 32, smem, d->stream>>>(a.m, d->cnt.p, d->cap_s, a.dCrow, a.is64, ccol, d->status.p + SC_WORDS, d->d_sc, ntiles, acc_ip); \
+    else        k_fused<Gv, false><<<grid, warps * 32, smem, d->stream>>>(a.m, d->cnt.p, d->cap_s, a.dCrow, a.is64, ccol, d->status.p + SC_WORDS, d->d_sc, ntiles, acc_ip); } while (0)
   switch (d->G) { case 4: LF(4); break; case 8: LF(8); break; case 16: LF(16); break; default: LF(32); break; }
 #undef LF
   d->launches++;
@@ -190,27 +190,31 @@ static bool ell_plan(bspgemm_dev* d) {
 }
 
 // Banded / block-diagonal fast path (band.cuh): B rows become (first, len) descriptors, output rows 128-bit bitmaps.
+static int build_desc(bspgemm_dev* d) {
+  const MulArgs& a = d->a;
+  d->pb.desc = false;                                  // whatever `bdesc` held is gone (bspgemm_dev_prepare_b sets it again)
+  CKS(d->bdesc.ensure(((size_t)a.m.Bn + 1) * 2 + 4));
+  const long long threads = (((long long)a.m.Bn + 31) / 32) * 32;
+  k_build_desc<<<(int)std::max<long long>(1, (threads + 255) / 256), 256, 0, d->stream>>>(a.m.Brow, a.m.Bcol, a.m.Bn, (u32)a.m.Bm, reinterpret_cast<uint2*>(d->bdesc.p), d->d_sc);
+  d->launches++;
+  CK(cudaGetLastError());
+  return BSPGEMM_OK;
+}
 static int launch_band(bspgemm_dev* d) {
   const MulArgs& a = d->a;
   int* ccol = d->user_ccol ? d->user_ccol : d->ccol.p;
-  CKS(d->bell.ensure(((size_t)a.m.Bn + 1) * 2 + 4));
-  uint2* desc = reinterpret_cast<uint2*>(d->bell.p);
-  {
-    const long long threads = (((long long)a.m.Bn + 31) / 32) * 32;
-    k_build_desc<<<(int)((threads + 255) / 256), 256, 0, d->stream>>>(a.m.Brow, a.m.Bcol, a.m.Bn, (u32)a.m.Bm, desc, d->d_sc);
-    d->launches++;
-    CK(cudaGetLastError());
-  }
+  if (!(b_prepared(d) && d->pb.desc)) CKS(build_desc(d));
+  uint2* desc = reinterpret_cast<uint2*>(d->bdesc.p);
   const u32 ntiles = (u32)(((size_t)a.m.An + BAND_THREADS - 1) / BAND_THREADS);
-  CKS(d->status.ensure((size_t)ntiles + 1));
-  CK(cudaMemsetAsync(d->status.p, 0, ((size_t)ntiles + 1) * sizeof(u64), d->stream));
+  u64* chain = nullptr;
+  CKS(chain_reserve(d, (size_t)ntiles + 1, &chain));
   CK(cudaEventRecord(d->ev[3], d->stream));
   int bps = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_band, BAND_THREADS, 0));
   const int grid = (int)std::max<long long>(1, std::min<long long>((long long)ntiles, (long long)d->sm_count * std::max(bps, 1)));
   BandArgs p{};
   p.Arow = a.m.Arow; p.Acol = a.m.Acol; p.desc = desc; p.An = a.m.An; p.Bn = a.m.Bn;
-  p.Crow = a.dCrow; p.is64 = a.is64; p.Ccol = ccol; p.status = d->status.p; p.sc = d->d_sc; p.ntiles = ntiles;
+  p.Crow = a.dCrow; p.is64 = a.is64; p.Ccol = ccol; p.status = chain; p.sc = d->d_sc; p.ntiles = ntiles;
   k_band<<<grid, BAND_THREADS, 0, d->stream>>>(p);
   d->launches++;
   CK(cudaGetLastError());
@@ -245,11 +249,15 @@ static int mul_launch_probe(bspgemm_dev* d) {
   const MulArgs& a = d->a;
   CK(cudaSetDevice(d->device));
   d->launches = 0;
+  d->fast = false;
   memset(&d->st, 0, sizeof d->st);
+  CKS(d->status.ensure(SC_WORDS + (size_t)a.m.An / 4 + 8192));      // scalars + the longest look-back chain of any pipeline
+  d->d_sc = reinterpret_cast<DevScalars*>(d->status.p);
   CK(cudaEventRecord(d->ev[0], d->stream));
   CK(cudaMemsetAsync(d->d_sc, 0, sizeof(DevScalars), d->stream));
-  const int nmax = std::max(a.m.An, a.m.Bn);
-  k_maxlen<<<std::max(1, std::min((nmax + 255) / 256, d->sm_count * 8)), 256, 0, d->stream>>>(a.m.Arow, a.m.An, a.m.Brow, a.m.Bn, d->d_sc);
+  const bool bprep = b_prepared(d);                                    // B's longest row is known (mul_launch_estimate)
+  const int nmax = bprep ? a.m.An : std::max(a.m.An, a.m.Bn);
+  k_maxlen<<<std::max(1, std::min((nmax + 255) / 256, d->sm_count * 8)), 256, 0, d->stream>>>(a.m.Arow, a.m.An, a.m.Brow, bprep ? 0 : a.m.Bn, d->d_sc);
   d->launches++;
   CK(cudaGetLastError());
   if (a.m.An > 0 && a.Bnnz > 0) {                                  // are the rows' columns clustered (banded / block-diagonal)?
@@ -269,6 +277,7 @@ static int mul_launch_estimate(bspgemm_dev* d) {
   const MulArgs& a = d->a;
   CK(cudaSetDevice(d->device));
   CK(cudaStreamSynchronize(d->stream));
+  if (b_prepared(d)) d->h_sc->max_len_b = d->pb.max_len_b;
   const DevScalars& h = *d->h_sc;
   const u64 bound = (u64)h.max_len_a * (u64)h.max_len_b;
   d->max_len_b = h.max_len_b;
@@ -435,8 +444,7 @@ static int mul_launch_main(bspgemm_dev* d) {
     CK(cudaEventRecord(d->ev[3], d->stream));
     const u32 rows_per_tile = FUSED_R;
     const u32 ntiles = (u32)((An + rows_per_tile - 1) / rows_per_tile);
-    CKS(d->status.ensure(ntiles + 1));
-    CK(cudaMemsetAsync(d->status.p, 0, (size_t)ntiles * sizeof(u64), d->stream));
+    { u64* chain = nullptr; CKS(chain_reserve(d, (size_t)ntiles + 1, &chain)); }
     CKS(launch_fused(d, ntiles, d->skip_estimate ? 1 : 0));
     CK(cudaEventRecord(d->ev[4], d->stream));
     if (d->have_m) CKS(staged ? launch_copy_rows(d) : launch_bins_ml<MODE_FILL>(d));
@@ -446,9 +454,9 @@ static int mul_launch_main(bspgemm_dev* d) {
     if (d->have_m) CKS(launch_bins_ml<MODE_COUNT>(d));
     CK(cudaEventRecord(d->ev[3], d->stream));
     const u32 ntiles = (u32)((An + SCAN_THREADS * SCAN_ITEMS - 1) / (SCAN_THREADS * SCAN_ITEMS));
-    CKS(d->status.ensure(ntiles + 1));
-    CK(cudaMemsetAsync(d->status.p, 0, (size_t)ntiles * sizeof(u64), d->stream));
-    k_scan<<<ntiles, SCAN_THREADS, 0, d->stream>>>(d->cnt.p, a.m.An, a.dCrow, a.is64, d->status.p, d->d_sc, ntiles);
+    u64* chain = nullptr;
+    CKS(chain_reserve(d, (size_t)ntiles + 1, &chain));
+    k_scan<<<ntiles, SCAN_THREADS, 0, d->stream>>>(d->cnt.p, a.m.An, a.dCrow, a.is64, chain, d->d_sc, ntiles);
     d->launches++;
     CK(cudaGetLastError());
   }
@@ -463,7 +471,7 @@ static int mul_launch_fill(bspgemm_dev* d) {
   CK(cudaSetDevice(d->device));
   CK(cudaStreamSynchronize(d->stream));
   const DevScalars& h = *d->h_sc;
-  if (d->use_band && h.band_fail) {
+  if (!d->fast && d->use_band && h.band_fail) {
     // the optimistic run/bitmap kernel met a B row that is not a run of consecutive columns, or an output row wider than
     // its register bitmap: nothing it wrote is used — the whole product is redone by the general kernels
     d->no_band = true;
@@ -474,11 +482,25 @@ static int mul_launch_fill(bspgemm_dev* d) {
     d->no_band = false;
     return rc;
   }
+  if (d->fast && ((h.err & 8u) || (d->use_band && h.band_fail))) {
+    // the cached plan does not fit this A (a row longer than the plan's LA / an output row wider than the register bitmap):
+    // nothing the kernel wrote is used — forget the plan and redo the product with fresh probes
+    d->pb.variant = -1;
+    int rc = mul_launch_probe(d);
+    if (rc == BSPGEMM_OK) rc = mul_launch_estimate(d);
+    if (rc == BSPGEMM_OK) rc = mul_launch_main(d);
+    if (rc == BSPGEMM_OK) rc = mul_launch_fill(d);
+    return rc;
+  }
   if (h.err & 1u) return fail(BSPGEMM_ERR_BADARG, "a column index of A is outside [0,Bn=%d)", a.m.Bn);
   if (h.err & 4u) return fail(BSPGEMM_ERR_BADARG, "a column index of B is outside [0,Bm=%d)", a.m.Bm);
   if (h.err & 2u) return fail(BSPGEMM_ERR_OVERFLOW32, "nnz(C) = %llu does not fit 32-bit row pointers", (unsigned long long)h.total_nnz);
   d->st.nnz = (int64_t)h.total_nnz;
   d->st.ip = (int64_t)h.total_ip;
+  if (b_prepared(d) && !d->fast) {            // remember what this B and this kind of A needed: the next product starts from it
+    d->pb.variant = (d->st.variant == 2 || d->st.variant == 3) ? d->st.variant : -1;
+    d->pb.sort_LAL = d->sort_LAL;
+  }
   if (d->used_mode == BSPGEMM_MODE_FUSED) { d->phase = 5; return BSPGEMM_OK; }
   if (d->user_ccol) { if ((u64)d->user_cap < h.total_nnz) return fail(BSPGEMM_ERR_CAPACITY, "output capacity %lld < nnz(C) %llu", (long long)d->user_cap, (unsigned long long)h.total_nnz); }
   else CKS(d->ccol.ensure((size_t)std::max<u64>(h.total_nnz, 1)));
@@ -503,13 +525,75 @@ static int mul_finish(bspgemm_dev* d) {
     if (top <= d->cap_s) s.rows_s += d->hist_rows[b]; else if (top <= CAP_M2) s.rows_m += d->hist_rows[b]; else s.rows_l += d->hist_rows[b];
   }
   float ms = 0;
-  cudaEventElapsedTime(&ms, d->ev[0], d->ev[5]); s.ms_total = ms;
-  cudaEventElapsedTime(&ms, d->ev[6], d->ev[1]); s.ms_estimate = ms;
-  cudaEventElapsedTime(&ms, d->ev[2], d->ev[3]); s.ms_symbolic = ms;
-  cudaEventElapsedTime(&ms, d->ev[3], d->ev[4]); s.ms_main = ms;
-  cudaEventElapsedTime(&ms, d->ev[4], d->ev[5]); s.ms_numeric = ms;
+  s.plan_cached = d->fast ? 1 : 0;
+  s.b_prepared = b_prepared(d) ? 1 : 0;
+  if (d->fast) {                               // replayed from the cached plan: one kernel between ev[3] and ev[4]
+    cudaEventElapsedTime(&ms, d->ev[0], d->ev[4]); s.ms_total = ms;
+    cudaEventElapsedTime(&ms, d->ev[3], d->ev[4]); s.ms_main = ms;
+  } else {
+    cudaEventElapsedTime(&ms, d->ev[0], d->ev[5]); s.ms_total = ms;
+    cudaEventElapsedTime(&ms, d->ev[6], d->ev[1]); s.ms_estimate = ms;
+    cudaEventElapsedTime(&ms, d->ev[2], d->ev[3]); s.ms_symbolic = ms;
+    cudaEventElapsedTime(&ms, d->ev[3], d->ev[4]); s.ms_main = ms;
+    cudaEventElapsedTime(&ms, d->ev[4], d->ev[5]); s.ms_numeric = ms;
+  }
   const int64_t rp = a.is64 ? 8 : 4;
   s.algorithmic_bytes = 4 * ((int64_t)a.m.An + 1) + 12 * a.Annz + 4 * s.ip + 4 * s.nnz + rp * ((int64_t)a.m.An + 1);
+  return BSPGEMM_OK;
+}
+
+// Product with a prepared B whose last product ran the sorting-network or the band kernel: launched straight from that plan —
+// no probe kernels, no ELL / descriptor build, no host round trip before the launch: one memset (scalars + look-back words),
+// the kernel, the read-back of the scalars.  What the probes would have established is checked where it is used: the kernels
+// flag a row of A longer than the plan's LA (err bit 3) or an output row the band kernel cannot hold (band_fail), and
+// mul_launch_fill then redoes the product the long way.  The host-side conditions of the plan are re-evaluated here.
+static bool env_overrides() {
+  static const char* names[] = {"BSPGEMM_NO_ELL", "BSPGEMM_CAP_S", "BSPGEMM_FORCE_ESTIMATE", "BSPGEMM_FORCE_ELL", "BSPGEMM_NO_SORT", "BSPGEMM_FORCE_SORT",
+                                "BSPGEMM_NO_BAND", "BSPGEMM_NO_PLAN_CACHE"};
+  for (const char* n : names) if (getenv(n)) return true;
+  return false;
+}
+static int mul_launch_fast(bspgemm_dev* d, bool* taken) {
+  const MulArgs& a = d->a;
+  *taken = false;
+  if (!b_prepared(d) || d->pb.variant < 0 || d->mode == BSPGEMM_MODE_TWOPHASE || d->user_ccol || env_overrides()) return BSPGEMM_OK;
+  const auto& pb = d->pb;
+  u64 ip_bound;
+  if (pb.variant == 2) {
+    const int LA = 1 << pb.sort_LAL;
+    if (pb.ell_W == 0 || (u64)a.Annz * 2ull < (u64)a.m.An * (u64)LA) return BSPGEMM_OK;      // "regular" rule of ell_plan
+    ip_bound = (u64)a.Annz * (u64)pb.max_len_b;
+  } else {
+    if (!pb.desc) return BSPGEMM_OK;
+    ip_bound = std::min<u64>((u64)a.Annz * (u64)pb.max_len_b, (u64)a.m.An * (u64)BAND_BITS);
+  }
+  if (ip_bound > (u64)d->ccol.cap) return BSPGEMM_OK;      // the arena of the earlier product is reused, never grown here
+  CK(cudaSetDevice(d->device));
+  d->launches = 0;
+  memset(&d->st, 0, sizeof d->st);
+  d->fast = true;
+  d->no_band = false;
+  d->skip_estimate = true; d->max_len_b = pb.max_len_b;
+  d->have_m = d->have_m2 = d->have_l = false;
+  d->used_mode = BSPGEMM_MODE_FUSED; d->st.mode = BSPGEMM_MODE_FUSED;
+  CKS(d->status.ensure(SC_WORDS + (size_t)a.m.An / 4 + 8192));
+  d->d_sc = reinterpret_cast<DevScalars*>(d->status.p);
+  CK(cudaEventRecord(d->ev[0], d->stream));
+  if (pb.variant == 2) {
+    d->use_band = false; d->use_ell = true; d->use_sort = true; d->ell_W = pb.ell_W; d->sort_LAL = pb.sort_LAL;
+    d->cap_s = 0; d->G = pb.ell_W;
+    d->st.cap_s = (1 << pb.sort_LAL) * pb.ell_W; d->st.group = pb.ell_W; d->st.variant = 2;
+    CKS(launch_sort(d, d->ccol.p));                       // chain_reserve clears scalars + chain, records ev[3]
+  } else {
+    d->use_band = true; d->use_ell = false; d->use_sort = false;
+    d->cap_s = BAND_BITS; d->G = 1;
+    d->st.cap_s = (int)BAND_BITS; d->st.group = 1; d->st.variant = 3; d->st.rows_per_tile = BAND_THREADS;
+    CKS(launch_band(d));
+  }
+  CK(cudaEventRecord(d->ev[4], d->stream));
+  CK(cudaMemcpyAsync(d->h_sc, d->d_sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, d->stream));
+  d->phase = 3;
+  *taken = true;
   return BSPGEMM_OK;
 }
 
@@ -521,9 +605,13 @@ static int mul_run_to_completion(bspgemm_dev* d) {
     memset(&d->st, 0, sizeof d->st); d->phase = 5;
     return BSPGEMM_OK;
   }
-  CKS(mul_launch_probe(d));
-  CKS(mul_launch_estimate(d));
-  CKS(mul_launch_main(d));
+  bool fast = false;
+  CKS(mul_launch_fast(d, &fast));
+  if (!fast) {
+    CKS(mul_launch_probe(d));
+    CKS(mul_launch_estimate(d));
+    CKS(mul_launch_main(d));
+  }
   CKS(mul_launch_fill(d));
   return mul_finish(d);
 }
@@ -539,7 +627,8 @@ static int dev_create(bspgemm_dev** out, int device) {
   d->device = device; d->sm_count = p.multiProcessorCount; d->smem_optin = p.sharedMemPerBlockOptin;
   CK(cudaStreamCreateWithFlags(&d->own_stream, cudaStreamNonBlocking));
   d->stream = d->own_stream;
-  CK(cudaMalloc((void**)&d->d_sc, sizeof(DevScalars)));
+  CKS(d->status.ensure(SC_WORDS + 8192));
+  d->d_sc = reinterpret_cast<DevScalars*>(d->status.p);
   CK(cudaMallocHost((void**)&d->h_sc, sizeof(DevScalars)));
   for (auto& e : d->ev) CK(cudaEventCreate(&e));
   CKS(set_kernel_attributes((int)d->smem_optin));
@@ -553,9 +642,8 @@ static void dev_destroy(bspgemm_dev* d) {
   if (!d) return;
   cudaSetDevice(d->device);
   cudaStreamSynchronize(d->stream);
-  d->ip.release(); d->cnt.release(); d->lists.release(); d->bitmaps.release(); d->status.release(); d->ccol.release(); d->temp.release(); d->tofs.release();
+  d->ip.release(); d->cnt.release(); d->lists.release(); d->bitmaps.release(); d->status.release(); d->ccol.release(); d->temp.release(); d->tofs.release(); d->bell.release(); d->bdesc.release();
   d->in_arow.release(); d->in_acol.release(); d->in_brow.release(); d->in_bcol.release(); d->crow_dev.release(); d->crow_tmp.release();
-  if (d->d_sc) cudaFree(d->d_sc);
   if (d->h_sc) cudaFreeHost(d->h_sc);
   for (auto& e : d->ev) if (e) cudaEventDestroy(e);
   if (d->own_stream) cudaStreamDestroy(d->own_stream);
@@ -584,6 +672,52 @@ extern "C" int bspgemm_dev_multiply(bspgemm_dev* h, void* stream,
   CKS(mul_run_to_completion(h));
   if (dCcol_out) *dCcol_out = h->ccol.p;
   if (nnz_out) *nnz_out = h->st.nnz;
+  return BSPGEMM_OK;
+}
+
+// B prepared once for many products.  The reference replicates B once, outside its timed region (every rank parses the file,
+// final/SpGEMM_mpi_omp.c:309, before the loop :318-328); on the GPU "B resident" includes its gather-friendly copy: the ELL
+// re-layout (rows sorted, 4W-byte aligned) or, when every row is a run of consecutive columns, the (first, len) descriptors.
+extern "C" int bspgemm_dev_prepare_b(bspgemm_dev* h, void* stream, const int* dBcol, const int* dBrow, int Bn, int Bm, int64_t Bnnz) {
+  if (!h || !dBrow || Bn < 0 || Bm < 0 || Bnnz < 0 || (Bnnz > 0 && !dBcol)) return fail(BSPGEMM_ERR_BADARG, "prepare_b: null pointer or negative size");
+  bspgemm_dev* d = h;
+  CK(cudaSetDevice(d->device));
+  d->stream = stream ? (cudaStream_t)stream : cudaStreamLegacy;
+  d->pb = bspgemm_dev::PreparedB{};
+  d->fast = false;
+  d->a = MulArgs{};
+  d->a.m = Csr{dBrow, dBcol, dBrow, dBcol, 0, Bn, Bm};      // only the B side is used below
+  d->a.Bnnz = Bnnz;
+  d->d_sc = reinterpret_cast<DevScalars*>(d->status.p);
+  CK(cudaMemsetAsync(d->d_sc, 0, sizeof(DevScalars), d->stream));
+  if (Bn > 0) {
+    k_maxlen<<<std::max(1, std::min((Bn + 255) / 256, d->sm_count * 8)), 256, 0, d->stream>>>(dBrow, 0, dBrow, Bn, d->d_sc);
+    CK(cudaGetLastError());
+    if (Bnnz > 0) CKS(build_desc(d));                         // proves (or refutes) "every row is a run" and validates the columns of run rows
+  }
+  CK(cudaMemcpyAsync(d->h_sc, d->d_sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, d->stream));
+  CK(cudaStreamSynchronize(d->stream));
+  const DevScalars hs = *d->h_sc;
+  auto& pb = d->pb;
+  pb.brow = dBrow; pb.bcol = dBcol; pb.Bn = Bn; pb.Bm = Bm; pb.Bnnz = Bnnz; pb.max_len_b = hs.max_len_b;
+  if (Bn > 0 && Bnnz > 0 && hs.band_fail == 0) pb.desc = true;
+  else if (hs.max_len_b >= 1 && hs.max_len_b <= 32) {
+    int W = 4; while (W < (int)hs.max_len_b) W <<= 1;
+    if ((u64)Bn * (u64)W <= 4ull * (u64)Bnnz + 4096ull) {     // the padding rule of ell_plan
+      CK(cudaMemsetAsync(d->d_sc, 0, sizeof(DevScalars), d->stream));
+      CKS(build_ell(d, W, true));
+      CK(cudaMemcpyAsync(d->h_sc, d->d_sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, d->stream));
+      CK(cudaStreamSynchronize(d->stream));
+      if (d->h_sc->err & 4u) return fail(BSPGEMM_ERR_BADARG, "a column index of B is outside [0,Bm=%d)", Bm);
+      pb.ell_W = W;
+    }
+  }
+  pb.valid = true;
+  return BSPGEMM_OK;
+}
+extern "C" int bspgemm_dev_forget_b(bspgemm_dev* h) {
+  if (!h) return fail(BSPGEMM_ERR_BADARG, "null handle");
+  h->pb = bspgemm_dev::PreparedB{};
   return BSPGEMM_OK;
 }
 
@@ -622,32 +756,42 @@ static int nccl_load(Nccl& n) {
 }
 #define NK(call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) return fail(BSPGEMM_ERR_NCCL, "%s failed: %s", #call, g.nccl.GetErrorString ? g.nccl.GetErrorString(r_) : "?"); } while (0)
 
+// One context ("task") per entry of the device list.  A device may be listed more than once (BSPGEMM_DEVICES=0,0,0 or
+// bspgemm_init_devices): several row-block shards then share one GPU — no NCCL communicator (NCCL refuses duplicate devices);
+// B is uploaded once per distinct device and shared by its shards.  This is how the sharding / displacement / gather path is
+// exercised on a single-GPU box; with distinct devices B is replicated by ncclBroadcast over NVLink.
 static int init_devices_locked(const int* devices, int ngpus) {
   if (g.inited) return fail(BSPGEMM_ERR_STATE, "bspgemm_init called twice");
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return fail(BSPGEMM_ERR_NOGPU, "no CUDA device visible; this library has no CPU fallback"); }
-  if (ngpus <= 0) ngpus = n;
-  if (ngpus > n) return fail(BSPGEMM_ERR_BADARG, "%d GPUs requested, %d visible", ngpus, n);
-  std::vector<int> ids(ngpus);
-  for (int i = 0; i < ngpus; ++i) ids[i] = devices ? devices[i] : i;
+  std::vector<int> ids;
+  if (devices) ids.assign(devices, devices + ngpus);
+  else if (const char* e = getenv("BSPGEMM_DEVICES")) {        // explicit task -> device map, overrides the count
+    for (const char* q = e; *q;) { char* end; const long v = strtol(q, &end, 10); if (end == q) break; ids.push_back((int)v); q = (*end == ',') ? end + 1 : end; }
+    if (ids.empty()) return fail(BSPGEMM_ERR_BADARG, "BSPGEMM_DEVICES=\"%s\" holds no device id", e);
+  } else {
+    if (ngpus <= 0) ngpus = n;
+    if (ngpus > n) return fail(BSPGEMM_ERR_BADARG, "%d GPUs requested, %d visible", ngpus, n);
+    for (int i = 0; i < ngpus; ++i) ids.push_back(i);
+  }
+  ngpus = (int)ids.size();
+  bool distinct = true;
+  for (int i = 0; i < ngpus; ++i) for (int k = 0; k < i; ++k) if (ids[i] == ids[k]) distinct = false;
+  auto undo = [&](int st) { for (auto* x : g.devs) dev_destroy(x); g.devs.clear(); g.comms.clear(); return st; };   // nothing half-built stays behind
   for (int i = 0; i < ngpus; ++i) {
     bspgemm_dev* d = nullptr;
     int s = dev_create(&d, ids[i]);
-    if (s != BSPGEMM_OK) { for (auto* x : g.devs) dev_destroy(x); g.devs.clear(); return s; }
+    if (s != BSPGEMM_OK) return undo(s);
     g.devs.push_back(d);
   }
-  if (ngpus > 1) {
+  if (ngpus > 1 && distinct) {
     int s = nccl_load(g.nccl);
     if (s == BSPGEMM_OK) {
       g.comms.assign(ngpus, nullptr);
       const ncclResult_t r = g.nccl.CommInitAll(g.comms.data(), ngpus, ids.data());
       if (r != ncclSuccess) s = fail(BSPGEMM_ERR_NCCL, "ncclCommInitAll failed: %s", g.nccl.GetErrorString ? g.nccl.GetErrorString(r) : "?");
     }
-    if (s != BSPGEMM_OK) {            // nothing half-built stays behind: a later bspgemm_init(1) starts from scratch
-      for (auto* x : g.devs) dev_destroy(x);
-      g.devs.clear(); g.comms.clear();
-      return s;
-    }
+    if (s != BSPGEMM_OK) return undo(s);
   }
   g.inited = true;
   return BSPGEMM_OK;
@@ -696,7 +840,12 @@ static int host_multiply(const int* Acol, const int* Arow, int An, const int* Bc
   std::vector<int> r0(ng + 1);
   for (int q = 0; q <= ng; ++q) r0[q] = (int)((int64_t)An * q / ng);
 
-  // upload A shards, and B to GPU 0
+  // upload A shards; B to task 0 and — without a communicator (tasks sharing GPUs) — to the first task of every other device
+  std::vector<int> b_owner(ng);                       // task whose copy of B task q reads
+  for (int q = 0; q < ng; ++q) {
+    b_owner[q] = q;
+    if (g.comms.empty()) for (int k = 0; k < q; ++k) if (g.devs[k]->device == g.devs[q]->device) { b_owner[q] = k; break; }
+  }
   for (int q = 0; q < ng; ++q) {
     bspgemm_dev* d = g.devs[q];
     CK(cudaSetDevice(d->device));
@@ -705,17 +854,18 @@ static int host_multiply(const int* Acol, const int* Arow, int An, const int* Bc
     const int64_t lo = Arow[r0[q]], hi = Arow[r0[q + 1]];
     CKS(d->in_arow.ensure((size_t)rows + 1));
     CKS(d->in_acol.ensure((size_t)std::max<int64_t>(hi - lo, 1)));
-    CKS(d->in_brow.ensure((size_t)Bn + 1));
-    CKS(d->in_bcol.ensure((size_t)std::max<int64_t>(Bnnz, 1)));
     CKS(d->crow_dev.ensure(((size_t)rows + 1) * rp));
     CK(cudaMemcpyAsync(d->in_arow.p, Arow + r0[q], ((size_t)rows + 1) * 4, cudaMemcpyHostToDevice, d->stream));
     if (hi > lo) CK(cudaMemcpyAsync(d->in_acol.p, Acol + lo, (size_t)(hi - lo) * 4, cudaMemcpyHostToDevice, d->stream));
-    if (q == 0) {
+    if (b_owner[q] != q) continue;
+    CKS(d->in_brow.ensure((size_t)Bn + 1));
+    CKS(d->in_bcol.ensure((size_t)std::max<int64_t>(Bnnz, 1)));
+    if (q == 0 || g.comms.empty()) {
       CK(cudaMemcpyAsync(d->in_brow.p, Brow, ((size_t)Bn + 1) * 4, cudaMemcpyHostToDevice, d->stream));
       if (Bnnz > 0) CK(cudaMemcpyAsync(d->in_bcol.p, Bcol, (size_t)Bnnz * 4, cudaMemcpyHostToDevice, d->stream));
     }
   }
-  if (ng > 1) {   // replicate B over NVLink
+  if (ng > 1 && !g.comms.empty()) {   // replicate B over NVLink: one upload + ncclBroadcast (the reference: every rank parses the file, :309)
     CK(cudaSetDevice(g.devs[0]->device));
     CK(cudaStreamSynchronize(g.devs[0]->stream));
     NK(g.nccl.GroupStart());
@@ -726,6 +876,8 @@ static int host_multiply(const int* Acol, const int* Arow, int An, const int* Bc
       for (int q = 0; q < ng; ++q) NK(g.nccl.Broadcast(g.devs[0]->in_bcol.p, g.devs[q]->in_bcol.p, (size_t)Bnnz, ncclInt32, 0, g.comms[q], g.devs[q]->stream));
       NK(g.nccl.GroupEnd());
     }
+  } else if (ng > 1) {                // shards sharing a GPU read the owner's copy once its upload has landed
+    for (int q = 0; q < ng; ++q) if (b_owner[q] == q) { CK(cudaSetDevice(g.devs[q]->device)); CK(cudaStreamSynchronize(g.devs[q]->stream)); }
   }
   // run the shards concurrently: launch phase k on every GPU, then wait
   for (int q = 0; q < ng; ++q) {
@@ -734,7 +886,7 @@ static int host_multiply(const int* Acol, const int* Arow, int An, const int* Bc
     const int64_t lo = Arow[r0[q]], hi = Arow[r0[q + 1]];
     // Arow holds absolute offsets; shift the base pointer so that Acol_dev[Arow[i]] addresses the shard copy
     const int* acol_dev = (const int*)((uintptr_t)d->in_acol.p - (uintptr_t)lo * 4u);
-    d->a.m = Csr{d->in_arow.p, acol_dev, d->in_brow.p, d->in_bcol.p, rows, Bn, Bm};
+    d->a.m = Csr{d->in_arow.p, acol_dev, g.devs[b_owner[q]]->in_brow.p, g.devs[b_owner[q]]->in_bcol.p, rows, Bn, Bm};
     d->a.Annz = hi - lo; d->a.Bnnz = Bnnz; d->a.dCrow = d->crow_dev.p; d->a.is64 = is64;
     d->user_ccol = nullptr; d->user_cap = 0;
     d->phase = 0;
@@ -832,10 +984,22 @@ extern "C" int bspgemm_intermediate_products(const int* Acol, const int* Arow, i
 }
 
 // ---- legacy-signature drop-ins (void, exit(1) on failure like final/utils.c:54-61) ----
+// The reference's signature has no "rows of B": Bn = max(Acol) + 1 (any valid CSR pair has at least that many B rows).  One
+// pass over Acol on up to 16 host threads (config 3: 6.7e7 entries).  The explicit-Bn entry points avoid it.
 static int derive_bn(const int* Acol, const int* Arow, int An) {
-  int mx = -1;
-  for (int64_t p = Arow[0]; p < Arow[An]; ++p) mx = std::max(mx, Acol[p]);
-  return mx + 1;
+  const int64_t lo = Arow[0], hi = Arow[An], n = hi - lo;
+  if (n <= 0) return 0;
+  const int nt = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)16, (int64_t)std::thread::hardware_concurrency(), n >> 20}));
+  std::vector<int> part(nt, -1);
+  auto scan = [&](int t) {
+    const int64_t b = lo + n * t / nt, e = lo + n * (t + 1) / nt;
+    int mx = -1;
+    for (int64_t p = b; p < e; ++p) mx = std::max(mx, Acol[p]);
+    part[t] = mx;
+  };
+  if (nt == 1) scan(0);
+  else { std::vector<std::thread> th; for (int t = 0; t < nt; ++t) th.emplace_back(scan, t); for (auto& x : th) x.join(); }
+  return *std::max_element(part.begin(), part.end()) + 1;
 }
 static void die_on(int s, const char* who) {
   if (s == BSPGEMM_OK) return;

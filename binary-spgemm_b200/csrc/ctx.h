@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <vector>
 #include <mutex>
+#include <thread>
 
 using namespace bsk;
 
@@ -62,8 +63,19 @@ struct bspgemm_dev {
   DevBuf<int> ccol;                 // output arena
   DevBuf<int> temp;                 // staging arena of the big rows (MODE_STAGE): Σ IP of the M/L rows
   DevBuf<u64> tofs;                 // per row: offset of its staged columns in temp
-  DevScalars* d_sc = nullptr;
+  DevScalars* d_sc = nullptr;       // = status.p: the scalars sit in front of the look-back words, so one memset clears both
   DevScalars* h_sc = nullptr;       // pinned
+  // B prepared once for many products (bspgemm_dev_prepare_b): its re-layout and the plan of the last product with it
+  struct PreparedB {
+    bool valid = false;
+    const int* brow = nullptr; const int* bcol = nullptr; int Bn = 0, Bm = 0; int64_t Bnnz = 0;   // identity of B (the caller keeps its contents unchanged)
+    u32 max_len_b = 0;
+    int ell_W = 0;                  // ELL copy of B in `bell` (every row sorted), 0: none
+    bool desc = false;              // every B row is a run of consecutive columns: descriptors in `bdesc`
+    int variant = -1, sort_LAL = 0; // plan of the last successful product with this B that can be replayed without probes (2 sort, 3 band)
+  } pb;
+  DevBuf<u32> bdesc;
+  bool fast = false;                // the product in flight was launched from the cached plan (no probes, no host round trip before the launch)
   cudaEvent_t ev[8] = {};
   // per-call state
   MulArgs a{};
@@ -89,7 +101,25 @@ struct bspgemm_dev {
 };
 
 
+// DevScalars live in the first SC_WORDS 64-bit words of `status`, the look-back chain words follow.
+constexpr size_t SC_WORDS = (sizeof(DevScalars) + 127) / 128 * 16;
+// Room for n chain words, zeroed.  A product replayed from the cached plan (d->fast) has not touched the scalars yet: they are
+// cleared by the same memset.  Growing the buffer in the middle of a product keeps the scalars (rare: it is sized per product).
+inline int chain_reserve(bspgemm_dev* d, size_t n, u64** chain) {
+  if (SC_WORDS + n > d->status.cap) { CK(cudaStreamSynchronize(d->stream)); CKS(d->status.ensure(SC_WORDS + n, true)); }
+  d->d_sc = reinterpret_cast<DevScalars*>(d->status.p);
+  *chain = d->status.p + SC_WORDS;
+  if (d->fast) CK(cudaMemsetAsync(d->status.p, 0, (SC_WORDS + n) * sizeof(u64), d->stream));
+  else         CK(cudaMemsetAsync(*chain, 0, n * sizeof(u64), d->stream));
+  return BSPGEMM_OK;
+}
+inline bool b_prepared(const bspgemm_dev* d) {
+  const auto& b = d->pb; const Csr& m = d->a.m;
+  return b.valid && b.brow == m.Brow && b.bcol == m.Bcol && b.Bn == m.Bn && b.Bm == m.Bm && b.Bnnz == d->a.Bnnz;
+}
+
 // ---- launchers defined next to the kernels they instantiate
+BSP_HIDDEN int build_ell(bspgemm_dev* d, int W, bool sorted);      // tu_ell.cu: CSR -> ELL copy of the current B into d->bell
 BSP_HIDDEN int set_attrs_ell(int smem_optin);                      // tu_ell.cu
 BSP_HIDDEN int launch_ell(bspgemm_dev* d);                         // tu_ell.cu: k_build_ell, then k_fused_ell or the sort kernel
 BSP_HIDDEN int launch_sort(bspgemm_dev* d, int* ccol);             // tu_ell.cu: dispatch on the ELL width ...

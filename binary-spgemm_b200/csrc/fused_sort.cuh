@@ -119,7 +119,10 @@ __global__ void __maxnreg__((sort_geom<W, LAL>().K >= 32 ? 96 : 80)) k_fused_sor
     return p.Arow[r0 + min((int)lane, nr)];
   };
   auto load_acol = [&](int ar, int& j0, int& j1) {                 // the tile's A nonzeros (<= 64), absent ones select row Bn
-    const int a0 = __shfl_sync(0xffffffffu, ar, 0), E = __shfl_sync(0xffffffffu, ar, R) - a0;
+    // a launch replayed from a cached plan (bspgemm.cu, mul_launch_fast) got LA from an earlier product: a longer row is flagged,
+    // never truncated silently (the host then redoes the product with a fresh plan)
+    { const int len = __shfl_down_sync(0xffffffffu, ar, 1) - ar; if ((int)lane < R && len > G.LA) atomicOr(&p.sc->err, 8u); }
+    const int a0 = __shfl_sync(0xffffffffu, ar, 0), E = min(__shfl_sync(0xffffffffu, ar, R) - a0, 64);
     j0 = p.Bn; j1 = p.Bn;
     if ((int)lane < E) j0 = acol_checked(p.Acol[a0 + (int)lane], p.Bn);
     if (32 + (int)lane < E) j1 = acol_checked(p.Acol[a0 + 32 + (int)lane], p.Bn);
@@ -152,7 +155,7 @@ __global__ void __maxnreg__((sort_geom<W, LAL>().K >= 32 ? 96 : 80)) k_fused_sor
       for (int u = 0; u < NQ; ++u) {
         const int slot = 2 * u + qd;
         int j = p.Bn;
-        if (slot < hi - lo) j = (int)lds32(acol_s + 4u * (u32)(lo - a0 + slot));
+        if (slot < hi - lo && lo - a0 + slot < 64) j = (int)lds32(acol_s + 4u * (u32)(lo - a0 + slot));   // (< 64: always, unless a stale plan's LA was exceeded — flagged above)
         const uint4 t4 = __ldcg(&Bell4[(size_t)j * LPR + pp]);        // every sector is used exactly once: keep it out of L1
         x[4 * u + 0] = t4.x; x[4 * u + 1] = t4.y; x[4 * u + 2] = t4.z; x[4 * u + 3] = t4.w;
       }
@@ -165,7 +168,7 @@ __global__ void __maxnreg__((sort_geom<W, LAL>().K >= 32 ? 96 : 80)) k_fused_sor
       const int slot = NQ >= LPR ? (int)ll * SLOTS + g : (int)(ll * NQ) / LPR;
       const int part0 = NQ >= LPR ? 0 : (int)(ll * NQ) % LPR;
       int j = p.Bn;
-      if (slot < hi - lo) j = (int)lds32(acol_s + 4u * (u32)(lo - a0 + slot));
+      if (slot < hi - lo && lo - a0 + slot < 64) j = (int)lds32(acol_s + 4u * (u32)(lo - a0 + slot));
 #pragma unroll
       for (int c = 0; c < PARTS; ++c) {
         const uint4 t4 = __ldg(&Bell4[(size_t)j * LPR + part0 + c]);
@@ -381,6 +384,9 @@ __global__ void __maxnreg__((sort_geom<W, LAL>().K >= 32 ? 96 : 80)) k_fused_sor
   // is shorter.  Lane l loads entries l and l+32 straight from Acol (whole rows: the same coalesced accesses).
   auto load_jtab = [&](int ar, int& j0, int& j1) {
     j0 = p.Bn; j1 = p.Bn;
+    // a launch replayed from a cached plan (bspgemm.cu, mul_launch_fast) got LA from an earlier product: a longer row is flagged,
+    // never truncated silently (the host then redoes the product with a fresh plan)
+    { const int len = __shfl_down_sync(0xffffffffu, ar, 1) - ar; if ((int)lane < R && len > LA) atomicOr(&p.sc->err, 8u); }
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int e = h * 32 + (int)lane, row = e / LA, slot = e % LA;

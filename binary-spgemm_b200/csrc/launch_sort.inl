@@ -43,11 +43,11 @@ template <int W, int LAL, bool ASYNC> static int launch_sort_t(bspgemm_dev* d, i
   const int grid = (int)std::max<long long>(1, std::min<long long>(want, d->sm_count));
   const size_t niter = ((size_t)ntiles + (size_t)grid * warps - 1) / ((size_t)grid * warps);
   const size_t nblocks = niter * grid + 1;
-  CKS(d->status.ensure(nblocks));
-  CK(cudaMemsetAsync(d->status.p, 0, nblocks * sizeof(u64), d->stream));
+  u64* chain = nullptr;
+  CKS(chain_reserve(d, nblocks, &chain));
   CK(cudaEventRecord(d->ev[3], d->stream));
   EllArgs p{};
-  p.blk_status = d->status.p;
+  p.blk_status = chain;
   p.Arow = a.m.Arow; p.Acol = a.m.Acol; p.Bell = d->bell.p; p.An = a.m.An; p.Bn = a.m.Bn;
   p.Bm = (u32)a.m.Bm; p.Crow = a.dCrow; p.is64 = a.is64; p.Ccol = ccol; p.sc = d->d_sc; p.ntiles = ntiles; p.nbuf = (u32)nbuf;
 #ifdef BSPGEMM_DEBUG_KNOBS

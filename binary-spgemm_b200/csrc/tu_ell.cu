@@ -14,21 +14,27 @@ int launch_sort(bspgemm_dev* d, int* ccol) {
   switch (d->ell_W) { case 4: return launch_sort_w4(d, ccol); case 8: return launch_sort_w8(d, ccol); case 16: return launch_sort_w16(d, ccol); default: return launch_sort_w32(d, ccol); }
 }
 
+int build_ell(bspgemm_dev* d, int W, bool sorted) {
+  const MulArgs& a = d->a;
+  d->pb.ell_W = 0;                                     // whatever copy `bell` held is gone (bspgemm_dev_prepare_b sets it again)
+  CKS(d->bell.ensure(((size_t)a.m.Bn + 1) * W + 4));
+  const long long threads = (((long long)a.m.Bn + ELL_RPT) / ELL_RPT) * (W / 4);     // ELL_RPT rows per thread
+  const int grid = (int)((threads + 255) / 256);
+#define BE(Wv) do { if (sorted) k_build_ell<Wv, true><<<grid, 256, 0, d->stream>>>(a.m.Brow, a.m.Bcol, a.m.Bn, (u32)a.m.Bm, d->bell.p, d->d_sc); \
+                    else k_build_ell<Wv, false><<<grid, 256, 0, d->stream>>>(a.m.Brow, a.m.Bcol, a.m.Bn, (u32)a.m.Bm, d->bell.p, d->d_sc); } while (0)
+  switch (W) { case 4: BE(4); break; case 8: BE(8); break; case 16: BE(16); break; default: BE(32); break; }
+#undef BE
+  d->launches++;
+  CK(cudaGetLastError());
+  return BSPGEMM_OK;
+}
+
 int launch_ell(bspgemm_dev* d) {
   const MulArgs& a = d->a;
   int* ccol = d->user_ccol ? d->user_ccol : d->ccol.p;
   const int W = d->ell_W, R = d->ell_R;
-  CKS(d->bell.ensure(((size_t)a.m.Bn + 1) * W + 4));
-  {
-    const long long threads = (((long long)a.m.Bn + ELL_RPT) / ELL_RPT) * (W / 4);     // ELL_RPT rows per thread
-    const int grid = (int)((threads + 255) / 256);
-#define BE(Wv) do { if (d->use_sort) k_build_ell<Wv, true><<<grid, 256, 0, d->stream>>>(a.m.Brow, a.m.Bcol, a.m.Bn, (u32)a.m.Bm, d->bell.p, d->d_sc); \
-                    else k_build_ell<Wv, false><<<grid, 256, 0, d->stream>>>(a.m.Brow, a.m.Bcol, a.m.Bn, (u32)a.m.Bm, d->bell.p, d->d_sc); } while (0)
-    switch (W) { case 4: BE(4); break; case 8: BE(8); break; case 16: BE(16); break; default: BE(32); break; }
-#undef BE
-    d->launches++;
-    CK(cudaGetLastError());
-  }
+  // the ELL copy of a prepared B (bspgemm_dev_prepare_b) is reused: sorted rows serve both kernels
+  if (!(b_prepared(d) && d->pb.ell_W == W)) CKS(build_ell(d, W, d->use_sort));
   if (d->use_sort) return launch_sort(d, ccol);
   const u32 ntiles = (u32)(((size_t)a.m.An + R - 1) / R);
   const int warps = d->ell_warps;
@@ -38,11 +44,11 @@ int launch_ell(bspgemm_dev* d) {
   const int grid = (int)std::max<long long>(1, std::min<long long>(want, d->sm_count));
   const size_t niter = ((size_t)ntiles + (size_t)grid * warps - 1) / ((size_t)grid * warps);
   const size_t nblocks = niter * grid + 1;
-  CKS(d->status.ensure(nblocks));
-  CK(cudaMemsetAsync(d->status.p, 0, nblocks * sizeof(u64), d->stream));
+  u64* chain = nullptr;
+  CKS(chain_reserve(d, nblocks, &chain));
   CK(cudaEventRecord(d->ev[3], d->stream));
   EllArgs p{};
-  p.blk_status = d->status.p;
+  p.blk_status = chain;
   p.Arow = a.m.Arow; p.Acol = a.m.Acol; p.Bell = d->bell.p; p.An = a.m.An; p.Bn = a.m.Bn;
   { const double inv = 4294967296.0 / (double)a.m.Bm * (1.0 - 1.0 / 1048576.0); float f = (float)inv; if ((double)f > inv) f = nextafterf(f, 0.0f); p.inv_bm = f; }
   p.SW = SW; p.lf16 = d->ell_lf16;

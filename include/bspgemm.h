@@ -91,9 +91,10 @@ void bspgemm_SpGEMM_bigslice(int *Acol, int *Arow, int An, int *Bcol, int *Brow,
                              int start_row, int end_row);                         /* :15-18 */
 
 /* ---- device-resident operator (one GPU; what each torch.distributed rank / each shard calls) ----
- * All pointers are device pointers on `device`.  Work is enqueued on `stream` (a cudaStream_t, NULL =
- * the handle's own stream) and the call returns after the result size is known (it synchronises the
- * stream twice: after work estimation and at the end).  dCrow: An+1 entries of 32- or 64-bit.
+ * All pointers are device pointers on `device`.  Work is enqueued on `stream` (a cudaStream_t; NULL = the CUDA
+ * legacy default stream, i.e. ordered after the caller's earlier default-stream work) and the call returns after
+ * the result size is known (it synchronises the stream after the probes and at the end; once, at the end, for a
+ * product replayed from the plan of a prepared B).  dCrow: An+1 entries of 32- or 64-bit.
  * *dCcol_out points into an arena owned by the handle, valid until the next multiply / destroy. */
 typedef struct bspgemm_dev bspgemm_dev;
 
@@ -120,6 +121,8 @@ typedef struct bspgemm_stats {
                                  ELL width W, ms_symbolic = the CSR->ELL re-layout of B */
   int32_t rows_per_tile;      /* fused kernels: consecutive rows per look-back tile */
   int32_t kernel_flags;       /* bit 0: variant 2 ran k_fused_sort_async (cp.async input) rather than k_fused_sort */
+  int32_t b_prepared;         /* 1: B was the matrix given to bspgemm_dev_prepare_b (its re-layout was not rebuilt) */
+  int32_t plan_cached;        /* 1: launched from the cached plan of the previous product (no probes, one kernel) */
 } bspgemm_stats;
 
 int bspgemm_dev_create(bspgemm_dev **h, int device);
@@ -131,6 +134,15 @@ int bspgemm_dev_multiply(bspgemm_dev *h, void *stream,
                          void *dCrow, int crow_is_i64,
                          int **dCcol_out, int64_t *nnz_out);
 int bspgemm_dev_get_stats(bspgemm_dev *h, bspgemm_stats *out);
+/* B resident once for many products — the reference replicates B once, before its timed loop (every rank parses the file,
+ * final/SpGEMM_mpi_omp.c:309 vs :318-328).  Builds B's gather-friendly copy in the handle (ELL re-layout, or run descriptors
+ * for banded matrices) and remembers the plan of the next product with it: later bspgemm_dev_multiply calls that pass the SAME
+ * dBcol/dBrow/Bn/Bm/Bnnz skip the re-layout and the probe kernels.  Contract: the caller does not modify B until the next
+ * bspgemm_dev_prepare_b / bspgemm_dev_forget_b.  A is free to change between products (a product the cached plan does not fit
+ * is detected on the device and redone with fresh probes).  Results are identical with and without it. */
+int bspgemm_dev_prepare_b(bspgemm_dev *h, void *stream,
+                          const int *dBcol, const int *dBrow, int Bn, int Bm, int64_t Bnnz);
+int bspgemm_dev_forget_b(bspgemm_dev *h);
 
 /* ---- COO -> CSC/CSR on the device.  Replaces coo2csc (final/coo2csc.c:22-64, final/coo2csc.h:5-13): same
  * argument list and the same result — col[0..n] pointers by `col_coo`, row[] = the `row_coo` values of each column in INPUT

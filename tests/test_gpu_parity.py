@@ -587,3 +587,109 @@ def test_sort_kernels_on_tiny_and_ragged_shapes(bs, oracle, monkeypatch, kernel)
             got_col, got_row, st = dev_multiply(bs, bs.MODE_AUTO, Acol, Arow, An, Bcol, Brow, Bn, Bm, i64=i64)
             msg = _explain(got_col, got_row, want_col, want_row)
             assert not msg, f"An={An} Bn={Bn} Bm={Bm} [{kernel}] i64={i64} variant={st['variant']}: {msg}"
+
+
+# ------------------------------------------------------------------------------------------------ prepared B / cached plan
+def _dev_handle_product(bs, h, dAc, dAr, An, Annz, dBc, dBr, Bn, Bm, Bnnz, i64=False):
+    import torch
+    dCr = torch.full((An + 1,), -7, dtype=torch.int64 if i64 else torch.int32, device=dAr.device)
+    ptr, nnz = h.multiply(dAc, dAr, An, Annz, dBc, dBr, Bn, Bm, Bnnz, dCr, crow_is_i64=i64)
+    torch.cuda.synchronize()
+    return bs.device_view(ptr, nnz, 0).cpu().numpy().copy(), dCr.cpu().numpy(), h.stats()
+
+
+def test_prepared_b_gives_identical_results_and_replays_the_plan(bs, oracle):
+    """bspgemm_dev_prepare_b: the ELL copy of B and the plan survive across products.  First product: probes, no re-layout;
+    following products: launched from the cached plan (one kernel).  Every result is compared with the oracle; then A changes
+    to rows LONGER than the plan's LA (detected on the device, redone with fresh probes), to ragged rows (host-side rule sends
+    it the long way), and back."""
+    import torch
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(dev)
+    n = 30011
+    brow, bcol = bs.gen_uniform(n, 8, 3)
+    dBr, dBc = t(brow), t(bcol)
+    h = bs.DeviceSpGEMM(0)
+    h.prepare_b(dBc, dBr, n, n, len(bcol))
+    rng = np.random.default_rng(5)
+
+    def product(arow, acol, An, expect_cached, expect_variant=2):
+        want_col, want_row = oracle.spgemm(acol, arow, An, bcol, brow, n)
+        got_col, got_row, st = _dev_handle_product(bs, h, t(acol), t(arow), An, len(acol), dBc, dBr, n, n, len(bcol))
+        msg = _explain(got_col, got_row, want_col, want_row)
+        assert not msg, msg
+        assert st["b_prepared"] == 1 and st["plan_cached"] == (1 if expect_cached else 0), st
+        if expect_variant is not None:
+            assert st["variant"] == expect_variant, st
+        return st
+
+    a8r, a8c = bs.gen_uniform(n, 8, 11)
+    st = product(a8r, a8c, n, False)                 # first product with this B: probes run, the ELL copy is reused
+    assert st["launches"] == 3                       # k_maxlen (A only), k_probe_span, the sort kernel: no k_build_ell in this product
+    st = product(a8r, a8c, n, True)                  # replayed
+    assert st["launches"] == 1
+    a8r2, a8c2 = bs.gen_uniform(n - 7, 8, 12)        # another A of the same kind (fewer rows): still replayed
+    product(a8r2, a8c2, n - 7, True)
+    a16r, a16c = bs.gen_uniform(n, 16, 13)           # rows longer than the plan's LA = 8: flagged by the kernel, redone
+    product(a16r, a16c, n, False)
+    product(a16r, a16c, n, True)                     # ... and the new plan (LA = 16) is cached
+    product(a8r, a8c, n, True)                       # shorter rows fit the LA = 16 plan
+    rr, rc = random_csr(rng, 5000, n, 3.0)           # ragged rows: not "regular" -> host-side rule declines the replay
+    product(rr, rc, 5000, False, expect_variant=None)
+    # an unrelated B through the same handle invalidates nothing silently: its product is correct, and so is the next prepared one
+    b2r, b2c = bs.gen_uniform(n, 4, 21)
+    want_col, want_row = oracle.spgemm(a8c, a8r, n, b2c, b2r, n)
+    got_col, got_row, st = _dev_handle_product(bs, h, t(a8c), t(a8r), n, len(a8c), t(b2c), t(b2r), n, n, len(b2c))
+    assert not _explain(got_col, got_row, want_col, want_row) and st["b_prepared"] == 0
+    product(a8r, a8c, n, False, expect_variant=None)  # the ELL buffer was overwritten: rebuilt, result still exact
+    h.forget_b()
+    want_col, want_row = oracle.spgemm(a8c, a8r, n, bcol, brow, n)
+    got_col, got_row, st = _dev_handle_product(bs, h, t(a8c), t(a8r), n, len(a8c), dBc, dBr, n, n, len(bcol))
+    assert not _explain(got_col, got_row, want_col, want_row) and st["b_prepared"] == 0 and st["plan_cached"] == 0
+    h.close()
+
+
+def test_prepared_b_band_plan(bs, oracle):
+    """Banded B: prepare_b keeps the run descriptors; the replayed product is the band kernel alone.  An A whose output rows are
+    wider than the register bitmap fails on the device and is redone by the general kernels."""
+    import torch
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(dev)
+    n = 20000
+    brow, bcol = bs.gen_banded(n, 32)
+    dBr, dBc = t(brow), t(bcol)
+    h = bs.DeviceSpGEMM(0)
+    h.prepare_b(dBc, dBr, n, n, len(bcol))
+    for k, cached in enumerate((False, True, True)):
+        want_col, want_row = oracle.spgemm(bcol, brow, n, bcol, brow, n)
+        got_col, got_row, st = _dev_handle_product(bs, h, dBc, dBr, n, len(bcol), dBc, dBr, n, n, len(bcol))
+        assert not _explain(got_col, got_row, want_col, want_row)
+        assert st["variant"] == 3 and st["plan_cached"] == (1 if cached else 0) and st["b_prepared"] == 1, st
+    assert st["launches"] == 1
+    wr, wc = bs.gen_uniform(n, 4, 9)                  # scattered A: output rows span far more than 128 columns
+    want_col, want_row = oracle.spgemm(wc, wr, n, bcol, brow, n)
+    got_col, got_row, st = _dev_handle_product(bs, h, t(wc), t(wr), n, len(wc), dBc, dBr, n, n, len(bcol))
+    assert not _explain(got_col, got_row, want_col, want_row)
+    assert st["plan_cached"] == 0 and st["variant"] != 3
+    h.close()
+
+
+def test_out_of_range_a_column_equal_to_bn_is_reported(bs):
+    """An A entry equal to Bn (the internal "no row" sentinel of the ELL kernels) is out of range like any other."""
+    import os
+    n = 4096
+    row, col = bs.gen_uniform(n, 8, 1)
+    bad = col.copy(); bad[len(bad) // 2] = n
+    for env in ({}, {"BSPGEMM_SORT_ASYNC": "1"}, {"BSPGEMM_NO_SORT": "1"}, {"BSPGEMM_NO_ELL": "1"}):
+        old = {k: os.environ.get(k) for k in env}
+        os.environ.update(env)
+        try:
+            with pytest.raises(bs.BSpGEMMError) as e:
+                dev_multiply(bs, bs.MODE_AUTO, bad, row, n, col, row, n, n)
+            assert e.value.status == bs.ERR_BADARG, env
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
