@@ -727,6 +727,7 @@ struct Nccl {
   ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -741,15 +742,17 @@ static Global g;
 static std::mutex g_mu;
 
 static int nccl_load(Nccl& n) {
-  // NCCL prints its version line to stdout at NCCL_DEBUG=VERSION (set on some boxes): the drivers' stdout is the CSV line
-  // (WARN still prints it: levels are NONE < VERSION < WARN < INFO).  Whatever level the environment asks for, NCCL's own
-  // messages go to stderr unless the caller chose a file.
+  // The drivers' stdout is the reference's CSV line and nothing else, but NCCL logs to stdout by default and ignores
+  // NCCL_DEBUG_FILE at level VERSION (which some boxes export): VERSION becomes WARN (same banner, no further output unless
+  // something goes wrong), and whatever level is asked for, the log goes to stderr unless the caller chose a file.
+  const char* dbg = getenv("NCCL_DEBUG");
+  if (dbg && !strcasecmp(dbg, "VERSION")) setenv("NCCL_DEBUG", "WARN", 1);
   if (!getenv("NCCL_DEBUG_FILE")) setenv("NCCL_DEBUG_FILE", "/dev/stderr", 1);
   const char* names[] = {"libnccl.so.2", "libnccl.so"};
   for (const char* nm : names) { n.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (n.lib) break; }
   if (!n.lib) return fail(BSPGEMM_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
 #define SYM(field, name) do { *(void**)(&n.field) = dlsym(n.lib, name); if (!n.field) return fail(BSPGEMM_ERR_NCCL, "libnccl lacks %s", name); } while (0)
-  SYM(CommInitAll, "ncclCommInitAll"); SYM(CommDestroy, "ncclCommDestroy"); SYM(Broadcast, "ncclBroadcast");
+  SYM(CommInitAll, "ncclCommInitAll"); SYM(CommDestroy, "ncclCommDestroy"); SYM(Broadcast, "ncclBroadcast"); SYM(AllGather, "ncclAllGather");
   SYM(GroupStart, "ncclGroupStart"); SYM(GroupEnd, "ncclGroupEnd"); SYM(GetErrorString, "ncclGetErrorString");
 #undef SYM
   return BSPGEMM_OK;
@@ -841,6 +844,7 @@ static int host_multiply(const int* Acol, const int* Arow, int An, const int* Bc
   for (int q = 0; q <= ng; ++q) r0[q] = (int)((int64_t)An * q / ng);
 
   // upload A shards; B to task 0 and — without a communicator (tasks sharing GPUs) — to the first task of every other device
+  const int64_t bchunk = (Bnnz + ng - 1) / ng;           // Bcol is uploaded in ng chunks (one per GPU) when a communicator exists
   std::vector<int> b_owner(ng);                       // task whose copy of B task q reads
   for (int q = 0; q < ng; ++q) {
     b_owner[q] = q;
@@ -859,21 +863,25 @@ static int host_multiply(const int* Acol, const int* Arow, int An, const int* Bc
     if (hi > lo) CK(cudaMemcpyAsync(d->in_acol.p, Acol + lo, (size_t)(hi - lo) * 4, cudaMemcpyHostToDevice, d->stream));
     if (b_owner[q] != q) continue;
     CKS(d->in_brow.ensure((size_t)Bn + 1));
-    CKS(d->in_bcol.ensure((size_t)std::max<int64_t>(Bnnz, 1)));
-    if (q == 0 || g.comms.empty()) {
+    CKS(d->in_bcol.ensure((size_t)std::max<int64_t>(bchunk * ng, 1)));
+    if (g.comms.empty() || ng == 1) {
       CK(cudaMemcpyAsync(d->in_brow.p, Brow, ((size_t)Bn + 1) * 4, cudaMemcpyHostToDevice, d->stream));
       if (Bnnz > 0) CK(cudaMemcpyAsync(d->in_bcol.p, Bcol, (size_t)Bnnz * 4, cudaMemcpyHostToDevice, d->stream));
+    } else {
+      // B crosses PCIe ONCE in total: GPU q uploads the q-th of ng equal chunks of Bcol over its own link (GPU 0 also Brow),
+      // NVLink replicates (ncclAllGather in place / ncclBroadcast) — the reference: every rank parses the whole file (:309)
+      if (q == 0) CK(cudaMemcpyAsync(d->in_brow.p, Brow, ((size_t)Bn + 1) * 4, cudaMemcpyHostToDevice, d->stream));
+      const int64_t c0 = bchunk * q, c1 = std::min<int64_t>(Bnnz, c0 + bchunk);
+      if (c1 > c0) CK(cudaMemcpyAsync(d->in_bcol.p + c0, Bcol + c0, (size_t)(c1 - c0) * 4, cudaMemcpyHostToDevice, d->stream));
     }
   }
-  if (ng > 1 && !g.comms.empty()) {   // replicate B over NVLink: one upload + ncclBroadcast (the reference: every rank parses the file, :309)
-    CK(cudaSetDevice(g.devs[0]->device));
-    CK(cudaStreamSynchronize(g.devs[0]->stream));
+  if (ng > 1 && !g.comms.empty()) {
     NK(g.nccl.GroupStart());
     for (int q = 0; q < ng; ++q) NK(g.nccl.Broadcast(g.devs[0]->in_brow.p, g.devs[q]->in_brow.p, (size_t)Bn + 1, ncclInt32, 0, g.comms[q], g.devs[q]->stream));
     NK(g.nccl.GroupEnd());
     if (Bnnz > 0) {
       NK(g.nccl.GroupStart());
-      for (int q = 0; q < ng; ++q) NK(g.nccl.Broadcast(g.devs[0]->in_bcol.p, g.devs[q]->in_bcol.p, (size_t)Bnnz, ncclInt32, 0, g.comms[q], g.devs[q]->stream));
+      for (int q = 0; q < ng; ++q) NK(g.nccl.AllGather(g.devs[q]->in_bcol.p + bchunk * q, g.devs[q]->in_bcol.p, (size_t)bchunk, ncclInt32, g.comms[q], g.devs[q]->stream));
       NK(g.nccl.GroupEnd());
     }
   } else if (ng > 1) {                // shards sharing a GPU read the owner's copy once its upload has landed
