@@ -562,6 +562,7 @@ static int mul_launch_fast(bspgemm_dev* d, bool* taken) {
   if (pb.variant == 2) {
     const int LA = 1 << pb.sort_LAL;
     if (pb.ell_W == 0 || (u64)a.Annz * 2ull < (u64)a.m.An * (u64)LA) return BSPGEMM_OK;      // "regular" rule of ell_plan
+    if (d->ell_pad != sort_pad_for(pb.ell_W, pb.sort_LAL, a.m.Bm)) return BSPGEMM_OK;          // the ELL copy's padding must be this plan's kernel's
     ip_bound = (u64)a.Annz * (u64)pb.max_len_b;
   } else {
     if (!pb.desc) return BSPGEMM_OK;
@@ -705,7 +706,9 @@ extern "C" int bspgemm_dev_prepare_b(bspgemm_dev* h, void* stream, const int* dB
     int W = 4; while (W < (int)hs.max_len_b) W <<= 1;
     if ((u64)Bn * (u64)W <= 4ull * (u64)Bnnz + 4096ull) {     // the padding rule of ell_plan
       CK(cudaMemsetAsync(d->d_sc, 0, sizeof(DevScalars), d->stream));
-      CKS(build_ell(d, W, true));
+      // padding: what the sort kernel of the likely plan wants — only rows of 16+ columns reach the big-tile geometries that have
+      // the floating-point network (fused_sort.cuh); a first product that needs the other value rebuilds the copy once
+      CKS(build_ell(d, W, true, (W >= 16 && (u32)Bm <= (1u << 23) && !getenv("BSPGEMM_SORT_INT")) ? 0x3F800000u : EMPTY));
       CK(cudaMemcpyAsync(d->h_sc, d->d_sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, d->stream));
       CK(cudaStreamSynchronize(d->stream));
       if (d->h_sc->err & 4u) return fail(BSPGEMM_ERR_BADARG, "a column index of B is outside [0,Bm=%d)", Bm);

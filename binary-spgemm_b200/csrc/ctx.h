@@ -70,11 +70,12 @@ struct bspgemm_dev {
     bool valid = false;
     const int* brow = nullptr; const int* bcol = nullptr; int Bn = 0, Bm = 0; int64_t Bnnz = 0;   // identity of B (the caller keeps its contents unchanged)
     u32 max_len_b = 0;
-    int ell_W = 0;                  // ELL copy of B in `bell` (every row sorted), 0: none
+    int ell_W = 0;                  // ELL copy of B in `bell` (every row sorted, padded with d->ell_pad), 0: none
     bool desc = false;              // every B row is a run of consecutive columns: descriptors in `bdesc`
     int variant = -1, sort_LAL = 0; // plan of the last successful product with this B that can be replayed without probes (2 sort, 3 band)
   } pb;
   DevBuf<u32> bdesc;
+  u32 ell_pad = EMPTY;              // padding value of the ELL copy in `bell`: EMPTY, or EMPTY_F for the floating-point sort network
   bool fast = false;                // the product in flight was launched from the cached plan (no probes, no host round trip before the launch)
   cudaEvent_t ev[8] = {};
   // per-call state
@@ -119,7 +120,8 @@ inline bool b_prepared(const bspgemm_dev* d) {
 }
 
 // ---- launchers defined next to the kernels they instantiate
-BSP_HIDDEN int build_ell(bspgemm_dev* d, int W, bool sorted);      // tu_ell.cu: CSR -> ELL copy of the current B into d->bell
+BSP_HIDDEN int build_ell(bspgemm_dev* d, int W, bool sorted, u32 pad);   // tu_ell.cu: CSR -> ELL copy of the current B into d->bell
+BSP_HIDDEN u32 sort_pad_for(int W, int LAL, int Bm);                // tu_ell.cu: padding the sort kernel of this plan expects (sort_plan_flt, fused_sort.cuh)
 BSP_HIDDEN int set_attrs_ell(int smem_optin);                      // tu_ell.cu
 BSP_HIDDEN int launch_ell(bspgemm_dev* d);                         // tu_ell.cu: k_build_ell, then k_fused_ell or the sort kernel
 BSP_HIDDEN int launch_sort(bspgemm_dev* d, int* ccol);             // tu_ell.cu: dispatch on the ELL width ...

@@ -89,7 +89,7 @@ __device__ __forceinline__ int acol_checked(int j, int Bn) { return (u32)j < (u3
 constexpr int ELL_RPT = 2;
 template <int W, bool SORTED>
 __global__ void __launch_bounds__(256) k_build_ell(const int* __restrict__ Brow, const int* __restrict__ Bcol, int Bn, u32 Bm,
-                                                   u32* __restrict__ Bell, DevScalars* sc) {
+                                                   u32* __restrict__ Bell, DevScalars* sc, const u32 pad) {   // pad: EMPTY, or EMPTY_F for the floating-point network (fused_sort.cuh)
   constexpr int LPR = W / 4;
   const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long H = ((long long)Bn + ELL_RPT) / ELL_RPT;             // rows per slab; row Bn (the all-EMPTY "no row" row) included
@@ -112,12 +112,12 @@ __global__ void __launch_bounds__(256) k_build_ell(const int* __restrict__ Brow,
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int o = bs[r] + part * 4 + k;
-      x[r][k] = (o < be[r]) ? (u32)__ldg(&Bcol[o]) : EMPTY;
+      x[r][k] = (o < be[r]) ? (u32)__ldg(&Bcol[o]) : pad;
     }
 #pragma unroll
   for (int r = 0; r < ELL_RPT; ++r) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) if (bs[r] + part * 4 + k < be[r] && x[r][k] >= Bm) { bad = 1; x[r][k] = EMPTY; }   // a column outside [0,Bm)
+    for (int k = 0; k < 4; ++k) if (bs[r] + part * 4 + k < be[r] && x[r][k] >= Bm) { bad = 1; x[r][k] = pad; }   // a column outside [0,Bm)
     if (SORTED) bitonic_sort_rows<4, LPR, 1>(x[r], (u32)part);          // 256 threads = whole rows: LPR divides 32
     if (live[r]) reinterpret_cast<uint4*>(Bell)[row[r] * LPR + part] = make_uint4(x[r][0], x[r][1], x[r][2], x[r][3]);
   }

@@ -16,6 +16,7 @@
 // The scan / deferred commit / tile pipeline are those of fused_ell.cuh (CtaChain): the aggregate of a tile is posted
 // when its rows are staged, the tile is committed one tile later from the other half of a ping-pong staging buffer.
 #pragma once
+#include <stdlib.h>
 #include "fused_ell.cuh"
 
 namespace bsk {
@@ -25,7 +26,7 @@ constexpr int SORT_MAX_WARPS = 32;        // CtaChain holds 32 warps; the launch
 struct SortGeom {          // compile-time geometry of k_fused_sort<W, LAL>
   int LPR, LA, S, NQ, K, RP, R, NP;
 };
-template <int W, int LAL> __host__ __device__ constexpr SortGeom sort_geom() {
+__host__ __device__ constexpr SortGeom sort_geom_rt(int W, int LAL) {
   SortGeom g{};
   g.LPR = W / 4;                               // lanes per B row (one uint4 each)
   g.LA = 1 << LAL;                             // B rows per output row (A row length, rounded up)
@@ -48,6 +49,23 @@ template <int W, int LAL> __host__ __device__ constexpr SortGeom sort_geom() {
   g.NP = np;
   g.R = g.RP * np;                             // rows per tile
   return g;
+}
+template <int W, int LAL> __host__ __device__ constexpr SortGeom sort_geom() { return sort_geom_rt(W, LAL); }
+// The cp.async kernel is the default for big tiles (32 keys per lane, one pass per tile); those also have the
+// floating-point network (FLT) when every key is below 2^23.
+__host__ __device__ constexpr bool sort_big_tile(int W, int LAL) { const SortGeom g = sort_geom_rt(W, LAL); return g.K == 32 && g.NP == 1; }
+constexpr u32 EMPTY_F = 0x3F800000u;        // padding of the ELL copy for the floating-point network: 1.0f
+constexpr u32 SORT_FLT_MAX_BM = 1u << 23;   // keys below 2^23: a + b and (a + b) - min(a, b) are exact in binary32
+// Host: which sort kernel a (W, LAL) plan runs, and whether with the floating-point network — ONE rule, used where the ELL copy
+// is built (its padding value depends on it) and where the kernel is launched.  BSPGEMM_SORT_SYNC / BSPGEMM_SORT_ASYNC force a
+// kernel, BSPGEMM_SORT_INT keeps the integer network (A/B runs, tests).
+static inline bool sort_plan_async(int W, int LAL) {
+  if (getenv("BSPGEMM_SORT_ASYNC")) return true;
+  if (getenv("BSPGEMM_SORT_SYNC")) return false;
+  return sort_big_tile(W, LAL);
+}
+static inline bool sort_plan_flt(int W, int LAL, int Bm) {
+  return sort_plan_async(W, LAL) && sort_big_tile(W, LAL) && (u32)Bm <= SORT_FLT_MAX_BM && !getenv("BSPGEMM_SORT_INT");
 }
 // staging words of one tile: R rows of LA*W keys, plus one pad word per 32 (bank skew)
 constexpr u32 SORT_HDR = 20;             // per staging buffer: [0] total, [1] tile, [2..2+R) inclusive row counts
@@ -336,11 +354,23 @@ __global__ void __maxnreg__((sort_geom<W, LAL>().K >= 32 ? 96 : 80)) k_fused_sor
 // Shared memory per warp: the input buffer + LAG staging buffers (the tile's B-row table stays in registers).  A tile can
 // only be committed once the offsets of ALL earlier tiles of the grid are known (the chain), about one iteration after it
 // was posted, and here the commit of tile t-LAG comes before tile t is staged: with LAG = 1 the warps wait for the chain in
-// every iteration (config 3: 3.64 ms, 2.61 ms with the scan switched off), so the host launches LAG = 2 — 12.7 KB per warp
-// at config 3, 18 warps per SM where the registers would allow 19 (3.11 ms).  Tried and dropped
-// (profiles/r01_sort_async_sweeps.txt): a CTA-wide pool of staging buffers shared by 19 warps (3.52 ms: the warps that find
-// the pool empty hold back the whole CTA), tiles of 2 rows with 16 keys per lane and 31 warps (3.15 ms: 128 more SHFL per
-// 1024 keys), the commit done by the helper warp (6.06 ms: one warp cannot copy 18 tiles per iteration).
+// every iteration (config 3: 3.64 ms, 2.61 ms with the scan switched off), so the host launches LAG = 2.
+//
+// Round 2 (profiles/r02_*): the loop body of the round-1 kernel was 43 KB of code (the instruction cache holds 32 KB: 6 % of
+// the warp time was spent waiting for instructions), 1111 of its 2187 warp instructions per 1024-key tile went to the ALU pipe
+// (65 % busy, the limiter of the sort phase) and only 619 of those were the comparators' VIMNMX proper.  Changes:
+//   * staging in 16-byte groups, XOR-swizzled instead of padded: the sorted keys leave the registers as STS.128 (8 instead of
+//     32 stores per lane and tile) and the commit reads aligned LDS.128 pairs, funnel-shifted by the destination's phase
+//     (16 LDS.128 instead of 32 LDS.32 with an address computation each).  (Tried: a 36-word stride — the padding cost the 18th
+//     warp, +5 %; the rare passes with a duplicate or padding fixed up out of line through shared memory — the call made ptxas
+//     spill loop invariants to local memory, one exposed LDL latency per tile, 14 % of the warp time.)
+//   * FLT (Bm <= 2^23: every key is a subnormal float with the same bit pattern): the network runs in the floating-point
+//     domain.  In-lane comparators take two neighbouring keys at a time, lo = FMNMX (ALU pipe), hi = (a + b) - lo as two
+//     FADD2 on packed register pairs (FMA pipe): 1 + 1 instructions per comparator instead of 1 + 2 (IMAD form) or 2 ALU.
+//     Cross-lane exchanges: lanes that keep the maximum hold NEGATED keys for the duration of the cross-lane stages, so that
+//     both partners execute the same FMNMX(own, -received) (the negation is a free source modifier): one ALU instruction
+//     per key instead of VIMNMX + predicated VIMNMX; switching a lane between the two representations is one FMUL2 per
+//     two keys.  Padding is 1.0f (EMPTY_F): larger than every key, and x + 1 - x == 1 exactly in this range.
 __device__ __forceinline__ void cp_async16(u32 dst_s, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst_s), "l"(src));
 }
@@ -348,11 +378,137 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __host__ __device__ constexpr u32 sort_input_words(int R, int LA, int W) { return (u32)(R * LA * W); }
 
-template <int W, int LAL>
+// staging buffer of the async kernel: header, then the keys in 16-byte groups of 4, group g = 8*l + j (l = the 32-key block, the
+// keys of one lane in the plain case) stored at group slot 8*l + (j ^ (l & 7)): the lanes' STS.128 (fixed j, 8 consecutive l) and
+// the commit's LDS.128 (fixed l, 8 consecutive j) are both bank-conflict-free WITHOUT padding words (a 36-word stride cost the
+// 18th warp of config 3); 8 spare words for the funnel's look-ahead
+__host__ __device__ constexpr u32 sort_stage_words_a(int R, int LA, int W) { const u32 n = (u32)(R * LA * W); return (SORT_HDR + n + 8u + 3u) & ~3u; }
+__device__ __forceinline__ u32 sgrp_s(u32 buf_s, u32 g) { return buf_s + 4u * SORT_HDR + 16u * ((g & ~7u) | ((g ^ (g >> 3)) & 7u)); }   // group g (keys 4g..4g+3)
+__device__ __forceinline__ u32 skey_s(u32 buf_s, u32 q) { return sgrp_s(buf_s, q >> 2) + 4u * (q & 3u); }
+
+// Staged keys -> dst[0..total), whole warp, 16-byte stores: `head` keys up to the first 16-byte boundary of dst, then chunks
+// of 4 keys — chunk c is keys head+4c .. head+4c+3, i.e. the aligned groups c and c+1 of the staging buffer shifted by head —
+// then the tail.
+template <int H>
+__device__ __forceinline__ void commit_body(int4* dst4, const u32 buf_s, const u32 body) {
+  const u32 lane = lane_id();
+  auto grp = [&](u32 g) { return lds128(sgrp_s(buf_s, g)); };
+  auto pick = [&](const uint4 a, const uint4 b) {
+    return H == 0 ? make_int4((int)a.x, (int)a.y, (int)a.z, (int)a.w) : H == 1 ? make_int4((int)a.y, (int)a.z, (int)a.w, (int)b.x)
+         : H == 2 ? make_int4((int)a.z, (int)a.w, (int)b.x, (int)b.y) : make_int4((int)a.w, (int)b.x, (int)b.y, (int)b.z);
+  };
+  u32 c = lane;
+  for (; c + 32u < body; c += 64u) {
+    const uint4 a0 = grp(c), a1 = grp(c + 32u);
+    uint4 b0 = a0, b1 = a1;
+    if (H) { b0 = grp(c + 1u); b1 = grp(c + 33u); }
+    dst4[c] = pick(a0, b0);
+    dst4[c + 32u] = pick(a1, b1);
+  }
+  if (c < body) {
+    const uint4 a0 = grp(c);
+    uint4 b0 = a0;
+    if (H) b0 = grp(c + 1u);
+    dst4[c] = pick(a0, b0);
+  }
+}
+__device__ __forceinline__ void commit_keys128(int* dst, const u32 buf_s, const u32 total) {
+  const u32 lane = lane_id();
+  const u32 head = min(total, (u32)(((16u - ((u32)(size_t)dst & 15u)) & 15u) >> 2));
+  const u32 body = (total - head) >> 2, tail = (total - head) & 3u;
+  if (lane < head) dst[lane] = (int)lds32(skey_s(buf_s, lane));
+  if (lane < tail) dst[head + 4u * body + lane] = (int)lds32(skey_s(buf_s, head + 4u * body + lane));
+  int4* dst4 = reinterpret_cast<int4*>(dst + head);
+  if (head == 0u) commit_body<0>(dst4, buf_s, body);
+  else if (head == 1u) commit_body<1>(dst4, buf_s, body);
+  else if (head == 2u) commit_body<2>(dst4, buf_s, body);
+  else commit_body<3>(dst4, buf_s, body);
+}
+
+// ---- the sorting network in the floating-point domain (see the header comment; same element order as bitonic_sort_rows)
+__device__ __forceinline__ float as_f(u32 v) { return __uint_as_float(v); }
+__device__ __forceinline__ u32 as_u(float v) { return __float_as_uint(v); }
+// two comparators on neighbouring registers: (a0,b0) and (a1,b1); minima to a, maxima to b
+__device__ __forceinline__ void cmp2_f(u32& a0, u32& a1, u32& b0, u32& b1) {
+  const float2 A = make_float2(as_f(a0), as_f(a1)), B = make_float2(as_f(b0), as_f(b1));
+  const float2 S2 = __fadd2_rn(A, B);
+  const float l0 = fminf(A.x, B.x), l1 = fminf(A.y, B.y);
+  const float2 H = __fadd2_rn(S2, make_float2(-l0, -l1));
+  a0 = as_u(l0); a1 = as_u(l1); b0 = as_u(H.x); b1 = as_u(H.y);
+}
+__device__ __forceinline__ void cmp1_f(u32& a, u32& b) {
+  const float x = as_f(a), y = as_f(b);
+  a = as_u(fminf(x, y)); b = as_u(fmaxf(x, y));
+}
+template <int K>
+__device__ __forceinline__ void flip_sign(u32 (&x)[K], const float sg) {     // x *= sg (sg = +-1), two keys per FMUL2
+  const float2 s2 = make_float2(sg, sg);
+#pragma unroll
+  for (int k = 0; k < K; k += 2) {
+    const float2 v = __fmul2_rn(make_float2(as_f(x[k]), as_f(x[k + 1])), s2);
+    x[k] = as_u(v.x); x[k + 1] = as_u(v.y);
+  }
+}
+template <int K, int S, int RUN>
+__device__ __forceinline__ void bitonic_sort_rows_f(u32 (&x)[K], const u32 ll) {
+  constexpr int N = K * S;
+  static_assert(K % 2 == 0, "pairs");
+#pragma unroll
+  for (int size = 2 * RUN; size <= N; size <<= 1) {
+    bool neg = false;                                                // this lane holds negated keys (cross-lane stages only)
+    if (size <= K) {                                                 // mirror inside the lane
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const int pk = k ^ (size - 1);
+        if (k < pk) cmp1_f(x[k], x[pk]);
+      }
+    } else {                                                         // mirror across lanes: register k <-> K-1-k of lane ^ (size/K-1)
+      const u32 lm = (u32)(size / K - 1);
+      neg = (ll & (u32)(size / (2 * K))) != 0u;                      // the lane keeps the maxima: as minima of negated keys
+      flip_sign<K>(x, neg ? -1.0f : 1.0f);
+#pragma unroll
+      for (int k = 0; k < K / 2; ++k) {
+        const float ya = as_f(__shfl_xor_sync(0xffffffffu, x[K - 1 - k], lm));
+        const float yb = as_f(__shfl_xor_sync(0xffffffffu, x[k], lm));
+        x[k] = as_u(fminf(as_f(x[k]), -ya));
+        x[K - 1 - k] = as_u(fminf(as_f(x[K - 1 - k]), -yb));
+      }
+    }
+#pragma unroll
+    for (int d = size >> 2; d >= 1; d >>= 1) {
+      if (d >= K) {                                                  // partner key lives in lane ^ (d/K)
+        const u32 ld = (u32)(d / K);
+        const bool want = (ll & ld) != 0u;
+        flip_sign<K>(x, want != neg ? -1.0f : 1.0f);
+        neg = want;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const float y = as_f(__shfl_xor_sync(0xffffffffu, x[k], ld));
+          x[k] = as_u(fminf(as_f(x[k]), -y));
+        }
+      } else {
+        if (d == K / 2 || (size <= K && d == size >> 2)) {           // first in-lane stage after the cross-lane ones: back to plain keys
+          if (size > K) { flip_sign<K>(x, neg ? -1.0f : 1.0f); neg = false; }
+        }
+        if (d >= 2) {                                                // both keys in this lane, two comparators per instruction pair
+#pragma unroll
+          for (int k = 0; k < K; k += 2)
+            if ((k & d) == 0) cmp2_f(x[k], x[k + 1], x[k | d], x[(k | d) + 1]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < K; k += 2) cmp1_f(x[k], x[k + 1]);
+        }
+      }
+    }
+  }
+}
+
+template <int W, int LAL, bool FLT>
 __global__ void __maxnreg__((sort_geom<W, LAL>().K >= 32 ? 96 : 80)) k_fused_sort_async(const EllArgs p) {
   constexpr SortGeom G = sort_geom<W, LAL>();
   constexpr int LPR = G.LPR, LA = G.LA, S = G.S, NQ = G.NQ, K = G.K, RP = G.RP, R = G.R, NP = G.NP;
-  constexpr u32 SWORDS = sort_stage_words(R, LA, W), IWORDS = sort_input_words(R, LA, W);
+  constexpr u32 SWORDS = sort_stage_words_a(R, LA, W), IWORDS = sort_input_words(R, LA, W);
+  constexpr u32 EMP = FLT ? EMPTY_F : EMPTY;                          // padding value of the ELL copy (k_build_ell's `pad`)
   constexpr int SH = NQ >= 8 ? 0 : NQ == 4 ? 1 : NQ == 2 ? 2 : 3;     // swz(L) = (L >> SH) & (NQ-1): 8 consecutive lanes hit 8 different 16-byte bank columns
   static_assert(NQ <= 8 && R * LA <= 64, "geometry");
   extern __shared__ __align__(16) u32 smem[];
@@ -433,8 +589,7 @@ __global__ void __maxnreg__((sort_geom<W, LAL>().K >= 32 ? 96 : 80)) k_fused_sor
     if ((int)lane < nrows) st_rowptr(p.Crow, p.is64, (size_t)(row0 + lane) + 1, excl + incl_mine, &p.sc->err);
     if (t == 0 && lane == 0) st_rowptr(p.Crow, p.is64, 0, 0, &p.sc->err);
     if (t == p.ntiles - 1 && lane == 0) p.sc->total_nnz = excl + total;
-    int* dst = p.Ccol + excl;
-    commit_keys(dst, buf_s, total);
+    commit_keys128(p.Ccol + excl, buf_s, total);
     __syncwarp();
   };
 
@@ -463,7 +618,7 @@ __global__ void __maxnreg__((sort_geom<W, LAL>().K >= 32 ? 96 : 80)) k_fused_sor
   while (tile < p.ntiles) {
     const u32 next = tile_of(iter + 1u);
     const int ar3 = load_rowptr(tile_of(iter + 3u));
-    const u32 buf_s = stage_s + cur_buf * (SWORDS * 4u), cur_s = buf_s + 4u * SORT_HDR;
+    const u32 buf_s = stage_s + cur_buf * (SWORDS * 4u);
     u32 x[NP][K];
     cp_async_wait_all();
     __syncwarp();
@@ -477,28 +632,22 @@ __global__ void __maxnreg__((sort_geom<W, LAL>().K >= 32 ? 96 : 80)) k_fused_sor
 #pragma unroll
     for (int q = 0; q < NP; ++q) {
       u32 (&k)[K] = x[q];
-      // every B row is ascending in the ELL copy (k_build_ell sorts it); big tiles: two of three in-lane maxima on the FMA pipe
-      // (cmpx, kernels.cuh: config 3, same box, 3.115 -> 3.072 ms)
-      bitonic_sort_rows<K, S, (W < K ? W : K), (K >= 32 ? 1 : 0)>(k, ll, p.one, p.mone);
+      // every B row is ascending in the ELL copy (k_build_ell sorts it)
+      if (FLT) bitonic_sort_rows_f<K, S, (W < K ? W : K)>(k, ll);
+      else     bitonic_sort_rows<K, S, (W < K ? W : K), (K >= 32 ? 1 : 0)>(k, ll, p.one, p.mone);   // big tiles: two of three in-lane maxima on the FMA pipe (cmpx, kernels.cuh)
       if (q == 0 && iter >= lag) commit(iter - lag, buf_s);        // frees the staging buffer this tile is about to use
-      // the row is ascending along (lane, register); EMPTY (padding) is the largest value
+      // the row is ascending along (lane, register); padding is the largest value
       u32 prev_last = __shfl_up_sync(0xffffffffu, k[K - 1], 1);
-      if (ll == 0) prev_last = EMPTY;                              // nothing before the row's first key (EMPTY never counts)
-      bool plain = (k[K - 1] != EMPTY) && (k[0] != prev_last);     // no padding in this lane, no duplicate
+      if (ll == 0) prev_last = EMP;                                // nothing before the row's first key (padding never counts)
+      bool plain = (k[K - 1] != EMP) && (k[0] != prev_last);       // no padding in this lane, no duplicate
 #pragma unroll
       for (int i = 1; i < K; ++i) plain = plain && (k[i] != k[i - 1]);
-      if (__all_sync(0xffffffffu, plain)) {
-        // the usual case: no duplicate, no padding anywhere in the pass — every key's place is known in advance
+      if (__all_sync(0xffffffffu, plain) && (NP == 1 || (run & (u32)(4 * K - 1)) == 0u)) {
+        // the usual case: no duplicate, no padding anywhere in the pass — the lane's K keys are K/4 whole groups (STS.128)
         ipc += (u32)K;
-        const u32 pos = lane * (u32)K;                             // rows of the pass back to back, lane-major
-        const u32 a0s = cur_s + 4u * (run + pos + ((run + pos) >> 5));
-        if (((run + pos) & 31u) + (u32)K <= 32u || (K % 32 == 0 && ((run + pos) & 31u) == 0u)) {
+        const u32 g0 = (run >> 2) + lane * (u32)(K / 4);
 #pragma unroll
-          for (int i = 0; i < K; ++i) sts32(a0s + 4u * (u32)(i + i / 32), k[i]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < K; ++i) { const u32 o = run + pos + (u32)i; sts32(cur_s + 4u * (o + (o >> 5)), k[i]); }
-        }
+        for (int i = 0; i < K; i += 4) sts128(sgrp_s(buf_s, g0 + (u32)(i / 4)), k[i], k[i + 1], k[i + 2], k[i + 3]);
 #pragma unroll
         for (int sq = 0; sq < RP; ++sq) { run += (u32)(K * S); if ((int)lane == q * RP + sq) incl_mine = run; }
       } else {
@@ -508,9 +657,9 @@ __global__ void __maxnreg__((sort_geom<W, LAL>().K >= 32 ? 96 : 80)) k_fused_sor
         u32 cnt = 0;
 #pragma unroll
         for (int i = 0; i < K; ++i) {
-          f[i] = (k[i] != EMPTY) && (k[i] != (i ? k[i - 1] : prev_last));
+          f[i] = (k[i] != EMP) && (k[i] != (i ? k[i - 1] : prev_last));
           cnt += f[i] ? 1u : 0u;
-          ipc += (k[i] != EMPTY) ? 1u : 0u;
+          ipc += (k[i] != EMP) ? 1u : 0u;
         }
         u32 inc = cnt;
 #pragma unroll
@@ -526,7 +675,7 @@ __global__ void __maxnreg__((sort_geom<W, LAL>().K >= 32 ? 96 : 80)) k_fused_sor
         }
         u32 o = rowbase + inc - cnt;
 #pragma unroll
-        for (int i = 0; i < K; ++i) if (f[i]) { sts32(cur_s + 4u * (o + (o >> 5)), k[i]); ++o; }
+        for (int i = 0; i < K; ++i) if (f[i]) { sts32(skey_s(buf_s, o), k[i]); ++o; }
       }
     }
     if (lane == 0) sts64(buf_s, run, tile);

@@ -14,19 +14,19 @@ static int pick_compute_warps(size_t per_warp, size_t fixed, int max_warps, size
   return w;
 }
 
-template <int W, int LAL, bool ASYNC> static int launch_sort_t(bspgemm_dev* d, int* ccol) {
+template <int W, int LAL, bool ASYNC, bool FLT> static int launch_sort_t(bspgemm_dev* d, int* ccol) {
   const MulArgs& a = d->a;
   constexpr SortGeom G = sort_geom<W, LAL>();
   const u32 ntiles = (u32)(((size_t)a.m.An + G.R - 1) / G.R);
   // warps per CTA: what the kernel's register count allows (registers are allocated per SM sub-partition: 80 -> 6 warps
   // each, 81..102 -> 5), one of them the chain helper
-  auto kern = ASYNC ? k_fused_sort_async<W, LAL> : k_fused_sort<W, LAL>;
+  auto kern = ASYNC ? k_fused_sort_async<W, LAL, FLT> : k_fused_sort<W, LAL>;
   cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, kern));
   const int max_compute = std::max(1, std::min(SORT_MAX_WARPS, fa.maxThreadsPerBlock / 32) - 1);
   // staging buffers per warp: 2 = commit one tile later; small tiles get 3 (commit lag 2) as long as that costs no warps.
   // ASYNC: the input buffer the cp.async copies land in + 2 staging buffers (the commit of tile t-2 comes before tile t is
   // staged, see fused_sort.cuh); nothing is kept back for L1, which the copies bypass.
-  const size_t one_buf = (size_t)sort_stage_words(G.R, G.LA, W) * 4, in_buf = (size_t)sort_input_words(G.R, G.LA, W) * 4, fixed = ELL_CTA_WORDS * 4 + 64;
+  const size_t one_buf = (size_t)(ASYNC ? sort_stage_words_a(G.R, G.LA, W) : sort_stage_words(G.R, G.LA, W)) * 4, in_buf = (size_t)sort_input_words(G.R, G.LA, W) * 4, fixed = ELL_CTA_WORDS * 4 + 64;
   auto warp_bytes = [&](int nb) { return ASYNC ? in_buf + (size_t)(nb - 1) * one_buf : (size_t)nb * one_buf + 256; };   // sync: + the next tile's <= 64 A nonzeros
   int nbuf = ASYNC ? 3 : 2;
   if (!ASYNC) {
@@ -53,11 +53,11 @@ template <int W, int LAL, bool ASYNC> static int launch_sort_t(bspgemm_dev* d, i
 #ifdef BSPGEMM_DEBUG_KNOBS
   p.debug_nochain = getenv("BSPGEMM_DEBUG_NOCHAIN") ? (u32)(G.R * G.LA * W) : 0u;   // WRONG RESULTS: timing experiments only
 #endif
-  d->st.rows_per_tile = G.R; d->st.variant = 2; d->st.kernel_flags = ASYNC ? 1 : 0;
+  d->st.rows_per_tile = G.R; d->st.variant = 2; d->st.kernel_flags = (ASYNC ? 1 : 0) | (FLT ? 2 : 0);
   p.one = 1u; p.mone = 0xffffffffu;
   if (getenv("BSPGEMM_VERBOSE")) {
-    fprintf(stderr, "k_fused_sort%s<%d,%d>: regs %d, maxThreadsPerBlock %d, static smem %zu, launch %d x %d threads, dyn smem %zu, nbuf %d\n",
-            ASYNC ? "_async" : "", W, LAL, fa.numRegs, fa.maxThreadsPerBlock, fa.sharedSizeBytes, grid, (warps + 1) * 32, smem, nbuf);
+    fprintf(stderr, "k_fused_sort%s<%d,%d>%s: regs %d, maxThreadsPerBlock %d, static smem %zu, launch %d x %d threads, dyn smem %zu, nbuf %d\n",
+            ASYNC ? "_async" : "", W, LAL, FLT ? " (floating-point network)" : "", fa.numRegs, fa.maxThreadsPerBlock, fa.sharedSizeBytes, grid, (warps + 1) * 32, smem, nbuf);
   }
   kern<<<grid, (warps + 1) * 32, smem, d->stream>>>(p);        // + the chain helper warp
   d->launches++;
@@ -68,19 +68,27 @@ template <int W, int LAL, bool ASYNC> static int launch_sort_t(bspgemm_dev* d, i
 #define SORT_CAT2(a, b) a##b
 #define SORT_CAT(a, b) SORT_CAT2(a, b)
 
+// the floating-point network exists for the big-tile geometries only (sort_big_tile)
+template <int Lv> static int set_attrs_l(int smem_optin) {
+  BSP_ATTR((k_fused_sort<SORT_W, Lv>));
+  BSP_ATTR((k_fused_sort_async<SORT_W, Lv, false>));
+  if constexpr (sort_big_tile(SORT_W, Lv)) BSP_ATTR((k_fused_sort_async<SORT_W, Lv, true>));
+  return BSPGEMM_OK;
+}
 int SORT_CAT(set_attrs_sort_w, SORT_W)(int smem_optin) {
-  BSP_ATTR((k_fused_sort<SORT_W, 2>)); BSP_ATTR((k_fused_sort<SORT_W, 3>)); BSP_ATTR((k_fused_sort<SORT_W, 4>)); BSP_ATTR((k_fused_sort<SORT_W, 5>));
-  BSP_ATTR((k_fused_sort_async<SORT_W, 2>)); BSP_ATTR((k_fused_sort_async<SORT_W, 3>)); BSP_ATTR((k_fused_sort_async<SORT_W, 4>)); BSP_ATTR((k_fused_sort_async<SORT_W, 5>));
+  CKS(set_attrs_l<2>(smem_optin)); CKS(set_attrs_l<3>(smem_optin)); CKS(set_attrs_l<4>(smem_optin)); CKS(set_attrs_l<5>(smem_optin));
   return BSPGEMM_OK;
 }
 
+template <int Lv> static int launch_sort_l(bspgemm_dev* d, int* ccol) {
+  const bool async = sort_plan_async(SORT_W, Lv);
+  const bool flt = d->ell_pad == EMPTY_F;                      // the ELL copy was built for the floating-point network (launch_ell / prepare_b)
+  if (flt != sort_plan_flt(SORT_W, Lv, d->a.m.Bm)) return fail(BSPGEMM_ERR_CUDA, "internal: ELL padding does not match the sort kernel of this plan");
+  if constexpr (sort_big_tile(SORT_W, Lv)) { if (flt) return launch_sort_t<SORT_W, Lv, true, true>(d, ccol); }
+  return async ? launch_sort_t<SORT_W, Lv, true, false>(d, ccol) : launch_sort_t<SORT_W, Lv, false, false>(d, ccol);
+}
 int SORT_CAT(launch_sort_w, SORT_W)(bspgemm_dev* d, int* ccol) {
-  const int L = d->sort_LAL;
   // Big tiles (32 keys per lane, one pass per tile: config 3) take the cp.async kernel, the others the register-prefetch
-  // one (config 2: 0.205 ms against 0.24 ms).  BSPGEMM_SORT_SYNC / BSPGEMM_SORT_ASYNC force one of them (A/B runs, tests).
-  const bool force_sync = getenv("BSPGEMM_SORT_SYNC") != nullptr, force_async = getenv("BSPGEMM_SORT_ASYNC") != nullptr;
-#define LS1(Lv) do { constexpr SortGeom g_ = sort_geom<SORT_W, Lv>(); \
-    return (force_async || (!force_sync && g_.K == 32 && g_.NP == 1)) ? launch_sort_t<SORT_W, Lv, true>(d, ccol) : launch_sort_t<SORT_W, Lv, false>(d, ccol); } while (0)
-  switch (L) { case 2: LS1(2); case 3: LS1(3); case 4: LS1(4); default: LS1(5); }
-#undef LS1
+  // one (config 2: 0.205 ms against 0.24 ms); see sort_plan_async / sort_plan_flt (fused_sort.cuh).
+  switch (d->sort_LAL) { case 2: return launch_sort_l<2>(d, ccol); case 3: return launch_sort_l<3>(d, ccol); case 4: return launch_sort_l<4>(d, ccol); default: return launch_sort_l<5>(d, ccol); }
 }

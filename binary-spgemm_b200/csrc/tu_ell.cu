@@ -2,6 +2,7 @@
 // ordered-table kernel k_fused_ell (fused_ell.cuh); the sorting-network kernels live in tu_sort_w*.cu, one per ELL width.
 #include "ctx.h"
 #include "fused_ell.cuh"
+#include "fused_sort.cuh"      // host-side plan helpers only (sort_plan_flt): the sort kernels are instantiated in tu_sort_w*.cu
 
 int set_attrs_ell(int smem_optin) {
 #define ATTR_E(Wv) BSP_ATTR((k_fused_ell<Wv, 1>)); BSP_ATTR((k_fused_ell<Wv, 2>)); BSP_ATTR((k_fused_ell<Wv, 4>)); BSP_ATTR((k_fused_ell<Wv, 8>))
@@ -14,14 +15,17 @@ int launch_sort(bspgemm_dev* d, int* ccol) {
   switch (d->ell_W) { case 4: return launch_sort_w4(d, ccol); case 8: return launch_sort_w8(d, ccol); case 16: return launch_sort_w16(d, ccol); default: return launch_sort_w32(d, ccol); }
 }
 
-int build_ell(bspgemm_dev* d, int W, bool sorted) {
+u32 sort_pad_for(int W, int LAL, int Bm) { return sort_plan_flt(W, LAL, Bm) ? EMPTY_F : EMPTY; }
+
+int build_ell(bspgemm_dev* d, int W, bool sorted, u32 pad) {
   const MulArgs& a = d->a;
-  d->pb.ell_W = 0;                                     // whatever copy `bell` held is gone (bspgemm_dev_prepare_b sets it again)
+  d->pb.ell_W = 0;                                     // whatever copy `bell` held is gone (set again below / by bspgemm_dev_prepare_b)
+  d->ell_pad = pad;
   CKS(d->bell.ensure(((size_t)a.m.Bn + 1) * W + 4));
   const long long threads = (((long long)a.m.Bn + ELL_RPT) / ELL_RPT) * (W / 4);     // ELL_RPT rows per thread
   const int grid = (int)((threads + 255) / 256);
-#define BE(Wv) do { if (sorted) k_build_ell<Wv, true><<<grid, 256, 0, d->stream>>>(a.m.Brow, a.m.Bcol, a.m.Bn, (u32)a.m.Bm, d->bell.p, d->d_sc); \
-                    else k_build_ell<Wv, false><<<grid, 256, 0, d->stream>>>(a.m.Brow, a.m.Bcol, a.m.Bn, (u32)a.m.Bm, d->bell.p, d->d_sc); } while (0)
+#define BE(Wv) do { if (sorted) k_build_ell<Wv, true><<<grid, 256, 0, d->stream>>>(a.m.Brow, a.m.Bcol, a.m.Bn, (u32)a.m.Bm, d->bell.p, d->d_sc, pad); \
+                    else k_build_ell<Wv, false><<<grid, 256, 0, d->stream>>>(a.m.Brow, a.m.Bcol, a.m.Bn, (u32)a.m.Bm, d->bell.p, d->d_sc, pad); } while (0)
   switch (W) { case 4: BE(4); break; case 8: BE(8); break; case 16: BE(16); break; default: BE(32); break; }
 #undef BE
   d->launches++;
@@ -33,8 +37,14 @@ int launch_ell(bspgemm_dev* d) {
   const MulArgs& a = d->a;
   int* ccol = d->user_ccol ? d->user_ccol : d->ccol.p;
   const int W = d->ell_W, R = d->ell_R;
-  // the ELL copy of a prepared B (bspgemm_dev_prepare_b) is reused: sorted rows serve both kernels
-  if (!(b_prepared(d) && d->pb.ell_W == W)) CKS(build_ell(d, W, d->use_sort));
+  // the ELL copy of a prepared B (bspgemm_dev_prepare_b) is reused when its width and padding are what this plan needs
+  // (sorted rows serve both kernels); otherwise it is (re)built — and stays the prepared copy if B is the prepared matrix
+  const u32 pad = d->use_sort ? sort_pad_for(W, d->sort_LAL, a.m.Bm) : EMPTY;
+  const bool prep = b_prepared(d);
+  if (!(prep && d->pb.ell_W == W && d->ell_pad == pad)) {
+    CKS(build_ell(d, W, d->use_sort || prep, pad));
+    if (prep) d->pb.ell_W = W;
+  }
   if (d->use_sort) return launch_sort(d, ccol);
   const u32 ntiles = (u32)(((size_t)a.m.An + R - 1) / R);
   const int warps = d->ell_warps;

@@ -633,7 +633,8 @@ def test_prepared_b_gives_identical_results_and_replays_the_plan(bs, oracle):
     a16r, a16c = bs.gen_uniform(n, 16, 13)           # rows longer than the plan's LA = 8: flagged by the kernel, redone
     product(a16r, a16c, n, False)
     product(a16r, a16c, n, True)                     # ... and the new plan (LA = 16) is cached
-    product(a8r, a8c, n, True)                       # shorter rows fit the LA = 16 plan
+    product(a8r, a8c, n, False)                      # half-length rows are not "regular" for the LA = 16 plan (host-side rule): fresh probes, LA = 8 again
+    product(a8r, a8c, n, True)
     rr, rc = random_csr(rng, 5000, n, 3.0)           # ragged rows: not "regular" -> host-side rule declines the replay
     product(rr, rc, 5000, False, expect_variant=None)
     # an unrelated B through the same handle invalidates nothing silently: its product is correct, and so is the next prepared one
