@@ -143,7 +143,8 @@ static int launch_copy_rows(bspgemm_dev* d) {
   const bool have[3] = { d->have_l, d->have_m2, d->have_m };
   for (int b = 0; b < 3; ++b) {
     if (!have[b]) continue;
-    k_copy_rows<<<d->sm_count * 8, 256, 0, d->stream>>>(ls[b], nl[b], d->cnt.p, d->tofs.p, d->temp.p, a.dCrow, a.is64, ccol);
+    if (b == 2) k_copy_rows<true><<<d->sm_count * 8, 256, 0, d->stream>>>(ls[b], nl[b], d->cnt.p, d->tofs.p, d->temp.p, a.dCrow, a.is64, ccol);   // M1: warp per row
+    else        k_copy_rows<false><<<d->sm_count * 8, 256, 0, d->stream>>>(ls[b], nl[b], d->cnt.p, d->tofs.p, d->temp.p, a.dCrow, a.is64, ccol);
     d->launches++;
     CK(cudaGetLastError());
   }
@@ -442,6 +443,27 @@ static int mul_launch_main(bspgemm_dev* d) {
     d->staged = staged;
     if (d->have_m) CKS(staged ? launch_bins_ml<MODE_STAGE>(d) : launch_bins_ml<MODE_COUNT>(d));
     CK(cudaEventRecord(d->ev[3], d->stream));
+    if (staged && !d->skip_estimate && !getenv("BSPGEMM_FUSED_S")) {
+      // Skewed matrices (big rows exist and were just staged with their counts): the S rows are counted and filled in two
+      // UNORDERED passes around the device scan instead of the ordered one-pass kernel.  Their intermediate products are a
+      // few percent of the total (R-MAT scale 22: 3e8 of 1.2e10), so walking them twice is cheap, while k_fused's in-order
+      // look-back made every warp wait for the slowest earlier tile when row costs differ by orders of magnitude (85 % of its
+      // warp time in the spin, profiles/r02_rmat20_kfused_stalls.txt: 112 of 527 ms per step at config 4).
+      CKS(launch_rows_warp<MODE_COUNT>(d));
+      const u32 nt = (u32)((An + SCAN_THREADS * SCAN_ITEMS - 1) / (SCAN_THREADS * SCAN_ITEMS));
+      u64* chain = nullptr;
+      CKS(chain_reserve(d, (size_t)nt + 1, &chain));
+      k_scan<<<nt, SCAN_THREADS, 0, d->stream>>>(d->cnt.p, a.m.An, a.dCrow, a.is64, chain, d->d_sc, nt);
+      d->launches++;
+      CK(cudaGetLastError());
+      CKS(launch_rows_warp<MODE_FILL>(d));
+      CK(cudaEventRecord(d->ev[4], d->stream));
+      CKS(launch_copy_rows(d));
+      CK(cudaEventRecord(d->ev[5], d->stream));
+      CK(cudaMemcpyAsync(d->h_sc, d->d_sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, d->stream));
+      d->phase = 3;
+      return BSPGEMM_OK;
+    }
     const u32 rows_per_tile = FUSED_R;
     const u32 ntiles = (u32)((An + rows_per_tile - 1) / rows_per_tile);
     { u64* chain = nullptr; CKS(chain_reserve(d, (size_t)ntiles + 1, &chain)); }
@@ -624,6 +646,9 @@ static int dev_create(bspgemm_dev** out, int device) {
   CK(cudaSetDevice(device));
   cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, device));
   if (p.major < 10) return fail(BSPGEMM_ERR_NOGPU, "device %d is sm_%d%d; this library is built for sm_100a only", device, p.major, p.minor);
+  // L2 fetch granularity: the gathers of B rows are 64-byte (config 3) random accesses; the device default fetches more than the
+  // row on a miss (profiles/r02_l2_fetch_granularity.txt).  BSPGEMM_L2_FETCH=32|64|128 overrides (device-wide limit).
+  if (const char* e = getenv("BSPGEMM_L2_FETCH")) { const int v = atoi(e); if (v == 32 || v == 64 || v == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)v); cudaGetLastError(); }
   bspgemm_dev* d = new bspgemm_dev();
   d->device = device; d->sm_count = p.multiProcessorCount; d->smem_optin = p.sharedMemPerBlockOptin;
   CK(cudaStreamCreateWithFlags(&d->own_stream, cudaStreamNonBlocking));

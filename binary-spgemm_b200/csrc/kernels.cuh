@@ -244,24 +244,35 @@ static __global__ void __launch_bounds__(256) k_build_lists(const u32* __restric
   else                  list_l[atomicAdd(&sc->n_l, 1u)] = (u32)i;
 }
 
-// MODE_STAGE epilogue: the staged rows go to their final place, Ccol[Crow[row] ..) (Crow is complete once the fused kernel
-// has run).  One CTA per listed row, grid-stride.
+// MODE_STAGE epilogue: the staged rows go to their final place, Ccol[Crow[row] ..) (Crow is complete once the scan / the fused
+// kernel has run).  WPR (warp per row: the M1 list, rows of <= 2048 columns): 8 rows in flight per CTA instead of one — with a CTA
+// per row the four dependent scalar loads in front of every short copy left the kernel at 4 % issue utilisation (R-MAT scale 22:
+// 55 ms for 46 GB).  Otherwise one CTA per listed row, grid-stride.  Eight independent loads per thread are in flight.
+template <bool WPR>
 static __global__ void __launch_bounds__(256) k_copy_rows(const u32* __restrict__ list, const u32* __restrict__ nlist, const u32* __restrict__ cnt,
                                                    const u64* __restrict__ tofs, const int* __restrict__ temp,
                                                    const void* __restrict__ Crow, int is64, int* __restrict__ Ccol) {
   const u32 n = *nlist;
-  for (u32 idx = blockIdx.x; idx < n; idx += gridDim.x) {
+  const u32 lane = lane_id();
+  const u32 first = WPR ? blockIdx.x * 8u + (threadIdx.x >> 5) : blockIdx.x, step = WPR ? gridDim.x * 8u : gridDim.x;
+  const u32 t = WPR ? lane : threadIdx.x, T = WPR ? 32u : 256u;
+  for (u32 idx = first; idx < n; idx += step) {
     const u32 row = list[idx];
     const u32 c = cnt[row];
     const int* __restrict__ src = temp + tofs[row];
     int* __restrict__ dst = Ccol + ld_rowptr(Crow, is64, (size_t)row);
-#pragma unroll 4
-    for (u32 i = threadIdx.x; i < c; i += 256) dst[i] = __ldcs(&src[i]);
+    u32 i = t;
+    for (; i + 7u * T < c; i += 8u * T) {
+      int v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = __ldcs(&src[i + (u32)k * T]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) dst[i + (u32)k * T] = v[k];
+    }
+    for (; i < c; i += T) dst[i] = __ldcs(&src[i]);
   }
 }
 
-// ------------------------------------------------------------------------------------------------ ordered table primitives
-// Monotone slot map: slot = floor((k-lo) * T / range) computed as umulhi(k-lo, floor(T*2^32/range)).
 __device__ __forceinline__ u32 slot_scale(u32 T, u32 range) { return (u32)((((u64)T) << 32) / range); }
 
 // Insert key x at/after slot s.  atomicMin keeps the smaller key in the slot; the larger one (the

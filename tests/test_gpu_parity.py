@@ -694,3 +694,101 @@ def test_out_of_range_a_column_equal_to_bn_is_reported(bs):
                     os.environ.pop(k, None)
                 else:
                     os.environ[k] = v
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE configs 4 and 5 at full size
+def _check_blocks_vs_oracle(bs, oracle, row, col, n, C, Cr, blocks):
+    """Bit-exact compare of contiguous row blocks of a device-resident result (C: int32 tensor, Cr: int64 row pointers)."""
+    for r0, r1 in blocks:
+        wc, wr = oracle.spgemm(col, row[r0:], r1 - r0, col, row, n)
+        gr = Cr[r0:r1 + 1].cpu().numpy()
+        assert (gr - gr[0] == wr).all(), f"row pointers differ in rows [{r0},{r1})"
+        got = C[int(gr[0]):int(gr[-1])].cpu().numpy()
+        assert len(got) == len(wc) and (got == wc).all(), f"columns differ in rows [{r0},{r1})"
+
+
+def _chunked_contract(C, Cr, nnz, n_cols, chunk=1 << 28):
+    """Result contract on a device-resident CSR too large for one-shot temporaries: columns in range, strictly ascending
+    inside every row (a descent is allowed only at a row boundary)."""
+    import torch
+    assert int(Cr[0]) == 0 and int(Cr[-1]) == nnz and bool((Cr[1:] >= Cr[:-1]).all())
+    starts = Cr[1:-1]
+    starts = starts[(starts > 0) & (starts < nnz)]
+    boundary = torch.zeros(0, dtype=torch.bool, device=C.device)
+    for a in range(0, nnz, chunk):
+        b = min(nnz, a + chunk)
+        x = C[a:b]
+        assert int(x.min()) >= 0 and int(x.max()) < n_cols
+        hi = min(nnz, b + 1)
+        d = C[a + 1:hi] > C[a:hi - 1]                        # d[p-a] : C[p+1] > C[p]
+        s = starts[(starts > a) & (starts <= hi - 1)] - 1 - a   # descents allowed at p = start-1
+        d[s] = True
+        assert bool(d.all()), f"a row is not strictly ascending in entries [{a},{hi})"
+        del d, x
+
+
+def test_config5_full_size_closed_form_and_oracle_blocks(bs, oracle):
+    """BASELINE config 5: banded n=2^24, d=32 (row i = columns i-16..i+15 clipped), C = A·A through bspgemm_dev_multiply (band
+    kernel, 131072 tiles).  The WHOLE output is compared with the closed form (row i of C = columns i-32..i+30 clipped), and the
+    closed form itself is pinned by the oracle on blocks at the start, in the middle and at the end."""
+    import torch
+    n = 1 << 24
+    row, col = bs.gen_banded(n, 32)
+    dev = torch.device("cuda:0")
+    dAr, dAc = torch.from_numpy(row).to(dev), torch.from_numpy(col).to(dev)
+    h = bs.DeviceSpGEMM(0)
+    dCr = torch.zeros(n + 1, dtype=torch.int32, device=dev)
+    ptr, nnz = h.multiply(dAc, dAr, n, len(col), dAc, dAr, n, n, len(col), dCr)
+    torch.cuda.synchronize()
+    st = h.stats()
+    assert st["variant"] == 3, st                                        # the band kernel ran
+    i = torch.arange(n, device=dev, dtype=torch.int64)
+    lo = torch.clamp(i - 32, min=0)
+    hi = torch.clamp(i + 30, max=n - 1)
+    want_row = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    want_row[1:] = torch.cumsum(hi - lo + 1, 0)
+    Cr = dCr.to(torch.int64)
+    assert torch.equal(Cr, want_row) and nnz == int(want_row[-1])
+    C = bs.device_view(ptr, nnz, 0)
+    for a in range(0, n, 1 << 22):                                       # closed-form columns, 2^22 rows at a time
+        b = min(n, a + (1 << 22))
+        lens = (hi - lo + 1)[a:b]
+        base = torch.repeat_interleave(lo[a:b] - want_row[a:b], lens)    # column = lo[row] + (p - Crow[row])
+        p0, p1 = int(want_row[a]), int(want_row[b])
+        want = (base + torch.arange(p0, p1, device=dev, dtype=torch.int64)).to(torch.int32)
+        assert torch.equal(C[p0:p1], want), f"columns differ from the closed form in rows [{a},{b})"
+        del base, want
+    _check_blocks_vs_oracle(bs, oracle, row, col, n, C, Cr, [(0, 20000), (n // 2 - 10000, n // 2 + 10000), (n - 20000, n)])
+    assert st["ip"] == oracle.intermediate_products(col, row, n, row)
+    h.close()
+
+
+def test_config4_full_size_rmat_scale22_sampled_blocks(bs, oracle):
+    """BASELINE config 4: R-MAT (.45,.22,.22,.11) scale 22, edge factor 16, C = A·A with 64-bit row pointers (nnz(C) = 1.15e10,
+    46 GB of columns; staging arena of the big rows, windowed bitmaps, CTA-wide sorts, int64 chain values).  Contract checks on
+    the whole output in chunks, the totals against the oracle's IP count, and bit-exact row blocks against the 64-bit oracle:
+    the hub rows at the start, the middle, the end and scattered rows."""
+    import torch
+    free, total = torch.cuda.mem_get_info(0)
+    if free < 150 * (1 << 30):
+        pytest.skip("needs ~130 GB of free device memory")
+    n = 1 << 22
+    row, col = bs.gen_rmat(22, 16, 0.45, 0.22, 0.22, 1)
+    dev = torch.device("cuda:0")
+    dAr, dAc = torch.from_numpy(row).to(dev), torch.from_numpy(col).to(dev)
+    h = bs.DeviceSpGEMM(0)
+    dCr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    ptr, nnz = h.multiply(dAc, dAr, n, len(col), dAc, dAr, n, n, len(col), dCr, crow_is_i64=True)
+    torch.cuda.synchronize()
+    st = h.stats()
+    assert nnz > (1 << 31) and st["rows_l"] > 0 and st["rows_m"] > 0, st     # every bin, and beyond the 32-bit ABI
+    assert st["ip"] == oracle.intermediate_products(col, row, n, row) and nnz <= st["ip"]
+    C = bs.device_view(ptr, nnz, 0)
+    _chunked_contract(C, dCr, nnz, n)
+    rng = np.random.default_rng(4)
+    blocks = [(0, 600), (n // 2 - 4000, n // 2 + 4000), (n - 8000, n)]
+    blocks += [(int(r), int(r) + 1) for r in rng.integers(0, n, 24)]
+    lens = np.diff(row)
+    blocks += [(int(r), int(r) + 1) for r in np.argsort(lens)[-3:]]          # the three longest rows of A
+    _check_blocks_vs_oracle(bs, oracle, row, col, n, C, dCr, blocks)
+    h.close()
