@@ -55,6 +55,9 @@ WORKLOADS = {
     "banded22": ("gen_banded", ((1 << 22), 32), "banded n=2^22 d=32, C=A*A"),
     "cfg4": ("gen_rmat", (22, 16, 0.45, 0.22, 0.22, 1), "BASELINE config 4: R-MAT (.45,.22,.22,.11) scale 22 edge factor 16, C=A*A (int64 row pointers)"),
     "cfg5": ("gen_banded", ((1 << 24), 32), "BASELINE config 5: banded n=2^24 d=32, C=A*A"),
+    # the one configuration with a PUBLISHED number: the report's n5e6_d5 (sprand, n = 5e6, nnz ~ 2.5e7), A*A in 0.62 s with
+    # 20 MPI tasks on one cluster node (PDF p.3 Fig 8, read off the chart)
+    "pub_n5e6_d5": ("gen_sprand", (5000000, 5.0, 1), "the report's n5e6_d5: sprand-like (Poisson(5) row lengths) n=5e6 nnz~2.5e7, C=A*A"),
     "small": ("gen_uniform", ((1 << 16), 8, 1), "uniform random boolean n=2^16 d=8 seed=1, C=A*A"),
 }
 

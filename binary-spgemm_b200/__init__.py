@@ -27,16 +27,18 @@ MODE_AUTO, MODE_FUSED, MODE_TWOPHASE = 0, 1, 2
 ABI_SYMBOLS = [
     "bspgemm_strerror", "bspgemm_last_error", "bspgemm_version",
     "bspgemm_init", "bspgemm_init_devices", "bspgemm_finalize", "bspgemm_num_gpus",
-    "bspgemm_csr", "bspgemm_csr_i64", "bspgemm_csr_into", "bspgemm_csr_slice",
+    "bspgemm_csr", "bspgemm_csr_i64", "bspgemm_csr_into", "bspgemm_csr_slice", "bspgemm_csr_masked",
     "bspgemm_intermediate_products",
-    "bspgemm_SpGEMM_mpi", "bspgemm_SpGEMM_omp", "bspgemm_SpGEMM_bigslice",
+    "bspgemm_csr_sharded", "bspgemm_result_shards", "bspgemm_result_nnz", "bspgemm_result_shard", "bspgemm_result_allgather",
+    "bspgemm_result_write", "bspgemm_result_free",
+    "bspgemm_SpGEMM_mpi", "bspgemm_SpGEMM_omp", "bspgemm_SpGEMM_bigslice", "bspgemm_SpGEMM_masked",
     "bspgemm_dev_create", "bspgemm_dev_destroy", "bspgemm_dev_set_mode",
-    "bspgemm_dev_multiply", "bspgemm_dev_get_stats", "bspgemm_dev_prepare_b", "bspgemm_dev_forget_b",
+    "bspgemm_dev_multiply", "bspgemm_dev_multiply_masked", "bspgemm_dev_get_stats", "bspgemm_dev_prepare_b", "bspgemm_dev_forget_b",
     "bspgemm_coo2csc", "bspgemm_coo2csc_dev",
 ]
 HOST_SYMBOLS = [
     "readCOO", "readCOO_status", "readCOO_convert", "coo2csc", "tictoc", "bs_time_stats",
-    "bs_gen_uniform", "bs_gen_rmat", "bs_gen_banded", "bs_gen_blockdiag", "bs_write_mtx",
+    "bs_gen_uniform", "bs_gen_sprand", "bs_gen_rmat", "bs_gen_banded", "bs_gen_blockdiag", "bs_write_mtx",
     "mm_read_banner", "mm_read_mtx_crd_size", "mm_write_banner", "mm_write_mtx_crd_size",
     "mm_is_valid", "mm_typecode_to_str",
 ]
@@ -108,6 +110,12 @@ def lib() -> C.CDLL:
                                            C.c_void_p, C.c_void_p, C.c_int, C.c_int64,
                                            C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64,
                                            C.c_void_p, C.c_int, C.POINTER(C.c_void_p), _I64P]
+        L.bspgemm_csr_masked.argtypes = common + [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]
+        L.bspgemm_dev_multiply_masked.argtypes = [C.c_void_p, C.c_void_p,
+                                                  C.c_void_p, C.c_void_p, C.c_int, C.c_int64,
+                                                  C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64,
+                                                  C.c_void_p, C.c_void_p, C.c_int64,
+                                                  C.c_void_p, C.c_int, C.POINTER(C.c_void_p), _I64P]
         L.bspgemm_dev_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         L.bspgemm_dev_prepare_b.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64]
         L.bspgemm_dev_forget_b.argtypes = [C.c_void_p]
@@ -133,6 +141,7 @@ def host() -> C.CDLL:
         H.bs_time_stats.restype = None
         gen_out = [C.POINTER(_I32P), C.POINTER(_I32P), _I64P]
         H.bs_gen_uniform.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64] + gen_out
+        H.bs_gen_sprand.argtypes = [C.c_uint32, C.c_double, C.c_uint64] + gen_out
         H.bs_gen_rmat.argtypes = [C.c_uint32, C.c_uint32, C.c_double, C.c_double, C.c_double, C.c_uint64] + gen_out
         H.bs_gen_banded.argtypes = [C.c_uint32, C.c_uint32] + gen_out
         H.bs_gen_blockdiag.argtypes = [C.c_uint32, C.c_uint32] + gen_out
@@ -224,6 +233,12 @@ def gen_uniform(n: int, d: int, seed: int = 1):
     return _take(row, n + 1, np.int32), _take(col, nnz, np.int32)
 
 
+def gen_sprand(n: int, d: float, seed: int = 1):
+    """Matlab sprand(n,n,d/n)>0 (Matlab/write_spm.m:5): uniformly random positions, Poisson(d) row lengths."""
+    row, col, nnz = _gen(host().bs_gen_sprand, n, float(d), seed)
+    return _take(row, n + 1, np.int32), _take(col, nnz, np.int32)
+
+
 def gen_rmat(scale: int, edge_factor: int = 16, a=0.45, b=0.22, c=0.22, seed: int = 1):
     row, col, nnz = _gen(host().bs_gen_rmat, scale, edge_factor, a, b, c, seed)
     return _take(row, (1 << scale) + 1, np.int32), _take(col, nnz, np.int32)
@@ -274,6 +289,17 @@ def spgemm_csr(Acol, Arow, An, Bcol, Brow, Bn, Bm, i64: bool = False):
     return _take(out, int(Crow[An]), np.int32), Crow
 
 
+def spgemm_csr_masked(Acol, Arow, An, Bcol, Brow, Bn, Bm, Fcol, Frow):
+    """SpGEMM_masked replacement (final/SpGEMM_mpi_omp.c:232-288): C = F .* (A·B) -> (Ccol, Crow)."""
+    L = lib()
+    Acol, Arow, Bcol, Brow, Fcol, Frow = (_i32(x) for x in (Acol, Arow, Bcol, Brow, Fcol, Frow))
+    Crow = np.zeros(An + 1, dtype=np.int32)
+    out = C.c_void_p()
+    _check(L.bspgemm_csr_masked(Acol.ctypes.data, Arow.ctypes.data, An, Bcol.ctypes.data, Brow.ctypes.data, Bn, Bm,
+                                Fcol.ctypes.data, Frow.ctypes.data, C.byref(out), Crow.ctypes.data), "bspgemm_csr_masked")
+    return _take(out, int(Crow[An]), np.int32), Crow
+
+
 def spgemm_csr_into(Acol, Arow, An, Bcol, Brow, Bn, Bm, Ccol_buf: np.ndarray):
     """SpGEMM_mat replacement (Matlab/inc/BSpGEMM.c:9-47): caller-allocated Ccol -> (nnz, Crow)."""
     L = lib()
@@ -308,6 +334,54 @@ def SpGEMM_mpi(Acol, Arow, An, Bcol, Brow, Bm, tBlock: int = 1):
     L.bspgemm_SpGEMM_mpi(Acol.ctypes.data, Arow.ctypes.data, An, Bcol.ctypes.data, Brow.ctypes.data, Bm,
                          C.byref(out), Crow.ctypes.data, tBlock)
     return _take(out, int(Crow[An]), np.int32), Crow
+
+
+class ShardedResult:
+    """bspgemm_csr_sharded: the product left on the GPUs (distributed consumer)."""
+
+    def __init__(self, Acol, Arow, An, Bcol, Brow, Bn, Bm, i64: bool = False):
+        L = lib()
+        Acol, Arow, Bcol, Brow = _i32(Acol), _i32(Arow), _i32(Bcol), _i32(Brow)
+        self._r = C.c_void_p()
+        self.An, self.i64 = An, i64
+        L.bspgemm_csr_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        _check(L.bspgemm_csr_sharded(Acol.ctypes.data, Arow.ctypes.data, An, Bcol.ctypes.data, Brow.ctypes.data, Bn, Bm, 1 if i64 else 0,
+                                     C.byref(self._r)), "bspgemm_csr_sharded")
+        L.bspgemm_result_shards.argtypes = [C.c_void_p]
+        L.bspgemm_result_nnz.argtypes = [C.c_void_p]
+        L.bspgemm_result_nnz.restype = C.c_int64
+        self.nshards = L.bspgemm_result_shards(self._r)
+        self.nnz = L.bspgemm_result_nnz(self._r)
+
+    def shard(self, q: int) -> dict:
+        L = lib()
+        dev, row0, rows = C.c_int(), C.c_int(), C.c_int()
+        nnz, disp = C.c_int64(), C.c_int64()
+        pc, pr = C.c_void_p(), C.c_void_p()
+        L.bspgemm_result_shard.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), _I64P, _I64P,
+                                           C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        _check(L.bspgemm_result_shard(self._r, q, C.byref(dev), C.byref(row0), C.byref(rows), C.byref(nnz), C.byref(disp), C.byref(pc), C.byref(pr)),
+               "bspgemm_result_shard")
+        return dict(device=dev.value, row0=row0.value, rows=rows.value, nnz=nnz.value, disp=disp.value, dCcol=pc.value or 0, dCrow=pr.value or 0)
+
+    def allgather(self):
+        """-> ([device address of the full Ccol on task q], [... of the full Crow])"""
+        L = lib()
+        cols, rows = (C.c_void_p * self.nshards)(), (C.c_void_p * self.nshards)()
+        L.bspgemm_result_allgather.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _check(L.bspgemm_result_allgather(self._r, cols, rows), "bspgemm_result_allgather")
+        return [c or 0 for c in cols], [r or 0 for r in rows]
+
+    def write(self, prefix: str, fmt: int = 0):
+        L = lib()
+        L.bspgemm_result_write.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        _check(L.bspgemm_result_write(self._r, os.fsencode(prefix), fmt), "bspgemm_result_write")
+
+    def free(self):
+        if self._r:
+            lib().bspgemm_result_free.argtypes = [C.c_void_p]
+            lib().bspgemm_result_free(self._r)
+            self._r = C.c_void_p()
 
 
 def intermediate_products(Acol, Arow, An, Brow, Bn) -> int:
@@ -360,6 +434,17 @@ class DeviceSpGEMM:
                                           self._p(dBcol), self._p(dBrow), Bn, Bm, Bnnz,
                                           self._p(dCrow), 1 if crow_is_i64 else 0, C.byref(out), C.byref(nnz)),
                "bspgemm_dev_multiply")
+        return out.value or 0, nnz.value
+
+    def multiply_masked(self, dAcol, dArow, An, Annz, dBcol, dBrow, Bn, Bm, Bnnz, dFcol, dFrow, Fnnz, dCrow, crow_is_i64=False, stream=None):
+        """bspgemm_dev_multiply_masked: C = F .* (A·B), returns (device address of Ccol, nnz(C))."""
+        out, nnz = C.c_void_p(), C.c_int64()
+        _check(lib().bspgemm_dev_multiply_masked(self._h, C.c_void_p(stream or 0),
+                                                 self._p(dAcol), self._p(dArow), An, Annz,
+                                                 self._p(dBcol), self._p(dBrow), Bn, Bm, Bnnz,
+                                                 self._p(dFcol), self._p(dFrow), Fnnz,
+                                                 self._p(dCrow), 1 if crow_is_i64 else 0, C.byref(out), C.byref(nnz)),
+               "bspgemm_dev_multiply_masked")
         return out.value or 0, nnz.value
 
     def prepare_b(self, dBcol, dBrow, Bn, Bm, Bnnz, stream=None):

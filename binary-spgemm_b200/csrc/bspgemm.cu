@@ -11,6 +11,7 @@
 #include "rows_sort.cuh"
 #include "band.cuh"
 #include "coo2csc.cuh"
+#include "mask.cuh"
 
 // ------------------------------------------------------------------------------------------------ errors
 static thread_local char g_err[512] = "";
@@ -37,7 +38,10 @@ extern "C" const char* bspgemm_version(void) { return "bspgemm-b200 0.1 (sm_100a
 
 
 static int g_cap_s_max() { const char* e = getenv("BSPGEMM_CAP_S"); int v = e ? atoi(e) : 512; if (v < 32) v = 32; if (v > 1024) v = 1024; int p = 32; while (p < v) p <<= 1; return p; }
-static const u32 CAP_M1 = 2048, CAP_M2 = 16384;
+static const u32 CAP_M1 = 2048;
+// rows above CAP_M2 intermediate products take the windowed-bitmap kernel, rows up to it the CTA-wide sort (BSPGEMM_CAP_M2: tuning knob)
+static u32 cap_m2_value() { const char* e = getenv("BSPGEMM_CAP_M2"); const int v = e ? atoi(e) : 16384; return v == 4096 ? 4096u : v == 8192 ? 8192u : 16384u; }
+#define CAP_M2 (cap_m2_value())
 
 // Every kernel that uses dynamic shared memory gets the opt-in maximum once, at context creation (BSP_ATTR, ctx.h).
 static int set_kernel_attributes(int smem_optin) {
@@ -669,6 +673,7 @@ static void dev_destroy(bspgemm_dev* d) {
   cudaSetDevice(d->device);
   cudaStreamSynchronize(d->stream);
   d->ip.release(); d->cnt.release(); d->lists.release(); d->bitmaps.release(); d->status.release(); d->ccol.release(); d->temp.release(); d->tofs.release(); d->bell.release(); d->bdesc.release();
+  d->m_crow.release(); d->m_frow.release(); d->m_fcol.release(); d->m_out.release();
   d->in_arow.release(); d->in_acol.release(); d->in_brow.release(); d->in_bcol.release(); d->crow_dev.release(); d->crow_tmp.release();
   if (d->h_sc) cudaFreeHost(d->h_sc);
   for (auto& e : d->ev) if (e) cudaEventDestroy(e);
@@ -699,6 +704,95 @@ extern "C" int bspgemm_dev_multiply(bspgemm_dev* h, void* stream,
   if (dCcol_out) *dCcol_out = h->ccol.p;
   if (nnz_out) *nnz_out = h->st.nnz;
   return BSPGEMM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ masked product
+// C = F .* (A·B): replaces SpGEMM_masked (final/SpGEMM_mpi_omp.c:232-288).  The unmasked rows come from the product pipeline
+// (ascending, distinct, in the arena, 64-bit row pointers in m_crow); the mask is applied by k_mask_rows (count -> k_scan ->
+// fill) into m_out.  A mask with unsorted / repeated columns (legal for the reference, whose mask is a flag array) is first
+// canonicalised with the product kernels themselves: F' = I·F.
+static int masked_multiply(bspgemm_dev* d, const int* dFcol, const int* dFrow, int64_t Fnnz, void* dCrow, int is64, int** dCcol_out, int64_t* nnz_out) {
+  const MulArgs user = d->a;                             // A, B as given; dCrow / is64 below are the caller's
+  const int An = user.m.An, Bm = user.m.Bm;
+  if (Fnnz < 0 || !dFrow || (Fnnz > 0 && !dFcol)) return fail(BSPGEMM_ERR_BADARG, "masked product: null mask");
+  CKS(d->m_crow.ensure((size_t)An + 1));
+  if (An == 0) {
+    CK(cudaMemsetAsync(dCrow, 0, is64 ? 8 : 4, d->stream)); CK(cudaStreamSynchronize(d->stream));
+    memset(&d->st, 0, sizeof d->st);
+    if (dCcol_out) *dCcol_out = d->m_out.p;
+    if (nnz_out) *nnz_out = 0;
+    return BSPGEMM_OK;
+  }
+  // 1. is the mask canonical (rows strictly ascending, columns in range)?
+  CK(cudaMemsetAsync(d->d_sc, 0, sizeof(DevScalars), d->stream));
+  k_mask_check<<<(An + 7) / 8, 256, 0, d->stream>>>(dFrow, dFcol, An, (u32)Bm, d->d_sc);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(d->h_sc, d->d_sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, d->stream));
+  CK(cudaStreamSynchronize(d->stream));
+  if (d->h_sc->err & 32u) return fail(BSPGEMM_ERR_BADARG, "a column index of the mask is outside [0,Bm=%d)", Bm);
+  const int* frow = dFrow; const int* fcol = dFcol;
+  if (d->h_sc->err & 16u) {
+    // F' = I·F: the product kernels sort and de-duplicate every row of F.  I = identity of order An, built in m_out / m_crow.
+    CKS(d->m_out.ensure((size_t)An));
+    CKS(d->m_frow.ensure((size_t)An + 1));
+    k_iota<<<(An + 1 + 255) / 256, 256, 0, d->stream>>>(d->m_frow.p, An + 1);       // row pointers 0..An
+    k_iota<<<(An + 255) / 256, 256, 0, d->stream>>>(d->m_out.p, An);                 // columns 0..An-1
+    CK(cudaGetLastError());
+    d->a.m = Csr{d->m_frow.p, d->m_out.p, dFrow, dFcol, An, An, Bm};
+    d->a.Annz = An; d->a.Bnnz = Fnnz; d->a.dCrow = d->m_crow.p; d->a.is64 = 1;
+    CKS(mul_run_to_completion(d));
+    const int64_t n1 = d->st.nnz;
+    if (n1 > 0x7fffffffLL) return fail(BSPGEMM_ERR_OVERFLOW32, "mask too large");
+    CKS(d->m_fcol.ensure((size_t)std::max<int64_t>(n1, 1)));
+    CK(cudaMemcpyAsync(d->m_fcol.p, d->ccol.p, (size_t)n1 * 4, cudaMemcpyDeviceToDevice, d->stream));
+    k_narrow_rowptr<<<(An + 1 + 255) / 256, 256, 0, d->stream>>>(d->m_crow.p, d->m_frow.p, An + 1);
+    CK(cudaGetLastError());
+    frow = d->m_frow.p; fcol = d->m_fcol.p;
+  }
+  // 2. the unmasked product, rows in the arena, 64-bit row pointers
+  d->a = user;
+  d->a.dCrow = d->m_crow.p; d->a.is64 = 1;
+  CKS(mul_run_to_completion(d));
+  const bspgemm_stats prod = d->st;
+  // 3. count, scan, fill
+  CKS(d->cnt.ensure((size_t)An + 1));
+  const int grid = std::max(1, std::min((An + 7) / 8, d->sm_count * 16));
+  k_mask_rows<MODE_COUNT><<<grid, 256, 0, d->stream>>>(frow, fcol, d->m_crow.p, d->ccol.p, An, d->cnt.p, nullptr, 0, nullptr);
+  CK(cudaGetLastError());
+  const u32 nt = (u32)(((size_t)An + SCAN_THREADS * SCAN_ITEMS - 1) / (SCAN_THREADS * SCAN_ITEMS));
+  d->fast = false;
+  CK(cudaMemsetAsync(d->d_sc, 0, sizeof(DevScalars), d->stream));
+  u64* chain = nullptr;
+  CKS(chain_reserve(d, (size_t)nt + 1, &chain));
+  k_scan<<<nt, SCAN_THREADS, 0, d->stream>>>(d->cnt.p, An, dCrow, is64, chain, d->d_sc, nt);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(d->h_sc, d->d_sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, d->stream));
+  CK(cudaStreamSynchronize(d->stream));
+  if (d->h_sc->err & 2u) return fail(BSPGEMM_ERR_OVERFLOW32, "nnz(C) = %llu does not fit 32-bit row pointers", (unsigned long long)d->h_sc->total_nnz);
+  const int64_t nnz = (int64_t)d->h_sc->total_nnz;
+  CKS(d->m_out.ensure((size_t)std::max<int64_t>(nnz, 1)));
+  k_mask_rows<MODE_FILL><<<grid, 256, 0, d->stream>>>(frow, fcol, d->m_crow.p, d->ccol.p, An, nullptr, dCrow, is64, d->m_out.p);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(d->stream));
+  d->st = prod; d->st.nnz = nnz; d->st.launches = prod.launches + 4;
+  if (dCcol_out) *dCcol_out = d->m_out.p;
+  if (nnz_out) *nnz_out = nnz;
+  return BSPGEMM_OK;
+}
+
+extern "C" int bspgemm_dev_multiply_masked(bspgemm_dev* h, void* stream,
+                                           const int* dAcol, const int* dArow, int An, int64_t Annz,
+                                           const int* dBcol, const int* dBrow, int Bn, int Bm, int64_t Bnnz,
+                                           const int* dFcol, const int* dFrow, int64_t Fnnz,
+                                           void* dCrow, int crow_is_i64, int** dCcol_out, int64_t* nnz_out) {
+  if (!h || !dArow || !dBrow || !dCrow || An < 0 || Bn < 0 || Bm < 0 || Annz < 0 || Bnnz < 0) return fail(BSPGEMM_ERR_BADARG, "null pointer or negative size");
+  if ((Annz > 0 && !dAcol) || (Bnnz > 0 && !dBcol)) return fail(BSPGEMM_ERR_BADARG, "null column array");
+  CK(cudaSetDevice(h->device));
+  h->stream = stream ? (cudaStream_t)stream : cudaStreamLegacy;
+  h->a.m = Csr{dArow, dAcol, dBrow, dBcol, An, Bn, Bm};
+  h->a.Annz = Annz; h->a.Bnnz = Bnnz; h->a.dCrow = dCrow; h->a.is64 = crow_is_i64 ? 1 : 0;
+  h->user_ccol = nullptr; h->user_cap = 0;
+  return masked_multiply(h, dFcol, dFrow, Fnnz, dCrow, crow_is_i64 ? 1 : 0, dCcol_out, nnz_out);
 }
 
 // B prepared once for many products.  The reference replicates B once, outside its timed region (every rank parses the file,
@@ -855,9 +949,21 @@ static int ensure_init() {
 // Shards rows [0,An) over `ng` GPUs as contiguous blocks (final/SpGEMM_mpi_omp.c:165-171), replicates B
 // (ncclBroadcast from GPU 0), runs all shards concurrently, gathers Ccol/Crow to the host at the
 // displacements (replaces :178-223).
+struct bspgemm_result {            // a product left sharded on the GPUs (bspgemm_csr_sharded): metadata + the all-gathered copies
+  int ng = 0, An = 0, Bm = 0, is64 = 0;
+  std::vector<int> r0;             // shard q owns rows [r0[q], r0[q+1])
+  std::vector<int64_t> disp;       // ... and columns [disp[q], disp[q+1]) of the global Ccol
+  std::vector<int*> full_col;      // per task, after bspgemm_result_allgather
+  std::vector<void*> full_row;
+  unsigned long long epoch = 0;    // the shards live in the contexts' arenas: stale after the next product
+};
+static unsigned long long g_epoch = 0;
+
 static int host_multiply(const int* Acol, const int* Arow, int An, const int* Bcol, const int* Brow, int Bn, int Bm,
-                         int** Ccol_malloc, int* Ccol_buf, int64_t capacity, void* Crow, int is64, int64_t* nnz_out, int ng_limit) {
-  if (!Arow || !Brow || !Crow || An < 0 || Bn < 0 || Bm < 0) return fail(BSPGEMM_ERR_BADARG, "null pointer or negative size");
+                         int** Ccol_malloc, int* Ccol_buf, int64_t capacity, void* Crow, int is64, int64_t* nnz_out, int ng_limit,
+                         bspgemm_result* keep = nullptr) {
+  if (!Arow || !Brow || (!Crow && !keep) || An < 0 || Bn < 0 || Bm < 0) return fail(BSPGEMM_ERR_BADARG, "null pointer or negative size");
+  ++g_epoch;
   CKS(ensure_init());
   // Every GPU of the communicator takes part (a collective on a subset of its ranks never completes): with fewer rows than
   // GPUs the surplus shards are empty — they join the broadcast of B and skip the product.  ng_limit == 1 (slice form) runs
@@ -944,6 +1050,10 @@ static int host_multiply(const int* Acol, const int* Arow, int An, const int* Bc
   const int64_t nnz = disp[ng];
   if (nnz_out) *nnz_out = nnz;
   if (!is64 && nnz > 0x7fffffffLL) return fail(BSPGEMM_ERR_OVERFLOW32, "nnz(C) = %lld does not fit 32-bit row pointers", (long long)nnz);
+  if (keep) {                      // distributed consumer: nothing is gathered (replaces the gather-to-root :203-223)
+    keep->ng = ng; keep->An = An; keep->Bm = Bm; keep->is64 = is64; keep->r0 = r0; keep->disp = disp; keep->epoch = g_epoch;
+    return BSPGEMM_OK;
+  }
   int* out = Ccol_buf;
   if (Ccol_malloc) {
     out = (int*)malloc((size_t)std::max<int64_t>(nnz, 1) * sizeof(int));
@@ -970,6 +1080,150 @@ static int host_multiply(const int* Acol, const int* Arow, int An, const int* Bc
   return BSPGEMM_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ distributed consumer
+// The reference gathers every rank's slice to rank 0 (MPI_Gatherv + MPI_Gather + a serial fix-up, final/SpGEMM_mpi_omp.c:203-223)
+// — the step its report blames for the multi-node slow-down.  Here the product can stay where it was computed: the shards
+// are handed out as device pointers, all-gathered GPU-to-GPU over NVLink (every GPU ends with the whole CSR, row pointers
+// already offset), or written one file per shard.
+extern "C" int bspgemm_csr_sharded(const int* Acol, const int* Arow, int An, const int* Bcol, const int* Brow, int Bn, int Bm,
+                                   int crow_is_i64, bspgemm_result** out) {
+  if (!out) return fail(BSPGEMM_ERR_BADARG, "null result handle");
+  bspgemm_result* r = new bspgemm_result();
+  int64_t nnz = 0;
+  const int st = host_multiply(Acol, Arow, An, Bcol, Brow, Bn, Bm, nullptr, nullptr, 0, nullptr, crow_is_i64 ? 1 : 0, &nnz, 1 << 30, r);
+  if (st != BSPGEMM_OK) { delete r; return st; }
+  *out = r;
+  return BSPGEMM_OK;
+}
+static int result_live(const bspgemm_result* r) {
+  if (!r) return fail(BSPGEMM_ERR_BADARG, "null result");
+  if (!g.inited || r->epoch != g_epoch) return fail(BSPGEMM_ERR_STATE, "the sharded result was overwritten by a later product (or the context was finalized)");
+  return BSPGEMM_OK;
+}
+extern "C" int bspgemm_result_shards(const bspgemm_result* r) { return r ? r->ng : 0; }
+extern "C" int64_t bspgemm_result_nnz(const bspgemm_result* r) { return r ? r->disp[r->ng] : 0; }
+extern "C" int bspgemm_result_shard(const bspgemm_result* r, int q, int* device, int* row0, int* rows, int64_t* nnz, int64_t* disp,
+                                    const int** dCcol, const void** dCrow) {
+  CKS(result_live(r));
+  if (q < 0 || q >= r->ng) return fail(BSPGEMM_ERR_BADARG, "shard %d out of range", q);
+  const bspgemm_dev* d = g.devs[q];
+  if (device) *device = d->device;
+  if (row0) *row0 = r->r0[q];
+  if (rows) *rows = r->r0[q + 1] - r->r0[q];
+  if (nnz) *nnz = r->disp[q + 1] - r->disp[q];
+  if (disp) *disp = r->disp[q];
+  if (dCcol) *dCcol = d->ccol.p;
+  if (dCrow) *dCrow = d->crow_dev.p;       // slice-relative, rows+1 entries (the reference's Crow_slice, :160-174)
+  return BSPGEMM_OK;
+}
+// Every task's GPU gets the whole CSR: Ccol (nnz ints) and Crow (An+1 row pointers, shard offsets applied on the owning GPU by
+// k_offset_rowptr before they travel).  Over a communicator: one grouped ncclBroadcast per shard ("all-gather-v"); tasks that
+// share GPUs: device-to-device copies.  The buffers belong to the result handle.
+extern "C" int bspgemm_result_allgather(bspgemm_result* r, int** dCcol_per_task, void** dCrow_per_task) {
+  CKS(result_live(r));
+  const int ng = r->ng; const size_t rp = r->is64 ? 8 : 4;
+  const int64_t nnz = r->disp[ng];
+  if (r->full_col.empty()) {
+    r->full_col.assign(ng, nullptr); r->full_row.assign(ng, nullptr);
+    for (int q = 0; q < ng; ++q) {
+      CK(cudaSetDevice(g.devs[q]->device));
+      CK(cudaMalloc((void**)&r->full_col[q], (size_t)std::max<int64_t>(nnz, 1) * 4));
+      CK(cudaMalloc(&r->full_row[q], ((size_t)r->An + 1) * rp));
+    }
+  }
+  for (int q = 0; q < ng; ++q) {             // the owner writes its offset row pointers into its own full array
+    bspgemm_dev* d = g.devs[q];
+    CK(cudaSetDevice(d->device));
+    CK(cudaMemsetAsync(r->full_row[q], 0, rp, d->stream));
+    const int rows = r->r0[q + 1] - r->r0[q];
+    if (rows > 0) {
+      k_offset_rowptr<<<(rows + 255) / 256, 256, 0, d->stream>>>((const char*)d->crow_dev.p + rp, (char*)r->full_row[q] + ((size_t)r->r0[q] + 1) * rp,
+                                                                  r->is64, (long long)rows, (long long)r->disp[q]);
+      CK(cudaGetLastError());
+    }
+  }
+  if (!g.comms.empty()) {
+    for (int s = 0; s < ng; ++s) {
+      const int rows = r->r0[s + 1] - r->r0[s]; const int64_t n_s = r->disp[s + 1] - r->disp[s];
+      if (rows == 0) continue;
+      NK(g.nccl.GroupStart());
+      for (int q = 0; q < ng; ++q) {
+        char* seg = (char*)r->full_row[q] + ((size_t)r->r0[s] + 1) * rp;
+        NK(g.nccl.Broadcast((char*)r->full_row[s] + ((size_t)r->r0[s] + 1) * rp, seg, (size_t)rows, r->is64 ? ncclInt64 : ncclInt32, s, g.comms[q], g.devs[q]->stream));
+        if (n_s > 0) NK(g.nccl.Broadcast(g.devs[s]->ccol.p, r->full_col[q] + r->disp[s], (size_t)n_s, ncclInt32, s, g.comms[q], g.devs[q]->stream));
+      }
+      NK(g.nccl.GroupEnd());
+    }
+  } else {
+    for (int s = 0; s < ng; ++s) { CK(cudaSetDevice(g.devs[s]->device)); CK(cudaStreamSynchronize(g.devs[s]->stream)); }
+    for (int s = 0; s < ng; ++s) {
+      const int rows = r->r0[s + 1] - r->r0[s]; const int64_t n_s = r->disp[s + 1] - r->disp[s];
+      if (rows == 0) continue;
+      for (int q = 0; q < ng; ++q) {
+        CK(cudaSetDevice(g.devs[q]->device));
+        if (q != s) CK(cudaMemcpyPeerAsync((char*)r->full_row[q] + ((size_t)r->r0[s] + 1) * rp, g.devs[q]->device,
+                                           (char*)r->full_row[s] + ((size_t)r->r0[s] + 1) * rp, g.devs[s]->device, (size_t)rows * rp, g.devs[q]->stream));
+        if (n_s > 0) CK(cudaMemcpyPeerAsync(r->full_col[q] + r->disp[s], g.devs[q]->device, g.devs[s]->ccol.p, g.devs[s]->device, (size_t)n_s * 4, g.devs[q]->stream));
+      }
+    }
+  }
+  for (int q = 0; q < ng; ++q) { CK(cudaSetDevice(g.devs[q]->device)); CK(cudaStreamSynchronize(g.devs[q]->stream)); }
+  for (int q = 0; q < ng; ++q) { if (dCcol_per_task) dCcol_per_task[q] = r->full_col[q]; if (dCrow_per_task) dCrow_per_task[q] = r->full_row[q]; }
+  return BSPGEMM_OK;
+}
+// One file per shard, written from the shard's own GPU: <prefix>.shard<q>.bin (format 0: 8 x int64 header {magic, An, Bm, row0,
+// rows, nnz, disp, 0}, then rows+1 slice-relative int64 row pointers, then nnz int32 columns) or <prefix>.shard<q>.mtx
+// (format 1: Matrix Market coordinate pattern, global dimensions, this shard's entries in the reference's transposed
+// convention — the text line of in-memory (row r, col c) is "c+1 r+1", so that readCOO gives the rows back, final/utils.c:66-77).
+extern "C" int bspgemm_result_write(const bspgemm_result* r, const char* prefix, int format) {
+  CKS(result_live(r));
+  if (!prefix || (format != 0 && format != 1)) return fail(BSPGEMM_ERR_BADARG, "bad prefix / format");
+  const size_t rp = r->is64 ? 8 : 4;
+  for (int q = 0; q < r->ng; ++q) {
+    bspgemm_dev* d = g.devs[q];
+    const int rows = r->r0[q + 1] - r->r0[q]; const int64_t n_q = r->disp[q + 1] - r->disp[q];
+    std::vector<char> rowbuf(((size_t)rows + 1) * rp); std::vector<int> col((size_t)std::max<int64_t>(n_q, 1));
+    CK(cudaSetDevice(d->device));
+    if (rows > 0) CK(cudaMemcpy(rowbuf.data(), d->crow_dev.p, ((size_t)rows + 1) * rp, cudaMemcpyDeviceToHost));
+    else memset(rowbuf.data(), 0, rowbuf.size());
+    if (n_q > 0) CK(cudaMemcpy(col.data(), d->ccol.p, (size_t)n_q * 4, cudaMemcpyDeviceToHost));
+    std::vector<int64_t> row64((size_t)rows + 1);
+    for (int i = 0; i <= rows; ++i) row64[i] = r->is64 ? ((const int64_t*)rowbuf.data())[i] : (int64_t)((const int*)rowbuf.data())[i];
+    char path[4096];
+    snprintf(path, sizeof path, "%s.shard%d.%s", prefix, q, format ? "mtx" : "bin");
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(BSPGEMM_ERR_BADARG, "cannot open %s", path);
+    bool ok = true;
+    if (format == 0) {
+      const int64_t hdr[8] = {0x3152534347505342LL /* "BSPGCSR1" */, r->An, r->Bm, r->r0[q], rows, n_q, r->disp[q], 0};
+      ok = fwrite(hdr, sizeof hdr, 1, f) == 1 && fwrite(row64.data(), 8, (size_t)rows + 1, f) == (size_t)rows + 1 &&
+           (n_q == 0 || fwrite(col.data(), 4, (size_t)n_q, f) == (size_t)n_q);
+    } else {
+      std::vector<char> buf(1 << 20);
+      setvbuf(f, buf.data(), _IOFBF, buf.size());
+      fprintf(f, "%%%%MatrixMarket matrix coordinate pattern general\n%% rows [%d,%d) of C, shard %d of %d\n%d %d %lld\n", r->r0[q], r->r0[q + 1], q, r->ng,
+              r->Bm, r->An, (long long)n_q);
+      for (int i = 0; i < rows; ++i)
+        for (int64_t p = row64[i]; p < row64[i + 1]; ++p) fprintf(f, "%d %d\n", col[p] + 1, r->r0[q] + i + 1);
+      ok = !ferror(f);
+      fflush(f); setvbuf(f, nullptr, _IONBF, 0);
+    }
+    if (fclose(f) != 0 || !ok) return fail(BSPGEMM_ERR_BADARG, "write to %s failed", path);
+  }
+  return BSPGEMM_OK;
+}
+extern "C" int bspgemm_result_free(bspgemm_result* r) {
+  if (!r) return BSPGEMM_OK;
+  if (g.inited && r->epoch != 0)
+    for (size_t q = 0; q < r->full_col.size(); ++q) {
+      if (q < g.devs.size()) cudaSetDevice(g.devs[q]->device);
+      if (r->full_col[q]) cudaFree(r->full_col[q]);
+      if (r->full_row[q]) cudaFree(r->full_row[q]);
+    }
+  delete r;
+  return BSPGEMM_OK;
+}
+
 extern "C" int bspgemm_csr(const int* Acol, const int* Arow, int An, const int* Bcol, const int* Brow, int Bn, int Bm, int** Ccol, int* Crow) {
   if (!Ccol) return fail(BSPGEMM_ERR_BADARG, "null Ccol");
   int64_t nnz = 0;
@@ -990,6 +1244,44 @@ extern "C" int bspgemm_csr_slice(const int* Acol, const int* Arow, int An, const
   if (!Ccol || start_row < 0 || end_row < start_row || end_row > An) return fail(BSPGEMM_ERR_BADARG, "bad slice [%d,%d) of %d rows", start_row, end_row, An);
   int64_t nnz = 0;
   return host_multiply(Acol, Arow + start_row, end_row - start_row, Bcol, Brow, Bn, Bm, Ccol, nullptr, 0, Crow, 0, &nnz, 1);
+}
+
+// Host-pointer masked product on GPU 0 (the reference's SpGEMM_masked is serial, :227-228): upload A, B, F; download C.
+extern "C" int bspgemm_csr_masked(const int* Acol, const int* Arow, int An, const int* Bcol, const int* Brow, int Bn, int Bm,
+                                  const int* Fcol, const int* Frow, int** Ccol, int* Crow) {
+  if (!Arow || !Brow || !Frow || !Crow || !Ccol || An < 0 || Bn < 0 || Bm < 0) return fail(BSPGEMM_ERR_BADARG, "null pointer or negative size");
+  CKS(ensure_init());
+  bspgemm_dev* d = g.devs[0];
+  CK(cudaSetDevice(d->device));
+  d->stream = d->own_stream;
+  const int64_t alo = Arow[0], Annz = (int64_t)Arow[An] - alo, Bnnz = (int64_t)Brow[Bn] - Brow[0], flo = Frow[0], Fnnz = (int64_t)Frow[An] - flo;
+  if (Annz < 0 || Bnnz < 0 || Fnnz < 0 || Brow[0] != 0) return fail(BSPGEMM_ERR_BADARG, "row pointers not monotone / Brow[0] != 0");
+  DevBuf<int> frow, fcol;
+  struct Guard { DevBuf<int>& a; DevBuf<int>& b; ~Guard() { a.release(); b.release(); } } guard{frow, fcol};
+  CKS(d->in_arow.ensure((size_t)An + 1)); CKS(d->in_acol.ensure((size_t)std::max<int64_t>(Annz, 1)));
+  CKS(d->in_brow.ensure((size_t)Bn + 1)); CKS(d->in_bcol.ensure((size_t)std::max<int64_t>(Bnnz, 1)));
+  CKS(frow.ensure((size_t)An + 1)); CKS(fcol.ensure((size_t)std::max<int64_t>(Fnnz, 1)));
+  CKS(d->crow_dev.ensure(((size_t)An + 1) * 4));
+  CK(cudaMemcpyAsync(d->in_arow.p, Arow, ((size_t)An + 1) * 4, cudaMemcpyHostToDevice, d->stream));
+  if (Annz) CK(cudaMemcpyAsync(d->in_acol.p, Acol + alo, (size_t)Annz * 4, cudaMemcpyHostToDevice, d->stream));
+  CK(cudaMemcpyAsync(d->in_brow.p, Brow, ((size_t)Bn + 1) * 4, cudaMemcpyHostToDevice, d->stream));
+  if (Bnnz) CK(cudaMemcpyAsync(d->in_bcol.p, Bcol, (size_t)Bnnz * 4, cudaMemcpyHostToDevice, d->stream));
+  CK(cudaMemcpyAsync(frow.p, Frow, ((size_t)An + 1) * 4, cudaMemcpyHostToDevice, d->stream));
+  if (Fnnz) CK(cudaMemcpyAsync(fcol.p, Fcol + flo, (size_t)Fnnz * 4, cudaMemcpyHostToDevice, d->stream));
+  const int* acol_dev = (const int*)((uintptr_t)d->in_acol.p - (uintptr_t)alo * 4u);
+  const int* fcol_dev = (const int*)((uintptr_t)fcol.p - (uintptr_t)flo * 4u);
+  d->a.m = Csr{d->in_arow.p, acol_dev, d->in_brow.p, d->in_bcol.p, An, Bn, Bm};
+  d->a.Annz = Annz; d->a.Bnnz = Bnnz; d->a.dCrow = d->crow_dev.p; d->a.is64 = 0;
+  d->user_ccol = nullptr; d->user_cap = 0;
+  int* dC = nullptr; int64_t nnz = 0;
+  CKS(masked_multiply(d, fcol_dev, frow.p, Fnnz, d->crow_dev.p, 0, &dC, &nnz));
+  int* out = (int*)malloc((size_t)std::max<int64_t>(nnz, 1) * sizeof(int));
+  if (!out) return fail(BSPGEMM_ERR_OOM, "malloc of %lld ints failed", (long long)nnz);
+  CK(cudaMemcpyAsync(Crow, d->crow_dev.p, ((size_t)An + 1) * 4, cudaMemcpyDeviceToHost, d->stream));
+  if (nnz) CK(cudaMemcpyAsync(out, dC, (size_t)nnz * 4, cudaMemcpyDeviceToHost, d->stream));
+  CK(cudaStreamSynchronize(d->stream));
+  *Ccol = out;
+  return BSPGEMM_OK;
 }
 
 extern "C" int bspgemm_intermediate_products(const int* Acol, const int* Arow, int An, const int* Brow, int Bn, int64_t* ip_out) {
@@ -1045,6 +1337,13 @@ static void die_on(int s, const char* who) {
 extern "C" void bspgemm_SpGEMM_mpi(int* Acol, int* Arow, int An, int* Bcol, int* Brow, int Bm, int** Ccol, int* Crow, int tBlock) {
   (void)tBlock;
   die_on(bspgemm_csr(Acol, Arow, An, Bcol, Brow, derive_bn(Acol, Arow, An), Bm, Ccol, Crow), "SpGEMM_mpi");
+}
+extern "C" void bspgemm_SpGEMM_masked(int* Acol, int* Arow, int An, int* Bcol, int* Brow, int Bm, int* Fcol, int* Frow, int** Ccol, int* Crow, int* Csize) {
+  // same argument list as the reference (final/SpGEMM_mpi_omp.c:232-235); the caller's growable *Ccol is replaced by an exact-size one
+  int* fresh = nullptr;
+  die_on(bspgemm_csr_masked(Acol, Arow, An, Bcol, Brow, derive_bn(Acol, Arow, An), Bm, Fcol, Frow, &fresh, Crow), "SpGEMM_masked");
+  if (Ccol) { free(*Ccol); *Ccol = fresh; } else free(fresh);
+  if (Csize) *Csize = Crow[An];
 }
 extern "C" void bspgemm_SpGEMM_omp(int* Acol, int* Arow, int An, int* Bcol, int* Brow, int Bm, int** Ccol, int* Crow, int tBlock) {
   (void)tBlock;

@@ -75,6 +75,8 @@ struct bspgemm_dev {
     int variant = -1, sort_LAL = 0; // plan of the last successful product with this B that can be replayed without probes (2 sort, 3 band)
   } pb;
   DevBuf<u32> bdesc;
+  // masked product (mask.cuh): 64-bit row pointers of the unmasked product, the canonical mask, the masked output
+  DevBuf<long long> m_crow; DevBuf<int> m_frow, m_fcol, m_out;
   u32 ell_pad = EMPTY;              // padding value of the ELL copy in `bell`: EMPTY, or EMPTY_F for the floating-point sort network
   bool fast = false;                // the product in flight was launched from the cached plan (no probes, no host round trip before the launch)
   cudaEvent_t ev[8] = {};

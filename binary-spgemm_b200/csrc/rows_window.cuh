@@ -119,21 +119,33 @@ __global__ void __launch_bounds__(1024, 1) k_rows_window(Csr m, const u32* __res
         if (w_lo != EMPTY) {
           const u32 q0 = w_lo >> 2, q1 = w_hi >> 2;
           if (MODE != MODE_COUNT && !restart) {
-            for (u32 qb = q0; qb <= q1; qb += nthr) {
-              const u32 q = qb + tid;
+            // Emission: every warp owns a contiguous slice of the touched range [q0,q1] (in 16-byte units).  Pass 1 counts the
+            // set bits of the slice, ONE block scan orders the 32 slices, pass 2 re-reads the slice in order (warp scan of the
+            // lanes' popcounts), writes the columns and clears the words.  (One block scan per 1024 units — up to 12 per window
+            // and row — made the kernel barrier-stall bound, profiles/r01_window_m2_*.)
+            const u32 span = q1 - q0 + 1u, per = (span + (u32)nwarps - 1u) / (u32)nwarps;
+            const u32 s0 = q0 + (u32)wid * per, s1 = min(q1 + 1u, s0 + per);
+            u32 c = 0;
+            for (u32 q = s0 + (u32)lane; q < s1; q += 32u) { const uint4 v = bm4[q]; c += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w); }
+            c = __reduce_add_sync(0xffffffffu, c);
+            u32 tot;
+            u32 o = block_excl_scan(lane == 0 ? c : 0u, s_red, &tot);       // exclusive offset of the warp's slice (lane 0 carries the warp's count)
+            o = __shfl_sync(0xffffffffu, o, 0);
+            for (u32 qb = s0; qb < s1; qb += 32u) {
+              const u32 q = qb + (u32)lane;
               uint4 v = make_uint4(0u, 0u, 0u, 0u);
-              if (q <= q1) { v = bm4[q]; bm4[q] = make_uint4(0u, 0u, 0u, 0u); }
-              u32 tot;
-              const u32 c = __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
-              const u32 o = block_excl_scan(c, s_red, &tot);
-              int* dst = Ccol + (base + done + o);
+              if (q < s1) { v = bm4[q]; bm4[q] = make_uint4(0u, 0u, 0u, 0u); }
+              const u32 cl = __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+              const u32 incl = warp_incl_scan(cl);
+              int* dst = Ccol + (base + done + o + incl - cl);
               const u32 col0 = start + (q << 7);
               u32 word = v.x; while (word) { const u32 b = __ffs(word) - 1; word &= word - 1; *dst++ = (int)(col0 + b); }
               word = v.y;     while (word) { const u32 b = __ffs(word) - 1; word &= word - 1; *dst++ = (int)(col0 + 32u + b); }
               word = v.z;     while (word) { const u32 b = __ffs(word) - 1; word &= word - 1; *dst++ = (int)(col0 + 64u + b); }
               word = v.w;     while (word) { const u32 b = __ffs(word) - 1; word &= word - 1; *dst++ = (int)(col0 + 96u + b); }
-              done += tot;
+              o += __shfl_sync(0xffffffffu, incl, 31);
             }
+            done += tot;
           } else {
             for (u32 q = q0 + tid; q <= q1; q += nthr) bm4[q] = make_uint4(0u, 0u, 0u, 0u);
           }

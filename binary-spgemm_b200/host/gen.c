@@ -6,6 +6,7 @@
 #include "mmio_compat.h"
 #include <stdlib.h>
 #include <string.h>
+#include <math.h>
 
 static inline uint64_t mix64(uint64_t z)
 {
@@ -44,6 +45,46 @@ int bs_gen_uniform(uint32_t n, uint32_t d, uint64_t seed, int32_t **row_out, int
     if (!col) { free(row); free(tmp); free(len); return 1; }
 #pragma omp parallel for schedule(static)
     for (int64_t r = 0; r < (int64_t)n; ++r) memcpy(col + row[r], tmp + (size_t)r * d, (size_t)len[r] * sizeof(int32_t));
+    free(tmp); free(len);
+    *row_out = row; *col_out = col; *nnz_out = row[n];
+    return 0;
+}
+
+/* The reference's own distribution: Matlab `sprand(n,n,d/n) > 0` (Matlab/write_spm.m:5) — about d*n entries at uniformly random
+ * positions, i.e. row lengths are Binomial(n, d/n) ~ Poisson(d): ragged rows, unlike bs_gen_uniform's fixed d per row.  The
+ * length of row r is drawn by inversion of the Poisson distribution (Knuth's product of uniforms, d is small), its columns are
+ * uniform in [0,n), sorted, repeats removed — all from the counter-based generator, so the matrix is a function of (n, d, seed). */
+int bs_gen_sprand(uint32_t n, double d, uint64_t seed, int32_t **row_out, int32_t **col_out, int64_t *nnz_out)
+{
+    if (d < 0 || d > 64) return 1;
+    const int cap = (int)(d * 4 + 32);                       /* P(len > cap) is astronomically small; lengths are clamped */
+    int32_t *row = (int32_t *)malloc(((size_t)n + 1) * sizeof(int32_t));
+    int32_t *tmp = (int32_t *)malloc((size_t)n * cap * sizeof(int32_t) + 4);
+    int32_t *len = (int32_t *)malloc(((size_t)n + 1) * sizeof(int32_t));
+    if (!row || !tmp || !len) { free(row); free(tmp); free(len); return 1; }
+    const double limit = exp(-d);
+#pragma omp parallel for schedule(static)
+    for (int64_t r = 0; r < (int64_t)n; ++r) {
+        int k = 0;
+        double prod = 1.0;
+        for (;;) {                                           /* Poisson(d): number of uniforms whose product stays above e^-d */
+            prod *= (double)((rng3(seed ^ 0x5eedull, (uint64_t)r, (uint64_t)(1000 + k)) >> 11) + 1) * (1.0 / 9007199254740993.0);
+            if (prod <= limit || k >= cap) break;
+            ++k;
+        }
+        int32_t *v = tmp + (size_t)r * cap;
+        for (int s = 0; s < k; ++s) v[s] = (int32_t)(((rng3(seed, (uint64_t)r, (uint64_t)s) >> 32) * (uint64_t)n) >> 32);
+        sort_u32(v, k);
+        int m = 0;
+        for (int s = 0; s < k; ++s) if (s == 0 || v[s] != v[s - 1]) v[m++] = v[s];
+        len[r] = m;
+    }
+    row[0] = 0;
+    for (uint32_t r = 0; r < n; ++r) row[r + 1] = row[r] + len[r];
+    int32_t *col = (int32_t *)malloc(((size_t)row[n] + 1) * sizeof(int32_t));
+    if (!col) { free(row); free(tmp); free(len); return 1; }
+#pragma omp parallel for schedule(static)
+    for (int64_t r = 0; r < (int64_t)n; ++r) memcpy(col + row[r], tmp + (size_t)r * cap, (size_t)len[r] * sizeof(int32_t));
     free(tmp); free(len);
     *row_out = row; *col_out = col; *nnz_out = row[n];
     return 0;

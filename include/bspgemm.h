@@ -73,10 +73,36 @@ int bspgemm_csr_into(const int *Acol, const int *Arow, int An,
 int bspgemm_csr_slice(const int *Acol, const int *Arow, int An,
                       const int *Bcol, const int *Brow, int Bn, int Bm,
                       int **Ccol, int *Crow, int start_row, int end_row);
+/* Masked product C = F .* (A·B): replaces SpGEMM_masked (final/SpGEMM_mpi_omp.c:232-288).  Row i of the result
+ * = the distinct columns of row i of A·B that occur in row i of the mask F (An x Bm, CSR, any column order, repeats allowed —
+ * the reference's mask is a flag array), ascending.  Same ownership rules as bspgemm_csr; runs on GPU 0 (the reference's
+ * version is serial too). */
+int bspgemm_csr_masked(const int *Acol, const int *Arow, int An,
+                       const int *Bcol, const int *Brow, int Bn, int Bm,
+                       const int *Fcol, const int *Frow,
+                       int **Ccol, int *Crow);
 /* Σ_{(i,j) in A} len(B_j): the intermediate-product count the throughput metric is quoted in
  * (trip count of final/SpGEMM_mpi_omp.c:33-37), computed by the work-estimation kernel on GPU 0. */
 int bspgemm_intermediate_products(const int *Acol, const int *Arow, int An,
                                   const int *Brow, int Bn, int64_t *ip_out);
+
+/* ---- distributed consumer: the product stays sharded on the GPUs instead of being gathered to one place
+ *      (the reference gathers to rank 0: MPI_Gatherv + MPI_Gather + serial fix-up, final/SpGEMM_mpi_omp.c:203-223).
+ *      bspgemm_csr_sharded runs the product of bspgemm_csr and returns a handle; the shards (device pointers into the contexts'
+ *      arenas: valid until the next product / bspgemm_finalize) can be inspected, all-gathered GPU-to-GPU so that every GPU
+ *      holds the whole CSR (row pointers offset on the owning GPU; ncclBroadcast per shard over NVLink), or written one file
+ *      per shard (format 0: binary, 1: Matrix Market pattern, readable by readCOO). ---- */
+typedef struct bspgemm_result bspgemm_result;
+int bspgemm_csr_sharded(const int *Acol, const int *Arow, int An,
+                        const int *Bcol, const int *Brow, int Bn, int Bm,
+                        int crow_is_i64, bspgemm_result **out);
+int bspgemm_result_shards(const bspgemm_result *r);
+int64_t bspgemm_result_nnz(const bspgemm_result *r);
+int bspgemm_result_shard(const bspgemm_result *r, int shard, int *device, int *row0, int *rows, int64_t *nnz, int64_t *disp,
+                         const int **dCcol, const void **dCrow /* slice-relative, rows+1 entries */);
+int bspgemm_result_allgather(bspgemm_result *r, int **dCcol_per_task, void **dCrow_per_task);
+int bspgemm_result_write(const bspgemm_result *r, const char *prefix, int format);
+int bspgemm_result_free(bspgemm_result *r);
 
 /* Legacy-signature drop-ins: same names' worth of arguments as the reference, void return, print to
  * stderr and exit(1) on failure like the reference's I/O paths.  Bn is derived as max(Acol)+1 bounded by
@@ -84,6 +110,8 @@ int bspgemm_intermediate_products(const int *Acol, const int *Arow, int An,
  * tBlock is accepted and ignored (it only sizes the CPU thread slices, :77). */
 void bspgemm_SpGEMM_mpi(int *Acol, int *Arow, int An, int *Bcol, int *Brow, int Bm,
                         int **Ccol, int *Crow, int tBlock);                       /* :155-158 */
+void bspgemm_SpGEMM_masked(int *Acol, int *Arow, int An, int *Bcol, int *Brow, int Bm,
+                           int *Fcol, int *Frow, int **Ccol, int *Crow, int *Csize);     /* :232-235 */
 void bspgemm_SpGEMM_omp(int *Acol, int *Arow, int An, int *Bcol, int *Brow, int Bm,
                         int **Ccol, int *Crow, int tBlock);                       /* :71-74  (GPU 0 only) */
 void bspgemm_SpGEMM_bigslice(int *Acol, int *Arow, int An, int *Bcol, int *Brow, int Bm,
@@ -133,6 +161,14 @@ int bspgemm_dev_multiply(bspgemm_dev *h, void *stream,
                          const int *dBcol, const int *dBrow, int Bn, int Bm, int64_t Bnnz,
                          void *dCrow, int crow_is_i64,
                          int **dCcol_out, int64_t *nnz_out);
+/* Device-resident masked product (see bspgemm_csr_masked).  dFcol/dFrow: the mask, An+1 row pointers (absolute offsets, like
+ * A's).  *dCcol_out points into a second arena of the handle (the unmasked rows occupy the first), valid until the next call. */
+int bspgemm_dev_multiply_masked(bspgemm_dev *h, void *stream,
+                                const int *dAcol, const int *dArow, int An, int64_t Annz,
+                                const int *dBcol, const int *dBrow, int Bn, int Bm, int64_t Bnnz,
+                                const int *dFcol, const int *dFrow, int64_t Fnnz,
+                                void *dCrow, int crow_is_i64,
+                                int **dCcol_out, int64_t *nnz_out);
 int bspgemm_dev_get_stats(bspgemm_dev *h, bspgemm_stats *out);
 /* B resident once for many products — the reference replicates B once, before its timed loop (every rank parses the file,
  * final/SpGEMM_mpi_omp.c:309 vs :318-328).  Builds B's gather-friendly copy in the handle (ELL re-layout, or run descriptors

@@ -57,6 +57,8 @@ void bs_time_stats(double *t, int times, double *mean, double *median, double *f
  *   banded  : row i holds columns i-d/2 .. i+d/2-1 clipped to [0,n)
  *   blockdiag: dense d x d blocks on the diagonal */
 int bs_gen_uniform(uint32_t n, uint32_t d, uint64_t seed, int32_t **row, int32_t **col, int64_t *nnz);
+/* the reference's own distribution, Matlab sprand(n,n,d/n)>0 (Matlab/write_spm.m:5): Poisson(d) row lengths */
+int bs_gen_sprand(uint32_t n, double d, uint64_t seed, int32_t **row, int32_t **col, int64_t *nnz);
 int bs_gen_rmat(uint32_t scale, uint32_t edge_factor, double a, double b, double c, uint64_t seed,
                 int32_t **row, int32_t **col, int64_t *nnz);
 int bs_gen_banded(uint32_t n, uint32_t d, int32_t **row, int32_t **col, int64_t *nnz);

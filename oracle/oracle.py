@@ -87,6 +87,22 @@ class Oracle:
         self.L.oracle_free(out)
         return Ccol, Crow
 
+    def spgemm_masked(self, Acol, Arow, An, Bcol, Brow, Bm, Fcol, Frow):
+        """C = F .* (A·B) (SpGEMM_masked, final/SpGEMM_mpi_omp.c:232-288) -> (Ccol int32[nnz], Crow int64[An+1])"""
+        Acol, Arow, Bcol, Brow, Fcol, Frow = (_i32(x) for x in (Acol, Arow, Bcol, Brow, Fcol, Frow))
+        Crow = np.zeros(An + 1, dtype=np.int64)
+        out = C.c_void_p()
+        self.L.oracle_spgemm_masked.restype = C.c_int64
+        self.L.oracle_spgemm_masked.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                                C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]
+        nnz = self.L.oracle_spgemm_masked(Acol.ctypes.data, Arow.ctypes.data, An, Bcol.ctypes.data, Brow.ctypes.data, Bm,
+                                          Fcol.ctypes.data, Frow.ctypes.data, C.byref(out), Crow.ctypes.data)
+        if nnz < 0:
+            raise MemoryError("oracle_spgemm_masked failed")
+        Ccol = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_int32)), shape=(max(nnz, 1),))[:nnz].copy()
+        self.L.oracle_free(out)
+        return Ccol, Crow
+
     def coo2csc(self, row_coo, col_coo, n, is_one_based=0):
         r = np.ascontiguousarray(row_coo, dtype=np.uint32)
         c = np.ascontiguousarray(col_coo, dtype=np.uint32)
@@ -166,6 +182,23 @@ class Ref:
         nnz = int(Crow[An])
         Ccol = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_int32)), shape=(max(nnz, 1),))[:nnz].copy()
         _libc.free(out)
+        return Ccol, Crow
+
+    def masked(self, Acol, Arow, An, Bcol, Brow, Bm, Fcol, Frow):
+        """The reference's own SpGEMM_masked (final/SpGEMM_mpi_omp.c:232-288; defined there, never called by its drivers).
+        Square matrices only: its flag array has An entries (:239)."""
+        Acol, Arow, Bcol, Brow, Fcol, Frow = (_i32(x) for x in (Acol, Arow, Bcol, Brow, Fcol, Frow))
+        self.L.SpGEMM_masked.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                         C.POINTER(C.c_void_p), C.c_void_p, C.POINTER(C.c_int)]
+        self.L.SpGEMM_masked.restype = None
+        Crow = np.zeros(An + 1, dtype=np.int32)
+        size = C.c_int(max(An, 1))
+        buf = C.c_void_p(_libc.malloc(max(An, 1) * 4))
+        self.L.SpGEMM_masked(Acol.ctypes.data, Arow.ctypes.data, An, Bcol.ctypes.data, Brow.ctypes.data, Bm,
+                             Fcol.ctypes.data, Frow.ctypes.data, C.byref(buf), Crow.ctypes.data, C.byref(size))
+        nnz = int(Crow[An])
+        Ccol = np.ctypeslib.as_array(C.cast(buf, C.POINTER(C.c_int32)), shape=(max(nnz, 1),))[:nnz].copy()
+        _libc.free(buf)
         return Ccol, Crow
 
     def omp(self, Acol, Arow, An, Bcol, Brow, Bm, tBlock):

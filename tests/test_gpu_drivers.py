@@ -185,3 +185,66 @@ def test_sharded_host_operator_tasks_sharing_one_gpu(gpu_ctx, oracle, tasks):
 def test_sharded_host_operator_over_nccl(gpu_ctx, oracle):
     """The same with one task per GPU: B uploaded once and replicated by ncclBroadcast over NVLink; includes An < #GPUs."""
     _multi_task_check(gpu_ctx, oracle, list(range(min(_ngpu(), 8))))
+
+
+# ------------------------------------------------------------------------------------------------ distributed consumer (N3)
+def _sharded_consumer_check(bs, oracle, devices, tmp_path):
+    import torch
+    rng = np.random.default_rng(123)
+    n = 30007
+    row, col = bs.gen_uniform(n, 8, 9)
+    want_col, want_row = oracle.spgemm(col, row, n, col, row, n)
+    bs.finalize()
+    try:
+        bs.init(devices=devices)
+        for i64 in (False, True):
+            R = bs.ShardedResult(col, row, n, col, row, n, n, i64=i64)
+            assert R.nshards == len(devices) and R.nnz == len(want_col)
+            rdt = torch.int64 if i64 else torch.int32
+            # (a) the shards where they were computed: slice-relative row pointers, displacements = the exclusive scan of the shard sizes
+            for q in range(R.nshards):
+                s = R.shard(q)
+                assert s["device"] == devices[q] and s["row0"] == (n * q) // len(devices) and s["disp"] == want_row[s["row0"]]
+                with torch.cuda.device(s["device"]):
+                    cr = bs.device_view(s["dCrow"], (s["rows"] + 1) * (2 if i64 else 1), s["device"]).cpu().numpy().view(np.int64 if i64 else np.int32)
+                    cc = bs.device_view(s["dCcol"], s["nnz"], s["device"]).cpu().numpy()
+                assert (cr == want_row[s["row0"]:s["row0"] + s["rows"] + 1] - want_row[s["row0"]]).all()
+                assert (cc == want_col[s["disp"]:s["disp"] + s["nnz"]]).all()
+            # (b) all-gather on the devices: every task holds the whole CSR, row pointers already offset
+            cols, rows = R.allgather()
+            for q in range(R.nshards):
+                with torch.cuda.device(devices[q]):
+                    fr = bs.device_view(rows[q], (n + 1) * (2 if i64 else 1), devices[q]).cpu().numpy().view(np.int64 if i64 else np.int32)
+                    fc = bs.device_view(cols[q], R.nnz, devices[q]).cpu().numpy()
+                assert (fr == want_row).all() and (fc == want_col).all(), (q, i64)
+            # (c) one file per shard
+            R.write(str(tmp_path / f"c{int(i64)}"), 0)
+            R.write(str(tmp_path / f"c{int(i64)}"), 1)
+            for q in range(R.nshards):
+                raw = np.fromfile(tmp_path / f"c{int(i64)}.shard{q}.bin", dtype=np.uint8)
+                hdr = raw[:64].view(np.int64)
+                assert hdr[0] == 0x3152534347505342 and hdr[1] == n and hdr[2] == n
+                r0, nr, nz, dp = (int(x) for x in hdr[3:7])
+                pr = raw[64:64 + 8 * (nr + 1)].view(np.int64)
+                pc = raw[64 + 8 * (nr + 1):].view(np.int32)
+                assert dp == want_row[r0] and (pr == want_row[r0:r0 + nr + 1] - want_row[r0]).all() and len(pc) == nz
+                assert (pc == want_col[dp:dp + nz]).all()
+                mr, mc, M, N, nnz = bs.readCOO(str(tmp_path / f"c{int(i64)}.shard{q}.mtx"))      # the shard alone, global dimensions
+                assert M == n and N == n and nnz == nz
+                assert (np.diff(mr.astype(np.int64))[r0:r0 + nr] == np.diff(want_row[r0:r0 + nr + 1])).all() and mr[r0] == 0
+                assert (mc.astype(np.int32) == pc).all()
+            R.free()
+    finally:
+        bs.finalize()
+        bs.init(1)
+
+
+def test_distributed_consumer_tasks_sharing_one_gpu(gpu_ctx, oracle, tmp_path):
+    """Shards left on the device, all-gather (device-to-device copies: no communicator), one file per shard."""
+    _sharded_consumer_check(gpu_ctx, oracle, [0, 0, 0], tmp_path)
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs two GPUs")
+def test_distributed_consumer_over_nccl(gpu_ctx, oracle, tmp_path):
+    """The same with one task per GPU: the all-gather is one grouped ncclBroadcast per shard over NVLink."""
+    _sharded_consumer_check(gpu_ctx, oracle, list(range(min(_ngpu(), 4))), tmp_path)

@@ -792,3 +792,76 @@ def test_config4_full_size_rmat_scale22_sampled_blocks(bs, oracle):
     blocks += [(int(r), int(r) + 1) for r in np.argsort(lens)[-3:]]          # the three longest rows of A
     _check_blocks_vs_oracle(bs, oracle, row, col, n, C, dCr, blocks)
     h.close()
+
+
+# ------------------------------------------------------------------------------------------------ masked product, iterated products (N4)
+def test_masked_product_matches_the_oracle(gpu_ctx, oracle, bs):
+    """C = F .* (A·B) (final/SpGEMM_mpi_omp.c:232-288) through the host-pointer operator and the device operator: sorted masks,
+    unsorted masks with repeats (canonicalised on the device), mask = A (the triangle pattern), empty masks, rectangular
+    shapes, skewed rows; bit-exact against the oracle's restatement (itself pinned by the compiled reference)."""
+    import torch
+    rng = np.random.default_rng(31)
+    cases = []
+    n = 20011
+    ar, ac = bs.gen_uniform(n, 8, 5)
+    fr, fc = random_csr(rng, n, n, 200.0)
+    cases.append(("uniform, sorted mask", ac, ar, n, ac, ar, n, n, fc, fr))
+    fr2, fc2 = random_csr(rng, n, n, 60.0, sort=False, dups=True)
+    cases.append(("uniform, unsorted mask with repeats", ac, ar, n, ac, ar, n, n, fc2, fr2))
+    cases.append(("mask = A", ac, ar, n, ac, ar, n, n, ac, ar))
+    cases.append(("empty mask", ac, ar, n, ac, ar, n, n, np.zeros(0, np.int32), np.zeros(n + 1, np.int32)))
+    rr, rc = bs.gen_rmat(12, 16, 0.45, 0.22, 0.22, 7)
+    m = 1 << 12
+    cases.append(("rmat, mask = A", rc, rr, m, rc, rr, m, m, rc, rr))
+    a2r, a2c = random_csr(rng, 300, 500, 7.0, sort=False, dups=True)
+    b2r, b2c = random_csr(rng, 500, 900, 9.0, sort=False, dups=True)
+    f2r, f2c = random_csr(rng, 300, 900, 90.0, sort=False, dups=True)
+    cases.append(("rectangular", a2c, a2r, 300, b2c, b2r, 500, 900, f2c, f2r))
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(dev)
+    h = bs.DeviceSpGEMM(0)
+    for name, Acol, Arow, An, Bcol, Brow, Bn, Bm, Fcol, Frow in cases:
+        want_col, want_row = oracle.spgemm_masked(Acol, Arow, An, Bcol, Brow, Bm, Fcol, Frow)
+        got_col, got_row = bs.spgemm_csr_masked(Acol, Arow, An, Bcol, Brow, Bn, Bm, Fcol, Frow)
+        msg = _explain(got_col, got_row, want_col, want_row)
+        assert not msg, (name, msg)
+        for i64 in (False, True):
+            dCr = torch.full((An + 1,), -3, dtype=torch.int64 if i64 else torch.int32, device=dev)
+            ptr, nnz = h.multiply_masked(t(Acol), t(Arow), An, len(Acol), t(Bcol), t(Brow), Bn, Bm, len(Bcol), t(Fcol), t(Frow), len(Fcol), dCr, crow_is_i64=i64)
+            torch.cuda.synchronize()
+            msg = _explain(bs.device_view(ptr, nnz, 0).cpu().numpy(), dCr.cpu().numpy(), want_col, want_row)
+            assert not msg, (name, i64, msg)
+    h.close()
+
+
+def test_iterated_products_stay_on_the_device(bs, oracle):
+    """Powers of a graph (the motivating application, report p.1: paths of length 2, 3, ...): A^2, then A^3 = A^2·A with the
+    prepared B = A, every factor device-resident between the products (the handle's arena is copied to a tensor of the caller
+    before the next product reuses it); then the masked closure step A .* A^3.  Compared with the oracle's chain."""
+    import torch
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(dev)
+    n = 6007
+    ar, ac = bs.gen_uniform(n, 3, 17)
+    dAr, dAc = t(ar), t(ac)
+    h = bs.DeviceSpGEMM(0)
+    h.prepare_b(dAc, dAr, n, n, len(ac))
+    cur_r, cur_c, d_r, d_c = ar, ac, dAr, dAc
+    for power in (2, 3, 4):
+        want_c, want_r = oracle.spgemm(cur_c, cur_r, n, ac, ar, n)
+        dCr = torch.zeros(n + 1, dtype=torch.int32, device=dev)
+        ptr, nnz = h.multiply(d_c, d_r, n, int(d_c.numel()), dAc, dAr, n, n, len(ac), dCr)
+        torch.cuda.synchronize()
+        d_c = bs.device_view(ptr, nnz, 0).clone()            # the next product overwrites the arena
+        d_r = dCr
+        assert h.stats()["b_prepared"] == 1
+        msg = _explain(d_c.cpu().numpy(), d_r.cpu().numpy(), want_c, want_r)
+        assert not msg, (power, msg)
+        cur_r, cur_c = want_r.astype(np.int32), want_c
+    want_c, want_r = oracle.spgemm_masked(cur_c, cur_r, n, ac, ar, n, ac, ar)          # A .* (A^4 · A)
+    dCr = torch.zeros(n + 1, dtype=torch.int32, device=dev)
+    ptr, nnz = h.multiply_masked(d_c, d_r, n, int(d_c.numel()), dAc, dAr, n, n, len(ac), dAc, dAr, len(ac), dCr)
+    torch.cuda.synchronize()
+    msg = _explain(bs.device_view(ptr, nnz, 0).cpu().numpy(), dCr.cpu().numpy(), want_c, want_r)
+    assert not msg, msg
+    h.close()

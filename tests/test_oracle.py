@@ -117,3 +117,46 @@ def test_reference_runs_with_several_tasks_through_the_shm_mpi_shim():
                          capture_output=True, text=True, timeout=120)
     f = out.stdout.strip().split(",")
     assert out.returncode == 0 and f[:4] == ["4", "2", "8", "6250"] and f[5:8] == ["50000", "25000", "12502"], out.stdout + out.stderr
+
+
+def _masked_cases(rng):
+    n = 700
+    ar, ac = random_csr(rng, n, n, 6.0)
+    br, bc = random_csr(rng, n, n, 5.0, sort=False, dups=True)
+    fr, fc = random_csr(rng, n, n, 40.0)                                # sorted, distinct mask
+    yield "square sorted mask", ac, ar, n, bc, br, n, fc, fr
+    fr2, fc2 = random_csr(rng, n, n, 25.0, sort=False, dups=True)       # the reference's mask is a flag array: any order, repeats
+    yield "square unsorted mask with repeats", ac, ar, n, bc, br, n, fc2, fr2
+    yield "mask = A (triangle pattern)", ac, ar, n, ac, ar, n, ac, ar
+    fr3 = np.zeros(n + 1, np.int32)
+    yield "empty mask", ac, ar, n, bc, br, n, np.zeros(0, np.int32), fr3
+
+
+def test_oracle_masked_matches_reference_and_scipy(oracle, ref):
+    """SpGEMM_masked (final/SpGEMM_mpi_omp.c:232-288) is defined by the reference but never called by its drivers; the
+    compiled reference function pins the restatement, scipy's (A@B).multiply(F) pins both."""
+    rng = np.random.default_rng(2024)
+    for name, ac, ar, An, bc, br, Bm, fc, fr in _masked_cases(rng):
+        got_col, got_row = oracle.spgemm_masked(ac, ar, An, bc, br, Bm, fc, fr)
+        ref_col, ref_row = ref.masked(ac, ar, An, bc, br, Bm, fc, fr)
+        assert (got_row == ref_row).all() and (got_col == ref_col).all(), name
+        A = sp.csr_matrix((np.ones(len(ac), np.int64), ac, ar), shape=(An, len(br) - 1))
+        B = sp.csr_matrix((np.ones(len(bc), np.int64), bc, br), shape=(len(br) - 1, Bm))
+        F = sp.csr_matrix((np.ones(len(fc), np.int64), fc, fr), shape=(An, Bm))
+        A.sum_duplicates(); B.sum_duplicates(); F.sum_duplicates()
+        P = (A @ B).multiply(F).tocsr()
+        P.eliminate_zeros(); P.sort_indices()
+        assert (P.indptr == got_row).all() and (P.indices == got_col).all(), name
+
+
+def test_oracle_masked_rectangular(oracle):
+    """Rectangular A (30 x 50) · B (50 x 90) with a 30 x 90 mask: beyond the reference (its flag array has An entries, :239)."""
+    rng = np.random.default_rng(9)
+    ar, ac = random_csr(rng, 30, 50, 7.0)
+    br, bc = random_csr(rng, 50, 90, 9.0, sort=False)
+    fr, fc = random_csr(rng, 30, 90, 30.0, sort=False, dups=True)
+    got_col, got_row = oracle.spgemm_masked(ac, ar, 30, bc, br, 90, fc, fr)
+    full_col, full_row = oracle.spgemm(ac, ar, 30, bc, br, 90)
+    for i in range(30):
+        want = sorted(set(full_col[full_row[i]:full_row[i + 1]]) & set(fc[fr[i]:fr[i + 1]]))
+        assert got_col[got_row[i]:got_row[i + 1]].tolist() == want
