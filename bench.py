@@ -69,6 +69,23 @@ def shard_bounds(n: int, rank: int, world: int):
     return (n * rank) // world, (n * (rank + 1)) // world
 
 
+def shard_bounds_ip(row_t, col_t, n: int, world: int):
+    """Contiguous row blocks of equal WORK: split points on the prefix sum of the rows' intermediate products
+    (+1 per row).  row_t / col_t: the CSR of A = B as tensors (any device).  Returns the world+1 boundaries; the product is the
+    same whatever the split."""
+    import torch
+    blen = (row_t[1:] - row_t[:-1]).to(torch.int64)
+    per_entry = blen[col_t.long()]
+    pre = torch.zeros(n + 1, dtype=torch.int64, device=row_t.device)
+    pre[1:] = torch.cumsum(torch.segment_reduce(per_entry, "sum", offsets=row_t.to(torch.int64)) + 1, 0) if hasattr(torch, "segment_reduce") else 0
+    targets = torch.tensor([int(pre[-1]) * q // world for q in range(1, world)], dtype=torch.int64, device=row_t.device)
+    cuts = torch.searchsorted(pre, targets).clamp(max=n).tolist()
+    b = [0] + cuts + [n]
+    for q in range(1, len(b)):
+        b[q] = max(b[q], b[q - 1])
+    return b
+
+
 def broadcast_csr(row, col, n: int, src: int, device):
     """Replicate a CSR matrix from `src` to every rank (torch.distributed broadcast: NCCL over NVLink on GPUs,
     gloo on CPU).  Stands in for every MPI rank reading the whole file (final/SpGEMM_mpi_omp.c:309)."""
@@ -259,6 +276,7 @@ def main():
     ap.add_argument("--validate", action="store_true", help="gather shards and compare with the oracle (small workloads)")
     ap.add_argument("--validate-rows", type=int, default=21000, help="rows per rank compared with the oracle after the timed region (0 = off)")
     ap.add_argument("--no-prepare", action="store_true", help="headline value without bspgemm_dev_prepare_b")
+    ap.add_argument("--split", default="rows", choices=["rows", "ip"], help="row blocks of equal rows (the reference's split) or of equal intermediate products")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -312,7 +330,13 @@ def main():
     else:
         d_row, d_col = torch.from_numpy(row).to(dev), torch.from_numpy(col).to(dev)
     nnzA = int(d_col.numel())
-    r0, r1 = shard_bounds(n, rank, world)
+    if args.split == "ip" and world > 1:
+        bounds = shard_bounds_ip(d_row, d_col, n, world)
+        r0, r1 = bounds[rank], bounds[rank + 1]
+        config["sharding"] = f"{world} contiguous row blocks of A with equal intermediate products (bounds {bounds}), B replicated"
+        os.environ["BSPGEMM_SPLIT"] = "ip"              # the single-process N-GPU operator (e2e) splits the same way
+    else:
+        r0, r1 = shard_bounds(n, rank, world)
     rows = r1 - r0
     shard_nnz = int(d_row[r1].item()) - int(d_row[r0].item())
     gen_s = time.time() - t0

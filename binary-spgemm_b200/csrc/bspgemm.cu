@@ -9,6 +9,7 @@
 #include "fused_ell.cuh"       // ELL_CTA_WORDS, ell_table_limit (planning only: the ELL kernels are instantiated in tu_ell.cu / tu_sort_w*.cu)
 #include "rows_window.cuh"
 #include "rows_sort.cuh"
+#include "rows_l2bm.cuh"
 #include "band.cuh"
 #include "coo2csc.cuh"
 #include "mask.cuh"
@@ -51,6 +52,7 @@ static int set_kernel_attributes(int smem_optin) {
   ATTR((k_rows_sort<32, 512, MODE_COUNT>)); ATTR((k_rows_sort<32, 512, MODE_FILL>)); ATTR((k_rows_sort<32, 512, MODE_STAGE>));
   ATTR((k_rows_sort<8, 256, MODE_COUNT>)); ATTR((k_rows_sort<8, 256, MODE_FILL>)); ATTR((k_rows_sort<8, 256, MODE_STAGE>));
   ATTR(k_rows_window<MODE_COUNT>); ATTR(k_rows_window<MODE_FILL>); ATTR(k_rows_window<MODE_STAGE>);
+  ATTR(k_rows_l2bm<MODE_COUNT>); ATTR(k_rows_l2bm<MODE_FILL>); ATTR(k_rows_l2bm<MODE_STAGE>);
 #undef ATTR_G
 #undef ATTR
   CKS(set_attrs_ell(smem_optin));
@@ -108,10 +110,23 @@ template <int MODE> static int launch_bins_ml(bspgemm_dev* d) {
   int bps = 0;
   const u64* tofs = d->tofs.p;
   if (MODE == MODE_STAGE) {
-    if (d->have_l && !d->use_window) return fail(BSPGEMM_ERR_CUDA, "internal: the global-bitmap kernel has no staged mode");
+    if (d->have_l && !d->use_window && !d->use_l2bm) return fail(BSPGEMM_ERR_CUDA, "internal: the global-bitmap kernel has no staged mode");
     ccol = d->temp.p;               // the kernels write row i at temp[tofs[i] ..)
   }
   // largest rows first; rows are handed out dynamically inside every kernel
+  if (d->use_l2bm) {         // L and M2 lists: bitmap over [0,Bm) in L2 + summary in shared memory (rows_l2bm.cuh), one CTA per SM
+    const size_t smem = (size_t)2 * l2b_summary_words(d->bm_words) * 4;
+    if (d->have_l) {
+      k_rows_l2bm<MODE><<<d->sm_count, 1024, smem, d->stream>>>(a.m, l3, &d->d_sc->n_l, ctr + 0, d->cnt.p, d->G_big, d->bitmaps.p, d->bm_words, a.dCrow, a.is64, ccol, tofs, d->d_sc);
+      d->launches++;
+      CK(cudaGetLastError());
+    }
+    if (d->have_m2) {
+      k_rows_l2bm<MODE><<<d->sm_count, 1024, smem, d->stream>>>(a.m, l2, &d->d_sc->n_m2, ctr + 1, d->cnt.p, d->G_big, d->bitmaps.p, d->bm_words, a.dCrow, a.is64, ccol, tofs, d->d_sc);
+      d->launches++;
+      CK(cudaGetLastError());
+    }
+  } else {
   if (d->have_l) {
     if (d->use_window)   // windowed shared-memory bitmap (rows_window.cuh)
       k_rows_window<MODE><<<d->sm_count, 1024, (size_t)WIN_WORDS * 4, d->stream>>>(a.m, l3, &d->d_sc->n_l, ctr + 0, d->cnt.p, d->G_big, WIN_WORDS, a.dCrow, a.is64, ccol, tofs, d->d_sc);
@@ -126,6 +141,7 @@ template <int MODE> static int launch_bins_ml(bspgemm_dev* d) {
     k_rows_sort<32, 512, MODE><<<d->sm_count * std::max(bps, 1), 512, smem, d->stream>>>(a.m, l2, &d->d_sc->n_m2, ctr + 1, d->ip.p, d->cnt.p, d->G_big, a.dCrow, a.is64, ccol, tofs, d->d_sc);
     d->launches++;
     CK(cudaGetLastError());
+  }
   }
   if (d->have_m) {       // cap_s < IP <= 2048: 256 threads, up to 8 keys per thread
     const size_t smem = (size_t)CAP_M1 * 4;
@@ -401,9 +417,19 @@ static int mul_launch_main(bspgemm_dev* d) {
     d->launches++;
     CK(cudaGetLastError());
   }
+  // Rows above 2048 products: bitmap over [0,Bm) in L2 with a shared-memory summary (rows_l2bm.cuh) when Bm allows
+  // — opt-in (BSPGEMM_L2BM=1): measured 3-4x SLOWER than the sort / window kernels on R-MAT (scale 20: 144 against 53 ms, scale 22:
+  // 1563 against 351 ms, profiles/r02_cfg4_notes.txt): power-law rows put most products on a few neighbouring hub columns, i.e. on
+  // the same bitmap words, and L2 serialises atomics per address.
+  d->use_l2bm = d->have_m2 && (u32)a.m.Bm <= L2B_MAX_BM && getenv("BSPGEMM_L2BM") != nullptr;
+  if (d->use_l2bm) {
+    d->bm_words = (u32)((((size_t)a.m.Bm + 31) / 32 + 31) & ~(size_t)31);
+    const size_t need = (size_t)d->sm_count * d->bm_words;
+    if (need > d->bitmaps.cap) { CKS(d->bitmaps.ensure(need)); CK(cudaMemsetAsync(d->bitmaps.p, 0, d->bitmaps.cap * sizeof(u32), d->stream)); }
+  }
   // Matrices of up to WIN_MAX_WINDOWS windows of columns: every big row goes through the windowed bitmap kernel
   d->use_window = (u64)a.m.Bm <= (u64)WIN_MAX_WINDOWS * WIN_WORDS * 32ull && !getenv("BSPGEMM_NO_WINDOW");
-  if (d->have_l && !d->use_window) {
+  if (d->have_l && !d->use_window && !d->use_l2bm) {
     d->bm_words = (u32)(((size_t)a.m.Bm + 31) / 32);
     d->l_grid = d->sm_count;
     const size_t need = (size_t)d->l_grid * d->bm_words;
@@ -436,7 +462,7 @@ static int mul_launch_main(bspgemm_dev* d) {
     // Ccol once the fused kernel has produced the row pointers — instead of a symbolic and a numeric pass that both gather
     // and de-duplicate the row.
     bool staged = false;
-    if (d->have_m && (!d->have_l || d->use_window) && !getenv("BSPGEMM_NO_STAGE")) {
+    if (d->have_m && (!d->have_l || d->use_window || d->use_l2bm) && !getenv("BSPGEMM_NO_STAGE")) {
       const size_t need = (size_t)std::max<u64>(ip_bound, 1);
       if (d->temp.cap >= need) staged = true;
       else {
@@ -447,7 +473,12 @@ static int mul_launch_main(bspgemm_dev* d) {
     d->staged = staged;
     if (d->have_m) CKS(staged ? launch_bins_ml<MODE_STAGE>(d) : launch_bins_ml<MODE_COUNT>(d));
     CK(cudaEventRecord(d->ev[3], d->stream));
-    if (staged && !d->skip_estimate && !getenv("BSPGEMM_FUSED_S")) {
+    // ... and matrices whose rows are all small and cheap (the report's sprand matrices: Poisson(5) rows, 25 products per row):
+    // the ordered kernel is bound by its look-back chain there (1.25 M tiles of 4 rows: 24 ms at n = 5e6), the two unordered
+    // passes by the rows themselves.
+    const bool cheap = !d->have_m && An >= 65536 && ip_bound / (u64)An <= 96ull;
+    if (((staged && !d->skip_estimate) || cheap) && !getenv("BSPGEMM_FUSED_S")) {
+      if (d->skip_estimate) CKS(launch_estimate_kernel(d));          // the warp-per-row kernels read ip[] (no host round trip needed)
       // Skewed matrices (big rows exist and were just staged with their counts): the S rows are counted and filled in two
       // UNORDERED passes around the device scan instead of the ordered one-pass kernel.  Their intermediate products are a
       // few percent of the total (R-MAT scale 22: 3e8 of 1.2e10), so walking them twice is cheap, while k_fused's in-order
@@ -462,7 +493,7 @@ static int mul_launch_main(bspgemm_dev* d) {
       CK(cudaGetLastError());
       CKS(launch_rows_warp<MODE_FILL>(d));
       CK(cudaEventRecord(d->ev[4], d->stream));
-      CKS(launch_copy_rows(d));
+      if (staged) CKS(launch_copy_rows(d));
       CK(cudaEventRecord(d->ev[5], d->stream));
       CK(cudaMemcpyAsync(d->h_sc, d->d_sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, d->stream));
       d->phase = 3;
@@ -974,8 +1005,31 @@ static int host_multiply(const int* Acol, const int* Arow, int An, const int* Bc
   if (Annz < 0 || Bnnz < 0 || b_base != 0) return fail(BSPGEMM_ERR_BADARG, "row pointers not monotone / Brow[0] != 0");
   if ((Annz > 0 && !Acol) || (Bnnz > 0 && !Bcol)) return fail(BSPGEMM_ERR_BADARG, "null column array");
   const size_t rp = is64 ? 8 : 4;
+  // Row blocks: equal rows per task like the reference (tasksize = An / numtasks, :165), or — BSPGEMM_SPLIT=ip — contiguous blocks
+  // of equal WORK: the split points are taken on the prefix sum of the rows' intermediate products (equal-row
+  // blocks leave the hub rows of a power-law matrix to one task).  The result is identical either way.
   std::vector<int> r0(ng + 1);
   for (int q = 0; q <= ng; ++q) r0[q] = (int)((int64_t)An * q / ng);
+  if (ng > 1 && An > 0) if (const char* sp = getenv("BSPGEMM_SPLIT")) if (!strcmp(sp, "ip")) {
+    std::vector<int64_t> pre((size_t)An + 1, 0);
+    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)16, (int64_t)std::thread::hardware_concurrency(), (int64_t)An >> 14}));
+    auto work = [&](int t) {
+      const int b = (int)((int64_t)An * t / nt), e = (int)((int64_t)An * (t + 1) / nt);
+      for (int i = b; i < e; ++i) {
+        int64_t w = 1;                                    // an empty row still costs a row
+        for (int64_t p = Arow[i]; p < Arow[i + 1]; ++p) { const int j = Acol[p]; if ((unsigned)j < (unsigned)Bn) w += Brow[j + 1] - Brow[j]; }
+        pre[(size_t)i + 1] = w;
+      }
+    };
+    if (nt == 1) work(0); else { std::vector<std::thread> th; for (int t = 0; t < nt; ++t) th.emplace_back(work, t); for (auto& x : th) x.join(); }
+    for (int i = 0; i < An; ++i) pre[(size_t)i + 1] += pre[i];
+    for (int q = 1; q < ng; ++q) {
+      const int64_t target = pre[An] * q / ng;
+      r0[q] = (int)(std::lower_bound(pre.begin(), pre.end(), target) - pre.begin());
+      if (r0[q] < r0[q - 1]) r0[q] = r0[q - 1];
+      if (r0[q] > An) r0[q] = An;
+    }
+  }
 
   // upload A shards; B to task 0 and — without a communicator (tasks sharing GPUs) — to the first task of every other device
   const int64_t bchunk = (Bnnz + ng - 1) / ng;           // Bcol is uploaded in ng chunks (one per GPU) when a communicator exists

@@ -21,7 +21,8 @@ template <int W, int LAL, bool ASYNC, bool FLT> static int launch_sort_t(bspgemm
   // warps per CTA: what the kernel's register count allows (registers are allocated per SM sub-partition: 80 -> 6 warps
   // each, 81..102 -> 5), one of them the chain helper
   auto kern = ASYNC ? k_fused_sort_async<W, LAL, FLT> : k_fused_sort<W, LAL>;
-  cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, kern));
+  static cudaFuncAttributes fa; static bool have_fa = false;     // per instantiation: the query costs microseconds on every launch otherwise
+  if (!have_fa) { CK(cudaFuncGetAttributes(&fa, kern)); have_fa = true; }
   const int max_compute = std::max(1, std::min(SORT_MAX_WARPS, fa.maxThreadsPerBlock / 32) - 1);
   // staging buffers per warp: 2 = commit one tile later; small tiles get 3 (commit lag 2) as long as that costs no warps.
   // ASYNC: the input buffer the cp.async copies land in + 2 staging buffers (the commit of tile t-2 comes before tile t is
