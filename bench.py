@@ -271,6 +271,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="auto", choices=["auto", "fused", "twophase"])
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-e2e", action="store_true", help="development runs: skip the host-pointer end-to-end measurement (e2e: null)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="target CPU work per reference step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--validate", action="store_true", help="gather shards and compare with the oracle (small workloads)")
@@ -491,89 +492,92 @@ def main():
     del h
 
     # ---------------- end to end: host CSR in -> host CSR out through the host-pointer C-ABI operator
-    if world > 1:
-        rc = torch.empty(n + 1, dtype=torch.int32).pin_memory(); rc.copy_(d_row)
-        cc = torch.empty(nnzA, dtype=torch.int32).pin_memory(); cc.copy_(d_col)
-        row_h, col_h = rc.numpy(), cc.numpy()
-    else:
-        rc = torch.from_numpy(row).pin_memory(); cc = torch.from_numpy(col).pin_memory()
-        row_h, col_h = rc.numpy(), cc.numpy()
-    out_cap = 16 if i64 else int(nnz) + 16
-    out_pin = torch.empty(out_cap, dtype=torch.int32).pin_memory()
-    out_h = out_pin.numpy()
-    torch.cuda.synchronize()
-    bs.init(1, devices=[local_rank])
-    e2e_steps = max(1, min(args.e2e_steps, args.steps))
-    a_row_h = row_h[r0:r1 + 1]
-    if i64:      # nnz(C) >= 2^31: the 64-bit row-pointer operator (callee-allocated output)
-        def e2e_call():
-            cc_, cr_ = bs.spgemm_csr(col_h, a_row_h, rows, col_h, row_h, n, n, i64=True)
-            return len(cc_), cr_
-    else:
-        def e2e_call():
-            return bs.spgemm_csr_into(col_h, a_row_h, rows, col_h, row_h, n, n, out_h)
-    e2e_nnz, _ = e2e_call()                                                                # warm-up (allocations)
-    barrier()
-    w0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_nnz, crow_h = e2e_call()
-    barrier()
-    e2e_wall = time.perf_counter() - w0
-    bs.finalize()
-    h2d = 4 * (rows + 1) + 4 * shard_nnz + 4 * (n + 1) + 4 * nnzA
-    d2h = 4 * rows + 4 * int(e2e_nnz)
-    e2 = torch.tensor([e2e_wall, 0.0], dtype=torch.float64, device=dev)
-    io = torch.tensor([float(h2d), float(d2h)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2, op=dist.ReduceOp.MAX)
-        dist.all_reduce(io, op=dist.ReduceOp.SUM)
-    e2e_s = float(e2[0]) / e2e_steps
-    e2e = {"value": ip_total / e2e_s, "unit": "IP/s", "h2d_bytes_per_step": int(io[0]), "d2h_bytes_per_step": int(io[1]),
-           "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "api": "bspgemm_csr_i64 (pinned host CSR in, malloc'ed host CSR out)" if i64 else "bspgemm_csr_into (pinned host CSR in, pinned host CSR out)",
-           "timer": "host CLOCK_MONOTONIC around the synchronous call, max over ranks"}
-    e2e["bound"] = "PCIe: %.1f GB/s of host<->device copies per GPU inside the call (device work is %.1f %% of it)" % (
-        (h2d + d2h) / e2e_s / 1e9, 100.0 * ms_per_step * 1e-3 / e2e_s)
-
-    # ---------------- N > 1: the library's real N-GPU drop-in, ONE process driving all GPUs (bspgemm_init(N) -> row-block shards,
-    #                  B uploaded once + ncclBroadcast, gather at displacements); the other ranks free their memory and idle on the
-    #                  store (a host-side wait: an NCCL barrier would park a spinning kernel on the GPUs rank 0 is about to use)
+    e2e = None
     e2e_per_rank = None
-    if world > 1:
-        e2e_per_rank = e2e
-        e2e_per_rank["api"] += " — every rank its own single-GPU context and its own upload of B"
-        del d_row, d_col, d_crow
-        torch.cuda.empty_cache()
-        store = dist.distributed_c10d._get_default_store()
-        barrier()
-        if rank == 0:
-            try:
-                out_all = torch.empty(16 if i64 else int(nnz_total) + 16, dtype=torch.int32).pin_memory()
-                out_all_h = out_all.numpy()
-                bs.init(world)
-                if i64:
-                    def sp_call():
-                        cc_, cr_ = bs.spgemm_csr(col_h, row_h, n, col_h, row_h, n, n, i64=True)
-                        return len(cc_), cr_
-                else:
-                    def sp_call():
-                        return bs.spgemm_csr_into(col_h, row_h, n, col_h, row_h, n, n, out_all_h)
-                sp_nnz, _ = sp_call()                                                   # warm-up (allocations, NCCL channels)
-                w0 = time.perf_counter()
-                for _ in range(e2e_steps):
-                    sp_nnz, _ = sp_call()
-                sp_s = (time.perf_counter() - w0) / e2e_steps
-                bs.finalize()
-                assert int(sp_nnz) == int(nnz_total), (sp_nnz, nnz_total)
-                e2e = {"value": ip_total / sp_s, "unit": "IP/s",
-                       "h2d_bytes_per_step": int(2 * (4 * (n + 1) + 4 * nnzA)), "d2h_bytes_per_step": int(4 * n + 4 * int(sp_nnz)),
-                       "ms_per_step": sp_s * 1e3, "steps": e2e_steps,
-                       "api": f"bspgemm_init({world}) + " + ("bspgemm_csr_i64" if i64 else "bspgemm_csr_into") + " in ONE process: A sharded into row blocks, "
-                              "B uploaded once and replicated by ncclBroadcast over NVLink, C gathered to pinned host memory at the displacements",
-                       "timer": "host CLOCK_MONOTONIC around the synchronous call (rank 0; the other ranks idle)"}
-            finally:
-                store.set("bspgemm_e2e_done", "1")
+    if not args.no_e2e:
+        if world > 1:
+            rc = torch.empty(n + 1, dtype=torch.int32).pin_memory(); rc.copy_(d_row)
+            cc = torch.empty(nnzA, dtype=torch.int32).pin_memory(); cc.copy_(d_col)
+            row_h, col_h = rc.numpy(), cc.numpy()
         else:
-            store.wait(["bspgemm_e2e_done"])
+            rc = torch.from_numpy(row).pin_memory(); cc = torch.from_numpy(col).pin_memory()
+            row_h, col_h = rc.numpy(), cc.numpy()
+        out_cap = 16 if i64 else int(nnz) + 16
+        out_pin = torch.empty(out_cap, dtype=torch.int32).pin_memory()
+        out_h = out_pin.numpy()
+        torch.cuda.synchronize()
+        bs.init(1, devices=[local_rank])
+        e2e_steps = max(1, min(args.e2e_steps, args.steps))
+        a_row_h = row_h[r0:r1 + 1]
+        if i64:      # nnz(C) >= 2^31: the 64-bit row-pointer operator (callee-allocated output)
+            def e2e_call():
+                cc_, cr_ = bs.spgemm_csr(col_h, a_row_h, rows, col_h, row_h, n, n, i64=True)
+                return len(cc_), cr_
+        else:
+            def e2e_call():
+                return bs.spgemm_csr_into(col_h, a_row_h, rows, col_h, row_h, n, n, out_h)
+        e2e_nnz, _ = e2e_call()                                                                # warm-up (allocations)
+        barrier()
+        w0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_nnz, crow_h = e2e_call()
+        barrier()
+        e2e_wall = time.perf_counter() - w0
+        bs.finalize()
+        h2d = 4 * (rows + 1) + 4 * shard_nnz + 4 * (n + 1) + 4 * nnzA
+        d2h = 4 * rows + 4 * int(e2e_nnz)
+        e2 = torch.tensor([e2e_wall, 0.0], dtype=torch.float64, device=dev)
+        io = torch.tensor([float(h2d), float(d2h)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(e2, op=dist.ReduceOp.MAX)
+            dist.all_reduce(io, op=dist.ReduceOp.SUM)
+        e2e_s = float(e2[0]) / e2e_steps
+        e2e = {"value": ip_total / e2e_s, "unit": "IP/s", "h2d_bytes_per_step": int(io[0]), "d2h_bytes_per_step": int(io[1]),
+               "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "api": "bspgemm_csr_i64 (pinned host CSR in, malloc'ed host CSR out)" if i64 else "bspgemm_csr_into (pinned host CSR in, pinned host CSR out)",
+               "timer": "host CLOCK_MONOTONIC around the synchronous call, max over ranks"}
+        e2e["bound"] = "PCIe: %.1f GB/s of host<->device copies per GPU inside the call (device work is %.1f %% of it)" % (
+            (h2d + d2h) / e2e_s / 1e9, 100.0 * ms_per_step * 1e-3 / e2e_s)
+
+        # ---------------- N > 1: the library's real N-GPU drop-in, ONE process driving all GPUs (bspgemm_init(N) -> row-block shards,
+        #                  B uploaded once + ncclBroadcast, gather at displacements); the other ranks free their memory and idle on the
+        #                  store (a host-side wait: an NCCL barrier would park a spinning kernel on the GPUs rank 0 is about to use)
+        e2e_per_rank = None
+        if world > 1:
+            e2e_per_rank = e2e
+            e2e_per_rank["api"] += " — every rank its own single-GPU context and its own upload of B"
+            del d_row, d_col, d_crow
+            torch.cuda.empty_cache()
+            store = dist.distributed_c10d._get_default_store()
+            barrier()
+            if rank == 0:
+                try:
+                    out_all = torch.empty(16 if i64 else int(nnz_total) + 16, dtype=torch.int32).pin_memory()
+                    out_all_h = out_all.numpy()
+                    bs.init(world)
+                    if i64:
+                        def sp_call():
+                            cc_, cr_ = bs.spgemm_csr(col_h, row_h, n, col_h, row_h, n, n, i64=True)
+                            return len(cc_), cr_
+                    else:
+                        def sp_call():
+                            return bs.spgemm_csr_into(col_h, row_h, n, col_h, row_h, n, n, out_all_h)
+                    sp_nnz, _ = sp_call()                                                   # warm-up (allocations, NCCL channels)
+                    w0 = time.perf_counter()
+                    for _ in range(e2e_steps):
+                        sp_nnz, _ = sp_call()
+                    sp_s = (time.perf_counter() - w0) / e2e_steps
+                    bs.finalize()
+                    assert int(sp_nnz) == int(nnz_total), (sp_nnz, nnz_total)
+                    e2e = {"value": ip_total / sp_s, "unit": "IP/s",
+                           "h2d_bytes_per_step": int(2 * (4 * (n + 1) + 4 * nnzA)), "d2h_bytes_per_step": int(4 * n + 4 * int(sp_nnz)),
+                           "ms_per_step": sp_s * 1e3, "steps": e2e_steps,
+                           "api": f"bspgemm_init({world}) + " + ("bspgemm_csr_i64" if i64 else "bspgemm_csr_into") + " in ONE process: A sharded into row blocks, "
+                                  "B uploaded once and replicated by ncclBroadcast over NVLink, C gathered to pinned host memory at the displacements",
+                           "timer": "host CLOCK_MONOTONIC around the synchronous call (rank 0; the other ranks idle)"}
+                finally:
+                    store.set("bspgemm_e2e_done", "1")
+            else:
+                store.wait(["bspgemm_e2e_done"])
 
     # ---------------- CPU baseline beside it (rank 0, N=1 only)
     cpu = None

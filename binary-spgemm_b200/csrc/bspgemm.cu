@@ -9,7 +9,7 @@
 #include "fused_ell.cuh"       // ELL_CTA_WORDS, ell_table_limit (planning only: the ELL kernels are instantiated in tu_ell.cu / tu_sort_w*.cu)
 #include "rows_window.cuh"
 #include "rows_sort.cuh"
-#include "rows_l2bm.cuh"
+#include "rows_bm.cuh"
 #include "band.cuh"
 #include "coo2csc.cuh"
 #include "mask.cuh"
@@ -52,7 +52,7 @@ static int set_kernel_attributes(int smem_optin) {
   ATTR((k_rows_sort<32, 512, MODE_COUNT>)); ATTR((k_rows_sort<32, 512, MODE_FILL>)); ATTR((k_rows_sort<32, 512, MODE_STAGE>));
   ATTR((k_rows_sort<8, 256, MODE_COUNT>)); ATTR((k_rows_sort<8, 256, MODE_FILL>)); ATTR((k_rows_sort<8, 256, MODE_STAGE>));
   ATTR(k_rows_window<MODE_COUNT>); ATTR(k_rows_window<MODE_FILL>); ATTR(k_rows_window<MODE_STAGE>);
-  ATTR(k_rows_l2bm<MODE_COUNT>); ATTR(k_rows_l2bm<MODE_FILL>); ATTR(k_rows_l2bm<MODE_STAGE>);
+  ATTR(k_rows_bm<MODE_COUNT>); ATTR(k_rows_bm<MODE_FILL>); ATTR(k_rows_bm<MODE_STAGE>);
 #undef ATTR_G
 #undef ATTR
   CKS(set_attrs_ell(smem_optin));
@@ -110,24 +110,17 @@ template <int MODE> static int launch_bins_ml(bspgemm_dev* d) {
   int bps = 0;
   const u64* tofs = d->tofs.p;
   if (MODE == MODE_STAGE) {
-    if (d->have_l && !d->use_window && !d->use_l2bm) return fail(BSPGEMM_ERR_CUDA, "internal: the global-bitmap kernel has no staged mode");
+    if (d->have_l && !d->use_window && !d->use_bm) return fail(BSPGEMM_ERR_CUDA, "internal: the global-bitmap kernel has no staged mode");
     ccol = d->temp.p;               // the kernels write row i at temp[tofs[i] ..)
   }
   // largest rows first; rows are handed out dynamically inside every kernel
-  if (d->use_l2bm) {         // L and M2 lists: bitmap over [0,Bm) in L2 + summary in shared memory (rows_l2bm.cuh), one CTA per SM
-    const size_t smem = (size_t)2 * l2b_summary_words(d->bm_words) * 4;
-    if (d->have_l) {
-      k_rows_l2bm<MODE><<<d->sm_count, 1024, smem, d->stream>>>(a.m, l3, &d->d_sc->n_l, ctr + 0, d->cnt.p, d->G_big, d->bitmaps.p, d->bm_words, a.dCrow, a.is64, ccol, tofs, d->d_sc);
-      d->launches++;
-      CK(cudaGetLastError());
-    }
-    if (d->have_m2) {
-      k_rows_l2bm<MODE><<<d->sm_count, 1024, smem, d->stream>>>(a.m, l2, &d->d_sc->n_m2, ctr + 1, d->cnt.p, d->G_big, d->bitmaps.p, d->bm_words, a.dCrow, a.is64, ccol, tofs, d->d_sc);
-      d->launches++;
-      CK(cudaGetLastError());
-    }
-  } else {
-  if (d->have_l) {
+  const bool bm_m2 = d->use_bm && getenv("BSPGEMM_BM_L_ONLY") == nullptr;        // (tuning knob: the M2 list stays on the CTA-wide sort)
+  if (d->use_bm && (d->have_l || (d->have_m2 && bm_m2))) {   // L and M2 lists in one launch: windowed shared-memory bitmap (rows_bm.cuh)
+    k_rows_bm<MODE><<<d->sm_count, BM_THREADS, BM_SMEM, d->stream>>>(a.m, l3, &d->d_sc->n_l, l2, &d->d_sc->n_m2, ctr + 0, d->cnt.p, a.dCrow, a.is64, ccol, tofs, d->d_sc, bm_m2 ? 1u : 0u);
+    d->launches++;
+    CK(cudaGetLastError());
+  }
+  if (d->have_l && !d->use_bm) {
     if (d->use_window)   // windowed shared-memory bitmap (rows_window.cuh)
       k_rows_window<MODE><<<d->sm_count, 1024, (size_t)WIN_WORDS * 4, d->stream>>>(a.m, l3, &d->d_sc->n_l, ctr + 0, d->cnt.p, d->G_big, WIN_WORDS, a.dCrow, a.is64, ccol, tofs, d->d_sc);
     else                 // matrices with more columns than WIN_MAX_WINDOWS windows: bitmap over [0,Bm) in global memory
@@ -135,13 +128,12 @@ template <int MODE> static int launch_bins_ml(bspgemm_dev* d) {
     d->launches++;
     CK(cudaGetLastError());
   }
-  if (d->have_m2) {      // 2048 < IP <= 16384: 512 threads, up to 32 keys per thread (rows_sort.cuh)
+  if (d->have_m2 && !bm_m2) {      // 2048 < IP <= 16384: 512 threads, up to 32 keys per thread (rows_sort.cuh)
     const size_t smem = (size_t)CAP_M2 * 4;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_rows_sort<32, 512, MODE>, 512, smem));
     k_rows_sort<32, 512, MODE><<<d->sm_count * std::max(bps, 1), 512, smem, d->stream>>>(a.m, l2, &d->d_sc->n_m2, ctr + 1, d->ip.p, d->cnt.p, d->G_big, a.dCrow, a.is64, ccol, tofs, d->d_sc);
     d->launches++;
     CK(cudaGetLastError());
-  }
   }
   if (d->have_m) {       // cap_s < IP <= 2048: 256 threads, up to 8 keys per thread
     const size_t smem = (size_t)CAP_M1 * 4;
@@ -417,19 +409,11 @@ static int mul_launch_main(bspgemm_dev* d) {
     d->launches++;
     CK(cudaGetLastError());
   }
-  // Rows above 2048 products: bitmap over [0,Bm) in L2 with a shared-memory summary (rows_l2bm.cuh) when Bm allows
-  // — opt-in (BSPGEMM_L2BM=1): measured 3-4x SLOWER than the sort / window kernels on R-MAT (scale 20: 144 against 53 ms, scale 22:
-  // 1563 against 351 ms, profiles/r02_cfg4_notes.txt): power-law rows put most products on a few neighbouring hub columns, i.e. on
-  // the same bitmap words, and L2 serialises atomics per address.
-  d->use_l2bm = d->have_m2 && (u32)a.m.Bm <= L2B_MAX_BM && getenv("BSPGEMM_L2BM") != nullptr;
-  if (d->use_l2bm) {
-    d->bm_words = (u32)((((size_t)a.m.Bm + 31) / 32 + 31) & ~(size_t)31);
-    const size_t need = (size_t)d->sm_count * d->bm_words;
-    if (need > d->bitmaps.cap) { CKS(d->bitmaps.ensure(need)); CK(cudaMemsetAsync(d->bitmaps.p, 0, d->bitmaps.cap * sizeof(u32), d->stream)); }
-  }
+  // Rows above 2048 products of matrices of up to BM_MAX_WINDOWS windows of columns: rows_bm.cuh (BSPGEMM_NO_BM: the round-1 kernels)
+  d->use_bm = d->have_m2 && (u64)a.m.Bm <= (u64)BM_MAX_WINDOWS * BM_WORDS * 32ull && !getenv("BSPGEMM_NO_BM");
   // Matrices of up to WIN_MAX_WINDOWS windows of columns: every big row goes through the windowed bitmap kernel
   d->use_window = (u64)a.m.Bm <= (u64)WIN_MAX_WINDOWS * WIN_WORDS * 32ull && !getenv("BSPGEMM_NO_WINDOW");
-  if (d->have_l && !d->use_window && !d->use_l2bm) {
+  if (d->have_l && !d->use_window && !d->use_bm) {
     d->bm_words = (u32)(((size_t)a.m.Bm + 31) / 32);
     d->l_grid = d->sm_count;
     const size_t need = (size_t)d->l_grid * d->bm_words;
@@ -462,8 +446,8 @@ static int mul_launch_main(bspgemm_dev* d) {
     // Ccol once the fused kernel has produced the row pointers — instead of a symbolic and a numeric pass that both gather
     // and de-duplicate the row.
     bool staged = false;
-    if (d->have_m && (!d->have_l || d->use_window || d->use_l2bm) && !getenv("BSPGEMM_NO_STAGE")) {
-      const size_t need = (size_t)std::max<u64>(ip_bound, 1);
+    if (d->have_m && (!d->have_l || d->use_window || d->use_bm) && !getenv("BSPGEMM_NO_STAGE")) {
+      const size_t need = (size_t)std::max<u64>(ip_bound, 1) + 3u * (size_t)An + 4u;      // every staged row is rounded up to 4 words
       if (d->temp.cap >= need) staged = true;
       else {
         size_t fr = 0, tot = 0; CK(cudaMemGetInfo(&fr, &tot));

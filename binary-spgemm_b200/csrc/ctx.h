@@ -88,7 +88,7 @@ struct bspgemm_dev {
   bool have_m = false, have_m2 = false, have_l = false;
   bool use_band = false, no_band = false;   // run/bitmap kernel for banded matrices (band.cuh); no_band: it failed on this input, redo generally
   bool staged = false;              // big rows went through the staging arena (one pass) in the last multiply
-  bool use_l2bm = false;            // M2/L bins: bitmap over [0,Bm) in L2 + shared-memory summary (rows_l2bm.cuh)
+  bool use_bm = false;              // M2/L bins: windowed shared-memory bitmap + summary, load-balanced walk (rows_bm.cuh)
   bool use_window = false;          // M/L bins: windowed shared-memory bitmap (rows_window.cuh) instead of table / global bitmap
   u32 bm_words = 0; int l_grid = 0;
   bool skip_estimate = false; u32 row_ip_bound = 0, max_len_b = 0;

@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(256) k_estimate(Csr m, u32* __restrict__ ip, D
 }
 
 // Row lists for the CTA-per-row bins (order inside a list is irrelevant).  tofs (optional): every listed row also gets
-// IP words of the staging arena (MODE_STAGE), handed out with one 64-bit atomic per warp.
+// IP words (rounded up to 4) of the staging arena (MODE_STAGE), handed out with one 64-bit atomic per warp.
 static __global__ void __launch_bounds__(256) k_build_lists(const u32* __restrict__ ip, int An, u32 cap_s, u32 cap_m1, u32 cap_m2,
                                                      u32* __restrict__ list_m1, u32* __restrict__ list_m2,
                                                      u32* __restrict__ list_l, u64* __restrict__ tofs, DevScalars* sc) {
@@ -228,7 +228,7 @@ static __global__ void __launch_bounds__(256) k_build_lists(const u32* __restric
   const u32 v = (i < An) ? ip[i] : 0u;
   const bool big = v > cap_s;
   if (tofs) {
-    const u32 mine = big ? v : 0u;
+    const u32 mine = big ? ((v + 3u) & ~3u) : 0u;     // 16-byte aligned rows: k_copy_rows reads them with 16-byte loads
     u64 inc = mine;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { const u64 t = __shfl_up_sync(0xffffffffu, inc, d); if ((int)lane_id() >= d) inc += t; }
@@ -245,31 +245,58 @@ static __global__ void __launch_bounds__(256) k_build_lists(const u32* __restric
 }
 
 // MODE_STAGE epilogue: the staged rows go to their final place, Ccol[Crow[row] ..) (Crow is complete once the scan / the fused
-// kernel has run).  WPR (warp per row: the M1 list, rows of <= 2048 columns): 8 rows in flight per CTA instead of one — with a CTA
-// per row the four dependent scalar loads in front of every short copy left the kernel at 4 % issue utilisation (R-MAT scale 22:
-// 55 ms for 46 GB).  Otherwise one CTA per listed row, grid-stride.  Eight independent loads per thread are in flight.
+// kernel has run).  WPR: one warp per row (the M1 list, rows of <= 2048 columns), otherwise one 256-thread CTA per row, grid-stride.
+// A staged row starts on a 16-byte boundary (k_build_lists), its destination anywhere: a warp reads 128 columns with one
+// 16-byte load per lane (four blocks = 64 bytes per lane in flight), transposes them through shuffles (lane l of store k takes
+// component l&3 of lane 8k + l/4) and writes four fully coalesced 128-byte stores.  With 4-byte loads the kernel sat at 58 % of
+// the DRAM bandwidth with the load/store queue full (lg_throttle, profiles/r02_rmat20_copy_ncu_summary.txt).  The list entry two
+// rows ahead and the (count, source, destination) of the next row are loaded before the current row is copied.
 template <bool WPR>
 static __global__ void __launch_bounds__(256) k_copy_rows(const u32* __restrict__ list, const u32* __restrict__ nlist, const u32* __restrict__ cnt,
                                                    const u64* __restrict__ tofs, const int* __restrict__ temp,
                                                    const void* __restrict__ Crow, int is64, int* __restrict__ Ccol) {
+  constexpr u32 U = 4;                                  // 128-column blocks in flight per warp
   const u32 n = *nlist;
-  const u32 lane = lane_id();
-  const u32 first = WPR ? blockIdx.x * 8u + (threadIdx.x >> 5) : blockIdx.x, step = WPR ? gridDim.x * 8u : gridDim.x;
-  const u32 t = WPR ? lane : threadIdx.x, T = WPR ? 32u : 256u;
+  const u32 lane = lane_id(), wid = threadIdx.x >> 5;
+  const u32 first = WPR ? blockIdx.x * 8u + wid : blockIdx.x, step = WPR ? gridDim.x * 8u : gridDim.x;
+  const u32 w0 = WPR ? 0u : wid, wstep = WPR ? 1u : 8u;
+  if (first >= n) return;
+  u32 r1 = (first + step < n) ? list[first + step] : 0u;
+  u32 c; u64 so, dofs;
+  { const u32 r0 = list[first]; c = cnt[r0]; so = tofs[r0]; dofs = ld_rowptr(Crow, is64, (size_t)r0); }
+  const u32 srcl0 = lane >> 2, comp = lane & 3u;
   for (u32 idx = first; idx < n; idx += step) {
-    const u32 row = list[idx];
-    const u32 c = cnt[row];
-    const int* __restrict__ src = temp + tofs[row];
-    int* __restrict__ dst = Ccol + ld_rowptr(Crow, is64, (size_t)row);
-    u32 i = t;
-    for (; i + 7u * T < c; i += 8u * T) {
-      int v[8];
+    const bool more = idx + step < n;
+    const u32 r2 = (idx + 2u * step < n && more) ? list[idx + 2u * step] : 0u;
+    u32 nc = 0; u64 nso = 0, ndo = 0;
+    if (more) { nc = cnt[r1]; nso = tofs[r1]; ndo = ld_rowptr(Crow, is64, (size_t)r1); }
+    const int4* __restrict__ src4 = reinterpret_cast<const int4*>(temp + so);
+    int* __restrict__ dst = Ccol + dofs;
+    const u32 nblk = (c + 127u) >> 7;
+    for (u32 b = w0; b < nblk; b += wstep * U) {
+      int4 v[U];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = __ldcs(&src[i + (u32)k * T]);
+      for (u32 u = 0; u < U; ++u) {
+        const u32 q = (b + u * wstep) * 32u + lane;     // 16-byte piece of the row; pieces that start beyond the row are not read
+        v[u] = make_int4(0, 0, 0, 0);
+        if (q * 4u < c) v[u] = __ldcs(src4 + q);
+      }
 #pragma unroll
-      for (int k = 0; k < 8; ++k) dst[i + (u32)k * T] = v[k];
+      for (u32 u = 0; u < U; ++u) {
+        const u32 bb = b + u * wstep;
+        if (bb < nblk) {                                // warp-uniform
+#pragma unroll
+          for (u32 k = 0; k < 4; ++k) {
+            const int sl = (int)(8u * k + srcl0);
+            const int x0 = __shfl_sync(0xffffffffu, v[u].x, sl), x1 = __shfl_sync(0xffffffffu, v[u].y, sl);
+            const int x2 = __shfl_sync(0xffffffffu, v[u].z, sl), x3 = __shfl_sync(0xffffffffu, v[u].w, sl);
+            const u32 e = bb * 128u + 32u * k + lane;
+            if (e < c) dst[e] = comp == 0u ? x0 : comp == 1u ? x1 : comp == 2u ? x2 : x3;
+          }
+        }
+      }
     }
-    for (; i < c; i += T) dst[i] = __ldcs(&src[i]);
+    c = nc; so = nso; dofs = ndo; r1 = r2;
   }
 }
 

@@ -457,7 +457,45 @@ def test_wide_matrices_keep_table_and_global_bitmap_bins(bs, oracle, monkeypatch
     """BSPGEMM_NO_WINDOW: the global-bitmap kernel of the L bin (the route of matrices with more than WIN_MAX_WINDOWS
     windows of columns) still matches."""
     monkeypatch.setenv("BSPGEMM_NO_WINDOW", "1")
+    monkeypatch.setenv("BSPGEMM_NO_BM", "1")
     test_every_bin_is_exercised(bs, oracle)
+
+
+def test_round1_big_row_kernels_still_match(bs, oracle, monkeypatch):
+    """BSPGEMM_NO_BM: the CTA-wide sort (rows_sort.cuh, 2049..16384 products) and the group-per-B-row window kernel
+    (rows_window.cuh) — the route of matrices wider than BM_MAX_WINDOWS windows for the sort — still match."""
+    monkeypatch.setenv("BSPGEMM_NO_BM", "1")
+    test_power_law_rows_sort_and_window_bins(bs, oracle)
+    test_window_bins_many_windows_unsorted_rows(bs, oracle, monkeypatch)
+
+
+def test_big_rows_dense_and_sparse_words(bs, oracle, monkeypatch):
+    """rows_bm.cuh: rows whose columns are long runs (dense bitmap words) next to scattered ones, A rows longer than one
+    chunk of 1024 entries, empty B rows in between, two windows."""
+    rng = np.random.default_rng(41)
+    Bm, k = 2_500_000, 4000
+    parts, blen = [], []
+    for i in range(k):
+        t = i % 4
+        if t == 0:   s0 = int(rng.integers(0, Bm - 4000)); c = np.arange(s0, s0 + int(rng.integers(500, 4000)))      # a run
+        elif t == 1: c = np.unique(rng.integers(0, Bm, int(rng.integers(1, 200))))                                   # scattered
+        elif t == 2: c = np.zeros(0, np.int64)                                                                       # empty
+        else:        s0 = int(rng.integers(0, 30000)); c = np.arange(s0, s0 + 64 * int(rng.integers(1, 40)), 2)      # every other column, low range
+        parts.append(c); blen.append(len(c))
+    Brow = np.concatenate([[0], np.cumsum(blen)]).astype(np.int32)
+    Bcol = np.concatenate(parts).astype(np.int32)
+    rows = [np.arange(0, k), rng.choice(k, 2500, replace=False), np.arange(0, k, 4)[:300], np.arange(1, k, 4)[:900], np.arange(3, k, 4)]
+    for _ in range(200):
+        rows.append(rng.choice(k, int(rng.integers(1, 120)), replace=False))
+    Arow = np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.int32)
+    Acol = np.concatenate(rows).astype(np.int32)
+    An = len(rows)
+    want_col, want_row = oracle.spgemm(Acol, Arow, An, Bcol, Brow, Bm)
+    for mode in (bs.MODE_FUSED, bs.MODE_TWOPHASE):
+        got_col, got_row, st = dev_multiply(bs, mode, Acol, Arow, An, Bcol, Brow, k, Bm, i64=True)
+        msg = _explain(got_col, got_row, want_col, want_row)
+        assert not msg, f"mode {mode}: {msg}"
+        assert st["rows_m"] > 0 and st["rows_l"] > 0
 
 
 def _band_csr(n, m, below, above):
