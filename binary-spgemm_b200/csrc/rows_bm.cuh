@@ -47,6 +47,7 @@ constexpr u32 BM_FLAGW = BM_PIECES / 4u;              // summary bytes, counted 
 constexpr u32 BM_LISTW = BM_PIECES / 2u;              // piece list (16-bit ids), counted in 32-bit words
 constexpr u32 BM_CHUNK = BM_THREADS;                  // A entries per chunk: one per thread
 constexpr u32 BM_STEP = 8;                            // products per thread between two barriers
+constexpr u32 BM_REGS = 16;                           // rows of up to 16 * 1024 products: the products stay in registers over all windows
 constexpr u32 BM_MAX_WINDOWS = 8;                     // host: wider matrices keep the sort / global-bitmap kernels
 constexpr size_t BM_SMEM = (size_t)(BM_WORDS + BM_FLAGW + BM_LISTW + 3u * (BM_CHUNK + 4u)) * 4u;
 static_assert(BM_PIECES <= 65536u, "piece ids are 16 bits");
@@ -106,149 +107,208 @@ __global__ void __launch_bounds__(BM_THREADS, 1) k_rows_bm(Csr m, const u32* __r
     const u64 base = (MODE == MODE_FILL) ? ld_rowptr(Crow, is64, (size_t)row) : (MODE == MODE_STAGE) ? tofs[row] : 0;
     u64 done = 0;
     u32 start = 0;
-    bool first = true, bad = false;
+    bool first = true, bad = false, small = false;
+    u32 rv[BM_REGS], have = 0;
     while (true) {                                    // windows
       u32 above = EMPTY;
       const u32 end = start + wbits;                  // Bm <= 2^31 and wbits < 2^21: no wrap
-      for (u32 c0 = 0; c0 < nA; c0 += BM_CHUNK) {
-        const u32 nc = min(BM_CHUNK, nA - c0);
-        if (first || nA > BM_CHUNK) {                 // (re)build the chunk's product index: one A entry per thread
-          u32 len = 0, bs = 0;                        // (the scan's barrier comes after everybody's last use of off[] / bst[])
-          if (tid < nc) {
-            const int j = m.Acol[(size_t)a0 + c0 + tid];
-            if ((u32)j < (u32)m.Bn) { bs = (u32)m.Brow[j]; len = (u32)m.Brow[j + 1] - bs; }
-          }
-          u32 tot;
-          const u32 o = bm_scan(len, s_red, flip, &tot);
-          off[tid] = o; bst[tid] = bs - o;            // address of product p of this B row: Bcol + bst + p (mod 2^32 arithmetic)
-          if (tid == BM_THREADS - 1) off[BM_CHUNK] = tot;
-          __syncthreads();
+      if (first && nA <= BM_CHUNK) {                  // one chunk: build the product index here, then decide how to walk
+        u32 len = 0, bs = 0;
+        if (tid < nA) {
+          const int j = m.Acol[(size_t)a0 + tid];
+          if ((u32)j < (u32)m.Bn) { bs = (u32)m.Brow[j]; len = (u32)m.Brow[j + 1] - bs; }
         }
-        const u32 T = off[BM_CHUNK];
-        const u32 per = ((T + BM_THREADS - 1u) / BM_THREADS) * 32u;       // products per warp (a multiple of 32)
-        const u32 steps = (per / 32u + BM_STEP - 1u) / BM_STEP;           // the same for every thread: the loop holds barriers
-        const u32 ws = wid * per, we = min(T, ws + per);
-        u32 p = ws + lane;
-        u32 e = 0, nx = 0, badd = 0;
-        if (p < we) {
-          u32 lo = 0, hi = nc;                        // off[lo] <= p < off[hi]
-          while (hi - lo > 1u) { const u32 mid = (lo + hi) >> 1; if (off[mid] <= p) lo = mid; else hi = mid; }
-          e = lo; nx = off[e + 1]; badd = bst[e];
-        }
-        for (u32 st = 0; st < steps; ++st) {
-          u32 v[BM_STEP], have = 0;
+        u32 tot;
+        const u32 o = bm_scan(len, s_red, flip, &tot);
+        off[tid] = o; bst[tid] = bs - o;
+        if (tid == BM_THREADS - 1) off[BM_CHUNK] = tot;
+        __syncthreads();
+        small = tot <= BM_REGS * BM_THREADS;
+        if (small) {                                  // SMALL ROW: every thread loads its (at most 16) products once
+          const u32 per = ((tot + BM_THREADS - 1u) / BM_THREADS) * 32u;
+          const u32 ws = wid * per, we = min(tot, ws + per);
+          u32 p = ws + lane;
+          have = 0;
+          if (p < we) {
+            u32 lo = 0, hi = nA;
+            while (hi - lo > 1u) { const u32 mid = (lo + hi) >> 1; if (off[mid] <= p) lo = mid; else hi = mid; }
+            u32 e = lo, nx = off[e + 1], badd = bst[e];
 #pragma unroll
-          for (int k = 0; k < (int)BM_STEP; ++k) {
-            v[k] = 0;
-            if (p < we) {
-              have |= 1u << k;
-              if (p >= nx) {                          // next B row (one step for B rows of 32+ entries, a few for shorter ones)
-                do { ++e; nx = off[e + 1]; } while (p >= nx);
-                badd = bst[e];
+            for (int k = 0; k < (int)BM_REGS; ++k) {
+              if (p < we) {
+                if (p >= nx) { do { ++e; nx = off[e + 1]; } while (p >= nx); badd = bst[e]; }
+                rv[k] = (u32)__ldg(&m.Bcol[(u32)(badd + p)]);
+                have |= 1u << k;
+                p += 32u;
               }
-              v[k] = (u32)__ldg(&m.Bcol[(u32)(badd + p)]);
-              p += 32u;
             }
           }
-          u32 w[BM_STEP], bit[BM_STEP];               // bit == 0: nothing to insert
+        }
+      }
+      if (small) {
+        // pass A / barrier / pass B straight from the registers: no walk, no loads in the second and later windows
 #pragma unroll
-          for (int k = 0; k < (int)BM_STEP; ++k) {
-            const u32 d = v[k] - start;               // wraps to a huge value below the window (already emitted)
-            w[k] = d >> 5; bit[k] = 0;
-            if ((have >> k) & 1u) {
-              if (d < wbits) bit[k] = 1u << (d & 31u);
-              else if (v[k] >= end) above = min(above, v[k]);
-            }
+        for (int k = 0; k < (int)BM_REGS; ++k)
+          if ((have >> k) & 1u) {
+            const u32 d = rv[k] - start;
+            if (d < wbits) {
+              const u32 w = d >> 5, bit = 1u << (d & 31u), o = bm[w];
+              if (!(o & bit)) bm[w] = o | bit;
+              fl[w >> 2] = 1;
+            } else if (rv[k] >= end) above = min(above, rv[k]);
           }
-          // pass A: plain read-modify-write (may lose concurrent updates of the same word) + summary byte
+        __syncthreads();
 #pragma unroll
-          for (int k = 0; k < (int)BM_STEP; ++k)
-            if (bit[k]) {
-              const u32 o = bm[w[k]];
-              if (!(o & bit[k])) bm[w[k]] = o | bit[k];
-              fl[w[k] >> 2] = 1;
+        for (int k = 0; k < (int)BM_REGS; ++k)
+          if ((have >> k) & 1u) {
+            const u32 d = rv[k] - start;
+            if (d < wbits) { const u32 w = d >> 5, bit = 1u << (d & 31u); if (!(bm[w] & bit)) atomicOr(&bm[w], bit); }
+          }
+        __syncthreads();
+      } else {
+        for (u32 c0 = 0; c0 < nA; c0 += BM_CHUNK) {
+          const u32 nc = min(BM_CHUNK, nA - c0);
+          if (nA > BM_CHUNK) {                          // several chunks: (re)build the chunk's product index, one A entry per thread
+            u32 len = 0, bs = 0;                        // (the scan's barrier comes after everybody's last use of off[] / bst[])
+            if (tid < nc) {
+              const int j = m.Acol[(size_t)a0 + c0 + tid];
+              if ((u32)j < (u32)m.Bn) { bs = (u32)m.Brow[j]; len = (u32)m.Brow[j + 1] - bs; }
             }
-          __syncthreads();
-          // pass B: whoever lost its bit repairs it atomically (no plain store runs concurrently)
-#pragma unroll
-          for (int k = 0; k < (int)BM_STEP; ++k)
-            if (bit[k] && !(bm[w[k]] & bit[k])) atomicOr(&bm[w[k]], bit[k]);
-          __syncthreads();
+            u32 tot;
+            const u32 o = bm_scan(len, s_red, flip, &tot);
+            off[tid] = o; bst[tid] = bs - o;            // address of product p of this B row: Bcol + bst + p (mod 2^32 arithmetic)
+            if (tid == BM_THREADS - 1) off[BM_CHUNK] = tot;
+            __syncthreads();
+          }
+          const u32 T = off[BM_CHUNK];
+          const u32 per = ((T + BM_THREADS - 1u) / BM_THREADS) * 32u;       // products per warp (a multiple of 32)
+          const u32 steps = (per / 32u + BM_STEP - 1u) / BM_STEP;           // the same for every thread: the loop holds barriers
+          const u32 ws = wid * per, we = min(T, ws + per);
+          u32 p = ws + lane;
+          u32 e = 0, nx = 0, badd = 0;
+          if (p < we) {
+            u32 lo = 0, hi = nc;                        // off[lo] <= p < off[hi]
+            while (hi - lo > 1u) { const u32 mid = (lo + hi) >> 1; if (off[mid] <= p) lo = mid; else hi = mid; }
+            e = lo; nx = off[e + 1]; badd = bst[e];
+          }
+          for (u32 st = 0; st < steps; ++st) {
+            u32 v[BM_STEP], have = 0;
+  #pragma unroll
+            for (int k = 0; k < (int)BM_STEP; ++k) {
+              v[k] = 0;
+              if (p < we) {
+                have |= 1u << k;
+                if (p >= nx) {                          // next B row (one step for B rows of 32+ entries, a few for shorter ones)
+                  do { ++e; nx = off[e + 1]; } while (p >= nx);
+                  badd = bst[e];
+                }
+                v[k] = (u32)__ldg(&m.Bcol[(u32)(badd + p)]);
+                p += 32u;
+              }
+            }
+            u32 w[BM_STEP], bit[BM_STEP];               // bit == 0: nothing to insert
+  #pragma unroll
+            for (int k = 0; k < (int)BM_STEP; ++k) {
+              const u32 d = v[k] - start;               // wraps to a huge value below the window (already emitted)
+              w[k] = d >> 5; bit[k] = 0;
+              if ((have >> k) & 1u) {
+                if (d < wbits) bit[k] = 1u << (d & 31u);
+                else if (v[k] >= end) above = min(above, v[k]);
+              }
+            }
+            // pass A: plain read-modify-write (may lose concurrent updates of the same word) + summary byte
+  #pragma unroll
+            for (int k = 0; k < (int)BM_STEP; ++k)
+              if (bit[k]) {
+                const u32 o = bm[w[k]];
+                if (!(o & bit[k])) bm[w[k]] = o | bit[k];
+                fl[w[k] >> 2] = 1;
+              }
+            __syncthreads();
+            // pass B: whoever lost its bit repairs it atomically (no plain store runs concurrently)
+  #pragma unroll
+            for (int k = 0; k < (int)BM_STEP; ++k)
+              if (bit[k] && !(bm[w[k]] & bit[k])) atomicOr(&bm[w[k]], bit[k]);
+            __syncthreads();
+          }
         }
       }
       above = __reduce_min_sync(FULL, above);
       if (lane == 0 && above != EMPTY) atomicMin(&s_above, above);
       if (first && tid == 0) s_idx[(it + 1u) & 1u] = nidx_reg;
-      // ---- emission, step 1: the ordered list of non-empty 16-byte pieces (thread t scans summary words 3 t .. 3 t + 2)
-      u32 f[3], np = 0;
-#pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        const u32 iw = tid * 3u + (u32)q;
-        f[q] = (iw < BM_FLAGW) ? (flw[iw] & 0x01010101u) : 0u;            // the walk's last barrier ordered the summary stores
-        np += __popc(f[q]);
-      }
-      u32 npieces;
-      u32 pos = bm_scan(np, s_red, flip, &npieces);                      // (its barrier also publishes s_above / s_idx)
-#pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        const u32 iw = tid * 3u + (u32)q;
-        if (f[q]) flw[iw] = 0u;
-        for (u32 b = f[q]; b; b &= b - 1u) plist[pos++] = (unsigned short)(iw * 4u + (((u32)__ffs((int)b) - 1u) >> 3));
-      }
-      const u32 nxt = s_above;
-      if (first) {                                    // next row, stage 1: its list entry
-        nidx = s_idx[(it + 1u) & 1u];
-        if (nidx < n) nrow = (int)(nidx < na ? list_a[nidx] : list_b[nidx - na]);
-      }
-      __syncthreads();
-      if (npieces) {
-        // ---- step 2: every thread sums an equal share of the list; offsets of the shares
-        const u32 K = (npieces + BM_THREADS - 1u) / BM_THREADS;
-        const u32 i0 = min(tid * K, npieces), i1 = min(i0 + K, npieces);
-        u32 c = 0;
-        for (u32 i = i0; i < i1; ++i) c += bm_popc4(bm4[plist[i]]);
-        u32 tot;
-        const u32 cbase = bm_scan(c, s_red, flip, &tot);
-        if (MODE != MODE_COUNT) {
-          cb[tid] = cbase;
-          if (tid == BM_THREADS - 1) cb[BM_THREADS] = tot;
-          __syncthreads();
-          // ---- step 3: thread t writes output positions [t Q, (t+1) Q) of this window
-          const u32 Q = (tot + BM_THREADS - 1u) / BM_THREADS;
-          const u32 o0 = tid * Q;
-          if (o0 < tot) {
-            u32 left = min(Q, tot - o0);
-            u32 lo = 0, hi = BM_THREADS;              // cb[lo] <= o0 < cb[hi]
-            while (hi - lo > 1u) { const u32 mid = (lo + hi) >> 1; if (cb[mid] <= o0) lo = mid; else hi = mid; }
-            u32 i = lo * K, run = cb[lo], k;
-            uint4 x;
-            while (true) { k = plist[i]; x = bm4[k]; const u32 pc = bm_popc4(x); if (run + pc > o0) break; run += pc; ++i; }
-            // drop the bits that belong to the threads before: whole words first, then bit by bit
-            u32 skip = o0 - run;
-#pragma unroll
-            for (int q = 0; q < 3; ++q) {
-              const u32 lowest = x.x ? x.x : x.y ? x.y : x.z;             // the lowest non-empty word of (x.x, x.y, x.z)
-              const u32 pc = __popc(lowest);
-              if ((x.x | x.y | x.z) && skip >= pc) { skip -= pc; if (x.x) x.x = 0u; else if (x.y) x.y = 0u; else x.z = 0u; }
-            }
-            for (; skip; --skip) { if (x.x) x.x &= x.x - 1u; else if (x.y) x.y &= x.y - 1u; else if (x.z) x.z &= x.z - 1u; else x.w &= x.w - 1u; }
-            int* q_out = Ccol + (base + done + o0);
-            // one loop of `left` iterations, the same trip count for every thread: lowest set bit of the 128-bit piece, next piece
-            // when this one is used up (listed pieces are never empty)
-            for (; left; --left) {
-              if (!(x.x | x.y | x.z | x.w)) { ++i; k = plist[i]; x = bm4[k]; }
-              const u32 wi = x.x ? 0u : x.y ? 1u : x.z ? 2u : 3u;
-              const u32 word = bm_word(x, wi);
-              const u32 bb = (u32)__ffs((int)word) - 1u;
-              const u32 rest = word & (word - 1u);
-              if (wi == 0u) x.x = rest; else if (wi == 1u) x.y = rest; else if (wi == 2u) x.z = rest; else x.w = rest;
-              *q_out++ = (int)(start + (k << 7) + (wi << 5) + bb);
+      u32 nxt;
+      {
+        // ---- emission, step 1: the ordered list of non-empty 16-byte pieces (thread t scans summary words 3 t .. 3 t + 2)
+        u32 f[3], np = 0;
+  #pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          const u32 iw = tid * 3u + (u32)q;
+          f[q] = (iw < BM_FLAGW) ? (flw[iw] & 0x01010101u) : 0u;            // the walk's last barrier ordered the summary stores
+          np += __popc(f[q]);
+        }
+        u32 npieces;
+        u32 pos = bm_scan(np, s_red, flip, &npieces);                      // (its barrier also publishes s_above / s_idx)
+  #pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          const u32 iw = tid * 3u + (u32)q;
+          if (f[q]) flw[iw] = 0u;
+          for (u32 b = f[q]; b; b &= b - 1u) plist[pos++] = (unsigned short)(iw * 4u + (((u32)__ffs((int)b) - 1u) >> 3));
+        }
+        nxt = s_above;
+        if (first) {                                    // next row, stage 1: its list entry
+          nidx = s_idx[(it + 1u) & 1u];
+          if (nidx < n) nrow = (int)(nidx < na ? list_a[nidx] : list_b[nidx - na]);
+        }
+        __syncthreads();
+        if (npieces) {
+          // ---- step 2: every thread sums an equal share of the list; offsets of the shares
+          const u32 K = (npieces + BM_THREADS - 1u) / BM_THREADS;
+          const u32 i0 = min(tid * K, npieces), i1 = min(i0 + K, npieces);
+          u32 c = 0;
+          for (u32 i = i0; i < i1; ++i) c += bm_popc4(bm4[plist[i]]);
+          u32 tot;
+          const u32 cbase = bm_scan(c, s_red, flip, &tot);
+          if (MODE != MODE_COUNT) {
+            cb[tid] = cbase;
+            if (tid == BM_THREADS - 1) cb[BM_THREADS] = tot;
+            __syncthreads();
+            // ---- step 3: thread t writes output positions [t Q, (t+1) Q) of this window
+            const u32 Q = (tot + BM_THREADS - 1u) / BM_THREADS;
+            const u32 o0 = tid * Q;
+            if (o0 < tot) {
+              u32 left = min(Q, tot - o0);
+              u32 lo = 0, hi = BM_THREADS;              // cb[lo] <= o0 < cb[hi]
+              while (hi - lo > 1u) { const u32 mid = (lo + hi) >> 1; if (cb[mid] <= o0) lo = mid; else hi = mid; }
+              u32 i = lo * K, run = cb[lo], k;
+              uint4 x;
+              while (true) { k = plist[i]; x = bm4[k]; const u32 pc = bm_popc4(x); if (run + pc > o0) break; run += pc; ++i; }
+              // drop the bits that belong to the threads before: whole words first, then bit by bit
+              u32 skip = o0 - run;
+  #pragma unroll
+              for (int q = 0; q < 3; ++q) {
+                const u32 lowest = x.x ? x.x : x.y ? x.y : x.z;             // the lowest non-empty word of (x.x, x.y, x.z)
+                const u32 pc = __popc(lowest);
+                if ((x.x | x.y | x.z) && skip >= pc) { skip -= pc; if (x.x) x.x = 0u; else if (x.y) x.y = 0u; else x.z = 0u; }
+              }
+              for (; skip; --skip) { if (x.x) x.x &= x.x - 1u; else if (x.y) x.y &= x.y - 1u; else if (x.z) x.z &= x.z - 1u; else x.w &= x.w - 1u; }
+              int* q_out = Ccol + (base + done + o0);
+              // one loop of `left` iterations, the same trip count for every thread: lowest set bit of the 128-bit piece, next piece
+              // when this one is used up (listed pieces are never empty)
+              for (; left; --left) {
+                if (!(x.x | x.y | x.z | x.w)) { ++i; k = plist[i]; x = bm4[k]; }
+                const u32 wi = x.x ? 0u : x.y ? 1u : x.z ? 2u : 3u;
+                const u32 word = bm_word(x, wi);
+                const u32 bb = (u32)__ffs((int)word) - 1u;
+                const u32 rest = word & (word - 1u);
+                if (wi == 0u) x.x = rest; else if (wi == 1u) x.y = rest; else if (wi == 2u) x.z = rest; else x.w = rest;
+                *q_out++ = (int)(start + (k << 7) + (wi << 5) + bb);
+              }
             }
           }
+          __syncthreads();                              // everybody has read the pieces: clear them
+          for (u32 i = tid; i < npieces; i += BM_THREADS) bm4[plist[i]] = make_uint4(0u, 0u, 0u, 0u);
+          done += tot;
         }
-        __syncthreads();                              // everybody has read the pieces: clear them
-        for (u32 i = tid; i < npieces; i += BM_THREADS) bm4[plist[i]] = make_uint4(0u, 0u, 0u, 0u);
-        done += tot;
       }
       if (tid == 0) s_above = EMPTY;
       if (first && nidx < n) { na0 = m.Arow[nrow]; na1 = m.Arow[nrow + 1]; }   // next row, stage 2: its row pointers
