@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(BM_THREADS, 1) k_rows_bm(Csr m, const u32* __r
     u64 done = 0;
     u32 start = 0;
     bool first = true, bad = false, small = false;
-    u32 rv[BM_REGS], have = 0;
+    u32 rv[BM_REGS], have = 0, nslots = 0;
     while (true) {                                    // windows
       u32 above = EMPTY;
       const u32 end = start + wbits;                  // Bm <= 2^31 and wbits < 2^21: no wrap
@@ -129,12 +129,14 @@ __global__ void __launch_bounds__(BM_THREADS, 1) k_rows_bm(Csr m, const u32* __r
           const u32 ws = wid * per, we = min(tot, ws + per);
           u32 p = ws + lane;
           have = 0;
+          nslots = per >> 5;                          // the same for every thread: whole register slots are skipped below
           if (p < we) {
             u32 lo = 0, hi = nA;
             while (hi - lo > 1u) { const u32 mid = (lo + hi) >> 1; if (off[mid] <= p) lo = mid; else hi = mid; }
             u32 e = lo, nx = off[e + 1], badd = bst[e];
 #pragma unroll
             for (int k = 0; k < (int)BM_REGS; ++k) {
+              if ((u32)k >= nslots) break;
               if (p < we) {
                 if (p >= nx) { do { ++e; nx = off[e + 1]; } while (p >= nx); badd = bst[e]; }
                 rv[k] = (u32)__ldg(&m.Bcol[(u32)(badd + p)]);
@@ -148,7 +150,8 @@ __global__ void __launch_bounds__(BM_THREADS, 1) k_rows_bm(Csr m, const u32* __r
       if (small) {
         // pass A / barrier / pass B straight from the registers: no walk, no loads in the second and later windows
 #pragma unroll
-        for (int k = 0; k < (int)BM_REGS; ++k)
+        for (int k = 0; k < (int)BM_REGS; ++k) {
+          if ((u32)k >= nslots) break;
           if ((have >> k) & 1u) {
             const u32 d = rv[k] - start;
             if (d < wbits) {
@@ -157,13 +160,16 @@ __global__ void __launch_bounds__(BM_THREADS, 1) k_rows_bm(Csr m, const u32* __r
               fl[w >> 2] = 1;
             } else if (rv[k] >= end) above = min(above, rv[k]);
           }
+        }
         __syncthreads();
 #pragma unroll
-        for (int k = 0; k < (int)BM_REGS; ++k)
+        for (int k = 0; k < (int)BM_REGS; ++k) {
+          if ((u32)k >= nslots) break;
           if ((have >> k) & 1u) {
             const u32 d = rv[k] - start;
             if (d < wbits) { const u32 w = d >> 5, bit = 1u << (d & 31u); if (!(bm[w] & bit)) atomicOr(&bm[w], bit); }
           }
+        }
         __syncthreads();
       } else {
         for (u32 c0 = 0; c0 < nA; c0 += BM_CHUNK) {
@@ -296,12 +302,12 @@ __global__ void __launch_bounds__(BM_THREADS, 1) k_rows_bm(Csr m, const u32* __r
               // when this one is used up (listed pieces are never empty)
               for (; left; --left) {
                 if (!(x.x | x.y | x.z | x.w)) { ++i; k = plist[i]; x = bm4[k]; }
-                const u32 wi = x.x ? 0u : x.y ? 1u : x.z ? 2u : 3u;
-                const u32 word = bm_word(x, wi);
-                const u32 bb = (u32)__ffs((int)word) - 1u;
+                const bool e0 = x.x != 0u, e1 = !e0 && x.y != 0u, e2 = !e0 && !e1 && x.z != 0u, e3 = !e0 && !e1 && !e2;   // selects, no branches
+                const u32 word = e0 ? x.x : e1 ? x.y : e2 ? x.z : x.w;
                 const u32 rest = word & (word - 1u);
-                if (wi == 0u) x.x = rest; else if (wi == 1u) x.y = rest; else if (wi == 2u) x.z = rest; else x.w = rest;
-                *q_out++ = (int)(start + (k << 7) + (wi << 5) + bb);
+                const u32 col = start + (k << 7) + (e0 ? 0u : e1 ? 32u : e2 ? 64u : 96u) + ((u32)__ffs((int)word) - 1u);
+                x.x = e0 ? rest : x.x; x.y = e1 ? rest : x.y; x.z = e2 ? rest : x.z; x.w = e3 ? rest : x.w;
+                *q_out++ = (int)col;
               }
             }
           }
