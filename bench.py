@@ -75,9 +75,12 @@ def shard_bounds_ip(row_t, col_t, n: int, world: int):
     same whatever the split."""
     import torch
     blen = (row_t[1:] - row_t[:-1]).to(torch.int64)
-    per_entry = blen[col_t.long()]
+    cs = torch.zeros(col_t.numel() + 1, dtype=torch.int64, device=row_t.device)
+    cs[1:] = torch.cumsum(blen[col_t.long()], 0)                  # prefix of "length of the selected B row" over A's nonzeros
+    r = row_t.long()
+    row_ip = cs[r[1:]] - cs[r[:-1]]                               # intermediate products of every row
     pre = torch.zeros(n + 1, dtype=torch.int64, device=row_t.device)
-    pre[1:] = torch.cumsum(torch.segment_reduce(per_entry, "sum", offsets=row_t.to(torch.int64)) + 1, 0) if hasattr(torch, "segment_reduce") else 0
+    pre[1:] = torch.cumsum(row_ip + 1, 0)                         # (+1: an empty row still costs a row)
     targets = torch.tensor([int(pre[-1]) * q // world for q in range(1, world)], dtype=torch.int64, device=row_t.device)
     cuts = torch.searchsorted(pre, targets).clamp(max=n).tolist()
     b = [0] + cuts + [n]
