@@ -436,6 +436,25 @@ class DeviceSpGEMM:
                "bspgemm_dev_multiply")
         return out.value or 0, nnz.value
 
+    def bound_multiply(self, dAcol, dArow, An, Annz, dBcol, dBrow, Bn, Bm, Bnnz, dCrow, crow_is_i64=False, stream=None):
+        """The same call with its arguments marshalled ONCE: returns a function () -> (Ccol address, nnz).  For callers that repeat
+        a product on the same buffers (the reference's timing loop, final/SpGEMM_mpi_omp.c:318-324): the per-call Python work
+        (five data_ptr() calls, seventeen ctypes conversions) otherwise sits between the caller's event and the first launch."""
+        out, nnz = C.c_void_p(), C.c_int64()
+        fn = lib().bspgemm_dev_multiply
+        argv = (self._h, C.c_void_p(stream or 0),
+                C.c_void_p(self._p(dAcol)), C.c_void_p(self._p(dArow)), C.c_int(An), C.c_int64(Annz),
+                C.c_void_p(self._p(dBcol)), C.c_void_p(self._p(dBrow)), C.c_int(Bn), C.c_int(Bm), C.c_int64(Bnnz),
+                C.c_void_p(self._p(dCrow)), C.c_int(1 if crow_is_i64 else 0), C.byref(out), C.byref(nnz))
+        keep = (dAcol, dArow, dBcol, dBrow, dCrow)          # the buffers stay alive as long as the bound call does
+
+        def call(_keep=keep):
+            st = fn(*argv)
+            if st:
+                _check(st, "bspgemm_dev_multiply")
+            return out.value or 0, nnz.value
+        return call
+
     def multiply_masked(self, dAcol, dArow, An, Annz, dBcol, dBrow, Bn, Bm, Bnnz, dFcol, dFrow, Fnnz, dCrow, crow_is_i64=False, stream=None):
         """bspgemm_dev_multiply_masked: C = F .* (A·B), returns (device address of Ccol, nnz(C))."""
         out, nnz = C.c_void_p(), C.c_int64()
