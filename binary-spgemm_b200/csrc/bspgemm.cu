@@ -53,7 +53,8 @@ static int set_kernel_attributes(int smem_optin) {
   ATTR((k_rows_sort<32, 512, MODE_COUNT>)); ATTR((k_rows_sort<32, 512, MODE_FILL>)); ATTR((k_rows_sort<32, 512, MODE_STAGE>));
   ATTR((k_rows_sort<8, 256, MODE_COUNT>)); ATTR((k_rows_sort<8, 256, MODE_FILL>)); ATTR((k_rows_sort<8, 256, MODE_STAGE>));
   ATTR(k_rows_window<MODE_COUNT>); ATTR(k_rows_window<MODE_FILL>); ATTR(k_rows_window<MODE_STAGE>);
-  ATTR(k_rows_bm<MODE_COUNT>); ATTR(k_rows_bm<MODE_FILL>); ATTR(k_rows_bm<MODE_STAGE>);
+  ATTR((k_rows_bm<MODE_COUNT, false>)); ATTR((k_rows_bm<MODE_FILL, false>)); ATTR((k_rows_bm<MODE_STAGE, false>));
+  ATTR((k_rows_bm<MODE_COUNT, true>)); ATTR((k_rows_bm<MODE_FILL, true>)); ATTR((k_rows_bm<MODE_STAGE, true>));
 #undef ATTR_G
 #undef ATTR
   CKS(set_attrs_ell(smem_optin));
@@ -115,11 +116,18 @@ template <int MODE> static int launch_bins_ml(bspgemm_dev* d) {
     ccol = d->temp.p;               // the kernels write row i at temp[tofs[i] ..)
   }
   // largest rows first; rows are handed out dynamically inside every kernel
+  // compressed single pass for rows of up to 16384 products: only where a row can need more than one window (BSPGEMM_BM_NO_COMP: off)
+  const u32 bm_cmode = ((u64)a.m.Bm > (u64)BM_WORDS * 32ull && (u32)a.m.Bm <= BM_COMP_MAX_BM && !getenv("BSPGEMM_BM_NO_COMP")) ? 1u : 0u;
   const bool bm_m2 = d->use_bm && getenv("BSPGEMM_BM_L_ONLY") == nullptr;        // (tuning knob: the M2 list stays on the CTA-wide sort)
-  if (d->use_bm && (d->have_l || (d->have_m2 && bm_m2))) {   // L and M2 lists in one launch: windowed shared-memory bitmap (rows_bm.cuh)
-    k_rows_bm<MODE><<<d->sm_count, BM_THREADS, BM_SMEM, d->stream>>>(a.m, l3, &d->d_sc->n_l, l2, &d->d_sc->n_m2, ctr + 0, d->cnt.p, a.dCrow, a.is64, ccol, tofs, d->d_sc, bm_m2 ? 1u : 0u);
+  if (d->use_bm) {           // long rows (and rows of more than 1024 A entries), then the medium rows: windowed shared-memory bitmap (rows_bm.cuh)
+    k_rows_bm<MODE, false><<<d->sm_count, BM_THREADS, BM_SMEM, d->stream>>>(a.m, l3, &d->d_sc->n_l, ctr + 0, d->cnt.p, a.dCrow, a.is64, ccol, tofs, d->d_sc, 0u);
     d->launches++;
     CK(cudaGetLastError());
+    if (d->have_m2 && bm_m2) {
+      k_rows_bm<MODE, true><<<d->sm_count, BM_THREADS, BM_SMEM, d->stream>>>(a.m, l2, &d->d_sc->n_m2, ctr + 1, d->cnt.p, a.dCrow, a.is64, ccol, tofs, d->d_sc, bm_cmode);
+      d->launches++;
+      CK(cudaGetLastError());
+    }
   }
   if (d->have_l && !d->use_bm) {
     if (d->use_window)   // windowed shared-memory bitmap (rows_window.cuh)
@@ -402,16 +410,19 @@ static int mul_launch_main(bspgemm_dev* d) {
   d->have_l = max_ip > CAP_M2;
   d->st.cap_s = (int)cap; d->st.group = d->G;
   CKS(d->cnt.ensure(An + 1));
+  // Rows above 2048 products of matrices of up to BM_MAX_WINDOWS windows of columns: rows_bm.cuh (BSPGEMM_NO_BM: the round-1 kernels).
+  // Its medium-row kernel keeps a row's products in registers and wants at most 1024 A entries per row: k_build_lists sends longer
+  // rows to the long-row list whatever their product count, so that list may be non-empty even when max_ip <= CAP_M2.
+  d->use_bm = d->have_m2 && (u64)a.m.Bm <= (u64)BM_MAX_WINDOWS * BM_WORDS * 32ull && !getenv("BSPGEMM_NO_BM");
+  if (d->use_bm) d->have_l = true;
   if (d->have_m) {
     CKS(d->lists.ensure(3 * An + 3));
     CKS(d->tofs.ensure(An + 1));
     k_build_lists<<<(int)((An + 255) / 256), 256, 0, d->stream>>>(d->ip.p, a.m.An, cap, CAP_M1, CAP_M2,
-        d->lists.p, d->lists.p + An, d->lists.p + 2 * An, d->tofs.p, d->d_sc);
+        d->lists.p, d->lists.p + An, d->lists.p + 2 * An, d->tofs.p, d->d_sc, a.m.Arow, d->use_bm ? BM_CHUNK : 0xffffffffu);
     d->launches++;
     CK(cudaGetLastError());
   }
-  // Rows above 2048 products of matrices of up to BM_MAX_WINDOWS windows of columns: rows_bm.cuh (BSPGEMM_NO_BM: the round-1 kernels)
-  d->use_bm = d->have_m2 && (u64)a.m.Bm <= (u64)BM_MAX_WINDOWS * BM_WORDS * 32ull && !getenv("BSPGEMM_NO_BM");
   // Matrices of up to WIN_MAX_WINDOWS windows of columns: every big row goes through the windowed bitmap kernel
   d->use_window = (u64)a.m.Bm <= (u64)WIN_MAX_WINDOWS * WIN_WORDS * 32ull && !getenv("BSPGEMM_NO_WINDOW");
   if (d->have_l && !d->use_window && !d->use_bm) {

@@ -223,7 +223,8 @@ __global__ void __launch_bounds__(256) k_estimate(Csr m, u32* __restrict__ ip, D
 // IP words (rounded up to 4) of the staging arena (MODE_STAGE), handed out with one 64-bit atomic per warp.
 static __global__ void __launch_bounds__(256) k_build_lists(const u32* __restrict__ ip, int An, u32 cap_s, u32 cap_m1, u32 cap_m2,
                                                      u32* __restrict__ list_m1, u32* __restrict__ list_m2,
-                                                     u32* __restrict__ list_l, u64* __restrict__ tofs, DevScalars* sc) {
+                                                     u32* __restrict__ list_l, u64* __restrict__ tofs, DevScalars* sc,
+                                                     const int* __restrict__ Arow, u32 max_na_m2) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const u32 v = (i < An) ? ip[i] : 0u;
   const bool big = v > cap_s;
@@ -240,7 +241,7 @@ static __global__ void __launch_bounds__(256) k_build_lists(const u32* __restric
   }
   if (!big) return;
   if (v <= cap_m1)      list_m1[atomicAdd(&sc->n_m1, 1u)] = (u32)i;
-  else if (v <= cap_m2) list_m2[atomicAdd(&sc->n_m2, 1u)] = (u32)i;
+  else if (v <= cap_m2 && (u32)(Arow[i + 1] - Arow[i]) <= max_na_m2) list_m2[atomicAdd(&sc->n_m2, 1u)] = (u32)i;   // (rows_bm.cuh's register path: <= 1024 A entries)
   else                  list_l[atomicAdd(&sc->n_l, 1u)] = (u32)i;
 }
 

@@ -52,6 +52,8 @@ constexpr u32 BM_MAX_WINDOWS = 8;                     // host: wider matrices ke
 constexpr size_t BM_SMEM = (size_t)(BM_WORDS + BM_FLAGW + BM_LISTW + 3u * (BM_CHUNK + 4u)) * 4u;
 static_assert(BM_PIECES <= 65536u, "piece ids are 16 bits");
 static_assert(3u * BM_THREADS >= BM_FLAGW, "three summary words per thread cover the summary");
+static_assert(2u * BM_THREADS <= BM_FLAGW && 2u * BM_THREADS * 2u <= (BM_THREADS + 4u) * 4u, "compressed pass: 2048 piece-bitmap words in the summary area, 2048 u16 ranks in cb");
+constexpr u32 BM_COMP_MAX_BM = 2u * BM_THREADS * 32u * 128u;   // 8,388,608 columns: piece ids are 16 bits
 
 // Block-wide exclusive scan with ONE barrier: lane 31 of every warp posts the warp's total, after the barrier every warp scans
 // the 32 totals itself.  red: 2 x 32 words, used alternately (a thread can be at most one scan ahead of the slowest one).
@@ -71,12 +73,13 @@ __device__ __forceinline__ u32 bm_scan(u32 v, u32* red, u32& flip, u32* total) {
 __device__ __forceinline__ u32 bm_popc4(const uint4& x) { return __popc(x.x) + __popc(x.y) + __popc(x.z) + __popc(x.w); }
 __device__ __forceinline__ u32 bm_word(const uint4& x, u32 i) { return i == 0 ? x.x : i == 1 ? x.y : i == 2 ? x.z : x.w; }
 
-template <int MODE>
+// SMALLK: the list holds rows of at most 16384 products and 1024 A entries (k_build_lists): products in registers, compressed single
+// pass when cmode; the walking code is compiled out.  !SMALLK: any row, walked per window; the register path is compiled out.
+template <int MODE, bool SMALLK>
 __global__ void __launch_bounds__(BM_THREADS, 1) k_rows_bm(Csr m, const u32* __restrict__ list_a, const u32* __restrict__ nlist_a,
-                                                           const u32* __restrict__ list_b, const u32* __restrict__ nlist_b,
                                                            u32* __restrict__ ctr, u32* __restrict__ cnt,
                                                            const void* __restrict__ Crow, int is64, int* __restrict__ Ccol,
-                                                           const u64* __restrict__ tofs, DevScalars* sc, u32 use_b) {
+                                                           const u64* __restrict__ tofs, DevScalars* sc, u32 cmode) {
   extern __shared__ __align__(16) u32 bm[];
   u32* const flw = bm + BM_WORDS;                     // summary bytes, read as words by the emission
   unsigned char* const fl = reinterpret_cast<unsigned char*>(flw);
@@ -85,6 +88,7 @@ __global__ void __launch_bounds__(BM_THREADS, 1) k_rows_bm(Csr m, const u32* __r
   u32* const bst = off + BM_CHUNK + 4u;               // BM_CHUNK: where every B row starts in Bcol, minus its off[]
   u32* const cb = bst + BM_CHUNK + 4u;                // BM_THREADS + 1: output offset of every thread's share of the piece list
   uint4* const bm4 = reinterpret_cast<uint4*>(bm);
+  unsigned short* const pre16 = reinterpret_cast<unsigned short*>(cb);   // compressed pass: slots before every word of the piece bitmap (dead before cb is written)
   __shared__ u32 s_red[64];
   __shared__ u32 s_idx[2], s_above;
   const u32 tid = threadIdx.x, lane = lane_id(), wid = tid >> 5;
@@ -92,12 +96,12 @@ __global__ void __launch_bounds__(BM_THREADS, 1) k_rows_bm(Csr m, const u32* __r
   constexpr u32 wbits = BM_WORDS << 5;
   u32 flip = 0;
   for (u32 q = tid; q < (BM_WORDS + BM_FLAGW) / 4u; q += BM_THREADS) bm4[q] = make_uint4(0u, 0u, 0u, 0u);
-  const u32 na = *nlist_a, n = na + (use_b ? *nlist_b : 0u);
+  const u32 n = *nlist_a;
   if (tid == 0) { s_idx[0] = atomicAdd(ctr, 1u); s_above = EMPTY; }
   __syncthreads();
   u32 idx = s_idx[0];
   int row = 0, a0 = 0, a1 = 0;
-  if (idx < n) { row = (int)(idx < na ? list_a[idx] : list_b[idx - na]); a0 = m.Arow[row]; a1 = m.Arow[row + 1]; }
+  if (idx < n) { row = (int)list_a[idx]; a0 = m.Arow[row]; a1 = m.Arow[row + 1]; }
   u32 it = 0;
   while (idx < n) {
     u32 nidx_reg = 0;
@@ -107,7 +111,7 @@ __global__ void __launch_bounds__(BM_THREADS, 1) k_rows_bm(Csr m, const u32* __r
     const u64 base = (MODE == MODE_FILL) ? ld_rowptr(Crow, is64, (size_t)row) : (MODE == MODE_STAGE) ? tofs[row] : 0;
     u64 done = 0;
     u32 start = 0;
-    bool first = true, bad = false, small = false;
+    bool first = true, bad = false, small = false, comp = false;
     u32 rv[BM_REGS], have = 0, nslots = 0;
     while (true) {                                    // windows
       u32 above = EMPTY;
@@ -123,8 +127,9 @@ __global__ void __launch_bounds__(BM_THREADS, 1) k_rows_bm(Csr m, const u32* __r
         off[tid] = o; bst[tid] = bs - o;
         if (tid == BM_THREADS - 1) off[BM_CHUNK] = tot;
         __syncthreads();
-        small = tot <= BM_REGS * BM_THREADS;
-        if (small) {                                  // SMALL ROW: every thread loads its (at most 16) products once
+        small = SMALLK && tot <= BM_REGS * BM_THREADS;
+        if (SMALLK && !small) bad = true;             // (cannot happen: the list was built from the same product counts)
+        if (SMALLK && small) {                        // every thread loads its (at most 16) products once
           const u32 per = ((tot + BM_THREADS - 1u) / BM_THREADS) * 32u;
           const u32 ws = wid * per, we = min(tot, ws + per);
           u32 p = ws + lane;
@@ -147,7 +152,78 @@ __global__ void __launch_bounds__(BM_THREADS, 1) k_rows_bm(Csr m, const u32* __r
           }
         }
       }
-      if (small) {
+      u32 npieces = 0;
+      if (SMALLK && small && cmode && first) {
+        // ---- COMPRESSED SINGLE PASS (rows of up to 16384 products, matrices wider than one window): instead of one bitmap pass
+        // per 1.44 M-column window, (1) mark the 128-column PIECES the row touches in a piece bitmap over all of [0,Bm) (Bm/128
+        // bits: 4 KB at Bm = 2^22), (2) rank them — piece -> slot, slots in column order, (3) set the products' bits in the
+        // slots (16 bytes each, the bitmap area holds 11264 of them), (4) emit the slots.  Marks and bits are plain
+        // read-modify-writes repaired by a second pass, like the windowed insert.  More than 11264 pieces: back to windows.
+        const u32 uBm = (u32)m.Bm;
+#pragma unroll
+        for (int k = 0; k < (int)BM_REGS; ++k) {
+          if ((u32)k >= nslots) break;
+          if ((have >> k) & 1u) {
+            const u32 v = rv[k];
+            if (v >= uBm) bad = true;
+            else { const u32 pc = v >> 7, b = 1u << (pc & 31u), o = flw[pc >> 5]; if (!(o & b)) flw[pc >> 5] = o | b; }
+          }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < (int)BM_REGS; ++k) {
+          if ((u32)k >= nslots) break;
+          if ((have >> k) & 1u) {
+            const u32 v = rv[k];
+            if (v < uBm) { const u32 pc = v >> 7, b = 1u << (pc & 31u); if (!(flw[pc >> 5] & b)) atomicOr(&flw[pc >> 5], b); }
+          }
+        }
+        if (tid == 0) s_idx[(it + 1u) & 1u] = nidx_reg;
+        __syncthreads();
+        const u32 w0 = flw[2u * tid], w1 = flw[2u * tid + 1u];            // thread t ranks the pieces of bitmap words 2 t, 2 t + 1
+        u32 pos = bm_scan(__popc(w0) + __popc(w1), s_red, flip, &npieces);
+        comp = npieces <= BM_PIECES;
+        if (comp) {
+          pre16[2u * tid] = (unsigned short)pos;
+          pre16[2u * tid + 1u] = (unsigned short)(pos + __popc(w0));
+          for (u32 b = w0; b; b &= b - 1u) plist[pos++] = (unsigned short)(tid * 64u + (u32)__ffs((int)b) - 1u);
+          for (u32 b = w1; b; b &= b - 1u) plist[pos++] = (unsigned short)(tid * 64u + 32u + (u32)__ffs((int)b) - 1u);
+        } else { flw[2u * tid] = 0u; flw[2u * tid + 1u] = 0u; npieces = 0; }
+        __syncthreads();
+        if (comp) {
+#pragma unroll
+          for (int k = 0; k < (int)BM_REGS; ++k) {
+            if ((u32)k >= nslots) break;
+            if ((have >> k) & 1u) {
+              const u32 v = rv[k];
+              if (v < uBm) {
+                const u32 pc = v >> 7, pw = flw[pc >> 5];
+                const u32 a = ((u32)pre16[pc >> 5] + __popc(pw & ((1u << (pc & 31u)) - 1u))) * 4u + ((v >> 5) & 3u);
+                const u32 bit = 1u << (v & 31u), o = bm[a];
+                if (!(o & bit)) bm[a] = o | bit;
+              }
+            }
+          }
+          __syncthreads();
+#pragma unroll
+          for (int k = 0; k < (int)BM_REGS; ++k) {
+            if ((u32)k >= nslots) break;
+            if ((have >> k) & 1u) {
+              const u32 v = rv[k];
+              if (v < uBm) {
+                const u32 pc = v >> 7, pw = flw[pc >> 5];
+                const u32 a = ((u32)pre16[pc >> 5] + __popc(pw & ((1u << (pc & 31u)) - 1u))) * 4u + ((v >> 5) & 3u);
+                const u32 bit = 1u << (v & 31u);
+                if (!(bm[a] & bit)) atomicOr(&bm[a], bit);
+              }
+            }
+          }
+          __syncthreads();
+        }
+      }
+      if (comp) {
+        // (the slots are filled; nothing to walk)
+      } else if (SMALLK) {
         // pass A / barrier / pass B straight from the registers: no walk, no loads in the second and later windows
 #pragma unroll
         for (int k = 0; k < (int)BM_REGS; ++k) {
@@ -239,11 +315,14 @@ __global__ void __launch_bounds__(BM_THREADS, 1) k_rows_bm(Csr m, const u32* __r
           }
         }
       }
-      above = __reduce_min_sync(FULL, above);
-      if (lane == 0 && above != EMPTY) atomicMin(&s_above, above);
-      if (first && tid == 0) s_idx[(it + 1u) & 1u] = nidx_reg;
-      u32 nxt;
-      {
+      u32 nxt = EMPTY;
+      if (comp) {
+        nidx = s_idx[(it + 1u) & 1u];                   // next row, stage 1: its list entry (published before the ranking scan)
+        if (nidx < n) nrow = (int)list_a[nidx];
+      } else {
+        above = __reduce_min_sync(FULL, above);
+        if (lane == 0 && above != EMPTY) atomicMin(&s_above, above);
+        if (first && tid == 0) s_idx[(it + 1u) & 1u] = nidx_reg;
         // ---- emission, step 1: the ordered list of non-empty 16-byte pieces (thread t scans summary words 3 t .. 3 t + 2)
         u32 f[3], np = 0;
   #pragma unroll
@@ -252,7 +331,6 @@ __global__ void __launch_bounds__(BM_THREADS, 1) k_rows_bm(Csr m, const u32* __r
           f[q] = (iw < BM_FLAGW) ? (flw[iw] & 0x01010101u) : 0u;            // the walk's last barrier ordered the summary stores
           np += __popc(f[q]);
         }
-        u32 npieces;
         u32 pos = bm_scan(np, s_red, flip, &npieces);                      // (its barrier also publishes s_above / s_idx)
   #pragma unroll
         for (int q = 0; q < 3; ++q) {
@@ -263,15 +341,18 @@ __global__ void __launch_bounds__(BM_THREADS, 1) k_rows_bm(Csr m, const u32* __r
         nxt = s_above;
         if (first) {                                    // next row, stage 1: its list entry
           nidx = s_idx[(it + 1u) & 1u];
-          if (nidx < n) nrow = (int)(nidx < na ? list_a[nidx] : list_b[nidx - na]);
+          if (nidx < n) nrow = (int)list_a[nidx];
         }
         __syncthreads();
+      }
+      {
+        // steps 2 and 3 read piece i of the list at bm4[comp ? i : plist[i]]; its columns start at 128 * plist[i] (+ window start)
         if (npieces) {
           // ---- step 2: every thread sums an equal share of the list; offsets of the shares
           const u32 K = (npieces + BM_THREADS - 1u) / BM_THREADS;
           const u32 i0 = min(tid * K, npieces), i1 = min(i0 + K, npieces);
           u32 c = 0;
-          for (u32 i = i0; i < i1; ++i) c += bm_popc4(bm4[plist[i]]);
+          for (u32 i = i0; i < i1; ++i) c += bm_popc4(bm4[comp ? i : (u32)plist[i]]);
           u32 tot;
           const u32 cbase = bm_scan(c, s_red, flip, &tot);
           if (MODE != MODE_COUNT) {
@@ -287,7 +368,7 @@ __global__ void __launch_bounds__(BM_THREADS, 1) k_rows_bm(Csr m, const u32* __r
               while (hi - lo > 1u) { const u32 mid = (lo + hi) >> 1; if (cb[mid] <= o0) lo = mid; else hi = mid; }
               u32 i = lo * K, run = cb[lo], k;
               uint4 x;
-              while (true) { k = plist[i]; x = bm4[k]; const u32 pc = bm_popc4(x); if (run + pc > o0) break; run += pc; ++i; }
+              while (true) { k = plist[i]; x = bm4[comp ? i : k]; const u32 pc = bm_popc4(x); if (run + pc > o0) break; run += pc; ++i; }
               // drop the bits that belong to the threads before: whole words first, then bit by bit
               u32 skip = o0 - run;
   #pragma unroll
@@ -301,7 +382,7 @@ __global__ void __launch_bounds__(BM_THREADS, 1) k_rows_bm(Csr m, const u32* __r
               // one loop of `left` iterations, the same trip count for every thread: lowest set bit of the 128-bit piece, next piece
               // when this one is used up (listed pieces are never empty)
               for (; left; --left) {
-                if (!(x.x | x.y | x.z | x.w)) { ++i; k = plist[i]; x = bm4[k]; }
+                if (!(x.x | x.y | x.z | x.w)) { ++i; k = plist[i]; x = bm4[comp ? i : k]; }
                 const bool e0 = x.x != 0u, e1 = !e0 && x.y != 0u, e2 = !e0 && !e1 && x.z != 0u, e3 = !e0 && !e1 && !e2;   // selects, no branches
                 const u32 word = e0 ? x.x : e1 ? x.y : e2 ? x.z : x.w;
                 const u32 rest = word & (word - 1u);
@@ -312,10 +393,11 @@ __global__ void __launch_bounds__(BM_THREADS, 1) k_rows_bm(Csr m, const u32* __r
             }
           }
           __syncthreads();                              // everybody has read the pieces: clear them
-          for (u32 i = tid; i < npieces; i += BM_THREADS) bm4[plist[i]] = make_uint4(0u, 0u, 0u, 0u);
+          for (u32 i = tid; i < npieces; i += BM_THREADS) bm4[comp ? i : (u32)plist[i]] = make_uint4(0u, 0u, 0u, 0u);
           done += tot;
         }
       }
+      if (comp) { flw[2u * tid] = 0u; flw[2u * tid + 1u] = 0u; }              // the piece bitmap (its owner clears it)
       if (tid == 0) s_above = EMPTY;
       if (first && nidx < n) { na0 = m.Arow[nrow]; na1 = m.Arow[nrow + 1]; }   // next row, stage 2: its row pointers
       first = false;
@@ -325,7 +407,7 @@ __global__ void __launch_bounds__(BM_THREADS, 1) k_rows_bm(Csr m, const u32* __r
       start = nxt & ~31u;
     }
     if (MODE != MODE_FILL && tid == 0) cnt[row] = (u32)done;
-    if (bad && tid == 0) atomicOr(&sc->err, 4u);
+    if (bad) atomicOr(&sc->err, 4u);                  // (windowed passes: every thread saw it; compressed pass: the thread that held the product)
     idx = nidx; row = nrow; a0 = na0; a1 = na1; ++it;
   }
 }

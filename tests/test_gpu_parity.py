@@ -437,7 +437,9 @@ def test_window_bins_many_windows_unsorted_rows(bs, oracle, monkeypatch):
         parts.append(c)
     Bcol = np.concatenate(parts).astype(np.int32)
     rows = [np.arange(0, 40), np.arange(1, 2000, 3), np.arange(2, 2000, 3), np.arange(40, 1500), np.arange(0, k),
-            rng.choice(k, 200, replace=False), np.arange(41, 3000, 3)]
+            rng.choice(k, 200, replace=False), np.arange(41, 3000, 3),
+            np.arange(42, 3000, 3)[:600],      # ~9 K scattered products: the compressed single pass of rows_bm.cuh (piece slots)
+            np.arange(42, 3000, 3)[:960]]      # ~14 K scattered products over 6 M columns: more than 11264 pieces -> back to windows
     for _ in range(50):
         rows.append(rng.choice(np.arange(40, k), int(rng.integers(0, 10)), replace=False))
     Arow = np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.int32)
