@@ -231,9 +231,13 @@ static __device__ __noinline__ void chain_helper(CtaChain* cc, u64* blk_status, 
 static __device__ __noinline__ void chain_helper_dyn(CtaChain* cc, u64* blk_status, u32* counter, u32 ntiles, u32 ncompute, u32 lag) {
   const u32 lane = lane_id();
   const u32 nblocks = (ntiles + ncompute - 1u) / ncompute;
+  // The first five iterations take the static ids it * gridDim.x + blockIdx.x, the global counter hands out the rest.  (All
+  // five claimed from the counter at kernel start gave every CTA five CONSECUTIVE ids: block 42, the first of one CTA, then
+  // waited for block 41, the fifth of another — every first commit of the kernel waited four iterations, ~30 us at config 3,
+  // and a shard of six iterations per CTA ran 2.5 times longer than its work: tools/shard_sweep.py, profiles/r02_sweeps.txt.)
   auto claim = [&](u32 it) {
     if (lane == 0) {
-      const u32 id = atomicAdd(counter, 1u);
+      const u32 id = it < 5u ? it * gridDim.x + blockIdx.x : 5u * gridDim.x + atomicAdd(counter, 1u);
       *reinterpret_cast<volatile u32*>(&cc->blkid[it & (CH_RING - 1u)]) = id;
       __threadfence_block();
       *reinterpret_cast<volatile u32*>(&cc->blkit[it & (CH_RING - 1u)]) = it + 1u;

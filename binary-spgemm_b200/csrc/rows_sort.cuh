@@ -129,22 +129,24 @@ __global__ void __maxnreg__(64) k_rows_sort(Csr m, const u32* __restrict__ list,
                                                  const u64* __restrict__ tofs, DevScalars* sc) {
   extern __shared__ __align__(16) u32 buf[];                 // KMAX*T words
   __shared__ u32 s_red[33], s_last[32];
-  __shared__ u32 s_idx, s_pos, s_nlong, s_bad;
+  __shared__ u32 s_idx[2], s_pos, s_nlong, s_bad;
   __shared__ uint4 s_long[RS_QCAP];                          // (start in Bcol, length, position in buf)
   const u32 t = threadIdx.x, lane = t & 31u, warp = t >> 5;
   constexpr u32 NW = T / 32;
   const u32 n = *nlist;
   const u32 SPW = 32u / (u32)G, sub = lane / (u32)G, off0 = lane % (u32)G;
-  if (t == 0) s_bad = 0;
-  while (true) {
+  if (t == 0) { s_bad = 0; s_idx[0] = atomicAdd(ctr, 1u); }
+  __syncthreads();
+  // The row after this one is fetched while this one is sorted: its list index (an atomic) at the top of the iteration, its list
+  // entry after the gather, its product count and row pointers after the sort — three of the six dependent global latencies
+  // (counter -> list -> Arow -> Acol -> Brow -> Bcol) that otherwise stand in front of every row's gather.
+  u32 idx = s_idx[0], ipr = 0, it = 0;
+  int row = 0, a0 = 0, a1 = 0;
+  if (idx < n) { row = (int)list[idx]; ipr = ip[row]; a0 = m.Arow[row]; a1 = m.Arow[row + 1]; }
+  while (idx < n) {
+    u32 nidx_reg = 0;
+    if (t == 0) { nidx_reg = atomicAdd(ctr, 1u); s_pos = 0; s_nlong = 0; }
     __syncthreads();
-    if (t == 0) { s_idx = atomicAdd(ctr, 1u); s_pos = 0; s_nlong = 0; }
-    __syncthreads();
-    const u32 idx = s_idx;
-    if (idx >= n) break;
-    const int row = (int)list[idx];
-    const u32 ipr = ip[row];
-    const int a0 = m.Arow[row], a1 = m.Arow[row + 1];
     // ---- gather: every warp takes batches of 32 A nonzeros; G lanes walk one B row; positions from a warp scan + one
     //      shared-memory atomic per batch (the order of the candidates in buf does not matter)
     for (int b0 = a0 + (int)warp * 32; b0 < a1; b0 += (int)NW * 32) {
@@ -174,7 +176,11 @@ __global__ void __maxnreg__(64) k_rows_sort(Csr m, const u32* __restrict__ list,
         for (u32 o = off0; o < slen; o += (u32)G) buf[spos + o] = (u32)__ldg(&m.Bcol[sbs + o]);
       }
     }
+    if (t == 0) s_idx[(it + 1u) & 1u] = nidx_reg;
     __syncthreads();
+    const u32 nidx = s_idx[(it + 1u) & 1u];
+    int nrow = 0;
+    if (nidx < n) nrow = (int)list[nidx];
     {
       const u32 nl = min(s_nlong, (u32)RS_QCAP);
       for (u32 q = 0; q < nl; ++q) {
@@ -191,6 +197,10 @@ __global__ void __maxnreg__(64) k_rows_sort(Csr m, const u32* __restrict__ list,
     else if (ipr <= (u32)(KMAX / 2) * T) c = cta_sort_dedup<KMAX / 2, T, MODE>(buf, ipr, (u32)m.Bm, dst, s_red, s_last, &s_bad);
     else                                 c = cta_sort_dedup<KMAX, T, MODE>(buf, ipr, (u32)m.Bm, dst, s_red, s_last, &s_bad);
     if (MODE != MODE_FILL && t == 0) cnt[row] = c;
+    u32 nipr = 0; int na0 = 0, na1 = 0;
+    if (nidx < n) { nipr = ip[nrow]; na0 = m.Arow[nrow]; na1 = m.Arow[nrow + 1]; }
+    idx = nidx; row = nrow; ipr = nipr; a0 = na0; a1 = na1; ++it;
+    __syncthreads();                                   // (s_pos / s_nlong are reset at the top of the next iteration)
   }
   __syncthreads();
   if (t == 0 && s_bad) atomicOr(&sc->err, 4u);
