@@ -33,6 +33,12 @@
 //   * one barrier per block scan (every warp scans the 32 warp totals itself, double-buffered), not three.
 //   * the window slides: the next one starts at the smallest column seen beyond the current one, so empty stretches of the
 //     column range cost nothing.  B rows need not be sorted.
+//   * MEDIUM ROWS (at most 16384 products and 1024 A entries: their own list and kernel instantiation, SMALLK) keep their products
+//     in registers (at most 16 per thread) and, where the matrix is wider than one window, take a COMPRESSED SINGLE PASS instead
+//     of one pass per window: the 128-column pieces the row touches are marked in a piece bitmap over all of [0,Bm) (4 KB at
+//     Bm = 2^22), ranked by one block scan (piece -> slot, slots in column order), the products' bits are set in the slots
+//     (16 bytes each; the bitmap area holds 11264 of them; more pieces than that: back to windows) and the slots are emitted
+//     like the pieces of a window.  A medium row pays the per-pass fixed costs once instead of three times at Bm = 2^22.
 //   * the next row's list entry and row pointers are fetched while the current row is processed.
 // MODE_COUNT: cnt[row]; MODE_FILL: columns at Ccol[Crow[row]..); MODE_STAGE: both, columns at Ccol[tofs[row]..) (staging arena).
 #pragma once

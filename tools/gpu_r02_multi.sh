@@ -5,16 +5,16 @@ O=gpurun_out; mkdir -p $O
 N=${N:-2}
 nvidia-smi --query-gpu=index,name,memory.total --format=csv,noheader | head -8
 if [ "$N" = "2" ]; then
-  timeout 900 python -m pytest tests -m gpu -x -q -k "two_gpus or over_nccl or sharded or consumer or validity_driver or reference_main" > $O/r02m${N}_gputests.log 2>&1; echo "gpu tests exit $?"; tail -4 $O/r02m${N}_gputests.log
+  timeout 900 python -m pytest tests -m gpu -x -q -k "two_gpus or over_nccl or sharded or consumer or validity_driver or reference_main" > $O/r02f${N}_gputests.log 2>&1; echo "gpu tests exit $?"; tail -4 $O/r02f${N}_gputests.log
 fi
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
-timeout 900 $TR bench.py --gpus $N --steps 10 --warmup 3 > $O/r02m${N}_cfg3.json 2> $O/r02m${N}_cfg3.err; echo "cfg3 exit $?"
-timeout 900 $TR bench.py --gpus $N --workload cfg5 --steps 5 --warmup 3 --no-cpu-baseline > $O/r02m${N}_cfg5.json 2> $O/r02m${N}_cfg5.err; echo "cfg5 exit $?"
-timeout 900 $TR bench.py --gpus $N --workload cfg4 --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --validate-rows 6000 > $O/r02m${N}_cfg4_rows.json 2> $O/r02m${N}_cfg4_rows.err; echo "cfg4 rows exit $?"
-timeout 900 $TR bench.py --gpus $N --workload cfg4 --split ip --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --validate-rows 6000 > $O/r02m${N}_cfg4_ip.json 2> $O/r02m${N}_cfg4_ip.err; echo "cfg4 ip exit $?"
+timeout 900 $TR bench.py --gpus $N --steps 10 --warmup 3 > $O/r02f${N}_cfg3.json 2> $O/r02f${N}_cfg3.err; echo "cfg3 exit $?"
+timeout 900 $TR bench.py --gpus $N --workload cfg5 --steps 5 --warmup 3 --no-cpu-baseline > $O/r02f${N}_cfg5.json 2> $O/r02f${N}_cfg5.err; echo "cfg5 exit $?"
+[ -n "$ROWS" ] && { timeout 900 $TR bench.py --gpus $N --workload cfg4 --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --validate-rows 6000 > $O/r02f${N}_cfg4_rows.json 2> $O/r02f${N}_cfg4_rows.err; echo "cfg4 rows exit $?"; }
+timeout 900 $TR bench.py --gpus $N --workload cfg4 --split ip --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --validate-rows 6000 > $O/r02f${N}_cfg4_ip.json 2> $O/r02f${N}_cfg4_ip.err; echo "cfg4 ip exit $?"
 python - <<PY
 import json, glob
-for f in sorted(glob.glob("gpurun_out/r02m${N}_*.json")):
+for f in sorted(glob.glob("gpurun_out/r02f${N}_*.json")):
     try:
         d = json.loads(open(f).read().strip().splitlines()[-1])
         e = d.get("e2e") or {}
