@@ -34,7 +34,7 @@ def test_version_and_strerror(bs):
     L = bs.lib()
     assert b"sm_100a" in L.bspgemm_version()
     assert L.bspgemm_strerror(bs.ERR_NOGPU) and b"fallback" in L.bspgemm_strerror(bs.ERR_NOGPU)
-    assert L.bspgemm_num_gpus() == 0 or True
+    assert L.bspgemm_num_gpus() >= 0          # 0 before bspgemm_init (another test of this session may have initialised a context)
 
 
 def test_no_cpu_fallback_without_gpu(bs):

@@ -181,3 +181,23 @@ def test_readCOO_parallel_tokenizer_matches_the_oracle_reader(bs, oracle, tmp_pa
     b.write_text("\n".join(head + bad) + "\n")
     with pytest.raises(OSError):
         bs.readCOO(str(b))
+
+
+def test_work_balanced_row_blocks_are_contiguous_and_even(bs):
+    """bench.py --split ip / BSPGEMM_SPLIT=ip: contiguous row blocks with equal intermediate products."""
+    import importlib.util, sys, torch
+    from pathlib import Path
+    spec = importlib.util.spec_from_file_location("bench_mod", Path(__file__).resolve().parents[1] / "bench.py")
+    bench = importlib.util.module_from_spec(spec); spec.loader.exec_module(bench)
+    row, col = bs.gen_rmat(13, 16, 0.45, 0.22, 0.22, 1)
+    n = len(row) - 1
+    blen = np.diff(row).astype(np.int64)
+    cs = np.concatenate([[0], np.cumsum(blen[col])])
+    ip = cs[row[1:]] - cs[row[:-1]]
+    for world in (2, 3, 8):
+        b = bench.shard_bounds_ip(torch.from_numpy(row), torch.from_numpy(col), n, world)
+        assert b[0] == 0 and b[-1] == n and all(x <= y for x, y in zip(b, b[1:])), b
+        work = [int(ip[b[q]:b[q + 1]].sum()) + (b[q + 1] - b[q]) for q in range(world)]
+        assert max(work) - min(work) <= 2 * int(ip.max()) + 2, (work, int(ip.max()))     # within one (largest) row of each other
+        rows_split = [int(ip[(n * q) // world:(n * (q + 1)) // world].sum()) for q in range(world)]
+        assert max(work) <= max(rows_split) + world                                      # never worse than equal rows
