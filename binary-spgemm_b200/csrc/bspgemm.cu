@@ -268,6 +268,7 @@ static int launch_estimate_kernel(bspgemm_dev* d) {
 
 // phase 0: longest rows of A and B (decides whether the work-estimation pass can be skipped)
 static int mul_launch_probe(bspgemm_dev* d) {
+  NvtxRange nvtx_("bspgemm.probe");
   const MulArgs& a = d->a;
   CK(cudaSetDevice(d->device));
   d->launches = 0;
@@ -296,6 +297,7 @@ static int mul_launch_probe(bspgemm_dev* d) {
 // phase 1: work estimation (north-star step 1) — skipped when maxlen(A)*maxlen(B) bounds every row's IP
 // by the S-bin capacity (then no row can leave the S bin and Σip <= nnzA*maxlen(B)).
 static int mul_launch_estimate(bspgemm_dev* d) {
+  NvtxRange nvtx_("bspgemm.estimate");
   const MulArgs& a = d->a;
   CK(cudaSetDevice(d->device));
   CK(cudaStreamSynchronize(d->stream));
@@ -323,6 +325,7 @@ static int mul_launch_estimate(bspgemm_dev* d) {
 
 // phase 2: bins, symbolic, scan / fused fill
 static int mul_launch_main(bspgemm_dev* d) {
+  NvtxRange nvtx_("bspgemm.main");
   const MulArgs& a = d->a;
   CK(cudaSetDevice(d->device));
   const size_t An = (size_t)a.m.An;
@@ -535,6 +538,7 @@ static int wait_stream(cudaStream_t s) {
 
 // phase 3 (two-phase mode only): numeric fill at the scanned row pointers
 static int mul_launch_fill(bspgemm_dev* d) {
+  NvtxRange nvtx_("bspgemm.fill");
   const MulArgs& a = d->a;
   CK(cudaSetDevice(d->device));
   CKS(wait_stream(d->stream));
@@ -622,6 +626,7 @@ static bool env_overrides() {
   return false;
 }
 static int mul_launch_fast(bspgemm_dev* d, bool* taken) {
+  NvtxRange nvtx_("bspgemm.fast");
   const MulArgs& a = d->a;
   *taken = false;
   if (!b_prepared(d) || d->pb.variant < 0 || d->mode == BSPGEMM_MODE_TWOPHASE || d->user_ccol || env_overrides()) return BSPGEMM_OK;
@@ -1004,6 +1009,7 @@ static unsigned long long g_epoch = 0;
 static int host_multiply(const int* Acol, const int* Arow, int An, const int* Bcol, const int* Brow, int Bn, int Bm,
                          int** Ccol_malloc, int* Ccol_buf, int64_t capacity, void* Crow, int is64, int64_t* nnz_out, int ng_limit,
                          bspgemm_result* keep = nullptr) {
+  NvtxRange nvtx_("bspgemm.host_multiply");
   if (!Arow || !Brow || (!Crow && !keep) || An < 0 || Bn < 0 || Bm < 0) return fail(BSPGEMM_ERR_BADARG, "null pointer or negative size");
   ++g_epoch;
   CKS(ensure_init());

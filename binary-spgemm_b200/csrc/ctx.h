@@ -18,6 +18,16 @@
 #include <stdarg.h>
 #include <math.h>
 #include <algorithm>
+#include <nvtx3/nvToolsExt.h>   // header-only: ranges are no-ops unless a tool (ncu --nvtx, nsys) injects its library
+
+// One NVTX range per phase of a product ("bspgemm.probe", ".estimate", ".main", ".fill", ".fast", ".host_multiply"; no "/" in the names, it is ncu's range separator): lets
+// `ncu --nvtx --nvtx-include "bspgemm.main/"` pick the launches of one phase.  RAII, so every early return closes its range.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 #include <vector>
 #include <mutex>
 #include <thread>
