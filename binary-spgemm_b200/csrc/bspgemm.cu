@@ -39,6 +39,8 @@ extern "C" const char* bspgemm_last_error(void) { return g_err; }
 extern "C" const char* bspgemm_version(void) { return "bspgemm-b200 0.1 (sm_100a)"; }
 
 
+static int wait_stream(cudaStream_t s);
+
 static int g_cap_s_max() { const char* e = getenv("BSPGEMM_CAP_S"); int v = e ? atoi(e) : 512; if (v < 32) v = 32; if (v > 1024) v = 1024; int p = 32; while (p < v) p <<= 1; return p; }
 static const u32 CAP_M1 = 2048;
 // rows above CAP_M2 intermediate products take the windowed-bitmap kernel, rows up to it the CTA-wide sort (BSPGEMM_CAP_M2: tuning knob)
@@ -477,7 +479,18 @@ static int mul_launch_main(bspgemm_dev* d) {
     // passes by the rows themselves.
     const bool cheap = !d->have_m && An >= 65536 && ip_bound / (u64)An <= 96ull;
     if (((staged && !d->skip_estimate) || cheap) && !getenv("BSPGEMM_FUSED_S")) {
-      if (d->skip_estimate) CKS(launch_estimate_kernel(d));          // the warp-per-row kernels read ip[] (no host round trip needed)
+      if (d->skip_estimate) {
+        CKS(launch_estimate_kernel(d));                               // the warp-per-row kernels read ip[]
+        if (cheap) {
+          // The bin capacity was sized from the bound max_len(A) x max_len(B) (Poisson(5) rows: ~20 x 20 -> 512), the rows hold a
+          // fraction of it (max ~110 -> 128): with the real maximum the per-warp table is 2 KB instead of 6.6 KB and twice as many
+          // rows are in flight per SM (64 instead of 32 warps) — one 20 us host round trip against milliseconds.
+          CK(cudaMemcpyAsync(d->h_sc, d->d_sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, d->stream));
+          CKS(wait_stream(d->stream));
+          u32 capr = 32; while (capr < d->h_sc->max_ip) capr <<= 1;
+          if (capr < d->cap_s) { d->cap_s = capr; d->st.cap_s = (int)capr; }
+        }
+      }
       // Skewed matrices (big rows exist and were just staged with their counts): the S rows are counted and filled in two
       // UNORDERED passes around the device scan instead of the ordered one-pass kernel.  Their intermediate products are a
       // few percent of the total (R-MAT scale 22: 3e8 of 1.2e10), so walking them twice is cheap, while k_fused's in-order

@@ -908,3 +908,16 @@ def test_iterated_products_stay_on_the_device(bs, oracle):
     msg = _explain(bs.device_view(ptr, nnz, 0).cpu().numpy(), dCr.cpu().numpy(), want_c, want_r)
     assert not msg, msg
     h.close()
+
+
+def test_sprand_cheap_rows_two_unordered_passes(bs, oracle):
+    """The report's matrices (Matlab sprand(n,n,d/n)>0, Poisson(d) rows; /root/reference/Matlab/write_spm.m:5): every row is small and
+    cheap, so the product runs as count -> device scan -> fill (no ordered one-pass kernel), with the warp bin sized from the
+    measured maximum of the rows' products instead of the bound max_len(A) x max_len(B)."""
+    n, d = 150_000, 5.0
+    row, col = bs.gen_sprand(n, d, 3)
+    want_col, want_row = oracle.spgemm(col, row, n, col, row, n)
+    got_col, got_row, st = dev_multiply(bs, bs.MODE_FUSED, col, row, n, col, row, n, n)
+    msg = _explain(got_col, got_row, want_col, want_row)
+    assert not msg, msg
+    assert st["rows_m"] == 0 and st["rows_l"] == 0 and st["cap_s"] <= 256, st
