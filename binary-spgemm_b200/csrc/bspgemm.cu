@@ -69,13 +69,22 @@ static int gidx(int G) { return G == 4 ? 0 : G == 8 ? 1 : G == 16 ? 2 : 3; }
 template <int MODE> static int launch_rows_warp(bspgemm_dev* d) {
   const MulArgs& a = d->a;
   int* ccol = d->user_ccol ? d->user_ccol : d->ccol.p;
+  // rows of up to 64 products: their own register-only kernel (BSPGEMM_NO_TINY: everything through k_rows_warp)
+  const u32 tiny_max = getenv("BSPGEMM_NO_TINY") ? 0u : TINY_MAX;
+  if (tiny_max) {
+    const long long want = ((long long)a.m.An + 7) / 8;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)d->sm_count * 8 * 2));
+    k_rows_tiny<MODE><<<grid, 256, 0, d->stream>>>(a.m, d->ip.p, d->cnt.p, a.dCrow, a.is64, ccol, d->d_sc);
+    d->launches++;
+    CK(cudaGetLastError());
+  }
   const size_t smem = (size_t)WARPS_S * (tab_words(d->cap_s) + d->cap_s) * sizeof(u32);
   int bps = 0;
 #define LW(Gv) do { \
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_rows_warp<Gv, MODE>, WARPS_S * 32, smem)); \
     const long long want = ((long long)a.m.An + WARPS_S - 1) / WARPS_S; \
     const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)d->sm_count * std::max(bps, 1) * 2)); \
-    k_rows_warp<Gv, MODE><<<grid, WARPS_S * 32, smem, d->stream>>>(a.m, d->ip.p, d->cnt.p, d->cap_s, a.dCrow, a.is64, ccol, d->d_sc); } while (0)
+    k_rows_warp<Gv, MODE><<<grid, WARPS_S * 32, smem, d->stream>>>(a.m, d->ip.p, d->cnt.p, d->cap_s, a.dCrow, a.is64, ccol, d->d_sc, tiny_max); } while (0)
   switch (d->G) { case 4: LW(4); break; case 8: LW(8); break; case 16: LW(16); break; default: LW(32); break; }
 #undef LW
   d->launches++;

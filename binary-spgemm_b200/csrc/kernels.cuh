@@ -487,7 +487,7 @@ __device__ __noinline__ u32 gather_row(const Csr& m, int row, u32 cap, u32* stag
 template <int G, int MODE>
 __global__ void __launch_bounds__(WARPS_S * 32) k_rows_warp(Csr m, const u32* __restrict__ ip, u32* __restrict__ cnt, u32 cap,
                                                            const void* __restrict__ Crow, int is64, int* __restrict__ Ccol,
-                                                           DevScalars* sc) {
+                                                           DevScalars* sc, u32 tiny_max) {
   extern __shared__ __align__(16) u32 smem[];
   const u32 warp = threadIdx.x >> 5, lane = lane_id();
   u32* tab = smem + (size_t)warp * (tab_words(cap) + cap);
@@ -495,7 +495,7 @@ __global__ void __launch_bounds__(WARPS_S * 32) k_rows_warp(Csr m, const u32* __
   const long long nw = (long long)gridDim.x * WARPS_S;
   for (long long row = (long long)blockIdx.x * WARPS_S + warp; row < m.An; row += nw) {
     const u32 ipr = ip[row];
-    if (ipr > cap) continue;
+    if (ipr > cap || ipr <= tiny_max) continue;        // (rows of up to tiny_max products: k_rows_tiny; tiny_max = 0: none, not even empty rows)
     u32 c = 0;
     if (ipr) {
       gather_row<G>(m, (int)row, cap, stage);
@@ -510,6 +510,101 @@ __global__ void __launch_bounds__(WARPS_S * 32) k_rows_warp(Csr m, const u32* __
     if (MODE == MODE_COUNT && lane == 0) cnt[row] = c;
     __syncwarp();
   }
+}
+
+// Rows of at most TINY_MAX (64) intermediate products — all of a sprand(d=5) matrix (Poisson rows, 25 products on average), the
+// small half of every power-law matrix: one warp per row, the row's candidates in ONE or TWO registers per lane, no table.
+// k_rows_warp spends 536 warp instructions on such a row (table set-up, a 128-key network) at 80 registers = 24 warps per SM
+// (profiles/r02_pub_rows_warp_ncu_summary.txt); here: lane per A entry -> warp scan of the B-row lengths -> lane per product
+// (binary search over the scan through shuffles) -> bitonic network over the lanes (15 shuffle stages for <= 32 keys, 21 for
+// <= 64) -> neighbour compare + ballot -> count / ranked stores.  Replaces the flag array + quickSort of SpGEMM_bigslice
+// (final/SpGEMM_mpi_omp.c:21, 33-47) for these rows like the other bins do.
+constexpr u32 TINY_MAX = 64;
+template <int NR>
+__device__ __forceinline__ void tiny_sort(u32 (&k)[NR], const u32 lane) {       // element i = r * 32 + lane, ascending
+#pragma unroll
+  for (u32 kk = 2; kk <= 32u * NR; kk <<= 1) {
+#pragma unroll
+    for (u32 j = kk >> 1; j > 0; j >>= 1) {
+      if (j >= 32u) {                                  // partner in the other register of the same lane (NR == 2, kk == 64: ascending)
+        const u32 lo = min(k[0], k[NR - 1]), hi = max(k[0], k[NR - 1]);
+        k[0] = lo; k[NR - 1] = hi;
+      } else {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          const u32 v = __shfl_xor_sync(0xffffffffu, k[r], (int)j);
+          const u32 i = (u32)r * 32u + lane;
+          const bool up = (i & kk) == 0u, lower = (lane & j) == 0u;
+          k[r] = (lower == up) ? min(k[r], v) : max(k[r], v);
+        }
+      }
+    }
+  }
+}
+template <int NR, int MODE>
+__device__ __forceinline__ u32 tiny_finish(u32 (&k)[NR], const u32 lane, const u32 Bm, int* __restrict__ dst, u32* bad) {
+  tiny_sort<NR>(k, lane);
+  u32 c = 0, before = 0;
+  const u32 last0 = __shfl_sync(0xffffffffu, k[0], 31);          // the element in front of register 1's lane 0
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    u32 prev = __shfl_up_sync(0xffffffffu, k[r], 1);
+    if (lane == 0) prev = (r == 0) ? EMPTY : last0;
+    if (k[r] != EMPTY && k[r] >= Bm) { *bad = 1; }
+    const bool keep = k[r] != EMPTY && k[r] < Bm && k[r] != prev;
+    const u32 mask = __ballot_sync(0xffffffffu, keep);
+    if (MODE == MODE_FILL && keep) dst[before + __popc(mask & ((1u << lane) - 1u))] = (int)k[r];
+    before += __popc(mask);
+    c = before;
+  }
+  return c;
+}
+template <int MODE>
+__global__ void __launch_bounds__(256) k_rows_tiny(Csr m, const u32* __restrict__ ip, u32* __restrict__ cnt,
+                                                   const void* __restrict__ Crow, int is64, int* __restrict__ Ccol, DevScalars* sc) {
+  __shared__ u32 st[8][TINY_MAX];
+  const u32 warp = threadIdx.x >> 5, lane = lane_id();
+  const long long nw = (long long)gridDim.x * 8;
+  u32 bad = 0;
+  for (long long row = (long long)blockIdx.x * 8 + warp; row < m.An; row += nw) {
+    const u32 ipr = ip[row];
+    if (ipr > TINY_MAX) continue;
+    u32 c = 0;
+    if (ipr) {
+      const int a0 = m.Arow[row], a1 = m.Arow[row + 1];
+      u32 filled = 0;
+      for (int b0 = a0; b0 < a1; b0 += 32) {           // 32 A entries at a time (one pass unless the row selects empty B rows galore)
+        const int jj = b0 + (int)lane;
+        u32 bs = 0, len = 0;
+        if (jj < a1) { const int j = m.Acol[jj]; if ((u32)j < (u32)m.Bn) { bs = (u32)m.Brow[j]; len = (u32)m.Brow[j + 1] - bs; } }
+        const u32 incl = warp_incl_scan(len);
+        const u32 tot = __shfl_sync(0xffffffffu, incl, 31);
+#pragma unroll
+        for (u32 h = 0; h < 2; ++h) {
+          if (h * 32u >= tot) break;                   // warp-uniform
+          const u32 q = h * 32u + lane;                // product q of this chunk: entry e = number of lanes whose scan is <= q
+          u32 e = 0;
+#pragma unroll
+          for (u32 step = 16; step; step >>= 1) { const u32 v = __shfl_sync(0xffffffffu, incl, (int)(e + step - 1u)); if (v <= q) e += step; }
+          const u32 e_bs = __shfl_sync(0xffffffffu, bs, (int)(e & 31u)), e_excl = __shfl_sync(0xffffffffu, incl - len, (int)(e & 31u));
+          if (q < tot && filled + q < TINY_MAX) st[warp][filled + q] = (u32)__ldg(&m.Bcol[e_bs + (q - e_excl)]);
+        }
+        filled += tot;
+      }
+      __syncwarp();
+      int* dst = (MODE == MODE_FILL) ? Ccol + ld_rowptr(Crow, is64, (size_t)row) : nullptr;
+      if (ipr <= 32u) {
+        u32 k[1] = { lane < ipr ? st[warp][lane] : EMPTY };
+        c = tiny_finish<1, MODE>(k, lane, (u32)m.Bm, dst, &bad);
+      } else {
+        u32 k[2] = { st[warp][lane], lane + 32u < ipr ? st[warp][lane + 32u] : EMPTY };
+        c = tiny_finish<2, MODE>(k, lane, (u32)m.Bm, dst, &bad);
+      }
+      __syncwarp();
+    }
+    if (MODE == MODE_COUNT && lane == 0) cnt[row] = c;
+  }
+  if (bad) atomicOr(&sc->err, 4u);
 }
 
 // ------------------------------------------------------------------------------------------------ fused one-pass kernel
