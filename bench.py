@@ -428,6 +428,8 @@ def main():
         kernel_name = "k_band (%d rows per tile, 128-bit register bitmap per row)" % last["rows_per_tile"]
     elif last.get("variant", 0) == 1:
         kernel_name = "k_fused_ell<W=%d,R=%d>" % (last["group"], last["rows_per_tile"])
+    elif last.get("kernel_flags", 0) & 4:
+        kernel_name = "k_rows_tiny + k_rows_warp<G=%d> count, k_scan, fill (small rows in two unordered passes)" % last["group"]
     else:
         kernel_name = "k_fused<G=%d>" % last["group"]
     roof_ms = main_ms

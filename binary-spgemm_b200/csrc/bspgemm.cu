@@ -505,6 +505,7 @@ static int mul_launch_main(bspgemm_dev* d) {
       // few percent of the total (R-MAT scale 22: 3e8 of 1.2e10), so walking them twice is cheap, while k_fused's in-order
       // look-back made every warp wait for the slowest earlier tile when row costs differ by orders of magnitude (85 % of its
       // warp time in the spin, profiles/r02_rmat20_kfused_stalls.txt: 112 of 527 ms per step at config 4).
+      d->st.kernel_flags |= 4;                                       // small rows: count -> scan -> fill (bench.py labels the kernel from this)
       CKS(launch_rows_warp<MODE_COUNT>(d));
       const u32 nt = (u32)((An + SCAN_THREADS * SCAN_ITEMS - 1) / (SCAN_THREADS * SCAN_ITEMS));
       u64* chain = nullptr;

@@ -148,7 +148,7 @@ typedef struct bspgemm_stats {
                                  2 = register sorting network (fused_sort.cuh); then cap_s = table words per row, group =
                                  ELL width W, ms_symbolic = the CSR->ELL re-layout of B */
   int32_t rows_per_tile;      /* fused kernels: consecutive rows per look-back tile */
-  int32_t kernel_flags;       /* bit 0: variant 2 ran k_fused_sort_async (cp.async input) rather than k_fused_sort */
+  int32_t kernel_flags;       /* bit 0: variant 2 ran k_fused_sort_async (cp.async input) rather than k_fused_sort; bit 1: floating-point network; bit 2: small rows ran as count -> scan -> fill (k_rows_tiny / k_rows_warp) instead of the ordered one-pass kernel */
   int32_t b_prepared;         /* 1: B was the matrix given to bspgemm_dev_prepare_b (its re-layout was not rebuilt) */
   int32_t plan_cached;        /* 1: launched from the cached plan of the previous product (no probes, one kernel) */
 } bspgemm_stats;
