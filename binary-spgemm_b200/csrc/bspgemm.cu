@@ -70,11 +70,11 @@ template <int MODE> static int launch_rows_warp(bspgemm_dev* d) {
   const MulArgs& a = d->a;
   int* ccol = d->user_ccol ? d->user_ccol : d->ccol.p;
   // rows of up to 64 products: their own register-only kernel (BSPGEMM_NO_TINY: everything through k_rows_warp)
-  const u32 tiny_max = getenv("BSPGEMM_NO_TINY") ? 0u : TINY_MAX;
+  const u32 tiny_max = getenv("BSPGEMM_NO_TINY") ? 0u : std::min<u32>(TINY_MAX, d->cap_s);      // (never beyond the warp bin: larger rows are on the CTA lists)
   if (tiny_max) {
     const long long want = ((long long)a.m.An + 7) / 8;
     const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)d->sm_count * 8 * 2));
-    k_rows_tiny<MODE><<<grid, 256, 0, d->stream>>>(a.m, d->ip.p, d->cnt.p, a.dCrow, a.is64, ccol, d->d_sc);
+    k_rows_tiny<MODE><<<grid, 256, 0, d->stream>>>(a.m, d->ip.p, d->cnt.p, a.dCrow, a.is64, ccol, d->d_sc, tiny_max);
     d->launches++;
     CK(cudaGetLastError());
   }

@@ -561,14 +561,15 @@ __device__ __forceinline__ u32 tiny_finish(u32 (&k)[NR], const u32 lane, const u
 }
 template <int MODE>
 __global__ void __launch_bounds__(256) k_rows_tiny(Csr m, const u32* __restrict__ ip, u32* __restrict__ cnt,
-                                                   const void* __restrict__ Crow, int is64, int* __restrict__ Ccol, DevScalars* sc) {
+                                                   const void* __restrict__ Crow, int is64, int* __restrict__ Ccol, DevScalars* sc,
+                                                   u32 tiny_max) {                     // <= TINY_MAX; rows above it belong to the other bins
   __shared__ u32 st[8][TINY_MAX];
   const u32 warp = threadIdx.x >> 5, lane = lane_id();
   const long long nw = (long long)gridDim.x * 8;
   u32 bad = 0;
   for (long long row = (long long)blockIdx.x * 8 + warp; row < m.An; row += nw) {
     const u32 ipr = ip[row];
-    if (ipr > TINY_MAX) continue;
+    if (ipr > tiny_max) continue;
     u32 c = 0;
     if (ipr) {
       const int a0 = m.Arow[row], a1 = m.Arow[row + 1];
