@@ -504,7 +504,7 @@ static int mul_launch_main(bspgemm_dev* d) {
       // UNORDERED passes around the device scan instead of the ordered one-pass kernel.  Their intermediate products are a
       // few percent of the total (R-MAT scale 22: 3e8 of 1.2e10), so walking them twice is cheap, while k_fused's in-order
       // look-back made every warp wait for the slowest earlier tile when row costs differ by orders of magnitude (85 % of its
-      // warp time in the spin, profiles/r02_rmat20_kfused_stalls.txt: 112 of 527 ms per step at config 4).
+      // warp time in the spin, profiles/r02_rmat20_kfused_ncu_summary.txt: 112 of 527 ms per step at config 4).
       d->st.kernel_flags |= 4;                                       // small rows: count -> scan -> fill (bench.py labels the kernel from this)
       CKS(launch_rows_warp<MODE_COUNT>(d));
       const u32 nt = (u32)((An + SCAN_THREADS * SCAN_ITEMS - 1) / (SCAN_THREADS * SCAN_ITEMS));
@@ -721,7 +721,7 @@ static int dev_create(bspgemm_dev** out, int device) {
   cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, device));
   if (p.major < 10) return fail(BSPGEMM_ERR_NOGPU, "device %d is sm_%d%d; this library is built for sm_100a only", device, p.major, p.minor);
   // L2 fetch granularity: the gathers of B rows are 64-byte (config 3) random accesses; the device default fetches more than the
-  // row on a miss (profiles/r02_l2_fetch_granularity.txt).  BSPGEMM_L2_FETCH=32|64|128 overrides (device-wide limit).
+  // row on a miss (measured: no effect, profiles/r02_sweeps.txt item 2).  BSPGEMM_L2_FETCH=32|64|128 overrides (device-wide limit).
   if (const char* e = getenv("BSPGEMM_L2_FETCH")) { const int v = atoi(e); if (v == 32 || v == 64 || v == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)v); cudaGetLastError(); }
   bspgemm_dev* d = new bspgemm_dev();
   d->device = device; d->sm_count = p.multiProcessorCount; d->smem_optin = p.sharedMemPerBlockOptin;
